@@ -1,0 +1,588 @@
+// Memory-bound fused kernels of the worker training step (sm_100a): LayerNorm fwd/bwd,
+// embedding fwd/bwd, softmax-cross-entropy fwd+bwd in one pass, bias-grad column reduce,
+// flat-buffer AdamW (fp32 master + bf16 compute copy + grad zeroing in one sweep),
+// grad-norm, casts.  All 16-byte vectorised; one HBM read + one write per tensor.
+// The reference operator ships no kernels; these serve the launched
+// DDP workers that BASELINE.json's samples/sec metric measures.
+#include "ptx.cuh"
+
+namespace aitj {
+
+// ------------------------------------------------------------------ LayerNorm forward
+// One warp per row; V = C / 256 uint4 vectors per lane (C % 256 == 0).
+template <int V>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ gamma,
+                                                            const __nv_bfloat16* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int M, float eps) {
+  constexpr int C = V * 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  float g[V * 8], b[V * 8];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    uint4 gu = *reinterpret_cast<const uint4*>(gamma + (i * 32 + lane) * 8);
+    uint4 bu = *reinterpret_cast<const uint4*>(beta + (i * 32 + lane) * 8);
+    const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 gf = unpack_bf16x2(gw[j]), bf = unpack_bf16x2(bw[j]);
+      g[i * 8 + 2 * j] = gf.x; g[i * 8 + 2 * j + 1] = gf.y;
+      b[i * 8 + 2 * j] = bf.x; b[i * 8 + 2 * j + 1] = bf.y;
+    }
+  }
+  for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
+    const __nv_bfloat16* xr = x + static_cast<size_t>(row) * C;
+    float v[V * 8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      uint4 u = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16x2(w[j]);
+        v[i * 8 + 2 * j] = f.x; v[i * 8 + 2 * j + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V * 8; ++i) { float d = v[i] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+    __nv_bfloat16* yr = y + static_cast<size_t>(row) * C;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a0 = (v[i * 8 + 2 * j] - mean) * rstd * g[i * 8 + 2 * j] + b[i * 8 + 2 * j];
+        float a1 = (v[i * 8 + 2 * j + 1] - mean) * rstd * g[i * 8 + 2 * j + 1] + b[i * 8 + 2 * j + 1];
+        ow[j] = pack_bf16x2(a0, a1);
+      }
+      *reinterpret_cast<uint4*>(yr + (i * 32 + lane) * 8) = o;
+    }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// dx (bf16), dgamma/dbeta accumulated (fp32 atomics) into flat grad buffer. If `dres` != null
+// the incoming residual-stream gradient is added to dx (fuses the residual branch add).
+template <int V>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                            const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in,
+                                                            const __nv_bfloat16* __restrict__ dres,
+                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int M) {
+  constexpr int C = V * 256;
+  __shared__ float red[8][C];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  float g[V * 8], dg[V * 8], db[V * 8];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    uint4 gu = *reinterpret_cast<const uint4*>(gamma + (i * 32 + lane) * 8);
+    const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 gf = unpack_bf16x2(gw[j]);
+      g[i * 8 + 2 * j] = gf.x; g[i * 8 + 2 * j + 1] = gf.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V * 8; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+
+  for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
+    const size_t base = static_cast<size_t>(row) * C;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[V * 8], dyv[V * 8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      uint4 xu = *reinterpret_cast<const uint4*>(x + base + (i * 32 + lane) * 8);
+      uint4 du = *reinterpret_cast<const uint4*>(dy + base + (i * 32 + lane) * 8);
+      const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w}, dw[4] = {du.x, du.y, du.z, du.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]);
+        const int k = i * 8 + 2 * j;
+        xh[k] = (xf.x - mean) * rstd; xh[k + 1] = (xf.y - mean) * rstd;
+        dyv[k] = df.x; dyv[k + 1] = df.y;
+        dg[k] += df.x * xh[k]; dg[k + 1] += df.y * xh[k + 1];
+        db[k] += df.x; db[k + 1] += df.y;
+        const float a0 = df.x * g[k], a1 = df.y * g[k + 1];
+        s1 += a0 + a1;
+        s2 += a0 * xh[k] + a1 * xh[k + 1];
+      }
+    }
+    s1 = warp_sum(s1) * (1.0f / C);
+    s2 = warp_sum(s2) * (1.0f / C);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float r[8];
+      if (dres != nullptr) {
+        uint4 ru = *reinterpret_cast<const uint4*>(dres + base + (i * 32 + lane) * 8);
+        const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = unpack_bf16x2(rw[j]); r[2 * j] = f.x; r[2 * j + 1] = f.y; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = 0.f;
+      }
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = i * 8 + 2 * j;
+        float a0 = rstd * (dyv[k] * g[k] - s1 - xh[k] * s2) + r[2 * j];
+        float a1 = rstd * (dyv[k + 1] * g[k + 1] - s1 - xh[k + 1] * s2) + r[2 * j + 1];
+        ow[j] = pack_bf16x2(a0, a1);
+      }
+      *reinterpret_cast<uint4*>(dx + base + (i * 32 + lane) * 8) = o;
+    }
+  }
+  // block reduce dgamma then dbeta through smem, one atomic per column per block
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][(i * 32 + lane) * 8 + j] = pass == 0 ? dg[i * 8 + j] : db[i * 8 + j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < warps_per_block; ++w) s += red[w][c];
+      atomicAdd((pass == 0 ? dgamma : dbeta) + c, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ embedding
+__global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __restrict__ tok,
+                                                            const __nv_bfloat16* __restrict__ wte,
+                                                            const __nv_bfloat16* __restrict__ wpe,
+                                                            __nv_bfloat16* __restrict__ out, int M, int T, int C) {
+  const int vec_per_row = C / 8;
+  const size_t total = static_cast<size_t>(M) * vec_per_row;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / vec_per_row), c = static_cast<int>(i % vec_per_row) * 8;
+    const int64_t t = tok[m];
+    uint4 a = *reinterpret_cast<const uint4*>(wte + t * C + c);
+    uint4 b = wpe ? *reinterpret_cast<const uint4*>(wpe + static_cast<size_t>(m % T) * C + c) : make_uint4(0, 0, 0, 0);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 fa = unpack_bf16x2(aw[j]), fb = unpack_bf16x2(bw[j]);
+      ow[j] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * C + c) = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __restrict__ tok,
+                                                            const __nv_bfloat16* __restrict__ dx,
+                                                            float* __restrict__ dwte, float* __restrict__ dwpe, int M,
+                                                            int T, int C) {
+  const int vec_per_row = C / 4;
+  const size_t total = static_cast<size_t>(M) * vec_per_row;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / vec_per_row), c = static_cast<int>(i % vec_per_row) * 4;
+    uint2 u = *reinterpret_cast<const uint2*>(dx + static_cast<size_t>(m) * C + c);
+    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+    float* p = dwte + tok[m] * C + c;
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(f0.x), "f"(f0.y), "f"(f1.x), "f"(f1.y)
+                 : "memory");
+    if (dwpe) {
+      float* q = dwpe + static_cast<size_t>(m % T) * C + c;
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(q), "f"(f0.x), "f"(f0.y), "f"(f1.x), "f"(f1.y)
+                   : "memory");
+    }
+  }
+}
+
+// ------------------------------------------------------------------ softmax cross-entropy fwd+bwd
+// One block per row. The row (bf16, Vp padded columns, V real) is staged in smem once; the
+// kernel writes the per-row loss and overwrites the logits with dlogits = (p - onehot) * gscale.
+__global__ void __launch_bounds__(512) softmax_xent_kernel(__nv_bfloat16* __restrict__ logits,
+                                                           const int64_t* __restrict__ target,
+                                                           float* __restrict__ loss, int V, int Vp, float gscale) {
+  extern __shared__ uint4 srow4[];
+  __shared__ float sred[16];
+  __shared__ float sbcast[2];
+  __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(srow4);
+  const int row = blockIdx.x;
+  __nv_bfloat16* g = logits + static_cast<size_t>(row) * Vp;
+  const int nvec = Vp / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 u = *reinterpret_cast<const uint4*>(g + i * 8);
+    srow4[i] = u;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16x2(w[j]);
+      const int c = i * 8 + 2 * j;
+      if (c < V) mx = fmaxf(mx, f.x);
+      if (c + 1 < V) mx = fmaxf(mx, f.y);
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) sred[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nwarps ? sred[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) sbcast[0] = t;
+  }
+  __syncthreads();
+  mx = sbcast[0];
+  const float LOG2E = 1.4426950408889634f;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 u = srow4[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16x2(w[j]);
+      const int c = i * 8 + 2 * j;
+      if (c < V) sum += exp2f((f.x - mx) * LOG2E);
+      if (c + 1 < V) sum += exp2f((f.y - mx) * LOG2E);
+    }
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) sred[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nwarps ? sred[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) sbcast[1] = t;
+  }
+  __syncthreads();
+  sum = sbcast[1];
+  const int tgt = static_cast<int>(target[row]);
+  const bool valid = tgt >= 0 && tgt < V;
+  if (threadIdx.x == 0) {
+    float l = 0.f;
+    if (valid) l = -(__bfloat162float(srow[tgt]) - mx - logf(sum));
+    loss[row] = l;
+  }
+  const float inv = valid ? gscale / sum : 0.f;
+  const float gs = valid ? gscale : 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 u = srow4[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16x2(w[j]);
+      const int c = i * 8 + 2 * j;
+      float p0 = c < V ? exp2f((f.x - mx) * LOG2E) * inv : 0.f;
+      float p1 = c + 1 < V ? exp2f((f.y - mx) * LOG2E) * inv : 0.f;
+      if (c == tgt) p0 -= gs;
+      if (c + 1 == tgt) p1 -= gs;
+      ow[j] = pack_bf16x2(p0, p1);
+    }
+    *reinterpret_cast<uint4*>(g + i * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------ bias grad: db[N] += colsum(dy[M,N])
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
+                                                     int M, int N, int rows_per_block) {
+  // block = 32 column-groups(8 cols each => 256 cols) x 8 row lanes
+  __shared__ float red[8][256];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col0 = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col0 < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      uint4 u = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * N + col0);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16x2(w[j]);
+        acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(db + blockIdx.x * 256 + c, s);
+  }
+}
+
+// ------------------------------------------------------------------ grad norm (sum of squares)
+__global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  __shared__ float sred[16];
+  float s = 0.f;
+  const size_t nvec = n / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(g)[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
+// ------------------------------------------------------------------ AdamW over a flat buffer
+// p,m,v fp32 master state; g fp32 grads (zeroed on the way out when zero_grad != 0);
+// p16 bf16 compute copy refreshed in the same sweep. wd_mask[i / 256] selects weight decay.
+// sumsq (device scalar, may be null) drives global-norm clipping without a host sync.
+struct AdamArgs {
+  float lr, beta1, beta2, eps, weight_decay, bc1, bc2, max_norm, grad_div;
+  int zero_grad;
+};
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    __nv_bfloat16* __restrict__ p16,
+                                                    const uint8_t* __restrict__ wd_mask,
+                                                    const float* __restrict__ sumsq, size_t n, AdamArgs a) {
+  float clip = 1.0f;
+  if (sumsq != nullptr && a.max_norm > 0.f) {
+    const float norm = sqrtf(*sumsq) / a.grad_div;
+    if (norm > a.max_norm) clip = a.max_norm / (norm + 1e-6f);
+  }
+  const float gmul = clip / a.grad_div;
+  const size_t nvec = n / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 gv = reinterpret_cast<float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    const float wd = wd_mask[(i * 4) >> 8] ? a.weight_decay : 0.f;
+    float* pp = reinterpret_cast<float*>(&pv);
+    float* gg = reinterpret_cast<float*>(&gv);
+    float* mm = reinterpret_cast<float*>(&mv);
+    float* vq = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = gg[j] * gmul;
+      mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * gr;
+      vq[j] = a.beta2 * vq[j] + (1.f - a.beta2) * gr * gr;
+      const float mh = mm[j] / a.bc1, vh = vq[j] / a.bc2;
+      pp[j] = pp[j] - a.lr * (mh / (sqrtf(vh) + a.eps) + wd * pp[j]);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (a.zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 o;
+    o.x = pack_bf16x2(pp[0], pp[1]);
+    o.y = pack_bf16x2(pp[2], pp[3]);
+    reinterpret_cast<uint2*>(p16)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in,
+                                                            __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t nvec = n / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+}
+
+// GELU forward/backward as standalone kernels (used when the GEMM backend is the library path).
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                       __nv_bfloat16* __restrict__ y, size_t n) {
+  const size_t nvec = n / 8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16x2(w[j]);
+      ow[j] = pack_bf16x2(gelu_tanh(f.x), gelu_tanh(f.y));
+    }
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                       const __nv_bfloat16* __restrict__ dy,
+                                                       __nv_bfloat16* __restrict__ dx, size_t n) {
+  const size_t nvec = n / 8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    uint4 d = reinterpret_cast<const uint4*>(dy)[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w}, dw[4] = {d.x, d.y, d.z, d.w};
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16x2(w[j]), g = unpack_bf16x2(dw[j]);
+      ow[j] = pack_bf16x2(g.x * gelu_tanh_grad(f.x), g.y * gelu_tanh_grad(f.y));
+    }
+    reinterpret_cast<uint4*>(dx)[i] = o;
+  }
+}
+
+static int grid_for(size_t work_items, int threads, int max_blocks) {
+  size_t b = (work_items + threads - 1) / threads;
+  if (b > static_cast<size_t>(max_blocks)) b = max_blocks;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace aitj
+
+extern "C" {
+using namespace aitj;
+#define S(p) reinterpret_cast<cudaStream_t>(p)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define LAUNCH_OK() (cudaPeekAtLastError() == cudaSuccess ? 0 : -30)
+
+int aitj_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, void* mean, void* rstd, int M,
+                       int C, float eps, void* stream) {
+  if (C % 256 || C > 2048) return -1;
+  const int blocks = min((M + 7) / 8, 148 * 8);
+#define LN_F(V) layernorm_fwd_kernel<V><<<blocks, 256, 0, S(stream)>>>(CBF(x), CBF(gamma), CBF(beta), BF(y), \
+    reinterpret_cast<float*>(mean), reinterpret_cast<float*>(rstd), M, eps)
+  switch (C / 256) {
+    case 1: LN_F(1); break; case 2: LN_F(2); break; case 3: LN_F(3); break; case 4: LN_F(4); break;
+    case 6: LN_F(6); break; case 8: LN_F(8); break; default: return -1;
+  }
+#undef LN_F
+  return LAUNCH_OK();
+}
+
+int aitj_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd,
+                       const void* dres, void* dx, void* dgamma, void* dbeta, int M, int C, void* stream) {
+  if (C % 256 || C > 1024) return -1;
+  const int blocks = min((M + 7) / 8, 148 * 2);
+#define LN_B(V) layernorm_bwd_kernel<V><<<blocks, 256, 0, S(stream)>>>(CBF(dy), CBF(x), CBF(gamma), \
+    reinterpret_cast<const float*>(mean), reinterpret_cast<const float*>(rstd), CBF(dres), BF(dx), \
+    reinterpret_cast<float*>(dgamma), reinterpret_cast<float*>(dbeta), M)
+  switch (C / 256) {
+    case 1: LN_B(1); break; case 2: LN_B(2); break; case 3: LN_B(3); break; case 4: LN_B(4); break;
+    default: return -1;
+  }
+#undef LN_B
+  return LAUNCH_OK();
+}
+
+int aitj_embedding_fwd(const void* tok, const void* wte, const void* wpe, void* out, int M, int T, int C,
+                       void* stream) {
+  if (C % 8) return -1;
+  const size_t total = static_cast<size_t>(M) * (C / 8);
+  embedding_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, S(stream)>>>(
+      reinterpret_cast<const int64_t*>(tok), CBF(wte), CBF(wpe), BF(out), M, T, C);
+  return LAUNCH_OK();
+}
+
+int aitj_embedding_bwd(const void* tok, const void* dx, void* dwte, void* dwpe, int M, int T, int C, void* stream) {
+  if (C % 4) return -1;
+  const size_t total = static_cast<size_t>(M) * (C / 4);
+  embedding_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, S(stream)>>>(
+      reinterpret_cast<const int64_t*>(tok), CBF(dx), reinterpret_cast<float*>(dwte), reinterpret_cast<float*>(dwpe),
+      M, T, C);
+  return LAUNCH_OK();
+}
+
+int aitj_softmax_xent(void* logits, const void* target, void* loss, int M, int V, int Vp, float gscale,
+                      void* stream) {
+  if (Vp % 8 || V > Vp) return -1;
+  const int smem = Vp * 2;
+  if (smem > 200 * 1024) return -2;
+  static int configured = 0;
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(softmax_xent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return -20;
+    configured = smem;
+  }
+  softmax_xent_kernel<<<M, 512, smem, S(stream)>>>(BF(logits), reinterpret_cast<const int64_t*>(target),
+                                                    reinterpret_cast<float*>(loss), V, Vp, gscale);
+  return LAUNCH_OK();
+}
+
+int aitj_colsum(const void* dy, void* db, int M, int N, void* stream) {
+  if (N % 8) return -1;
+  const int rows_per_block = 512;
+  dim3 grid((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<grid, 256, 0, S(stream)>>>(CBF(dy), reinterpret_cast<float*>(db), M, N, rows_per_block);
+  return LAUNCH_OK();
+}
+
+int aitj_sumsq(const void* g, long long n, void* out, void* stream) {
+  if (n % 4) return -1;
+  sumsq_kernel<<<grid_for(static_cast<size_t>(n) / 4, 512, 148 * 4), 512, 0, S(stream)>>>(
+      reinterpret_cast<const float*>(g), static_cast<size_t>(n), reinterpret_cast<float*>(out));
+  return LAUNCH_OK();
+}
+
+int aitj_adamw(void* p, void* g, void* m, void* v, void* p16, const void* wd_mask, const void* sumsq, long long n,
+               float lr, float beta1, float beta2, float eps, float weight_decay, int step, float max_norm,
+               float grad_div, int zero_grad, void* stream) {
+  if (n % 256) return -1;
+  AdamArgs a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  a.bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  a.max_norm = max_norm; a.grad_div = grad_div; a.zero_grad = zero_grad;
+  adamw_kernel<<<grid_for(static_cast<size_t>(n) / 4, 256, 148 * 8), 256, 0, S(stream)>>>(
+      reinterpret_cast<float*>(p), reinterpret_cast<float*>(g), reinterpret_cast<float*>(m),
+      reinterpret_cast<float*>(v), BF(p16), reinterpret_cast<const uint8_t*>(wd_mask),
+      reinterpret_cast<const float*>(sumsq), static_cast<size_t>(n), a);
+  return LAUNCH_OK();
+}
+
+int aitj_cast_f32_bf16(const void* in, void* out, long long n, void* stream) {
+  if (n % 4) return -1;
+  cast_f32_bf16_kernel<<<grid_for(static_cast<size_t>(n) / 4, 256, 148 * 8), 256, 0, S(stream)>>>(
+      reinterpret_cast<const float*>(in), BF(out), static_cast<size_t>(n));
+  return LAUNCH_OK();
+}
+
+int aitj_gelu_fwd(const void* x, void* y, long long n, void* stream) {
+  if (n % 8) return -1;
+  gelu_fwd_kernel<<<grid_for(static_cast<size_t>(n) / 8, 256, 148 * 8), 256, 0, S(stream)>>>(CBF(x), BF(y),
+                                                                                             static_cast<size_t>(n));
+  return LAUNCH_OK();
+}
+int aitj_gelu_bwd(const void* x, const void* dy, void* dx, long long n, void* stream) {
+  if (n % 8) return -1;
+  gelu_bwd_kernel<<<grid_for(static_cast<size_t>(n) / 8, 256, 148 * 8), 256, 0, S(stream)>>>(
+      CBF(x), CBF(dy), BF(dx), static_cast<size_t>(n));
+  return LAUNCH_OK();
+}
+}  // extern "C"

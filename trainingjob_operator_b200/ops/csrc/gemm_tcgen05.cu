@@ -1,0 +1,385 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring ->
+// tcgen05.mma (one elected thread) -> fp32 accumulators in TMEM (double buffered) ->
+// tcgen05.ld epilogue with fused bias / GELU / dGELU / residual / fp32 (split-K, red.add) output.
+//
+//   out[M,N] (+)= opA[M,K] * opB[N,K]^T
+//     a_mn == 0 : A stored [M,K] row-major (K contiguous, "K-major")
+//     a_mn == 1 : A stored [K,M] row-major (M contiguous, "MN-major")   -> used by wgrad
+//     b_mn == 0 : B stored [N,K] row-major                               -> forward  (x @ W^T)
+//     b_mn == 1 : B stored [K,N] row-major                               -> dgrad    (dy @ W), wgrad
+//
+// Warp roles (192 threads, 1 CTA / SM):  warp0 = TMA producer, warp1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane group = warp_id % 4).
+//
+// The reference operator has no GPU code; this kernel belongs to the launched
+// workers' training step that BASELINE.json measures (samples/sec).
+#include "ptx.cuh"
+
+namespace aitj {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+
+enum : int {
+  EPI_BIAS = 1,       // + bias[N]
+  EPI_GELU = 2,       // gelu_tanh(.)
+  EPI_RESIDUAL = 4,   // + residual[M,ldc]
+  EPI_SAVE_PRE = 8,   // aux[M,ldc] <- value before GELU (bf16)
+  EPI_DGELU = 16,     // * gelu'(aux[M,ldc])
+  EPI_OUT_F32 = 32,   // out is fp32 (plain store)
+  EPI_ACCUM = 64,     // out is fp32, red.global.add (split-K / grad accumulation)
+  EPI_BIAS_ROW = 128  // reserved
+};
+
+struct GemmArgs {
+  int M, N, K;
+  int ldc;
+  void* out;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* aux;
+  int flags;
+  int split_k;
+  int tiles_m, tiles_n;
+  int k_blocks, k_per_split;
+};
+
+struct WorkItem {
+  int m_blk, n_blk, kb0, kb1;
+};
+
+__device__ __forceinline__ WorkItem decode_work(const GemmArgs& a, int w) {
+  const int num_tiles = a.tiles_m * a.tiles_n;
+  const int split = w / num_tiles;
+  const int t = w - split * num_tiles;
+  constexpr int GROUP_M = 8;
+  const int group_sz = GROUP_M * a.tiles_n;
+  const int g = t / group_sz;
+  const int first_m = g * GROUP_M;
+  const int gm = min(a.tiles_m - first_m, GROUP_M);
+  const int r = t - g * group_sz;
+  WorkItem wi;
+  wi.m_blk = first_m + (r % gm);
+  wi.n_blk = r / gm;
+  wi.kb0 = split * a.k_per_split;
+  wi.kb1 = min(a.k_blocks, wi.kb0 + a.k_per_split);
+  return wi;
+}
+
+template <int kBlockN>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& a, const uint32_t (&r)[32], int row, int col0) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  const int flags = a.flags;
+  const size_t off = static_cast<size_t>(row) * a.ldc + col0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (col0 + q * 8 >= a.N) break;
+    float* x = v + q * 8;
+    if (flags & EPI_BIAS) {
+      uint4 b = *reinterpret_cast<const uint4*>(a.bias + col0 + q * 8);
+      float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+      x[0] += b0.x; x[1] += b0.y; x[2] += b1.x; x[3] += b1.y;
+      x[4] += b2.x; x[5] += b2.y; x[6] += b3.x; x[7] += b3.y;
+    }
+    if (flags & EPI_SAVE_PRE) {
+      uint4 o;
+      o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+      o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+      *reinterpret_cast<uint4*>(a.aux + off + q * 8) = o;
+    }
+    if (flags & EPI_GELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
+    }
+    if (flags & EPI_DGELU) {
+      uint4 h = *reinterpret_cast<const uint4*>(a.aux + off + q * 8);
+      float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y), h2 = unpack_bf16x2(h.z), h3 = unpack_bf16x2(h.w);
+      x[0] *= gelu_tanh_grad(h0.x); x[1] *= gelu_tanh_grad(h0.y);
+      x[2] *= gelu_tanh_grad(h1.x); x[3] *= gelu_tanh_grad(h1.y);
+      x[4] *= gelu_tanh_grad(h2.x); x[5] *= gelu_tanh_grad(h2.y);
+      x[6] *= gelu_tanh_grad(h3.x); x[7] *= gelu_tanh_grad(h3.y);
+    }
+    if (flags & EPI_RESIDUAL) {
+      uint4 h = *reinterpret_cast<const uint4*>(a.residual + off + q * 8);
+      float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y), h2 = unpack_bf16x2(h.z), h3 = unpack_bf16x2(h.w);
+      x[0] += h0.x; x[1] += h0.y; x[2] += h1.x; x[3] += h1.y;
+      x[4] += h2.x; x[5] += h2.y; x[6] += h3.x; x[7] += h3.y;
+    }
+    if (flags & EPI_ACCUM) {
+      float* o = reinterpret_cast<float*>(a.out) + off + q * 8;
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3])
+                   : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + 4), "f"(x[4]), "f"(x[5]), "f"(x[6]),
+                   "f"(x[7])
+                   : "memory");
+    } else if (flags & EPI_OUT_F32) {
+      float* o = reinterpret_cast<float*>(a.out) + off + q * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+      o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + off + q * 8) = o;
+    }
+  }
+}
+
+template <int kBlockN, bool kAMN, bool kBMN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmArgs args) {
+  constexpr int kStageA = BLOCK_M * BLOCK_K * 2;
+  constexpr int kStageB = kBlockN * BLOCK_K * 2;
+  constexpr int kStageBytes = kStageA + kStageB;
+  constexpr int kStages = (kBlockN == 256) ? 4 : 6;
+  constexpr uint32_t kTmemCols = 2 * kBlockN;
+  constexpr uint32_t kIdesc = make_idesc_bf16(BLOCK_M, kBlockN, kAMN ? 1u : 0u, kBMN ? 1u : 0u);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_work = args.tiles_m * args.tiles_n * args.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const WorkItem wi = decode_work(args, w);
+        for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kStageA;
+          if constexpr (!kAMN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, wi.m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], wi.m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
+          }
+          if constexpr (!kBMN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, wi.n_blk * kBlockN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockN / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], wi.n_blk * kBlockN + j * 64, kb * BLOCK_K);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const WorkItem wi = decode_work(args, w);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBlockN;
+        for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kStageA;
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+            const uint64_t da = kAMN ? make_sw128_desc(a_addr + ks * 2048, BLOCK_K * 128, 1024)
+                                     : make_sw128_desc(a_addr + ks * UMMA_K * 2, 16, 1024);
+            const uint64_t db = kBMN ? make_sw128_desc(b_addr + ks * 2048, BLOCK_K * 128, 1024)
+                                     : make_sw128_desc(b_addr + ks * UMMA_K * 2, 16, 1024);
+            umma_bf16(d_tmem, da, db, kIdesc, (kb > wi.kb0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int lg = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const WorkItem wi = decode_work(args, w);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = wi.m_blk * BLOCK_M + lg * 32 + lane;
+      const bool has_k = wi.kb1 > wi.kb0;
+#pragma unroll 1
+      for (int c = 0; c < kBlockN / 32; ++c) {
+        const int col0 = wi.n_blk * kBlockN + c * 32;
+        if (col0 >= args.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * kBlockN + c * 32 + (static_cast<uint32_t>(lg * 32) << 16), r);
+        tmem_ld_wait();
+        if (row < args.M && has_k) epilogue_chunk<kBlockN>(args, r, row, col0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row stride `ld` elements.
+static int encode_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                          uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -10;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int kBlockN, bool kAMN, bool kBMN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int max_ctas,
+                       cudaStream_t stream) {
+  constexpr int kStages = (kBlockN == 256) ? 4 : 6;
+  constexpr int kStageBytes = BLOCK_M * BLOCK_K * 2 + kBlockN * BLOCK_K * 2;
+  constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  static bool configured = false;
+  auto kern = gemm_bf16_tcgen05_kernel<kBlockN, kAMN, kBMN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return -20;
+    configured = true;
+  }
+  const int num_work = args.tiles_m * args.tiles_n * args.split_k;
+  int grid = num_work < num_sms() ? num_work : num_sms();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  kern<<<grid, kGemmThreads, kSmem, stream>>>(ta, tb, args);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
+}
+
+}  // namespace aitj
+
+extern "C" {
+
+// Returns 0 on success. See file header for operand conventions. lda/ldb/ldc in elements.
+// block_n: 128 or 256 (0 = auto). split_k > 1 requires EPI_ACCUM. max_ctas: 0 = all SMs.
+int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
+                   int a_mn, int b_mn, const void* bias, const void* residual, void* aux, int flags, int split_k,
+                   int block_n, int max_ctas, void* stream_ptr) {
+  using namespace aitj;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((N & 7) || (ldc & 7) || (lda & 7) || (ldb & 7)) return -1;
+  if (split_k > 1 && !(flags & EPI_ACCUM)) return -2;
+  if (block_n == 0) block_n = (N > 128) ? 256 : 128;
+  if (block_n != 128 && block_n != 256) return -3;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_ptr);
+
+  GemmArgs args;
+  args.M = M; args.N = N; args.K = K; args.ldc = ldc; args.out = out;
+  args.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  args.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  args.aux = reinterpret_cast<__nv_bfloat16*>(aux);
+  args.flags = flags;
+  args.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  args.tiles_n = (N + block_n - 1) / block_n;
+  args.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  if (split_k < 1) split_k = 1;
+  if (split_k > args.k_blocks) split_k = args.k_blocks;
+  args.k_per_split = (args.k_blocks + split_k - 1) / split_k;
+  args.split_k = (args.k_blocks + args.k_per_split - 1) / args.k_per_split;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = encode_bf16_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
+  else       rc = encode_bf16_2d(&ta, A, M, K, lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!b_mn) rc = encode_bf16_2d(&tb, B, K, N, ldb, BLOCK_K, block_n);
+  else       rc = encode_bf16_2d(&tb, B, N, K, ldb, 64, BLOCK_K);
+  if (rc) return rc - 1000;
+
+#define AITJ_DISPATCH(BN)                                                                     \
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, args, max_ctas, stream);   \
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ta, tb, args, max_ctas, stream);     \
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ta, tb, args, max_ctas, stream);     \
+  return launch_gemm<BN, true, true>(ta, tb, args, max_ctas, stream);
+  if (block_n == 256) { AITJ_DISPATCH(256) }
+  AITJ_DISPATCH(128)
+#undef AITJ_DISPATCH
+}
+
+int aitj_num_sms() { return aitj::num_sms(); }
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+"""Python entry points of the hand-written sm_100a kernels (ctypes -> libaitj_kernels.so).
+
+Every function launches on ``torch.cuda.current_stream()`` and works on preallocated
+tensors, so a whole training step can be captured in one CUDA graph.  There is deliberately
+no eager/PyTorch fallback here: on a GPU box a missing library raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib
+
+EPI_BIAS = 1
+EPI_GELU = 2
+EPI_RESIDUAL = 4
+EPI_SAVE_PRE = 8
+EPI_DGELU = 16
+EPI_OUT_F32 = 32
+EPI_ACCUM = 64
+
+_NUM_SMS = None
+
+
+def num_sms() -> int:
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _NUM_SMS
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, gelu=False, dgelu=False,
+         save_pre=False, accumulate=False, split_k=1, block_n=0, max_ctas=0):
+    """out[M,N] (+)= opA[M,K] @ opB[N,K]^T on tcgen05 tensor cores (bf16 in, fp32 accumulate).
+
+    a_mn=False: ``a`` is [M,K]; a_mn=True: ``a`` is [K,M] (its transpose is used).
+    b_mn=False: ``b`` is [N,K]; b_mn=True: ``b`` is [K,N].
+    ``out`` bf16 -> plain store; fp32 -> store, or red.add when ``accumulate`` (needed for split_k>1).
+    Epilogue: +bias[N] -> (aux<-pre) -> gelu -> *gelu'(aux) -> +residual[M,N].
+    """
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+    if a_mn:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
+    assert out.shape[0] == M and out.shape[1] == N, (out.shape, M, N)
+    flags = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+    if gelu:
+        flags |= EPI_GELU
+    if residual is not None:
+        flags |= EPI_RESIDUAL
+        assert residual.stride(0) == out.stride(0)
+    if save_pre:
+        flags |= EPI_SAVE_PRE
+    if dgelu:
+        flags |= EPI_DGELU
+    if save_pre or dgelu:
+        assert aux is not None and aux.stride(0) == out.stride(0)
+    if out.dtype == torch.float32:
+        flags |= EPI_ACCUM if accumulate else EPI_OUT_F32
+    else:
+        assert out.dtype == torch.bfloat16 and not accumulate
+    lib.call("aitj_gemm_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
+             out.stride(0), int(a_mn), int(b_mn), _ptr(bias), _ptr(residual), _ptr(aux), flags, int(split_k),
+             int(block_n), int(max_ctas), _stream())
+    return out
+
+
+def auto_split_k(M: int, N: int, K: int, block_n: int = 0) -> int:
+    """Split-K factor that fills the SMs for a weight-gradient shaped GEMM (small MxN, huge K)."""
+    bn = block_n or (256 if N > 128 else 128)
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    sms = num_sms()
+    if tiles >= sms:
+        return 1
+    kb = (K + 63) // 64
+    return max(1, min(kb, sms // tiles))
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
+    M, C = x.shape
+    lib.call("aitj_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+             rstd.data_ptr(), M, C, float(eps), _stream())
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
+    """dx = LN'(dy) (+ dres); dgamma/dbeta (fp32) are accumulated."""
+    M, C = x.shape
+    lib.call("aitj_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+             _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), M, C, _stream())
+    return dx
+
+
+def embedding_fwd(tok, wte, wpe, out, T):
+    M, C = out.shape
+    lib.call("aitj_embedding_fwd", tok.data_ptr(), wte.data_ptr(), _ptr(wpe), out.data_ptr(), M, T, C, _stream())
+    return out
+
+
+def embedding_bwd(tok, dx, dwte, dwpe, T):
+    M, C = dx.shape
+    lib.call("aitj_embedding_bwd", tok.data_ptr(), dx.data_ptr(), dwte.data_ptr(), _ptr(dwpe), M, T, C, _stream())
+
+
+def softmax_xent(logits, target, loss, V, gscale):
+    """In place: logits[M,Vp] <- dlogits = (softmax - onehot) * gscale; loss[M] <- per-row NLL."""
+    M, Vp = logits.shape
+    lib.call("aitj_softmax_xent", logits.data_ptr(), target.data_ptr(), loss.data_ptr(), M, V, Vp, float(gscale),
+             _stream())
+
+
+def colsum(dy, db):
+    M, N = dy.shape
+    lib.call("aitj_colsum", dy.data_ptr(), db.data_ptr(), M, N, _stream())
+
+
+def sumsq(g, out):
+    lib.call("aitj_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), _stream())
+
+
+def adamw(p, g, m, v, p16, wd_mask, *, lr, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.1, step=1, sumsq_buf=None,
+          max_norm=0.0, grad_div=1.0, zero_grad=True):
+    lib.call("aitj_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p16.data_ptr(), wd_mask.data_ptr(),
+             _ptr(sumsq_buf), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+             int(step), float(max_norm), float(grad_div), int(bool(zero_grad)), _stream())
+
+
+def cast_f32_bf16(src, dst):
+    lib.call("aitj_cast_f32_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+
+
+def gelu_fwd(x, y):
+    lib.call("aitj_gelu_fwd", x.data_ptr(), y.data_ptr(), x.numel(), _stream())
+
+
+def gelu_bwd(x, dy, dx):
+    lib.call("aitj_gelu_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), _stream())

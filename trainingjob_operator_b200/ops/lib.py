@@ -1,0 +1,103 @@
+"""ctypes loader for ``libaitj_kernels.so`` (the hand-written sm_100a kernels).
+
+The library is a plain C ABI: every entry point takes raw device pointers and a CUDA stream
+handle and returns 0 or a negative error code.  ``check`` turns non-zero codes into
+exceptions so a missing or failing kernel is never silent (no eager fallback on a GPU box).
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from pathlib import Path
+
+_LIB = None
+_LOCK = threading.Lock()
+LIB_PATH = Path(__file__).resolve().parent / "libaitj_kernels.so"
+
+# launch counter: every successful launch through `call` increments it; bench.py reports the
+# delta over the timed region as "gpu_launches".
+LAUNCHES = 0
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        if not LIB_PATH.exists():
+            if not build_if_missing:
+                raise KernelError(f"{LIB_PATH} missing; run python -m trainingjob_operator_b200.ops.build")
+            from .build import build_kernels
+
+            build_kernels()
+        lib = ctypes.CDLL(str(LIB_PATH))
+        _declare(lib)
+        _LIB = lib
+    return _LIB
+
+
+def available() -> bool:
+    try:
+        load(build_if_missing=False)
+        return True
+    except Exception:
+        return False
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_longlong
+_F = ctypes.c_float
+
+_SIGS = {
+    "aitj_gemm_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
+    "aitj_num_sms": [],
+    "aitj_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "aitj_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "aitj_embedding_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "aitj_embedding_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "aitj_softmax_xent": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "aitj_colsum": [_P, _P, _I, _I, _P],
+    "aitj_sumsq": [_P, _L, _P, _P],
+    "aitj_adamw": [_P, _P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
+    "aitj_cast_f32_bf16": [_P, _P, _L, _P],
+    "aitj_gelu_fwd": [_P, _P, _L, _P],
+    "aitj_gelu_bwd": [_P, _P, _P, _L, _P],
+}
+
+
+def _declare(lib) -> None:
+    for name, argtypes in _SIGS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            continue
+        fn.argtypes = argtypes
+        fn.restype = _I
+    for name in dir(lib):
+        pass
+
+
+def declare(name: str, argtypes) -> None:
+    """Register an extra entry point (used by optional kernels such as the NVLS collectives)."""
+    _SIGS[name] = argtypes
+    if _LIB is not None:
+        fn = getattr(_LIB, name)
+        fn.argtypes = argtypes
+        fn.restype = _I
+
+
+def call(name: str, *args) -> int:
+    global LAUNCHES
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise KernelError(f"{name} failed with code {rc}")
+    LAUNCHES += 1
+    return rc

@@ -1,0 +1,255 @@
+"""Numerics self-check of every hand-written kernel against a plain fp32 PyTorch reference.
+
+Run as ``python -m trainingjob_operator_b200.ops.selfcheck --case <name>`` (one process per
+case: a trapping kernel poisons its CUDA context, so cases are isolated) or ``--case all``.
+Exit code 0 = pass.  ``tests/test_gpu_kernels.py`` drives it under ``@pytest.mark.gpu``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import sys
+import time
+
+import torch
+
+from . import functional as F
+
+
+def _rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
+    got = got.float()
+    ref = ref.float()
+    return float((got - ref).norm() / (ref.norm() + 1e-12))
+
+
+def _rand(*shape, scale=1.0, dtype=torch.bfloat16):
+    return (torch.randn(*shape, device="cuda", dtype=torch.float32) * scale).to(dtype)
+
+
+def _check(name, got, ref, tol):
+    err = _rel_err(got, ref)
+    ok = err < tol and bool(torch.isfinite(got.float()).all())
+    print(f"  {name:<44s} rel_err={err:.3e} tol={tol:.1e} {'ok' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+# ----------------------------------------------------------------------------- GEMM cases
+def _gemm_case(M, N, K, a_mn, b_mn, **kw):
+    a = _rand(K, M) if a_mn else _rand(M, K)
+    b = _rand(K, N) if b_mn else _rand(N, K)
+    A = (a.t() if a_mn else a).float()
+    B = (b.t() if b_mn else b).float()
+    ref = A @ B.t()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    F.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, **kw)
+    torch.cuda.synchronize()
+    return _check(f"gemm M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} {kw}", out, ref, 1e-2)
+
+
+def case_gemm_tn():
+    ok = True
+    for (M, N, K) in [(128, 256, 64), (128, 128, 64), (256, 256, 128), (512, 768, 768), (1000, 776, 200),
+                      (4096, 2304, 768), (384, 50304, 768)]:
+        ok &= _gemm_case(M, N, K, False, False)
+    ok &= _gemm_case(512, 512, 512, False, False, block_n=128)
+    ok &= _gemm_case(2048, 768, 3072, False, False, max_ctas=7)
+    return ok
+
+
+def case_gemm_nn():
+    ok = True
+    for (M, N, K) in [(128, 256, 64), (256, 256, 256), (512, 768, 2304), (1000, 776, 200), (2048, 768, 50304 // 8)]:
+        ok &= _gemm_case(M, N, K, False, True)
+    ok &= _gemm_case(512, 512, 512, False, True, block_n=128)
+    return ok
+
+
+def case_gemm_tt():
+    ok = True
+    for (M, N, K) in [(128, 256, 64), (256, 256, 256), (2304, 768, 4096), (776, 1000, 200)]:
+        ok &= _gemm_case(M, N, K, True, True)
+    ok &= _gemm_case(256, 512, 512, True, False)
+    ok &= _gemm_case(512, 512, 512, True, True, block_n=128)
+    return ok
+
+
+def case_gemm_epilogue():
+    ok = True
+    M, N, K = 512, 768, 768
+    a, b = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = _rand(N)
+    res = _rand(M, N)
+    pre_ref = a.float() @ b.float().t() + bias.float()
+    # bias + gelu + save_pre
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    aux = torch.empty_like(out)
+    F.gemm(a, b, out, bias=bias, gelu=True, save_pre=True, aux=aux)
+    ok &= _check("bias+gelu", out, torch.nn.functional.gelu(pre_ref, approximate="tanh"), 1e-2)
+    ok &= _check("save_pre", aux, pre_ref, 1e-2)
+    # bias + residual
+    F.gemm(a, b, out, bias=bias, residual=res)
+    ok &= _check("bias+residual", out, pre_ref + res.float(), 1e-2)
+    # dgelu
+    h = _rand(M, N)
+    hf = h.float().requires_grad_(True)
+    g = torch.nn.functional.gelu(hf, approximate="tanh")
+    dy = a.float() @ b.float().t()
+    (gref,) = torch.autograd.grad(g, hf, dy)
+    F.gemm(a, b, out, dgelu=True, aux=h)
+    ok &= _check("dgelu", out, gref, 1.5e-2)
+    # fp32 store + accumulate with split-K
+    o32 = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    F.gemm(a, b, o32)
+    ok &= _check("out_f32", o32, dy, 1e-2)
+    o32.fill_(1.0)
+    F.gemm(a, b, o32, accumulate=True, split_k=4)
+    ok &= _check("accumulate split_k=4", o32, dy + 1.0, 1e-2)
+    # wgrad-shaped: dW[N_out,K_in] += dy^T x
+    Mtok, Nout, Kin = 4096, 768, 768
+    dyv, x = _rand(Mtok, Nout), _rand(Mtok, Kin)
+    dw = torch.zeros(Nout, Kin, device="cuda", dtype=torch.float32)
+    sk = F.auto_split_k(Nout, Kin, Mtok)
+    F.gemm(dyv, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=sk)
+    ok &= _check(f"wgrad split_k={sk}", dw, dyv.float().t() @ x.float(), 1e-2)
+    torch.cuda.synchronize()
+    return ok
+
+
+# ----------------------------------------------------------------------------- fused ops
+def case_fused_ops():
+    ok = True
+    torch.manual_seed(0)
+    M, C = 1000, 768
+    x = _rand(M, C)
+    gamma, beta = _rand(C) + 1.0, _rand(C, scale=0.1)
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device="cuda")
+    rstd = torch.empty(M, device="cuda")
+    F.layernorm_fwd(x, gamma, beta, y, mean, rstd)
+    xf = x.float().requires_grad_(True)
+    gf, bf = gamma.float().requires_grad_(True), beta.float().requires_grad_(True)
+    yref = torch.nn.functional.layer_norm(xf, (C,), gf, bf, 1e-5)
+    ok &= _check("layernorm fwd", y, yref, 1e-2)
+    dy = _rand(M, C)
+    dres = _rand(M, C)
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros(C, device="cuda")
+    dbeta = torch.zeros(C, device="cuda")
+    F.layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=dres)
+    gx, gg, gb = torch.autograd.grad(yref, (xf, gf, bf), dy.float())
+    ok &= _check("layernorm bwd dx(+dres)", dx, gx + dres.float(), 1e-2)
+    ok &= _check("layernorm bwd dgamma", dgamma, gg, 1e-2)
+    ok &= _check("layernorm bwd dbeta", dbeta, gb, 1e-2)
+
+    # embedding
+    V, T, B = 1024, 64, 8
+    wte, wpe = _rand(V, C), _rand(T, C)
+    tok = torch.randint(0, V, (B * T,), device="cuda")
+    out = torch.empty(B * T, C, device="cuda", dtype=torch.bfloat16)
+    F.embedding_fwd(tok, wte, wpe, out, T)
+    pos = torch.arange(B * T, device="cuda") % T
+    ok &= _check("embedding fwd", out, wte.float()[tok] + wpe.float()[pos], 1e-2)
+    dxe = _rand(B * T, C)
+    dwte = torch.zeros(V, C, device="cuda")
+    dwpe = torch.zeros(T, C, device="cuda")
+    F.embedding_bwd(tok, dxe, dwte, dwpe, T)
+    rwte = torch.zeros(V, C, device="cuda").index_add_(0, tok, dxe.float())
+    rwpe = torch.zeros(T, C, device="cuda").index_add_(0, pos, dxe.float())
+    ok &= _check("embedding bwd dwte", dwte, rwte, 1e-3)
+    ok &= _check("embedding bwd dwpe", dwpe, rwpe, 1e-3)
+
+    # softmax cross entropy (padded vocab)
+    Mx, Vv, Vp = 256, 50257, 50304
+    logits = _rand(Mx, Vp, scale=2.0)
+    tgt = torch.randint(0, Vv, (Mx,), device="cuda")
+    lf = logits[:, :Vv].float().requires_grad_(True)
+    lref = torch.nn.functional.cross_entropy(lf, tgt, reduction="none")
+    (gl,) = torch.autograd.grad(lref.sum() / Mx, lf)
+    loss = torch.empty(Mx, device="cuda")
+    work = logits.clone()
+    F.softmax_xent(work, tgt, loss, Vv, 1.0 / Mx)
+    ok &= _check("xent loss", loss, lref, 1e-2)
+    ok &= _check("xent dlogits", work[:, :Vv], gl, 2e-2)
+    ok &= bool((work[:, Vv:] == 0).all())
+
+    # colsum
+    dyc = _rand(3000, 2304)
+    db = torch.zeros(2304, device="cuda")
+    F.colsum(dyc, db)
+    ok &= _check("colsum", db, dyc.float().sum(0), 1e-3)
+
+    # adamw vs torch.optim.AdamW, two steps, with decay mask
+    n = 256 * 40
+    p0 = torch.randn(n, device="cuda")
+    mask = torch.zeros(n // 256, dtype=torch.uint8, device="cuda")
+    mask[:20] = 1
+    p = p0.clone()
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    p16 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    pa = torch.nn.Parameter(p0[: 256 * 20].clone())
+    pb = torch.nn.Parameter(p0[256 * 20:].clone())
+    opt = torch.optim.AdamW([{"params": [pa], "weight_decay": 0.1}, {"params": [pb], "weight_decay": 0.0}], lr=1e-2,
+                            betas=(0.9, 0.95), eps=1e-8)
+    for step in (1, 2):
+        g = torch.randn(n, device="cuda")
+        pa.grad = g[: 256 * 20].clone()
+        pb.grad = g[256 * 20:].clone()
+        opt.step()
+        gg = g.clone()
+        F.adamw(p, gg, m, v, p16, mask, lr=1e-2, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.1, step=step)
+        ok &= bool((gg == 0).all())
+    ref = torch.cat([pa.detach(), pb.detach()])
+    ok &= _check("adamw p", p, ref, 1e-5)
+    ok &= _check("adamw p16", p16, ref, 1e-2)
+
+    # sumsq + clipping path
+    g = torch.randn(n, device="cuda")
+    ss = torch.zeros(1, device="cuda")
+    F.sumsq(g, ss)
+    ok &= _check("sumsq", ss, (g * g).sum().reshape(1), 1e-4)
+
+    # gelu standalone
+    xg = _rand(4096, 3072)
+    yg = torch.empty_like(xg)
+    F.gelu_fwd(xg, yg)
+    ok &= _check("gelu fwd", yg, torch.nn.functional.gelu(xg.float(), approximate="tanh"), 1e-2)
+    torch.cuda.synchronize()
+    return ok
+
+
+CASES = {
+    "gemm_tn": case_gemm_tn,
+    "gemm_nn": case_gemm_nn,
+    "gemm_tt": case_gemm_tt,
+    "gemm_epilogue": case_gemm_epilogue,
+    "fused_ops": case_fused_ops,
+}
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default="all")
+    args = ap.parse_args(argv)
+    if not torch.cuda.is_available():
+        print("no CUDA device", file=sys.stderr)
+        return 2
+    torch.manual_seed(1234)
+    names = list(CASES) if args.case == "all" else [args.case]
+    ok = True
+    for n in names:
+        print(f"[selfcheck] {n}", flush=True)
+        t0 = time.time()
+        try:
+            r = CASES[n]()
+        except Exception as e:  # noqa: BLE001
+            print(f"  EXCEPTION {type(e).__name__}: {e}", flush=True)
+            r = False
+        print(f"[selfcheck] {n}: {'PASS' if r else 'FAIL'} ({time.time() - t0:.1f}s)", flush=True)
+        ok &= bool(r)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
