@@ -1,0 +1,149 @@
+"""Object-meta helpers shared by every kind served by the store (apimachinery ``metav1`` analogue).
+
+Objects travel as JSON-compatible dicts (``apiVersion/kind/metadata/spec/status``) so the
+wire format stays a subset of the Kubernetes API the reference is written against
+(pkg/client/clientset/versioned/typed/aitrainingjob/v1/aitrainingjob.go:66-190).
+"""
+from __future__ import annotations
+
+import copy
+import datetime as _dt
+import uuid
+from typing import Any, Dict, Iterable, List, Optional, Tuple
+
+from . import constants as C
+
+TIME_FMT = "%Y-%m-%dT%H:%M:%SZ"
+
+
+def now() -> _dt.datetime:
+    return _dt.datetime.now(_dt.timezone.utc)
+
+
+def format_time(t: Optional[_dt.datetime] = None) -> str:
+    """RFC3339 at second precision, like metav1.Time's JSON form."""
+    return (t or now()).strftime(TIME_FMT)
+
+
+def parse_time(s: Optional[str]) -> Optional[_dt.datetime]:
+    if not s:
+        return None
+    try:
+        return _dt.datetime.strptime(s, TIME_FMT).replace(tzinfo=_dt.timezone.utc)
+    except ValueError:
+        s2 = s.replace("Z", "+00:00")
+        return _dt.datetime.fromisoformat(s2)
+
+
+def seconds_since(s: Optional[str], ref: Optional[_dt.datetime] = None) -> float:
+    t = parse_time(s)
+    if t is None:
+        return 0.0
+    return ((ref or now()) - t).total_seconds()
+
+
+def new_uid() -> str:
+    return str(uuid.uuid4())
+
+
+def deepcopy(obj):
+    return copy.deepcopy(obj)
+
+
+def meta(obj: Dict[str, Any]) -> Dict[str, Any]:
+    return obj.setdefault("metadata", {})
+
+
+def name_of(obj) -> str:
+    return obj.get("metadata", {}).get("name", "")
+
+
+def namespace_of(obj) -> str:
+    return obj.get("metadata", {}).get("namespace", "")
+
+
+def uid_of(obj) -> str:
+    return obj.get("metadata", {}).get("uid", "")
+
+
+def labels_of(obj) -> Dict[str, str]:
+    return obj.get("metadata", {}).get("labels") or {}
+
+
+def annotations_of(obj) -> Dict[str, str]:
+    return obj.get("metadata", {}).get("annotations") or {}
+
+
+def resource_version(obj) -> str:
+    return str(obj.get("metadata", {}).get("resourceVersion", ""))
+
+
+def key_of(obj) -> str:
+    """``<namespace>/<name>`` (controller.KeyFunc)."""
+    ns = namespace_of(obj)
+    return f"{ns}/{name_of(obj)}" if ns else name_of(obj)
+
+
+def split_key(key: str) -> Tuple[str, str]:
+    if "/" in key:
+        ns, name = key.split("/", 1)
+        return ns, name
+    return "", key
+
+
+def owner_reference(owner: Dict[str, Any], controller: bool = True) -> Dict[str, Any]:
+    """OwnerReference for ``owner`` (controller.go:161-173: controller=true, blockOwnerDeletion=true)."""
+    return {
+        "apiVersion": owner.get("apiVersion", C.API_VERSION),
+        "kind": owner.get("kind", C.KIND),
+        "name": name_of(owner),
+        "uid": uid_of(owner),
+        "controller": controller,
+        "blockOwnerDeletion": True,
+    }
+
+
+def get_controller_of(obj) -> Optional[Dict[str, Any]]:
+    for ref in obj.get("metadata", {}).get("ownerReferences") or []:
+        if ref.get("controller"):
+            return ref
+    return None
+
+
+def owner_uids(obj) -> List[str]:
+    return [r.get("uid", "") for r in obj.get("metadata", {}).get("ownerReferences") or [] if r.get("uid")]
+
+
+# --- label selectors --------------------------------------------------------------------------
+def parse_selector(sel: Optional[str]) -> Dict[str, str]:
+    """``a=b,c=d`` (equality only) -> dict. ``a==b`` accepted."""
+    out: Dict[str, str] = {}
+    if not sel:
+        return out
+    for part in sel.split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "==" in part:
+            k, v = part.split("==", 1)
+        elif "=" in part:
+            k, v = part.split("=", 1)
+        else:
+            raise ValueError(f"unsupported selector term {part!r}")
+        out[k.strip()] = v.strip()
+    return out
+
+
+def format_selector(sel: Dict[str, str]) -> str:
+    return ",".join(f"{k}={v}" for k, v in sorted(sel.items()))
+
+
+def selector_matches(selector: Dict[str, str], labels: Dict[str, str]) -> bool:
+    return all(labels.get(k) == v for k, v in selector.items())
+
+
+def condition(conds: Iterable[Dict[str, Any]], ctype: str) -> Optional[Dict[str, Any]]:
+    for c in conds or []:
+        if c.get("type") == ctype:
+            return c
+    return None

@@ -1,0 +1,194 @@
+// pybind11 bindings of the native control-plane runtime (work-queue, expectations, object
+// store, process supervisor).  Blocking calls release the GIL so reconcile workers, informer
+// threads and the supervisor's reaper run truly concurrently.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "store.h"
+#include "supervisor.h"
+#include "workqueue.h"
+
+namespace py = pybind11;
+using namespace aitj;
+
+namespace {
+
+py::dict obj_to_dict(const StoredObject& o) {
+  py::dict d;
+  d["kind"] = o.kind;
+  d["namespace"] = o.ns;
+  d["name"] = o.name;
+  d["uid"] = o.uid;
+  d["data"] = py::bytes(o.data);
+  d["labels"] = o.labels;
+  d["owner_uids"] = o.owner_uids;
+  d["rv"] = o.rv;
+  return d;
+}
+
+StoredObject make_obj(const std::string& kind, const std::string& ns, const std::string& name, const std::string& uid,
+                      const py::bytes& data, const Labels& labels, const std::vector<std::string>& owners) {
+  StoredObject o;
+  o.kind = kind;
+  o.ns = ns;
+  o.name = name;
+  o.uid = uid;
+  o.data = static_cast<std::string>(data);
+  o.labels = labels;
+  o.owner_uids = owners;
+  return o;
+}
+
+py::object store_error_type;
+
+[[noreturn]] void raise_store_error(const StoreError& e) {
+  py::object exc = store_error_type(py::str(e.what()));
+  exc.attr("reason") = e.reason;
+  PyErr_SetObject(store_error_type.ptr(), exc.ptr());
+  throw py::error_already_set();
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_aitj_core, m) {
+  m.doc() = "native control-plane core: work-queue, expectations, watchable store, process supervisor";
+
+  store_error_type = py::reinterpret_borrow<py::object>(
+      PyErr_NewException("trainingjob_operator_b200.core._aitj_core.StoreError", PyExc_RuntimeError, nullptr));
+  m.attr("StoreError") = store_error_type;
+  static py::exception<SpawnError> spawn_exc(m, "SpawnError", PyExc_OSError);
+  py::register_exception_translator([](std::exception_ptr p) {
+    try {
+      if (p) std::rethrow_exception(p);
+    } catch (const SpawnError& e) {
+      py::object exc = py::reinterpret_steal<py::object>(
+          PyObject_CallFunction(spawn_exc.ptr(), "is", e.err, e.what()));
+      if (exc) PyErr_SetObject(spawn_exc.ptr(), exc.ptr());
+    }
+  });
+
+  py::class_<WorkQueue>(m, "WorkQueue")
+      .def(py::init<std::string, double, double, double, int>(), py::arg("name") = "queue",
+           py::arg("base_delay") = 0.005, py::arg("max_delay") = 1000.0, py::arg("qps") = 10.0,
+           py::arg("burst") = 100)
+      .def("add", &WorkQueue::add)
+      .def("add_after", &WorkQueue::add_after)
+      .def("add_rate_limited", &WorkQueue::add_rate_limited)
+      .def("forget", &WorkQueue::forget)
+      .def("num_requeues", &WorkQueue::num_requeues)
+      .def("get", &WorkQueue::get, py::arg("timeout") = -1.0, py::call_guard<py::gil_scoped_release>())
+      .def("done", &WorkQueue::done)
+      .def("__len__", &WorkQueue::len)
+      .def("len_waiting", &WorkQueue::len_waiting)
+      .def("shutdown", &WorkQueue::shutdown)
+      .def("shutting_down", &WorkQueue::shutting_down)
+      .def_property_readonly("name", &WorkQueue::name);
+
+  py::class_<Expectations>(m, "Expectations")
+      .def(py::init<double>(), py::arg("ttl") = 300.0)
+      .def("expect_creations", &Expectations::expect_creations)
+      .def("expect_deletions", &Expectations::expect_deletions)
+      .def("set", &Expectations::set)
+      .def("raise_expectations", &Expectations::raise)
+      .def("lower_expectations", &Expectations::lower)
+      .def("creation_observed", &Expectations::creation_observed)
+      .def("deletion_observed", &Expectations::deletion_observed)
+      .def("satisfied", &Expectations::satisfied)
+      .def("delete", &Expectations::erase)
+      .def("peek", &Expectations::peek);
+
+  py::class_<Store>(m, "Store")
+      .def(py::init<std::string, size_t>(), py::arg("wal_path") = "", py::arg("history") = 16384)
+      .def("current_rv", &Store::current_rv)
+      .def("create",
+           [](Store& s, const std::string& kind, const std::string& ns, const std::string& name,
+              const std::string& uid, const py::bytes& data, const Labels& labels,
+              const std::vector<std::string>& owners) {
+             try {
+               return obj_to_dict(s.create(make_obj(kind, ns, name, uid, data, labels, owners)));
+             } catch (const StoreError& e) { raise_store_error(e); }
+           })
+      .def("update",
+           [](Store& s, const std::string& kind, const std::string& ns, const std::string& name,
+              const std::string& uid, const py::bytes& data, const Labels& labels,
+              const std::vector<std::string>& owners, uint64_t expected_rv) {
+             try {
+               return obj_to_dict(s.update(make_obj(kind, ns, name, uid, data, labels, owners), expected_rv));
+             } catch (const StoreError& e) { raise_store_error(e); }
+           })
+      .def("get",
+           [](Store& s, const std::string& kind, const std::string& ns, const std::string& name) {
+             try {
+               return obj_to_dict(s.get(kind, ns, name));
+             } catch (const StoreError& e) { raise_store_error(e); }
+           })
+      .def("list",
+           [](Store& s, const std::string& kind, const std::string& ns, const Labels& selector) {
+             auto r = s.list(kind, ns, selector);
+             py::list items;
+             for (auto& o : r.first) items.append(obj_to_dict(o));
+             return py::make_tuple(items, r.second);
+           },
+           py::arg("kind"), py::arg("namespace") = "", py::arg("selector") = Labels{})
+      .def("remove",
+           [](Store& s, const std::string& kind, const std::string& ns, const std::string& name,
+              const std::string& expected_uid) {
+             try {
+               py::list out;
+               for (auto& o : s.remove(kind, ns, name, expected_uid)) out.append(obj_to_dict(o));
+               return out;
+             } catch (const StoreError& e) { raise_store_error(e); }
+           },
+           py::arg("kind"), py::arg("namespace"), py::arg("name"), py::arg("expected_uid") = "")
+      .def("watch_open",
+           [](Store& s, const std::string& kind, const std::string& ns, uint64_t since_rv) {
+             try {
+               return s.watch_open(kind, ns, since_rv);
+             } catch (const StoreError& e) { raise_store_error(e); }
+           },
+           py::arg("kind"), py::arg("namespace") = "", py::arg("since_rv") = 0)
+      .def("watch_next",
+           [](Store& s, int64_t id, double timeout) -> py::object {
+             std::optional<WatchEvent> ev;
+             {
+               py::gil_scoped_release rel;
+               ev = s.watch_next(id, timeout);
+             }
+             if (!ev) return py::none();
+             return py::make_tuple(ev->type, obj_to_dict(ev->obj));
+           },
+           py::arg("id"), py::arg("timeout") = 1.0)
+      .def("watch_close", &Store::watch_close)
+      .def("num_watchers", &Store::num_watchers)
+      .def("count", &Store::count)
+      .def("compact", &Store::compact);
+
+  py::class_<Supervisor>(m, "Supervisor")
+      .def(py::init<>())
+      .def("spawn", &Supervisor::spawn, py::arg("id"), py::arg("argv"), py::arg("env"), py::arg("cwd") = "",
+           py::arg("stdout_path") = "", py::arg("stderr_path") = "", py::arg("cpus") = std::vector<int>{})
+      .def("kill", &Supervisor::kill_proc, py::arg("id"), py::arg("sig") = 15, py::arg("group") = true)
+      .def("alive", &Supervisor::alive)
+      .def("pid_of", &Supervisor::pid_of)
+      .def("list", &Supervisor::list)
+      .def("poll_exits",
+           [](Supervisor& s, double timeout) {
+             std::vector<ExitEvent> evs;
+             {
+               py::gil_scoped_release rel;
+               evs = s.poll_exits(timeout);
+             }
+             py::list out;
+             for (auto& e : evs) {
+               py::dict d;
+               d["id"] = e.id;
+               d["pid"] = e.pid;
+               d["exit_code"] = e.exit_code;
+               d["signal"] = e.signal;
+               d["wall_time_s"] = e.wall_time_s;
+               out.append(d);
+             }
+             return out;
+           },
+           py::arg("timeout") = 1.0);
+}

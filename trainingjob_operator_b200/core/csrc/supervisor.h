@@ -1,0 +1,289 @@
+// Process supervisor: the kubelet analogue of the single-box design.
+// The reference never runs processes itself -- it creates Pods (pkg/controller/pod.go:483-546)
+// and reads their phase / container exit codes back (pod.go:339-379).  Here one OS process
+// (its own process group) is spawned per replica and observed directly:
+//   * fork + execve with explicit env / cwd / stdio redirection / CPU affinity,
+//   * exec failure is reported synchronously with errno (the CreateContainerError analogue,
+//     pkg/apis/aitrainingjob/v1/constants.go:46-56),
+//   * exit is observed through a pidfd + poll() reaper thread; a signal N is reported as exit
+//     code 128+N (so `kill -9` => 137, matching example/paddle-mnist.yaml:7),
+//   * kill() signals the whole process group.
+#pragma once
+#include <fcntl.h>
+#include <poll.h>
+#include <sched.h>
+#include <signal.h>
+#include <sys/eventfd.h>
+#include <sys/stat.h>
+#include <sys/syscall.h>
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cerrno>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace aitj {
+
+struct SpawnError : std::runtime_error {
+  int err;
+  SpawnError(int e, const std::string& msg) : std::runtime_error(msg), err(e) {}
+};
+
+struct ExitEvent {
+  std::string id;
+  int pid = 0;
+  int exit_code = 0;  // 128+signal when killed by a signal
+  int signal = 0;
+  double wall_time_s = 0.0;
+};
+
+struct ProcInfo {
+  std::string id;
+  int pid = 0;
+  int pidfd = -1;
+  std::chrono::steady_clock::time_point started;
+};
+
+class Supervisor {
+ public:
+  Supervisor() {
+    wake_fd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+    reaper_ = std::thread([this] { reap_loop(); });
+  }
+  ~Supervisor() {
+    stop_ = true;
+    wake();
+    if (reaper_.joinable()) reaper_.join();
+    if (wake_fd_ >= 0) close(wake_fd_);
+  }
+
+  // Spawns argv[0] (PATH lookup) as a new process-group leader. Throws SpawnError(errno).
+  int spawn(const std::string& id, const std::vector<std::string>& argv, const std::map<std::string, std::string>& env,
+            const std::string& cwd, const std::string& stdout_path, const std::string& stderr_path,
+            const std::vector<int>& cpus) {
+    if (argv.empty()) throw SpawnError(EINVAL, "empty argv");
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (procs_.count(id)) throw SpawnError(EEXIST, "process id already supervised: " + id);
+    }
+    std::vector<std::string> env_strs;
+    env_strs.reserve(env.size());
+    for (auto& kv : env) env_strs.push_back(kv.first + "=" + kv.second);
+    std::vector<char*> c_argv, c_env;
+    for (auto& a : argv) c_argv.push_back(const_cast<char*>(a.c_str()));
+    c_argv.push_back(nullptr);
+    for (auto& e : env_strs) c_env.push_back(const_cast<char*>(e.c_str()));
+    c_env.push_back(nullptr);
+
+    int errpipe[2];
+    if (pipe2(errpipe, O_CLOEXEC) != 0) throw SpawnError(errno, "pipe2 failed");
+
+    cpu_set_t mask;
+    CPU_ZERO(&mask);
+    for (int c : cpus) if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &mask);
+
+    pid_t pid = fork();
+    if (pid < 0) {
+      int e = errno;
+      close(errpipe[0]);
+      close(errpipe[1]);
+      throw SpawnError(e, std::string("fork failed: ") + strerror(e));
+    }
+    if (pid == 0) {
+      // child: async-signal-safe calls only
+      setpgid(0, 0);
+      sigset_t all;
+      sigemptyset(&all);
+      sigprocmask(SIG_SETMASK, &all, nullptr);
+      int stage = 1;
+      if (!cwd.empty() && chdir(cwd.c_str()) != 0) goto fail;
+      stage = 2;
+      if (!stdout_path.empty()) {
+        int fd = open(stdout_path.c_str(), O_WRONLY | O_CREAT | O_APPEND, 0644);
+        if (fd < 0) goto fail;
+        dup2(fd, 1);
+        if (stderr_path.empty() || stderr_path == stdout_path) dup2(fd, 2);
+        if (fd > 2) close(fd);
+      }
+      if (!stderr_path.empty() && stderr_path != stdout_path) {
+        int fd = open(stderr_path.c_str(), O_WRONLY | O_CREAT | O_APPEND, 0644);
+        if (fd < 0) goto fail;
+        dup2(fd, 2);
+        if (fd > 2) close(fd);
+      }
+      {
+        int nfd = open("/dev/null", O_RDONLY);
+        if (nfd >= 0) { dup2(nfd, 0); if (nfd > 2) close(nfd); }
+      }
+      if (!cpus.empty()) sched_setaffinity(0, sizeof(mask), &mask);
+      stage = 3;
+      execvpe(c_argv[0], c_argv.data(), c_env.data());
+    fail: {
+      int code[2] = {errno, stage};
+      ssize_t w = write(errpipe[1], code, sizeof(code));
+      (void)w;
+      _exit(127);
+    }
+    }
+    // parent
+    close(errpipe[1]);
+    setpgid(pid, pid);  // close the race with the child's own setpgid
+    int code[2] = {0, 0};
+    ssize_t n;
+    do { n = read(errpipe[0], code, sizeof(code)); } while (n < 0 && errno == EINTR);
+    close(errpipe[0]);
+    if (n == static_cast<ssize_t>(sizeof(code))) {
+      int st;
+      waitpid(pid, &st, 0);
+      const char* what = code[1] == 1 ? "chdir" : code[1] == 2 ? "open log" : "exec";
+      throw SpawnError(code[0], std::string(what) + " failed: " + strerror(code[0]) + " (" + argv[0] + ")");
+    }
+    ProcInfo info;
+    info.id = id;
+    info.pid = pid;
+    info.pidfd = static_cast<int>(syscall(SYS_pidfd_open, pid, 0));
+    info.started = std::chrono::steady_clock::now();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      procs_[id] = info;
+    }
+    wake();
+    return pid;
+  }
+
+  // Signal the process group (or only the leader). Returns false if unknown / already gone.
+  bool kill_proc(const std::string& id, int sig, bool group) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = procs_.find(id);
+    if (it == procs_.end()) return false;
+    int rc = group ? ::kill(-it->second.pid, sig) : ::kill(it->second.pid, sig);
+    if (rc != 0 && group) rc = ::kill(it->second.pid, sig);
+    return rc == 0;
+  }
+
+  bool alive(const std::string& id) {
+    std::lock_guard<std::mutex> lk(mu_);
+    return procs_.count(id) > 0;
+  }
+  int pid_of(const std::string& id) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = procs_.find(id);
+    return it == procs_.end() ? -1 : it->second.pid;
+  }
+  std::vector<std::pair<std::string, int>> list() {
+    std::lock_guard<std::mutex> lk(mu_);
+    std::vector<std::pair<std::string, int>> out;
+    for (auto& kv : procs_) out.emplace_back(kv.first, kv.second.pid);
+    return out;
+  }
+
+  // Blocks up to timeout_s for reaped children.
+  std::vector<ExitEvent> poll_exits(double timeout_s) {
+    std::unique_lock<std::mutex> lk(ev_mu_);
+    if (events_.empty())
+      ev_cv_.wait_for(lk, std::chrono::duration<double>(timeout_s), [&] { return !events_.empty() || stop_.load(); });
+    std::vector<ExitEvent> out(events_.begin(), events_.end());
+    events_.clear();
+    return out;
+  }
+
+ private:
+  void wake() {
+    uint64_t one = 1;
+    ssize_t w = write(wake_fd_, &one, sizeof(one));
+    (void)w;
+  }
+
+  void reap_loop() {
+    while (!stop_) {
+      std::vector<pollfd> fds;
+      std::vector<std::string> ids;
+      fds.push_back({wake_fd_, POLLIN, 0});
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto& kv : procs_) {
+          if (kv.second.pidfd >= 0) {
+            fds.push_back({kv.second.pidfd, POLLIN, 0});
+            ids.push_back(kv.first);
+          }
+        }
+      }
+      int rc = poll(fds.data(), fds.size(), 500);
+      if (rc < 0 && errno != EINTR) { usleep(1000); continue; }
+      if (fds[0].revents & POLLIN) {
+        uint64_t v;
+        ssize_t r = read(wake_fd_, &v, sizeof(v));
+        (void)r;
+      }
+      for (size_t i = 1; i < fds.size(); ++i) {
+        if (!(fds[i].revents & (POLLIN | POLLHUP | POLLERR))) continue;
+        reap(ids[i - 1]);
+      }
+      // pidfd_open can fail on exotic kernels: fall back to WNOHANG polling for those.
+      std::vector<std::string> nofd;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto& kv : procs_) if (kv.second.pidfd < 0) nofd.push_back(kv.first);
+      }
+      for (auto& id : nofd) reap(id, true);
+    }
+  }
+
+  void reap(const std::string& id, bool nohang = false) {
+    ProcInfo info;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = procs_.find(id);
+      if (it == procs_.end()) return;
+      info = it->second;
+    }
+    int st = 0;
+    pid_t r = waitpid(info.pid, &st, nohang ? WNOHANG : 0);
+    if (r == 0) return;
+    ExitEvent ev;
+    ev.id = id;
+    ev.pid = info.pid;
+    if (r < 0) {
+      ev.exit_code = 255;
+    } else if (WIFSIGNALED(st)) {
+      ev.signal = WTERMSIG(st);
+      ev.exit_code = 128 + ev.signal;
+    } else {
+      ev.exit_code = WEXITSTATUS(st);
+    }
+    ev.wall_time_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - info.started).count();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      procs_.erase(id);
+    }
+    if (info.pidfd >= 0) close(info.pidfd);
+    {
+      std::lock_guard<std::mutex> lk(ev_mu_);
+      events_.push_back(ev);
+    }
+    ev_cv_.notify_all();
+  }
+
+  std::mutex mu_;
+  std::map<std::string, ProcInfo> procs_;
+  std::mutex ev_mu_;
+  std::condition_variable ev_cv_;
+  std::deque<ExitEvent> events_;
+  std::atomic<bool> stop_{false};
+  int wake_fd_ = -1;
+  std::thread reaper_;
+};
+
+}  // namespace aitj

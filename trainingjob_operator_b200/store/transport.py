@@ -1,0 +1,222 @@
+"""Transports between the typed clients and the API server.
+
+``LocalTransport`` calls an in-process ``APIServer`` directly (all-in-one daemon, tests);
+``HTTPTransport`` speaks the REST/watch wire protocol to ``store.http.APIHTTPServer`` -- the
+process boundary the reference crosses with client-go's ``rest.Interface``
+(pkg/client/clientset/versioned/typed/aitrainingjob/v1/aitrainingjob_client.go:69-89, APIPath
+``/apis``).  Both expose the same five calls so clientsets, informers and the CLI are agnostic.
+"""
+from __future__ import annotations
+
+import http.client
+import json
+import socket
+import threading
+import urllib.parse
+from typing import Any, Dict, Iterator, Optional
+
+from ..api import register as R
+from .apiserver import APIError, APIServer
+
+
+class Transport:
+    def create(self, info, namespace, obj): raise NotImplementedError
+    def get(self, info, namespace, name): raise NotImplementedError
+    def list(self, info, namespace="", label_selector="", field_selector=""): raise NotImplementedError
+    def update(self, info, namespace, name, obj, subresource=""): raise NotImplementedError
+    def patch(self, info, namespace, name, patch, patch_type="application/merge-patch+json", subresource=""):
+        raise NotImplementedError
+    def delete(self, info, namespace, name, grace_period_seconds=None, uid=""): raise NotImplementedError
+    def delete_collection(self, info, namespace, label_selector="", grace_period_seconds=None):
+        raise NotImplementedError
+    def watch(self, info, namespace="", resource_version="", label_selector="", timeout=None):
+        raise NotImplementedError
+
+
+class LocalTransport(Transport):
+    def __init__(self, server: APIServer):
+        self.server = server
+
+    def create(self, info, namespace, obj):
+        return self.server.create(info, namespace, obj)
+
+    def get(self, info, namespace, name):
+        return self.server.get(info, namespace, name)
+
+    def list(self, info, namespace="", label_selector="", field_selector=""):
+        return self.server.list(info, namespace, label_selector, field_selector)
+
+    def update(self, info, namespace, name, obj, subresource=""):
+        return self.server.update(info, namespace, name, obj, subresource)
+
+    def patch(self, info, namespace, name, patch, patch_type="application/merge-patch+json", subresource=""):
+        return self.server.patch(info, namespace, name, patch, patch_type, subresource)
+
+    def delete(self, info, namespace, name, grace_period_seconds=None, uid=""):
+        return self.server.delete(info, namespace, name, grace_period_seconds, uid)
+
+    def delete_collection(self, info, namespace, label_selector="", grace_period_seconds=None):
+        return self.server.delete_collection(info, namespace, label_selector, grace_period_seconds)
+
+    def watch(self, info, namespace="", resource_version="", label_selector="", timeout=None):
+        return self.server.watch(info, namespace, resource_version, label_selector, timeout)
+
+
+class _HTTPWatch:
+    """Streaming watch: newline-delimited JSON events over a chunked response."""
+
+    def __init__(self, conn: http.client.HTTPConnection, resp: http.client.HTTPResponse):
+        self._conn = conn
+        self._resp = resp
+        self._closed = False
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> Dict[str, Any]:
+        while not self._closed:
+            try:
+                line = self._resp.readline()
+            except (socket.timeout, TimeoutError):
+                continue
+            except (OSError, http.client.HTTPException, ValueError, AttributeError):
+                break
+            if not line:
+                break
+            line = line.strip()
+            if not line:
+                continue
+            ev = json.loads(line)
+            if ev.get("type") == "ERROR":
+                self.close()
+                raise APIError.from_status(ev.get("object", {}))
+            return ev
+        self.close()
+        raise StopIteration
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            try:
+                self._conn.close()
+            except Exception:  # noqa: BLE001
+                pass
+
+
+class HTTPTransport(Transport):
+    """``--master http://127.0.0.1:8001`` style endpoint (or ``unix:///path.sock``)."""
+
+    def __init__(self, master: str, timeout: float = 30.0, user_agent: str = "trainingjob-operator"):
+        if "://" not in master:
+            master = "http://" + master
+        self.master = master.rstrip("/")
+        u = urllib.parse.urlparse(self.master)
+        self._host = u.hostname or "127.0.0.1"
+        self._port = u.port or 8001
+        self._timeout = timeout
+        self._ua = user_agent
+        self._local = threading.local()
+
+    def _conn(self) -> http.client.HTTPConnection:
+        c = getattr(self._local, "conn", None)
+        if c is None:
+            c = http.client.HTTPConnection(self._host, self._port, timeout=self._timeout)
+            self._local.conn = c
+        return c
+
+    def _request(self, method: str, path: str, params: Optional[Dict[str, Any]] = None, body: Any = None,
+                 content_type: str = "application/json") -> Dict[str, Any]:
+        q = {k: v for k, v in (params or {}).items() if v not in (None, "")}
+        url = path + ("?" + urllib.parse.urlencode(q) if q else "")
+        data = None if body is None else json.dumps(body).encode()
+        headers = {"Accept": "application/json", "User-Agent": self._ua}
+        if data is not None:
+            headers["Content-Type"] = content_type
+        last: Optional[Exception] = None
+        for attempt in range(2):
+            conn = self._conn()
+            try:
+                conn.request(method, url, body=data, headers=headers)
+                resp = conn.getresponse()
+                raw = resp.read()
+                break
+            except (OSError, http.client.HTTPException) as e:
+                last = e
+                conn.close()
+                self._local.conn = None
+        else:
+            raise APIError(503, "ServiceUnavailable", f"cannot reach API server {self.master}: {last}")
+        out = json.loads(raw) if raw else {}
+        if resp.status >= 400:
+            if isinstance(out, dict) and out.get("kind") == "Status":
+                raise APIError.from_status(out)
+            raise APIError(resp.status, "InternalError", raw.decode(errors="replace")[:500])
+        return out
+
+    def create(self, info, namespace, obj):
+        ns = namespace or (obj.get("metadata", {}).get("namespace", "") if info.namespaced else "")
+        return self._request("POST", info.path(ns or ("default" if info.namespaced else "")), body=obj)
+
+    def get(self, info, namespace, name):
+        return self._request("GET", info.path(namespace or ("default" if info.namespaced else ""), name))
+
+    def list(self, info, namespace="", label_selector="", field_selector=""):
+        return self._request("GET", info.path(namespace), {"labelSelector": label_selector,
+                                                           "fieldSelector": field_selector})
+
+    def update(self, info, namespace, name, obj, subresource=""):
+        p = info.path(namespace or ("default" if info.namespaced else ""), name)
+        if subresource:
+            p += "/" + subresource
+        return self._request("PUT", p, body=obj)
+
+    def patch(self, info, namespace, name, patch, patch_type="application/merge-patch+json", subresource=""):
+        p = info.path(namespace or ("default" if info.namespaced else ""), name)
+        if subresource:
+            p += "/" + subresource
+        return self._request("PATCH", p, body=patch, content_type=patch_type)
+
+    def delete(self, info, namespace, name, grace_period_seconds=None, uid=""):
+        body = {}
+        if grace_period_seconds is not None:
+            body["gracePeriodSeconds"] = grace_period_seconds
+        if uid:
+            body["preconditions"] = {"uid": uid}
+        return self._request("DELETE", info.path(namespace or ("default" if info.namespaced else ""), name),
+                             body=body or None)
+
+    def delete_collection(self, info, namespace, label_selector="", grace_period_seconds=None):
+        return self._request("DELETE", info.path(namespace), {"labelSelector": label_selector,
+                                                              "gracePeriodSeconds": grace_period_seconds})
+
+    def watch(self, info, namespace="", resource_version="", label_selector="", timeout=None):
+        q = {"watch": "true", "resourceVersion": resource_version, "labelSelector": label_selector}
+        if timeout is not None:
+            q["timeoutSeconds"] = int(max(1, timeout))
+        url = info.path(namespace) + "?" + urllib.parse.urlencode({k: v for k, v in q.items() if v not in (None, "")})
+        conn = http.client.HTTPConnection(self._host, self._port, timeout=5.0)
+        try:
+            conn.request("GET", url, headers={"Accept": "application/json", "User-Agent": self._ua})
+            resp = conn.getresponse()
+        except (OSError, http.client.HTTPException) as e:
+            conn.close()
+            raise APIError(503, "ServiceUnavailable", f"cannot reach API server {self.master}: {e}") from None
+        if resp.status >= 400:
+            raw = resp.read()
+            conn.close()
+            try:
+                raise APIError.from_status(json.loads(raw))
+            except ValueError:
+                raise APIError(resp.status, "InternalError", raw.decode(errors="replace")[:300]) from None
+        return _HTTPWatch(conn, resp)
+
+    def raw_get(self, path: str) -> Any:
+        return self._request("GET", path)
+
+
+def transport_for(master: Optional[str] = None, server: Optional[APIServer] = None) -> Transport:
+    if server is not None:
+        return LocalTransport(server)
+    if not master:
+        raise ValueError("either an in-process APIServer or --master URL is required")
+    return HTTPTransport(master)
