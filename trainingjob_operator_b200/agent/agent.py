@@ -1,0 +1,632 @@
+"""Node agent: the kube-scheduler + kubelet analogue for one 8xB200 box.
+
+The reference has no such component -- it relies on Kubernetes to place pods, start containers and
+report ``pod.status``.  On a single box those roles collapse into this
+agent, which keeps the exact object contract the controller logic reads
+(/root/reference/pkg/controller/pod.go:339-379, status.go:339-358):
+
+* **nodes**: one ``Node`` per GPU (``gpu-0`` .. ``gpu-7``, Ready <=> NVML health) plus ``cpu-0`` for
+  replicas that request no GPU; "node not Ready" is how a GPU fault reaches the ``NodeFail`` path
+  (pod.go:407-419).  Fault injection: annotate a node with ``aitj.b200/inject-fault``.
+* **scheduler**: binds Pending pods (``spec.nodeName``) to free healthy GPUs, highest ``priority``
+  label first (pod.go:503-505), honours ``schedulerName`` (pod.go:524-526) by ignoring pods addressed
+  to a foreign scheduler; when nothing fits it writes the ``PodScheduled=False`` condition whose message
+  the controller surfaces (pod.go:457-467).
+* **kubelet**: one OS process (own process group) per container through the native supervisor
+  (``core/csrc/supervisor.h``): ``CUDA_VISIBLE_DEVICES`` pinning, CPU affinity, log capture, init
+  containers in order; ``containerStatuses`` waiting/running/terminated with exit codes (signal N =>
+  128+N); exec failures surface as ``CreateContainerError`` / ``CreateContainerConfigError`` waiting
+  reasons (constants.go:46-56); graceful delete = SIGTERM, grace period, SIGKILL, then the pod object
+  is removed; a vanished pod object kills its processes (orphan sweep, garbage_collection.go analogue).
+"""
+from __future__ import annotations
+
+import os
+import shlex
+import signal
+import threading
+import time
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+from ..api import constants as C
+from ..api import meta as M
+from ..client.informers import DeletedFinalStateUnknown, SharedInformerFactory
+from ..core import _aitj_core as core
+from ..store.apiserver import APIError
+from ..utils import klog, metrics
+
+GPU_RESOURCE = "nvidia.com/gpu"
+OWN_SCHEDULERS = ("", "default-scheduler", "aitj-scheduler")
+PRIORITY_NAMES = {"critical": 1000, "high": 100, "medium": 50, "normal": 50, "low": 10}
+_PASS_ENV = ("PATH", "HOME", "USER", "LANG", "LC_ALL", "LD_LIBRARY_PATH", "VIRTUAL_ENV", "PYTHONPATH", "TMPDIR",
+             "CUDA_HOME", "NCCL_DEBUG", "NCCL_SOCKET_IFNAME", "NCCL_IB_DISABLE", "TORCH_NCCL_ASYNC_ERROR_HANDLING",
+             "GRAFT_REPO_ROOT", "HF_HOME", "TORCH_HOME", "XDG_CACHE_HOME")
+
+metrics.describe("aitj_spawn_seconds", "pod bound -> all containers started")
+
+
+def detect_gpu_count() -> int:
+    env = os.environ.get("AITJ_NUM_GPUS")
+    if env is not None:
+        return int(env)
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        return int(pynvml.nvmlDeviceGetCount())
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        import torch
+
+        return int(torch.cuda.device_count())
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+def nvml_health_prober() -> Callable[[int], Tuple[bool, str]]:
+    """(healthy, reason) per GPU index from NVML; always healthy when NVML is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+    except Exception:  # noqa: BLE001
+        return lambda idx: (True, "")
+
+    def probe(idx: int) -> Tuple[bool, str]:
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            pynvml.nvmlDeviceGetMemoryInfo(h)
+            try:
+                ecc = pynvml.nvmlDeviceGetTotalEccErrors(h, pynvml.NVML_MEMORY_ERROR_TYPE_UNCORRECTED,
+                                                         pynvml.NVML_VOLATILE_ECC)
+                if ecc and ecc > 0:
+                    return False, f"{ecc} uncorrected volatile ECC errors"
+            except Exception:  # noqa: BLE001 - not supported / disabled
+                pass
+            return True, ""
+        except Exception as e:  # noqa: BLE001 - fallen off the bus, Xid, ...
+            return False, f"NVML: {e}"
+
+    return probe
+
+
+def pod_gpu_request(pod: dict) -> int:
+    n = 0
+    for c in pod.get("spec", {}).get("containers") or []:
+        res = c.get("resources") or {}
+        v = (res.get("limits") or {}).get(GPU_RESOURCE, (res.get("requests") or {}).get(GPU_RESOURCE, 0))
+        try:
+            n += int(v)
+        except (TypeError, ValueError):
+            pass
+    return n
+
+
+def pod_priority(pod: dict) -> int:
+    raw = M.labels_of(pod).get(C.LABEL_PRIORITY, "")
+    if not raw:
+        return 0
+    try:
+        return int(raw)
+    except ValueError:
+        return PRIORITY_NAMES.get(raw.lower(), 0)
+
+
+@dataclass
+class _PodState:
+    key: str
+    uid: str
+    containers: Dict[str, str] = field(default_factory=dict)   # container name -> supervisor id
+    started: bool = False
+    init_index: int = 0
+    term_sent_at: float = 0.0
+    bound_at: float = 0.0
+    spawn_failures: int = 0
+    next_retry: float = 0.0
+
+
+class NodeAgent:
+    def __init__(self, clientset, num_gpus: Optional[int] = None, workdir: str = "/tmp/aitj-agent",
+                 health_prober: Optional[Callable[[int], Tuple[bool, str]]] = None, health_period: float = 2.0,
+                 cpu_slots: int = 64, image_map: Optional[Dict[str, List[str]]] = None,
+                 supervisor=None, node_prefix: str = ""):
+        self.cs = clientset
+        self.num_gpus = detect_gpu_count() if num_gpus is None else int(num_gpus)
+        self.workdir = workdir
+        self.log_dir = os.path.join(workdir, "logs")
+        os.makedirs(self.log_dir, exist_ok=True)
+        self.prober = health_prober or nvml_health_prober()
+        self.health_period = health_period
+        self.cpu_slots = cpu_slots
+        self.image_map = image_map or {}
+        self.sup = supervisor or core.Supervisor()
+        self.prefix = node_prefix
+        self.queue = core.WorkQueue("agent-pods", 0.02, 5.0, 200.0, 400)
+        self._states: Dict[str, _PodState] = {}
+        self._lock = threading.RLock()
+        self._factory = SharedInformerFactory(clientset, 0.0)
+        self._pod_informer = self._factory.core().v1().pods()
+        self._node_informer = self._factory.core().v1().nodes()
+        self._pod_informer.informer().add_event_handler(add=self._on_pod, update=lambda o, n: self._on_pod(n),
+                                                        delete=self._on_pod_delete)
+        self._node_informer.informer().add_event_handler(update=lambda o, n: self._kick_pending())
+        self.pod_lister = self._pod_informer.lister()
+        self.node_lister = self._node_informer.lister()
+        self._threads: List[threading.Thread] = []
+        self._injected: Dict[str, str] = {}
+
+    # ------------------------------------------------------------------ nodes
+    def gpu_node(self, idx: int) -> str:
+        return f"{self.prefix}gpu-{idx}"
+
+    @property
+    def cpu_node(self) -> str:
+        return f"{self.prefix}cpu-0"
+
+    def node_names(self) -> List[str]:
+        return [self.gpu_node(i) for i in range(self.num_gpus)] + [self.cpu_node]
+
+    def register_nodes(self) -> None:
+        for i in range(self.num_gpus):
+            self._ensure_node(self.gpu_node(i), "gpu", {GPU_RESOURCE: "1"}, i)
+        self._ensure_node(self.cpu_node, "cpu", {"cpu": str(os.cpu_count() or 1), "pods": str(self.cpu_slots)}, -1)
+
+    def _ensure_node(self, name: str, ntype: str, capacity: Dict[str, str], gpu_index: int) -> None:
+        node = {"apiVersion": "v1", "kind": "Node",
+                "metadata": {"name": name, "labels": {"aitj.b200/type": ntype, "aitj.b200/gpu-index": str(gpu_index),
+                                                      "kubernetes.io/hostname": name}},
+                "spec": {},
+                "status": {"capacity": capacity, "allocatable": capacity,
+                           "conditions": [self._ready_condition(True, "KubeletReady", "agent is posting ready status")],
+                           "nodeInfo": {"kubeletVersion": "aitj-agent/1.0", "architecture": "amd64"}}}
+        try:
+            self.cs.core_v1().nodes().create(node)
+        except APIError as e:
+            if e.reason != "AlreadyExists":
+                raise
+            self._set_node_ready(name, True, "KubeletReady", "agent is posting ready status")
+
+    @staticmethod
+    def _ready_condition(ok: bool, reason: str, message: str) -> dict:
+        now = M.format_time()
+        return {"type": "Ready", "status": "True" if ok else "False", "reason": reason, "message": message,
+                "lastHeartbeatTime": now, "lastTransitionTime": now}
+
+    def _set_node_ready(self, name: str, ok: bool, reason: str, message: str) -> None:
+        try:
+            node = self.cs.core_v1().nodes().get(name)
+        except APIError:
+            return
+        conds = node.setdefault("status", {}).setdefault("conditions", [])
+        cur = M.condition(conds, "Ready")
+        want = "True" if ok else "False"
+        if cur is not None and cur.get("status") == want and cur.get("reason") == reason:
+            return
+        new = self._ready_condition(ok, reason, message)
+        if cur is None:
+            conds.append(new)
+        else:
+            cur.update(new)
+        try:
+            self.cs.core_v1().nodes().update_status(node)
+            klog.info("node %s Ready=%s (%s: %s)", name, want, reason, message)
+        except APIError as e:
+            klog.warning("node %s status update failed: %s", name, e.message)
+
+    def _health_loop(self, stop: threading.Event) -> None:
+        while not stop.wait(self.health_period):
+            self.check_health_once()
+
+    def check_health_once(self) -> None:
+        for i in range(self.num_gpus):
+            name = self.gpu_node(i)
+            injected = ""
+            try:
+                node = self.node_lister.get(name)
+                injected = M.annotations_of(node).get(C.ANN_INJECT_FAULT, "")
+            except APIError:
+                pass
+            if injected:
+                self._set_node_ready(name, False, "InjectedFault", injected)
+                continue
+            ok, why = self.prober(i)
+            if ok:
+                self._set_node_ready(name, True, "KubeletReady", "agent is posting ready status")
+            else:
+                self._set_node_ready(name, False, "GPUUnhealthy", why)
+
+    # ------------------------------------------------------------------ informer handlers
+    def _on_pod(self, pod: dict) -> None:
+        self.queue.add(M.key_of(pod))
+
+    def _on_pod_delete(self, obj) -> None:
+        pod = obj.obj if isinstance(obj, DeletedFinalStateUnknown) else obj
+        self.queue.add(M.key_of(pod))
+        self._kick_pending()
+
+    def _kick_pending(self) -> None:
+        for pod in self.pod_lister.list():
+            if not pod.get("spec", {}).get("nodeName"):
+                self.queue.add(M.key_of(pod))
+
+    # ------------------------------------------------------------------ main loops
+    def start(self, stop: threading.Event) -> None:
+        self.register_nodes()
+        self._factory.start(stop)
+        self._factory.wait_for_cache_sync(stop)
+        for target, name in ((self._sync_loop, "agent-sync"), (self._reap_loop, "agent-reap"),
+                             (self._health_loop, "agent-health"), (self._sweep_loop, "agent-sweep")):
+            t = threading.Thread(target=target, args=(stop,), name=name, daemon=True)
+            t.start()
+            self._threads.append(t)
+        threading.Thread(target=lambda: (stop.wait(), self.queue.shutdown()), daemon=True).start()
+
+    def run(self, stop: threading.Event) -> None:
+        self.start(stop)
+        stop.wait()
+        self.shutdown()
+
+    def shutdown(self, kill: bool = False) -> None:
+        if kill:
+            for sid, _pid in self.sup.list():
+                self.sup.kill(sid, signal.SIGKILL, True)
+
+    def _sync_loop(self, stop: threading.Event) -> None:
+        while not stop.is_set():
+            key = self.queue.get(0.5)
+            if key is None:
+                if self.queue.shutting_down():
+                    return
+                continue
+            try:
+                self.sync_pod(key)
+                self.queue.forget(key)
+            except APIError as e:
+                if e.reason not in ("NotFound",):
+                    klog.V(2).info("agent: sync %s: %s", key, e.message)
+                    self.queue.add_rate_limited(key)
+            except Exception as e:  # noqa: BLE001
+                klog.error("agent: sync %s failed: %r", key, e)
+                self.queue.add_rate_limited(key)
+            finally:
+                self.queue.done(key)
+
+    def _reap_loop(self, stop: threading.Event) -> None:
+        while not stop.is_set():
+            for ev in self.sup.poll_exits(0.5):
+                self._on_exit(ev)
+
+    def _sweep_loop(self, stop: threading.Event) -> None:
+        while not stop.wait(5.0):
+            self.sweep_orphans()
+
+    # ------------------------------------------------------------------ per-pod sync
+    def _mine(self, node_name: str) -> bool:
+        return node_name in self.node_names()
+
+    def sync_pod(self, key: str) -> None:
+        ns, name = M.split_key(key)
+        try:
+            pod = self.pod_lister.namespaced(ns).get(name)
+        except APIError:
+            self._kill_pod_processes(key, signal.SIGKILL)
+            with self._lock:
+                self._states.pop(key, None)
+            return
+        st = self._states.get(key)
+        if st is not None and st.uid != M.uid_of(pod):
+            # same name, new incarnation: the old processes must not survive
+            self._kill_pod_processes(key, signal.SIGKILL)
+            with self._lock:
+                self._states.pop(key, None)
+            st = None
+        node = pod.get("spec", {}).get("nodeName") or ""
+        if pod.get("metadata", {}).get("deletionTimestamp"):
+            if not node or self._mine(node):
+                self._terminate(pod, key)
+            return
+        phase = pod.get("status", {}).get("phase") or C.POD_PENDING
+        if not node:
+            if phase == C.POD_PENDING:
+                self.schedule(pod)
+            return
+        if not self._mine(node):
+            return
+        if phase == C.POD_PENDING:
+            self._start_pod(pod, key)
+
+    # ------------------------------------------------------------------ scheduler
+    def _free_gpus(self) -> List[int]:
+        ready = set()
+        for n in self.node_lister.list():
+            nm = M.name_of(n)
+            if not nm.startswith(f"{self.prefix}gpu-"):
+                continue
+            if any(c.get("type") == "Ready" and c.get("status") == "True"
+                   for c in n.get("status", {}).get("conditions") or []):
+                ready.add(int(nm.rsplit("-", 1)[1]))
+        busy = set()
+        for p in self.pod_lister.list():
+            if not p.get("spec", {}).get("nodeName"):
+                continue
+            if (p.get("status", {}).get("phase") or C.POD_PENDING) in (C.POD_SUCCEEDED, C.POD_FAILED):
+                continue
+            for g in (M.annotations_of(p).get(C.ANN_GPUS) or "").split(","):
+                if g.strip():
+                    busy.add(int(g))
+        return sorted(ready - busy)
+
+    def schedule(self, pod: dict) -> None:
+        if (pod.get("spec", {}).get("schedulerName") or "") not in OWN_SCHEDULERS:
+            return
+        want = pod_gpu_request(pod)
+        ns, name = M.namespace_of(pod), M.name_of(pod)
+        if want == 0:
+            self._bind(pod, self.cpu_node, [])
+            return
+        # higher-priority pending pods go first: yield if someone more important is waiting
+        mine = (pod_priority(pod), )
+        for other in self.pod_lister.list():
+            if other.get("spec", {}).get("nodeName") or M.uid_of(other) == M.uid_of(pod):
+                continue
+            if other.get("metadata", {}).get("deletionTimestamp") or pod_gpu_request(other) == 0:
+                continue
+            if (pod_priority(other),) > mine:
+                self.queue.add_after(M.key_of(pod), 0.05)
+                free = self._free_gpus()
+                if len(free) < pod_gpu_request(other) + want:
+                    self._mark_unschedulable(pod, f"0/{self.num_gpus} nodes are available: waiting for "
+                                             f"higher-priority pod {M.name_of(other)}.")
+                    return
+        with self._lock:
+            free = self._free_gpus()
+            if len(free) < want:
+                total = self.num_gpus
+                self._mark_unschedulable(pod, f"0/{total} nodes are available: {total - len(free)} Insufficient "
+                                         f"{GPU_RESOURCE}, {len(free)} free but {want} requested.")
+                return
+            gpus = free[:want]
+            self._bind(pod, self.gpu_node(gpus[0]), gpus)
+
+    def _mark_unschedulable(self, pod: dict, message: str) -> None:
+        conds = pod.get("status", {}).get("conditions") or []
+        cur = M.condition(conds, "PodScheduled")
+        if cur is not None and cur.get("status") == "False" and cur.get("message") == message:
+            return
+        patch = {"status": {"phase": C.POD_PENDING, "conditions": [
+            {"type": "PodScheduled", "status": "False", "reason": "Unschedulable", "message": message,
+             "lastTransitionTime": M.format_time()}]}}
+        self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch, subresource="status")
+
+    def _bind(self, pod: dict, node: str, gpus: List[int]) -> None:
+        patch = {"spec": {"nodeName": node},
+                 "metadata": {"annotations": {C.ANN_GPUS: ",".join(str(g) for g in gpus)}},
+                 "status": {"phase": C.POD_PENDING, "hostIP": "127.0.0.1", "podIP": "127.0.0.1",
+                            "conditions": [{"type": "PodScheduled", "status": "True",
+                                            "lastTransitionTime": M.format_time()}]}}
+        self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch)
+        klog.V(2).info("scheduled %s -> %s gpus=%s", M.key_of(pod), node, gpus)
+        self.queue.add(M.key_of(pod))
+
+    # ------------------------------------------------------------------ kubelet: start
+    def _container_argv(self, c: dict) -> Tuple[Optional[List[str]], str]:
+        cmd = list(c.get("command") or [])
+        args = list(c.get("args") or [])
+        if not cmd:
+            mapped = self.image_map.get(c.get("image", ""))
+            if mapped:
+                cmd = list(mapped)
+            elif not args:
+                return None, (f"container {c.get('name')}: no command; image {c.get('image')!r} cannot be pulled on a "
+                              "single box (pass --image-map image=command)")
+        return [str(x) for x in cmd + args], ""
+
+    def _container_env(self, pod: dict, c: dict, gpus: List[int]) -> Dict[str, str]:
+        env = {k: os.environ[k] for k in _PASS_ENV if k in os.environ}
+        env["CUDA_VISIBLE_DEVICES"] = ",".join(str(g) for g in gpus)
+        env["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
+        env.setdefault("NCCL_IB_DISABLE", "1")
+        env.setdefault("NCCL_SOCKET_IFNAME", "lo")
+        env["AITJ_POD_NAME"] = M.name_of(pod)
+        env["AITJ_POD_NAMESPACE"] = M.namespace_of(pod)
+        env["AITJ_POD_UID"] = M.uid_of(pod)
+        env["AITJ_NODE_NAME"] = pod.get("spec", {}).get("nodeName", "")
+        env["AITJ_WORKDIR"] = self.workdir
+        env["PYTHONUNBUFFERED"] = "1"
+        for e in c.get("env") or []:
+            if "name" in e:
+                env[str(e["name"])] = str(e.get("value", ""))
+        return env
+
+    def _cpus_for(self, gpus: List[int]) -> List[int]:
+        ncpu = os.cpu_count() or 1
+        if not gpus or self.num_gpus <= 0 or ncpu < self.num_gpus * 2:
+            return []
+        per = ncpu // self.num_gpus
+        out: List[int] = []
+        for g in gpus:
+            out += list(range(g * per, (g + 1) * per))
+        return out
+
+    def log_path(self, pod: dict, container: str) -> str:
+        return os.path.join(self.log_dir, f"{M.namespace_of(pod)}_{M.name_of(pod)}_{container}.log")
+
+    def _start_pod(self, pod: dict, key: str) -> None:
+        with self._lock:
+            st = self._states.get(key)
+            if st is None:
+                st = self._states[key] = _PodState(key=key, uid=M.uid_of(pod), bound_at=time.monotonic())
+            if st.started or time.monotonic() < st.next_retry:
+                return
+        spec = pod.get("spec", {})
+        gpus = [int(g) for g in (M.annotations_of(pod).get(C.ANN_GPUS) or "").split(",") if g.strip()]
+        inits = spec.get("initContainers") or []
+        mains = spec.get("containers") or []
+        # init containers run one at a time; `_on_exit` advances the index
+        if st.init_index < len(inits):
+            c = inits[st.init_index]
+            if c["name"] not in st.containers:
+                self._spawn_container(pod, st, c, gpus, init=True)
+            return
+        statuses = []
+        ok = True
+        for c in mains:
+            if c["name"] in st.containers:
+                continue
+            err = self._spawn_container(pod, st, c, gpus, init=False)
+            if err:
+                ok = False
+                break
+        if not ok:
+            return
+        st.started = True
+        now = M.format_time()
+        for c in mains:
+            statuses.append({"name": c["name"], "image": c.get("image", ""), "ready": True, "restartCount": 0,
+                             "state": {"running": {"startedAt": now}}})
+        patch = {"status": {"phase": C.POD_RUNNING, "startTime": pod.get("status", {}).get("startTime") or now,
+                            "containerStatuses": statuses,
+                            "conditions": [{"type": "PodScheduled", "status": "True"},
+                                           {"type": "Ready", "status": "True", "lastTransitionTime": now}]}}
+        self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch, subresource="status")
+        metrics.observe("aitj_spawn_seconds", time.monotonic() - st.bound_at)
+
+    def _spawn_container(self, pod: dict, st: _PodState, c: dict, gpus: List[int], init: bool) -> str:
+        argv, err = self._container_argv(c)
+        reason = "CreateContainerConfigError"
+        if argv is not None:
+            sid = f"{st.key}/{st.uid[:8]}/{c['name']}"
+            try:
+                cwd = c.get("workingDir") or ""
+                self.sup.spawn(sid, argv, self._container_env(pod, c, gpus), cwd, self.log_path(pod, c["name"]), "",
+                               self._cpus_for(gpus))
+                st.containers[c["name"]] = sid
+                return ""
+            except OSError as e:
+                err = str(e)
+                reason = "CreateContainerError"
+        st.spawn_failures += 1
+        st.next_retry = time.monotonic() + min(30.0, 0.5 * (2 ** min(st.spawn_failures, 6)))
+        self.queue.add_after(st.key, st.next_retry - time.monotonic() + 0.01)
+        now = M.format_time()
+        cs = {"name": c["name"], "image": c.get("image", ""), "ready": False, "restartCount": 0,
+              "state": {"waiting": {"reason": reason, "message": err}}}
+        patch = {"status": {"phase": C.POD_PENDING, "startTime": pod.get("status", {}).get("startTime") or now,
+                            "containerStatuses": [cs]}}
+        try:
+            self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch, subresource="status")
+        except APIError:
+            pass
+        klog.warning("pod %s container %s: %s: %s", st.key, c["name"], reason, err)
+        return err or reason
+
+    # ------------------------------------------------------------------ kubelet: exits
+    def _on_exit(self, ev: Dict[str, Any]) -> None:
+        sid = ev["id"]
+        key = "/".join(sid.split("/")[:2])
+        cname = sid.split("/")[-1]
+        with self._lock:
+            st = self._states.get(key)
+        if st is None or st.containers.get(cname) != sid:
+            return
+        ns, name = M.split_key(key)
+        try:
+            pod = self.cs.core_v1().pods(ns).get(name)
+        except APIError:
+            return
+        if M.uid_of(pod) != st.uid:
+            return
+        code, sig = int(ev["exit_code"]), int(ev["signal"])
+        now = M.format_time()
+        term = {"exitCode": code, "reason": "Completed" if code == 0 else "Error", "finishedAt": now}
+        if sig:
+            term["signal"] = sig
+            term["message"] = f"killed by signal {sig}"
+        inits = [c["name"] for c in pod.get("spec", {}).get("initContainers") or []]
+        if cname in inits:
+            if code == 0:
+                st.init_index += 1
+                st.containers.pop(cname, None)
+                self.queue.add(key)
+                return
+            patch = {"status": {"phase": C.POD_FAILED, "reason": "InitContainerFailed",
+                                "message": f"init container {cname} exited with {code}",
+                                "initContainerStatuses": [{"name": cname, "state": {"terminated": term}}]}}
+            self.cs.core_v1().pods(ns).patch(name, patch, subresource="status")
+            return
+        statuses = M.deepcopy(pod.get("status", {}).get("containerStatuses") or [])
+        found = False
+        for cs in statuses:
+            if cs.get("name") == cname:
+                cs["state"] = {"terminated": term}
+                cs["ready"] = False
+                found = True
+        if not found:
+            statuses.append({"name": cname, "ready": False, "restartCount": 0, "state": {"terminated": term}})
+        want = [c["name"] for c in pod.get("spec", {}).get("containers") or []]
+        terms = {cs["name"]: cs["state"]["terminated"] for cs in statuses if "terminated" in (cs.get("state") or {})}
+        status: Dict[str, Any] = {"containerStatuses": statuses}
+        if all(n in terms for n in want):
+            status["phase"] = C.POD_SUCCEEDED if all(terms[n]["exitCode"] == 0 for n in want) else C.POD_FAILED
+        klog.V(2).info("pod %s container %s exited code=%d signal=%d", key, cname, code, sig)
+        try:
+            self.cs.core_v1().pods(ns).patch(name, {"status": status}, subresource="status")
+        except APIError as e:
+            klog.warning("status update of %s failed: %s", key, e.message)
+        self._kick_pending()
+
+    # ------------------------------------------------------------------ kubelet: terminate
+    def _alive_ids(self, key: str) -> List[str]:
+        with self._lock:
+            st = self._states.get(key)
+            ids = list(st.containers.values()) if st else []
+        return [sid for sid in ids if self.sup.alive(sid)]
+
+    def _kill_pod_processes(self, key: str, sig: int) -> None:
+        for sid in self._alive_ids(key):
+            self.sup.kill(sid, sig, True)
+
+    def _terminate(self, pod: dict, key: str) -> None:
+        alive = self._alive_ids(key)
+        ns, name = M.namespace_of(pod), M.name_of(pod)
+        if not alive:
+            try:
+                self.cs.core_v1().pods(ns).delete(name, grace_period_seconds=0)
+            except APIError as e:
+                if e.reason != "NotFound":
+                    raise
+            with self._lock:
+                self._states.pop(key, None)
+            self._kick_pending()
+            return
+        grace = float(pod["metadata"].get("deletionGracePeriodSeconds") or 0)
+        age = M.seconds_since(pod["metadata"].get("deletionTimestamp"))
+        with self._lock:
+            st = self._states.get(key)
+        if st is not None and not st.term_sent_at:
+            st.term_sent_at = time.monotonic()
+            self._kill_pod_processes(key, signal.SIGTERM)
+        if age >= grace or (st is not None and time.monotonic() - st.term_sent_at >= grace):
+            self._kill_pod_processes(key, signal.SIGKILL)
+        self.queue.add_after(key, 0.05 if grace <= 1 else 0.2)
+
+    # ------------------------------------------------------------------ orphan sweep
+    def sweep_orphans(self) -> int:
+        """Kill supervised processes whose pod record is gone or was replaced (GC analogue)."""
+        n = 0
+        for sid, _pid in self.sup.list():
+            key = "/".join(sid.split("/")[:2])
+            uid8 = sid.split("/")[2] if sid.count("/") >= 3 else ""
+            ns, name = M.split_key(key)
+            try:
+                pod = self.pod_lister.namespaced(ns).get(name)
+                if not uid8 or M.uid_of(pod).startswith(uid8):
+                    continue
+            except APIError:
+                pass
+            klog.info("orphan process %s: owning pod is gone, killing", sid)
+            self.sup.kill(sid, signal.SIGKILL, True)
+            n += 1
+        return n

@@ -1,0 +1,39 @@
+"""Stand-alone node agent daemon (``python -m trainingjob_operator_b200.cmd.agent --master URL``)."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+from ..agent.agent import NodeAgent
+from ..client.clientset import new_for_config
+from ..signals import setup_signal_handler
+from ..utils import klog
+from .options import TrainingJobOperatorOption, resolve_master
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="aitj-agent")
+    ap.add_argument("--master", default="")
+    ap.add_argument("--kubeconfig", default="")
+    ap.add_argument("--gpus", type=int, default=None)
+    ap.add_argument("--workdir", default=os.path.expanduser("~/.aitj"))
+    ap.add_argument("--image-map", action="append", default=[], help="image=command (repeatable)")
+    ap.add_argument("--v", type=int, default=0)
+    args = ap.parse_args(argv)
+    klog.configure(args.v, True)
+    master = resolve_master(TrainingJobOperatorOption(master_url=args.master, kubeconfig=args.kubeconfig))
+    import shlex
+
+    image_map = {kv.split("=", 1)[0]: shlex.split(kv.split("=", 1)[1]) for kv in args.image_map if "=" in kv}
+    agent = NodeAgent(new_for_config(master=master), num_gpus=args.gpus, workdir=args.workdir, image_map=image_map)
+    stop = setup_signal_handler()
+    agent.start(stop)
+    print(f"aitj-agent up: {agent.num_gpus} GPU slot(s), master {master}", flush=True)
+    stop.wait()
+    agent.shutdown(kill=False)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,176 @@
+"""Elastic rescale: real semantics for ``minReplicas`` / ``maxReplicas`` / ``edlPolicy``.
+
+In the reference these fields are API surface only (/root/reference/pkg/apis/aitrainingjob/v1/
+replica.go:10-11,19 -- never read by any controller code): scale-up just
+creates pods whose environment disagrees with the already running ones (pod.go:186-193, env fixed at
+creation pod.go:528) and scale-down is unimplemented (pod.go:688-689).  Here a change of the desired
+world size bumps a *rendezvous generation* kept in ``status.rendezvous``:
+
+* every replica is created for one generation and gets ``AITJ_RENDEZVOUS_GENERATION``,
+  ``WORLD_SIZE`` and a generation-specific ``MASTER_PORT``;
+* running workers watch ``status.rendezvous`` (``runtime.elastic``) and, at a step boundary,
+  tear their process group down and re-initialise with the new world size -- survivors keep their
+  step state on the device and broadcast it to joiners over NVLink;
+* ranks whose index falls out of range leave voluntarily and are then deleted (``pod.py``);
+* ``edlPolicy: Auto`` lets the controller pick ``replicas`` within [min, max] from the number of
+  healthy, free GPU slots; ``Manual`` honours user edits within the bounds; ``Never`` freezes the size
+  the job started with.
+A restart also bumps the generation so re-created replicas rendezvous on a fresh port.
+"""
+from __future__ import annotations
+
+import socket
+import threading
+from typing import Dict, List, Optional
+
+from ..api import constants as C
+from ..api import meta as M
+from ..api.types import AITrainingJob, Rendezvous
+from ..store.apiserver import APIError
+from ..utils import klog, metrics
+
+metrics.describe("aitj_rendezvous_generations_total", "rendezvous generation bumps (scale up/down, restart)")
+
+_PORT_LOCK = threading.Lock()
+_RECENT_PORTS: List[int] = []
+
+
+def allocate_port() -> int:
+    """A free loopback TCP port (bind to 0, remember the last few so two jobs do not race to one)."""
+    with _PORT_LOCK:
+        for _ in range(32):
+            s = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            try:
+                s.bind(("127.0.0.1", 0))
+                port = s.getsockname()[1]
+            finally:
+                s.close()
+            if port not in _RECENT_PORTS:
+                _RECENT_PORTS.append(port)
+                del _RECENT_PORTS[:-64]
+                return port
+        return port
+
+
+def desired_world_sizes(job: AITrainingJob) -> Dict[str, int]:
+    return {rt: int(spec.replicas or 0) for rt, spec in job.spec.replica_specs.items()}
+
+
+def clamp_replicas(spec, value: int) -> int:
+    lo = spec.min_replicas if spec.min_replicas is not None else 0
+    hi = spec.max_replicas if spec.max_replicas is not None else max(value, lo)
+    return max(lo, min(hi, value))
+
+
+class ElasticMixin:
+    """Mixed into ``TrainingJobController``."""
+
+    def reconcile_rendezvous(self, job: AITrainingJob, pods: List[dict]) -> None:
+        want = desired_world_sizes(job)
+        rdv = job.status.rendezvous
+        if rdv is None:
+            job.status.rendezvous = Rendezvous(generation=1, world_sizes=want, master_port=allocate_port(),
+                                               changed_at=M.format_time())
+            return
+        frozen = self._frozen_roles(job)
+        effective = {rt: (rdv.world_sizes.get(rt, n) if rt in frozen else n) for rt, n in want.items()}
+        if effective != rdv.world_sizes:
+            # only a running/starting job needs a new generation; before any pod exists just adopt the sizes
+            if pods:
+                self.bump_rendezvous(job, "rescale", effective)
+                self.trace_rescale(job)
+            else:
+                rdv.world_sizes = effective
+
+    def _frozen_roles(self, job: AITrainingJob) -> set:
+        """Roles with ``edlPolicy: Never`` keep the world size they started with."""
+        rdv = job.status.rendezvous
+        if rdv is None:
+            return set()
+        return {rt for rt, spec in job.spec.replica_specs.items()
+                if spec.edl_policy == C.EDL_POLICY_NEVER and rt in rdv.world_sizes and job.status.start_running_time}
+
+    def bump_rendezvous(self, job: AITrainingJob, why: str, world_sizes: Optional[Dict[str, int]] = None) -> None:
+        rdv = job.status.rendezvous
+        if rdv is None:
+            rdv = job.status.rendezvous = Rendezvous(generation=0, world_sizes=desired_world_sizes(job))
+        rdv.generation += 1
+        rdv.master_port = allocate_port()
+        rdv.changed_at = M.format_time()
+        if world_sizes is not None:
+            rdv.world_sizes = dict(world_sizes)
+        klog.info("job %s: rendezvous generation %d (%s): world %s port %d", job.key(), rdv.generation, why,
+                  rdv.world_sizes, rdv.master_port)
+        metrics.inc("aitj_rendezvous_generations_total", labels={"reason": why})
+
+    def trace_rescale(self, job: AITrainingJob) -> None:
+        import json
+        import time
+
+        raw = job.annotations.get(C.ANN_TRACE)
+        try:
+            tr = json.loads(raw) if raw else {}
+        except ValueError:
+            tr = {}
+        tr.setdefault("rescales", []).append({"generation": job.status.rendezvous.generation,
+                                              "at": round(time.time(), 4),
+                                              "world": dict(job.status.rendezvous.world_sizes)})
+        tr["rescales"] = tr["rescales"][-16:]
+        job.set_annotation(C.ANN_TRACE, json.dumps(tr, sort_keys=True))
+
+    def forget_rendezvous(self, key: str) -> None:
+        return
+
+    # ------------------------------------------------------------------ edlPolicy: Auto
+    def reconcile_elastic(self, job: AITrainingJob, pods: List[dict]) -> bool:
+        """For ``edlPolicy: Auto`` roles choose replicas in [min,max] from free healthy GPU slots.
+        Returns True when the job spec was patched (the caller stops; the update event re-queues)."""
+        if job.status.phase in (C.PHASE_TERMINATING, C.PHASE_RESTARTING) or job.status.restart_replica_name:
+            return False
+        patch: Dict[str, dict] = {}
+        ready = None
+        for rt, spec in job.spec.replica_specs.items():
+            if spec.edl_policy != C.EDL_POLICY_AUTO:
+                continue
+            if spec.min_replicas is None and spec.max_replicas is None:
+                continue
+            if ready is None:
+                ready = self._free_gpu_slots(job)
+            cur = int(spec.replicas or 0)
+            mine = [p for p in pods if M.labels_of(p).get(C.LABEL_REPLICA_NAME) == rt.lower()]
+            unschedulable = [p for p in mine if not p.get("spec", {}).get("nodeName")
+                             and self.get_pod_scheduling_message(p)]
+            target = cur
+            if unschedulable:
+                target = cur - len(unschedulable)          # shrink to what fits
+            elif ready > 0 and all(p.get("status", {}).get("phase") == C.POD_RUNNING for p in mine) \
+                    and len(mine) == cur:
+                target = cur + ready                       # grow into free slots
+            target = clamp_replicas(spec, target)
+            if target != cur:
+                klog.info("job %s role %s: edlPolicy Auto: replicas %d -> %d (free slots %d, unschedulable %d)",
+                          job.key(), rt, cur, target, ready, len(unschedulable))
+                patch[rt] = {"replicas": target}
+                ready = max(0, ready - max(0, target - cur))
+        if not patch:
+            return False
+        try:
+            self.trainingjob_client.elasticdeeplearning_v1().aitrainingjobs(job.namespace).patch(
+                job.name, {"spec": {"replicaSpecs": patch}})
+        except APIError as e:
+            klog.warning("auto-scale patch of %s failed: %s", job.key(), e.message)
+            return False
+        metrics.inc("aitj_autoscale_total")
+        return True
+
+    def _free_gpu_slots(self, job: AITrainingJob) -> int:
+        ready_nodes = {n for n in self.get_node_status() if n.startswith("gpu-")}
+        busy = set()
+        for pod in self.pod_lister.list():
+            node = pod.get("spec", {}).get("nodeName")
+            if node and pod.get("status", {}).get("phase") in (C.POD_PENDING, C.POD_RUNNING, None):
+                busy.add(node)
+                for g in (M.annotations_of(pod).get(C.ANN_GPUS) or "").split(","):
+                    if g.strip():
+                        busy.add(f"gpu-{g.strip()}")
+        return len(ready_nodes - busy)
