@@ -1,0 +1,118 @@
+"""Flat parameter / gradient / optimizer-state storage for the hand-written training engines.
+
+Everything a worker trains lives in five contiguous device buffers laid out for 180 GB of HBM3e and
+one-sweep kernels: fp32 master weights ``p32``, their bf16 compute copy ``p16`` (what the tcgen05
+GEMMs read through TMA), fp32 gradients ``g32`` (wgrad GEMMs ``red.add`` into it, split-K and
+micro-batches accumulate for free), and AdamW moments ``m`` / ``v``.  Tensors are padded to 256
+elements so the per-256-element weight-decay mask of the AdamW kernel lines up, and the contiguous
+layout makes gradient buckets plain slices (DDP all-reduce without a flatten/unflatten copy).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+
+ALIGN = 256
+
+
+@dataclass
+class ParamSpec:
+    name: str
+    shape: Tuple[int, ...]
+    decay: bool
+    init: str = "normal"      # normal | zeros | ones
+    std: float = 0.02
+    offset: int = 0
+    numel: int = 0
+    padded: int = 0
+
+
+class FlatParams:
+    def __init__(self, specs: Iterable[ParamSpec], device, with_optimizer_state: bool = True, seed: int = 0):
+        self.specs: List[ParamSpec] = list(specs)
+        off = 0
+        for s in self.specs:
+            n = 1
+            for d in s.shape:
+                n *= d
+            s.numel = n
+            s.padded = (n + ALIGN - 1) // ALIGN * ALIGN
+            s.offset = off
+            off += s.padded
+        self.total = off
+        self.device = torch.device(device)
+        self.p32 = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.p16 = torch.zeros(self.total, dtype=torch.bfloat16, device=self.device)
+        self.g32 = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        if with_optimizer_state:
+            self.m = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+            self.v = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        else:
+            self.m = self.v = None
+        mask = torch.zeros(self.total // ALIGN, dtype=torch.uint8)
+        for s in self.specs:
+            if s.decay:
+                mask[s.offset // ALIGN:(s.offset + s.padded) // ALIGN] = 1
+        self.wd_mask = mask.to(self.device)
+        self.by_name: Dict[str, ParamSpec] = {s.name: s for s in self.specs}
+        self.init_parameters(seed)
+
+    def init_parameters(self, seed: int = 0) -> None:
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(seed)
+        for s in self.specs:
+            view = self.p32[s.offset:s.offset + s.numel].view(s.shape)
+            if s.init == "zeros":
+                view.zero_()
+            elif s.init == "ones":
+                view.fill_(1.0)
+            else:
+                view.copy_(torch.randn(s.shape, generator=gen, dtype=torch.float32) * s.std)
+        self.refresh_compute_copy()
+
+    def refresh_compute_copy(self) -> None:
+        self.p16.copy_(self.p32)
+
+    # -- views ---------------------------------------------------------------------------------
+    def _view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        s = self.by_name[name]
+        return buf[s.offset:s.offset + s.numel].view(s.shape)
+
+    def w16(self, name: str) -> torch.Tensor:
+        return self._view(self.p16, name)
+
+    def w32(self, name: str) -> torch.Tensor:
+        return self._view(self.p32, name)
+
+    def grad(self, name: str) -> torch.Tensor:
+        return self._view(self.g32, name)
+
+    def range_of(self, first: str, last: str) -> Tuple[int, int]:
+        a, b = self.by_name[first], self.by_name[last]
+        return a.offset, b.offset + b.padded
+
+    def num_parameters(self) -> int:
+        return sum(s.numel for s in self.specs)
+
+    # -- state (checkpoint / elastic hand-off) ------------------------------------------------------
+    def state_tensors(self) -> List[torch.Tensor]:
+        out = [self.p32]
+        if self.m is not None:
+            out += [self.m, self.v]
+        return out
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        d = {"p32": self.p32}
+        if self.m is not None:
+            d["m"] = self.m
+            d["v"] = self.v
+        return d
+
+    def load_state_dict(self, d: Dict[str, torch.Tensor]) -> None:
+        self.p32.copy_(d["p32"])
+        if self.m is not None and "m" in d:
+            self.m.copy_(d["m"])
+            self.v.copy_(d["v"])
+        self.refresh_compute_copy()

@@ -367,7 +367,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                     float* __restrict__ m, float* __restrict__ v,
                                                     __nv_bfloat16* __restrict__ p16,
                                                     const uint8_t* __restrict__ wd_mask,
-                                                    const float* __restrict__ sumsq, size_t n, AdamArgs a) {
+                                                    const float* __restrict__ sumsq,
+                                                    const float* __restrict__ dyn, size_t n, AdamArgs a) {
+  // dyn (device, optional) = {lr, bias_correction1, bias_correction2}: lets a captured CUDA graph replay
+  // with a per-step learning rate / step count without re-capturing.
+  if (dyn != nullptr) { a.lr = dyn[0]; a.bc1 = dyn[1]; a.bc2 = dyn[2]; }
   float clip = 1.0f;
   if (sumsq != nullptr && a.max_norm > 0.f) {
     const float norm = sqrtf(*sumsq) / a.grad_div;
@@ -550,8 +554,8 @@ int aitj_sumsq(const void* g, long long n, void* out, void* stream) {
   return LAUNCH_OK();
 }
 
-int aitj_adamw(void* p, void* g, void* m, void* v, void* p16, const void* wd_mask, const void* sumsq, long long n,
-               float lr, float beta1, float beta2, float eps, float weight_decay, int step, float max_norm,
+int aitj_adamw(void* p, void* g, void* m, void* v, void* p16, const void* wd_mask, const void* sumsq,
+               const void* dyn, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float max_norm,
                float grad_div, int zero_grad, void* stream) {
   if (n % 256) return -1;
   AdamArgs a;
@@ -562,7 +566,7 @@ int aitj_adamw(void* p, void* g, void* m, void* v, void* p16, const void* wd_mas
   adamw_kernel<<<grid_for(static_cast<size_t>(n) / 4, 256, 148 * 8), 256, 0, S(stream)>>>(
       reinterpret_cast<float*>(p), reinterpret_cast<float*>(g), reinterpret_cast<float*>(m),
       reinterpret_cast<float*>(v), BF(p16), reinterpret_cast<const uint8_t*>(wd_mask),
-      reinterpret_cast<const float*>(sumsq), static_cast<size_t>(n), a);
+      reinterpret_cast<const float*>(sumsq), reinterpret_cast<const float*>(dyn), static_cast<size_t>(n), a);
   return LAUNCH_OK();
 }
 

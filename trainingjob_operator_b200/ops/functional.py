@@ -135,9 +135,11 @@ def sumsq(g, out):
 
 
 def adamw(p, g, m, v, p16, wd_mask, *, lr, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.1, step=1, sumsq_buf=None,
-          max_norm=0.0, grad_div=1.0, zero_grad=True):
+          max_norm=0.0, grad_div=1.0, zero_grad=True, dyn=None):
+    """One sweep: AdamW on fp32 master state + bf16 compute copy refresh + grad zeroing.
+    ``dyn`` (device float[3] = lr, 1-beta1^t, 1-beta2^t) overrides lr/step for CUDA-graph replay."""
     lib.call("aitj_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p16.data_ptr(), wd_mask.data_ptr(),
-             _ptr(sumsq_buf), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+             _ptr(sumsq_buf), _ptr(dyn), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
              int(step), float(max_norm), float(grad_div), int(bool(zero_grad)), _stream())
 
 

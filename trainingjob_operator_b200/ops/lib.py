@@ -65,7 +65,7 @@ _SIGS = {
     "aitj_softmax_xent": [_P, _P, _P, _I, _I, _I, _F, _P],
     "aitj_colsum": [_P, _P, _I, _I, _P],
     "aitj_sumsq": [_P, _L, _P, _P],
-    "aitj_adamw": [_P, _P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
+    "aitj_adamw": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
     "aitj_cast_f32_bf16": [_P, _P, _L, _P],
     "aitj_gelu_fwd": [_P, _P, _L, _P],
     "aitj_gelu_bwd": [_P, _P, _P, _L, _P],

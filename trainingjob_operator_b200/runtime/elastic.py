@@ -1,0 +1,147 @@
+"""Worker-side elastic agent: follow ``status.rendezvous`` of the owning AITrainingJob.
+
+The reference declares ``minReplicas`` / ``maxReplicas`` / ``edlPolicy`` but delegates membership
+changes to an external Paddle EDL runtime (SURVEY.md §0.3, §2.4 "Elastic DP").  Here the controller
+publishes a rendezvous *generation* (``controller/elastic.py``) and every worker runs this watcher:
+a side thread polls the job object on the API server (``AITJ_MASTER``); at each step boundary the
+ranks agree -- one tiny MAX all-reduce -- on the newest generation any of them has seen, so they all
+leave the old process group at the same step.  The watcher also reports lifecycle timestamps and the
+final metrics back onto the job (annotations), which is how reconcile->first-step and rescale latency
+are measured end to end.
+"""
+from __future__ import annotations
+
+import json
+import os
+import threading
+import time
+from typing import Any, Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+ANN_METRICS = "aitj.b200/metrics"
+ANN_WORKER_TRACE = "aitj.b200/worker-trace"
+ANN_RESCALE = "aitj.b200/rescale-trace"
+
+
+def env_int(name: str, default: int = 0) -> int:
+    try:
+        return int(os.environ.get(name, default))
+    except (TypeError, ValueError):
+        return default
+
+
+def rendezvous_from_env() -> Dict[str, int]:
+    return {"world": env_int("WORLD_SIZE", 1), "port": env_int("MASTER_PORT", 29500),
+            "generation": env_int("AITJ_RENDEZVOUS_GENERATION", 0)}
+
+
+class ElasticWatcher:
+    def __init__(self, master: str, namespace: str, job: str, role: str, generation: int, poll: float = 0.1):
+        from ..api import register as R
+        from ..store.transport import HTTPTransport
+
+        self._t = HTTPTransport(master, timeout=5.0, user_agent="aitj-worker")
+        self._info = R.AITRAININGJOB
+        self.ns, self.job, self.role = namespace, job, role
+        self.generation = generation
+        self.poll = poll
+        self._latest: Optional[Dict[str, Any]] = None
+        self._lock = threading.Lock()
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._loop, name="elastic-watch", daemon=True)
+        self._thread.start()
+        self.check_every = max(1, env_int("AITJ_ELASTIC_CHECK_EVERY", 1))
+        self._n = 0
+
+    @classmethod
+    def from_env(cls, generation: int) -> Optional["ElasticWatcher"]:
+        master = os.environ.get("AITJ_MASTER")
+        job = os.environ.get("TRAININGJOB_NAME")
+        if not master or not job:
+            return None
+        return cls(master, os.environ.get("TRAININGJOB_NAMESPACE", "default"), job,
+                   os.environ.get("TRAININGJOB_REPLICA_NAME", "trainer"), generation)
+
+    # ------------------------------------------------------------------ polling thread
+    def _fetch(self) -> Optional[Dict[str, Any]]:
+        try:
+            obj = self._t.get(self._info, self.ns, self.job)
+        except Exception:  # noqa: BLE001 - API server briefly unreachable: keep training
+            return None
+        rdv = (obj.get("status") or {}).get("rendezvous")
+        if not rdv:
+            return None
+        sizes = rdv.get("worldSizes") or {}
+        world = None
+        for k, v in sizes.items():
+            if k.lower() == self.role.lower():
+                world = int(v)
+        if world is None:
+            return None
+        return {"generation": int(rdv.get("generation", 0)), "world": world, "port": int(rdv.get("masterPort", 0))}
+
+    def _loop(self) -> None:
+        while not self._stop.wait(self.poll):
+            r = self._fetch()
+            if r is None:
+                continue
+            with self._lock:
+                if self._latest is None or r["generation"] > self._latest["generation"]:
+                    r["observed_at"] = time.time()
+                    self._latest = r
+
+    def _wait_for(self, generation: int, timeout: float = 30.0) -> Optional[Dict[str, Any]]:
+        deadline = time.time() + timeout
+        while time.time() < deadline:
+            with self._lock:
+                if self._latest is not None and self._latest["generation"] >= generation:
+                    return dict(self._latest)
+            time.sleep(0.01)
+        return None
+
+    # ------------------------------------------------------------------ step-boundary agreement
+    def agree(self, device: torch.device) -> Optional[Dict[str, Any]]:
+        """Newest rendezvous record every current rank can adopt now, or None."""
+        self._n += 1
+        if self._n % self.check_every:
+            return None
+        with self._lock:
+            mine = self._latest["generation"] if self._latest else self.generation
+        newest = mine
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            t = torch.tensor([mine], dtype=torch.int64, device=device if device.type == "cuda" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            newest = int(t[0])
+        if newest <= self.generation:
+            return None
+        return self._wait_for(newest)
+
+    def adopted(self, generation: int) -> None:
+        self.generation = generation
+
+    # ------------------------------------------------------------------ reporting
+    def _annotate(self, key: str, value: Any) -> None:
+        try:
+            self._t.patch(self._info, self.ns, self.job, {"metadata": {"annotations": {key: json.dumps(value)}}})
+        except Exception:  # noqa: BLE001
+            pass
+
+    def report_trace(self, rank: int, trace: Dict[str, float]) -> None:
+        if rank == 0:
+            self._annotate(ANN_WORKER_TRACE, {k: round(v, 4) for k, v in trace.items()})
+
+    def report_rescale(self, rank: int, rec: Dict[str, Any]) -> None:
+        if rank == 0:
+            rec = dict(rec)
+            rec["at"] = round(time.time(), 4)
+            self._annotate(ANN_RESCALE, rec)
+
+    def report_result(self, result: Dict[str, Any]) -> None:
+        keep = {k: result.get(k) for k in ("samples_per_sec", "ms_per_step", "global_batch", "world", "steps_done",
+                                           "loss_first", "loss_last", "gpu_launches", "cuda_graph")}
+        self._annotate(ANN_METRICS, keep)
+
+    def stop(self) -> None:
+        self._stop.set()

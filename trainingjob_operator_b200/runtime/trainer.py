@@ -1,0 +1,141 @@
+"""Training-step driver for the hand-written engines: pinned-host input feed, CUDA-graph replay,
+bucketed gradient all-reduce overlapped with backward, fused optimizer sweep, loss read-back.
+
+One ``step()`` is exactly what BASELINE.json's samples/sec counts and what ``bench.py`` times:
+H2D copy of this step's tokens from pinned memory -> forward -> backward (+ all-reduce) ->
+AdamW -> D2H of the loss.  The reference operator has no training loop; this is the
+launched workers' loop.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..parallel.ddp import BucketAllReducer
+
+
+class SyntheticTokens:
+    """Synthetic token stream of the named shape, staged in pinned host memory (no dataset access)."""
+
+    def __init__(self, vocab: int, batch: int, seq: int, n_batches: int = 8, seed: int = 0, pin: bool = True):
+        g = torch.Generator().manual_seed(seed)
+        self.batches = []
+        for _ in range(n_batches):
+            tok = torch.randint(0, vocab, (batch * seq,), generator=g, dtype=torch.int64)
+            tgt = torch.roll(tok, -1)
+            if pin and torch.cuda.is_available():
+                tok, tgt = tok.pin_memory(), tgt.pin_memory()
+            self.batches.append((tok, tgt))
+        self.i = 0
+        self.bytes_per_step = 2 * batch * seq * 8
+
+    def next(self):
+        b = self.batches[self.i % len(self.batches)]
+        self.i += 1
+        return b
+
+
+def cosine_lr(step: int, base_lr: float, warmup: int = 10, total: int = 10000, min_ratio: float = 0.1) -> float:
+    if step < warmup:
+        return base_lr * (step + 1) / warmup
+    t = min(1.0, (step - warmup) / max(1, total - warmup))
+    return base_lr * (min_ratio + (1 - min_ratio) * 0.5 * (1 + math.cos(math.pi * t)))
+
+
+class EngineTrainer:
+    def __init__(self, engine, lr: float = 3e-4, weight_decay: float = 0.1, max_norm: float = 1.0,
+                 use_graph: bool = True, allreduce: Optional[str] = None, group=None):
+        self.engine = engine
+        self.lr = lr
+        self.weight_decay = weight_decay
+        self.max_norm = max_norm
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.step_count = 0
+        self.cuda = engine.dev.type == "cuda"
+        backend = allreduce or os.environ.get("AITJ_ALLREDUCE", "nccl")
+        self.reducer = BucketAllReducer(engine.params.g32, engine.grad_buckets(), group, backend) \
+            if self.world > 1 else None
+        engine.grad_hook = self.reducer.hook if self.reducer else None
+        self.use_graph = use_graph and self.cuda
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss_host = torch.zeros(1, dtype=torch.float32)
+        if self.cuda:
+            self.loss_host = self.loss_host.pin_memory()
+        self.graph_error: Optional[str] = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ one step of device work
+    def _device_step(self) -> None:
+        e = self.engine
+        e.forward()
+        e.backward()
+        if self.reducer:
+            self.reducer.wait()
+        e.optimizer_step(lr=self.lr, step=max(1, self.step_count), weight_decay=self.weight_decay,
+                         max_norm=self.max_norm, grad_div=float(self.world), use_dyn=True)
+
+    def _capture(self) -> None:
+        from ..ops import lib
+
+        # warm-up on a side stream (allocator, cuDNN plans, NCCL channels) before capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._device_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        before = lib.LAUNCHES
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                self._device_step()
+            self.graph = g
+            self.launches_per_step = lib.LAUNCHES - before
+        except Exception as ex:  # noqa: BLE001 - fall back to eager replay
+            self.graph = None
+            self.use_graph = False
+            self.graph_error = f"{type(ex).__name__}: {ex}"
+            torch.cuda.synchronize()
+
+    def count_launches_eager(self) -> int:
+        from ..ops import lib
+
+        before = lib.LAUNCHES
+        self._device_step()
+        return lib.LAUNCHES - before
+
+    # ------------------------------------------------------------------ public step
+    def step(self, tok_host: torch.Tensor, tgt_host: torch.Tensor, read_loss: bool = True) -> Optional[float]:
+        e = self.engine
+        self.step_count += 1
+        e.tok.copy_(tok_host, non_blocking=True)
+        e.tgt.copy_(tgt_host, non_blocking=True)
+        e.set_step_scalars(cosine_lr(self.step_count, self.lr), self.step_count)
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+                # the two warm-up passes + capture consumed optimizer steps on real data; that is fine for
+                # synthetic-data benchmarking and is excluded from timing by the caller's warm-up
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._device_step()
+        else:
+            self._device_step()
+        if not read_loss:
+            return None
+        self.loss_host.copy_(e.loss, non_blocking=True)
+        if self.cuda:
+            torch.cuda.current_stream().synchronize()
+        return float(self.loss_host[0])
+
+    def state_tensors(self) -> List[torch.Tensor]:
+        return self.engine.params.state_tensors()

@@ -1,0 +1,433 @@
+"""Worker runtime: the process the node agent launches for every replica of a benchmark job.
+
+Reads the environment contract injected by the controller (the reference's 13 variables,
+/root/reference/pkg/controller/pod.go:548-652, plus the torch / elastic dialect added in
+``controller/pod.py``), joins ``torch.distributed`` (NCCL over NVLink 5 / NVSwitch on GPUs, gloo on
+CPU), builds the requested model and runs the measured training loop:
+
+* every step: H2D of the step's inputs from pinned memory, forward, backward + bucketed all-reduce,
+  fused optimizer sweep, D2H of the loss;
+* timing: W untimed warm-up steps, then exactly K steps bracketed by barrier + synchronize, CUDA
+  events on the device, max over ranks; rank 0 writes the result JSON and patches it onto the job;
+* elastic (``runtime.elastic``): a side thread watches ``status.rendezvous``; at a step boundary all
+  ranks agree on the newest generation, tear the process group down and re-rendezvous with the new
+  world size; survivors keep params / optimizer state / step on the device and broadcast them to
+  joiners; ranks that fall out of range leave with exit 0;
+* restart: ``TRAININGJOB_REPLICA_RESTARTCOUNT`` > 0 => resume from the newest checkpoint written by
+  rank 0 every ``--ckpt-every`` steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import signal
+import sys
+import time
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .elastic import ElasticWatcher, env_int, rendezvous_from_env
+from .trainer import EngineTrainer, SyntheticTokens
+
+
+# ------------------------------------------------------------------------------------ adapters
+class EngineAdapter:
+    """GPT-2 / BERT-shaped transformer on the hand-written engine (CUDA only)."""
+
+    def __init__(self, name: str, batch: int, seq: int, args):
+        from ..models.gpt2 import GPT2Config, GPT2Engine, flops_per_token
+
+        if name == "gpt2":
+            cfg, causal = GPT2Config.small(), True
+        elif name == "gpt2-tiny":
+            cfg, causal = GPT2Config.tiny(), True
+        elif name == "bert":
+            cfg, causal = GPT2Config(vocab_size=30522, n_layer=12, n_head=12, n_embd=768, block_size=512,
+                                     name="bert-base"), False
+        else:
+            raise ValueError(name)
+        seq = min(seq, cfg.block_size)
+        self.cfg = cfg
+        self.engine = GPT2Engine(cfg, batch, seq, "cuda", seed=args.seed, gemm_backend=args.gemm, causal=causal)
+        self.batch, self.seq = batch, seq
+        self.data = SyntheticTokens(cfg.vocab_size, batch, seq, n_batches=4, seed=args.seed + 1)
+        self.h2d_bytes = self.data.bytes_per_step
+        self.d2h_bytes = 4
+        self.flops_per_step = flops_per_token(cfg, seq) * batch * seq
+        self.trainer: Optional[EngineTrainer] = None
+        self.args = args
+        self.describe = {"model": cfg.name, "seq_len": seq, "params": self.engine.num_parameters(),
+                         "gemm": args.gemm}
+
+    def bind(self, group=None) -> None:
+        old = self.trainer
+        self.trainer = EngineTrainer(self.engine, lr=self.args.lr, use_graph=not self.args.no_graph, group=group)
+        if old is not None:
+            self.trainer.step_count = old.step_count
+
+    def train_step(self) -> float:
+        tok, tgt = self.data.next()
+        return self.trainer.step(tok, tgt)
+
+    def state_tensors(self) -> List[torch.Tensor]:
+        return self.engine.params.state_tensors()
+
+    def after_state_load(self) -> None:
+        self.engine.params.refresh_compute_copy()
+
+    @property
+    def step_count(self) -> int:
+        return self.trainer.step_count if self.trainer else 0
+
+    @step_count.setter
+    def step_count(self, v: int) -> None:
+        if self.trainer:
+            self.trainer.step_count = v
+
+    def launches_per_step(self) -> int:
+        t = self.trainer
+        if t.launches_per_step:
+            return t.launches_per_step
+        return 0
+
+
+class TorchAdapter:
+    """nn.Module models (MNIST CNN, ResNet-50, CPU MLP) through ``parallel.flat_ddp``."""
+
+    def __init__(self, name: str, batch: int, args, device: torch.device):
+        from ..models.mnist_cnn import MLP, MnistCNN
+
+        self.name, self.batch, self.dev, self.args = name, batch, device, args
+        g = torch.Generator().manual_seed(args.seed + 1)
+        if name == "mnist":
+            self.module = MnistCNN()
+            shape, ncls = (1, 28, 28), 10
+        elif name == "resnet50":
+            from ..models.resnet50 import build_resnet50
+
+            self.module = build_resnet50()
+            shape, ncls = (3, 224, 224), 1000
+        elif name == "mlp":
+            self.module = MLP()
+            shape, ncls = (64,), 10
+        else:
+            raise ValueError(name)
+        torch.manual_seed(args.seed)
+        self.module = self.module.to(device)
+        self.channels_last = device.type == "cuda" and len(shape) == 3
+        if self.channels_last:
+            self.module = self.module.to(memory_format=torch.channels_last)
+        pin = device.type == "cuda"
+        self.batches = []
+        for _ in range(4):
+            x = torch.randn(batch, *shape, generator=g)
+            y = torch.randint(0, ncls, (batch,), generator=g)
+            if pin:
+                x, y = x.pin_memory(), y.pin_memory()
+            self.batches.append((x, y))
+        self.i = 0
+        self.x_dev = torch.empty(batch, *shape, device=device)
+        if self.channels_last:
+            self.x_dev = self.x_dev.contiguous(memory_format=torch.channels_last)
+        self.y_dev = torch.empty(batch, dtype=torch.int64, device=device)
+        self.h2d_bytes = self.batches[0][0].numel() * 4 + batch * 8
+        self.d2h_bytes = 4
+        self.ddp = None
+        self._steps = 0
+        self.loss_host = torch.zeros(1).pin_memory() if pin else torch.zeros(1)
+        self.describe = {"model": name, "params": sum(p.numel() for p in self.module.parameters())}
+        self.flops_per_step = 0.0
+
+    def bind(self, group=None) -> None:
+        from ..parallel.flat_ddp import FlatDDP
+
+        backend = "nccl" if self.dev.type == "cuda" else "gloo"
+        if self.ddp is None:
+            self.ddp = FlatDDP(self.module, group=group, backend=backend, lr=self.args.lr,
+                               optimizer="adamw" if self.name != "mlp" else "sgd")
+        else:  # re-bind after a re-rendezvous: keep buffers, rebuild the reducer for the new group
+            from ..parallel.ddp import BucketAllReducer
+
+            self.ddp.group = group
+            self.ddp.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.ddp.reducer = BucketAllReducer(self.ddp.g32, self.ddp.buckets, group, backend, 0) \
+                if self.ddp.world > 1 else None
+            if self.ddp.reducer is not None and not getattr(self.ddp, "_hooked", False):
+                for idx, p in enumerate(self.ddp.params):
+                    p.register_post_accumulate_grad_hook(self.ddp._make_hook(idx))
+        self.ddp._hooked = self.ddp.reducer is not None or getattr(self.ddp, "_hooked", False)
+
+    def train_step(self) -> float:
+        x, y = self.batches[self.i % len(self.batches)]
+        self.i += 1
+        self.x_dev.copy_(x, non_blocking=True)
+        self.y_dev.copy_(y, non_blocking=True)
+        if self.dev.type == "cuda":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = torch.nn.functional.cross_entropy(self.module(self.x_dev), self.y_dev)
+        else:
+            loss = torch.nn.functional.cross_entropy(self.module(self.x_dev), self.y_dev)
+        loss.backward()
+        self.ddp.finish_backward()
+        self.ddp.step()
+        self._steps += 1
+        self.loss_host.copy_(loss.detach().float().reshape(1), non_blocking=True)
+        if self.dev.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        return float(self.loss_host[0])
+
+    def state_tensors(self) -> List[torch.Tensor]:
+        return self.ddp.state_tensors()
+
+    def after_state_load(self) -> None:
+        return
+
+    @property
+    def step_count(self) -> int:
+        return self._steps
+
+    @step_count.setter
+    def step_count(self, v: int) -> None:
+        self._steps = v
+        if self.ddp is not None:
+            self.ddp.step_count = v
+
+    def launches_per_step(self) -> int:
+        return 1 if self.dev.type == "cuda" else 0
+
+
+def build_adapter(args, device: torch.device):
+    if args.model in ("gpt2", "gpt2-tiny", "bert"):
+        if device.type != "cuda":
+            raise RuntimeError(f"model {args.model} needs a CUDA device (hand-written sm_100a kernels)")
+        return EngineAdapter(args.model, args.batch, args.seq, args)
+    return TorchAdapter(args.model, args.batch, args, device)
+
+
+# ------------------------------------------------------------------------------------ process group
+def init_process_group(rank: int, world: int, port: int, device: torch.device, timeout_s: float = 120.0):
+    import datetime
+
+    backend = "nccl" if device.type == "cuda" else "gloo"
+    kw: Dict[str, Any] = {}
+    if device.type == "cuda":
+        kw["device_id"] = device
+    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            timeout=datetime.timedelta(seconds=timeout_s), **kw)
+
+
+def max_over_ranks(value: float, device: torch.device) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device if device.type == "cuda" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+# ------------------------------------------------------------------------------------ checkpoint
+def ckpt_path(args) -> str:
+    d = args.ckpt_dir or os.path.join(os.environ.get("AITJ_WORKDIR", "/tmp"), "ckpt")
+    os.makedirs(d, exist_ok=True)
+    job = os.environ.get("TRAININGJOB_NAME", "job")
+    return os.path.join(d, f"{job}.pt")
+
+
+def save_checkpoint(args, adapter, step: int) -> None:
+    tmp = ckpt_path(args) + ".tmp"
+    torch.save({"step": step, "state": [t.detach().cpu() for t in adapter.state_tensors()]}, tmp)
+    os.replace(tmp, ckpt_path(args))
+
+
+def load_checkpoint(args, adapter) -> int:
+    p = ckpt_path(args)
+    if not os.path.exists(p):
+        return 0
+    ck = torch.load(p, map_location="cpu")
+    for dst, src in zip(adapter.state_tensors(), ck["state"]):
+        dst.copy_(src)
+    adapter.after_state_load()
+    return int(ck["step"])
+
+
+# ------------------------------------------------------------------------------------ main loop
+def run(args) -> Dict[str, Any]:
+    t_proc = time.time()
+    rank = env_int("RANK", env_int("TRAININGJOB_REPLICA_INDEX", 0))
+    rdv = rendezvous_from_env()
+    world, port, generation = rdv["world"], rdv["port"], rdv["generation"]
+    use_cuda = torch.cuda.is_available() and not args.cpu
+    device = torch.device("cuda", env_int("LOCAL_RANK", 0) if torch.cuda.device_count() > 1 else 0) \
+        if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(device)
+    trace = {"process_start": t_proc, "torch_imported": time.time()}
+    if world > 1:
+        init_process_group(rank, world, port, device)
+    trace["rendezvous_done"] = time.time()
+    adapter = build_adapter(args, device)
+    adapter.bind(None)
+    watcher = ElasticWatcher.from_env(generation)
+    if watcher is not None and not args.elastic:
+        watcher.poll = 5.0  # reporting only
+
+    restart_count = env_int("TRAININGJOB_REPLICA_RESTARTCOUNT", 0)
+    start_step = 0
+    if restart_count > 0 and args.ckpt_every > 0:
+        start_step = load_checkpoint(args, adapter)
+        adapter.step_count = start_step
+    if world > 1:
+        from ..parallel.ddp import broadcast_state
+
+        broadcast_state(adapter.state_tensors(), 0)
+        adapter.after_state_load()
+
+    stop = {"flag": False}
+    signal.signal(signal.SIGTERM, lambda *_: stop.__setitem__("flag", True))
+
+    total = args.warmup + args.steps if args.steps > 0 else 1 << 60
+    losses: List[float] = []
+    rescales: List[Dict[str, Any]] = []
+    timing: Dict[str, Any] = {}
+    ev0 = ev1 = None
+    t_wall0 = 0.0
+    step = 0
+    first_step_done = False
+    from ..ops import lib as oplib
+
+    launches0 = 0
+    while step < total and not stop["flag"]:
+        # ---- elastic: agree on the newest rendezvous generation at the step boundary ------------
+        if watcher is not None and args.elastic:
+            target = watcher.agree(device)
+            if target is not None and target["generation"] != generation:
+                t0 = time.time()
+                new_world = target["world"]
+                if dist.is_initialized():
+                    if use_cuda:
+                        torch.cuda.synchronize()
+                    dist.destroy_process_group()
+                if rank >= new_world:
+                    print(f"[worker {rank}] leaving: world shrinks to {new_world} (generation {target['generation']})",
+                          flush=True)
+                    return {"left": True, "generation": target["generation"], "step": step}
+                generation, world, port = target["generation"], new_world, target["port"]
+                if world > 1:
+                    init_process_group(rank, world, port, device)
+                    from ..parallel.ddp import broadcast_state
+
+                    st = torch.tensor([adapter.step_count, step], dtype=torch.int64,
+                                      device=device if use_cuda else "cpu")
+                    dist.broadcast(st, 0)
+                    broadcast_state(adapter.state_tensors(), 0)
+                    adapter.after_state_load()
+                    adapter.step_count = int(st[0])
+                adapter.bind(None)
+                watcher.adopted(generation)
+                loss = adapter.train_step()   # first step at the new world size completes the rescale
+                step += 1
+                dt = time.time() - t0
+                rescales.append({"generation": generation, "world": world, "seconds": dt,
+                                 "since_change": time.time() - target.get("observed_at", t0)})
+                print(f"[worker {rank}] rescaled to world={world} gen={generation} in {dt:.3f}s", flush=True)
+                watcher.report_rescale(rank, rescales[-1])
+                continue
+        # ---- timed region bookkeeping ----------------------------------------------------------------
+        if step == args.warmup and args.steps > 0:
+            if world > 1:
+                dist.barrier()
+            if use_cuda:
+                torch.cuda.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            t_wall0 = time.perf_counter()
+            launches0 = oplib.LAUNCHES
+        loss = adapter.train_step()
+        losses.append(loss)
+        step += 1
+        if not first_step_done:
+            first_step_done = True
+            trace["first_step_done"] = time.time()
+            if watcher is not None:
+                watcher.report_trace(rank, trace)
+        if args.ckpt_every > 0 and rank == 0 and step % args.ckpt_every == 0:
+            save_checkpoint(args, adapter, adapter.step_count)
+        if args.step_sleep > 0:
+            time.sleep(args.step_sleep)
+
+    result: Dict[str, Any] = {"rank": rank, "world": world, "steps_done": step, "generation": generation,
+                              "final_loss": losses[-1] if losses else None, "rescales": rescales, "trace": trace}
+    if args.steps > 0 and step >= total:
+        if use_cuda:
+            ev1.record()
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t_wall0
+        dev_ms = ev0.elapsed_time(ev1) if use_cuda else wall * 1e3
+        dev_ms = max_over_ranks(dev_ms, device)
+        global_batch = args.batch * world
+        graph_launches = adapter.launches_per_step()
+        eager_launches = (oplib.LAUNCHES - launches0)
+        result.update({
+            "ms_per_step": dev_ms / args.steps,
+            "samples_per_sec": global_batch * args.steps / (dev_ms / 1e3),
+            "wall_ms_per_step": wall * 1e3 / args.steps,
+            "global_batch": global_batch, "batch_per_gpu": args.batch,
+            "h2d_bytes_per_step": adapter.h2d_bytes, "d2h_bytes_per_step": adapter.d2h_bytes,
+            "gpu_launches": graph_launches * args.steps if graph_launches else eager_launches,
+            "launches_per_step": graph_launches or (eager_launches // max(1, args.steps)),
+            "loss_first": losses[0] if losses else None, "loss_last": losses[-1] if losses else None,
+            "flops_per_step": getattr(adapter, "flops_per_step", 0.0),
+            "describe": adapter.describe,
+            "cuda_graph": bool(getattr(getattr(adapter, "trainer", None), "graph", None)),
+            "graph_error": getattr(getattr(adapter, "trainer", None), "graph_error", None),
+        })
+    if rank == 0 and args.result:
+        os.makedirs(os.path.dirname(os.path.abspath(args.result)), exist_ok=True)
+        with open(args.result + ".tmp", "w") as f:
+            json.dump(result, f)
+        os.replace(args.result + ".tmp", args.result)
+    if rank == 0 and watcher is not None:
+        watcher.report_result(result)
+    if dist.is_initialized():
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+    return result
+
+
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser(prog="aitj-worker")
+    ap.add_argument("--model", default="gpt2", choices=["gpt2", "gpt2-tiny", "bert", "resnet50", "mnist", "mlp"])
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch size")
+    ap.add_argument("--seq", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=20, help="timed steps (0 = run until SIGTERM)")
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "cublas"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--elastic", action="store_true")
+    ap.add_argument("--result", default="")
+    ap.add_argument("--ckpt-dir", default="")
+    ap.add_argument("--ckpt-every", type=int, default=0)
+    ap.add_argument("--step-sleep", type=float, default=0.0)
+    return ap.parse_args(argv)
+
+
+def main(argv=None) -> int:
+    args = parse_args(argv)
+    res = run(args)
+    if res.get("samples_per_sec"):
+        print(f"[worker {res['rank']}] {res['samples_per_sec']:.1f} samples/s  {res['ms_per_step']:.3f} ms/step "
+              f"loss {res.get('loss_first')} -> {res.get('loss_last')}", flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
