@@ -1,0 +1,208 @@
+"""API server semantics, in process and over HTTP (SURVEY.md §4 component tier, C8 contract)."""
+import json
+import threading
+import time
+import urllib.request
+
+import pytest
+import yaml
+
+from trainingjob_operator_b200.api import constants as C
+from trainingjob_operator_b200.api import register as R
+from trainingjob_operator_b200.api.types import AITrainingJob
+from trainingjob_operator_b200.client.clientset import new_for_config
+from trainingjob_operator_b200.store.apiserver import APIError, APIServer, json_patch, merge_patch
+from trainingjob_operator_b200.store.http import APIHTTPServer
+
+from test_api import example
+
+
+@pytest.fixture(params=["local", "http"])
+def cs(request):
+    api = APIServer()
+    if request.param == "local":
+        yield new_for_config(server=api)
+        return
+    srv = APIHTTPServer(api).start()
+    try:
+        yield new_for_config(master=srv.url)
+    finally:
+        srv.stop()
+
+
+def pod(name, labels=None, owner=None, node="", phase=None):
+    p = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": name, "labels": labels or {}},
+         "spec": {"containers": [{"name": "aitj-c", "command": ["true"]}]}}
+    if node:
+        p["spec"]["nodeName"] = node
+    if phase:
+        p["status"] = {"phase": phase}
+    if owner:
+        p["metadata"]["ownerReferences"] = [owner]
+    return p
+
+
+def test_crud_resource_version_and_optimistic_concurrency(cs):
+    jobs = cs.elasticdeeplearning_v1().aitrainingjobs("default")
+    created = jobs.create(AITrainingJob.from_dict(example()))
+    assert created.uid and created.resource_version and created.metadata["creationTimestamp"]
+    assert created.namespace == "default" and created.metadata["generation"] == 1
+    got = jobs.get("paddle-mnist")
+    got.status.phase = "Pending"
+    updated = jobs.update(got)
+    assert int(updated.resource_version) > int(created.resource_version)
+    assert updated.metadata["generation"] == 1            # status-only change keeps generation
+    with pytest.raises(APIError) as ei:
+        jobs.update(got)                                   # stale resourceVersion
+    assert ei.value.reason == "Conflict" and ei.value.code == 409
+    updated.spec.replica_specs["trainer"].replicas = 3
+    assert jobs.update(updated).metadata["generation"] == 2
+    with pytest.raises(APIError) as ei:
+        jobs.create(AITrainingJob.from_dict(example()))
+    assert ei.value.reason == "AlreadyExists"
+    lst = jobs.list()
+    assert [j.name for j in lst.items] == ["paddle-mnist"] and lst.metadata["resourceVersion"]
+    jobs.delete("paddle-mnist")
+    with pytest.raises(APIError) as ei:
+        jobs.get("paddle-mnist")
+    assert ei.value.reason == "NotFound" and ei.value.code == 404
+
+
+def test_update_status_only_touches_status(cs):
+    jobs = cs.elasticdeeplearning_v1().aitrainingjobs("default")
+    j = jobs.create(AITrainingJob.from_dict(example()))
+    j.status.phase = "Running"
+    j.spec.replica_specs["trainer"].replicas = 7        # must be ignored by the status subresource
+    out = jobs.update_status(j)
+    assert out.status.phase == "Running" and out.spec.replica_specs["trainer"].replicas == 1
+
+
+def test_admission_rejects_invalid_jobs(cs):
+    bad = example()
+    bad["spec"]["replicaSpecs"]["trainer"]["restartPolicy"] = "Bogus"
+    with pytest.raises(APIError) as ei:
+        cs.elasticdeeplearning_v1().aitrainingjobs("default").create(AITrainingJob.from_dict(bad))
+    assert ei.value.code == 422 and ei.value.reason == "Invalid" and "restartPolicy" in ei.value.message
+
+
+def test_patch_merge_and_json(cs):
+    jobs = cs.elasticdeeplearning_v1().aitrainingjobs("default")
+    jobs.create(AITrainingJob.from_dict(example()))
+    p = jobs.patch("paddle-mnist", {"metadata": {"annotations": {"Preempted": "by test"}},
+                                    "spec": {"replicaSpecs": {"trainer": {"replicas": 4}}}})
+    assert p.annotations["Preempted"] == "by test" and p.spec.replica_specs["trainer"].replicas == 4
+    assert p.spec.replica_specs["trainer"].restart_policy == "OnNodeFailWithExitCode"   # untouched siblings survive
+    p = jobs.patch("paddle-mnist", {"metadata": {"annotations": {"Preempted": None}}})
+    assert "Preempted" not in p.annotations
+    p = jobs.patch("paddle-mnist", [{"op": "replace", "path": "/spec/replicaSpecs/trainer/replicas", "value": 2}],
+                   "application/json-patch+json")
+    assert p.spec.replica_specs["trainer"].replicas == 2
+    assert merge_patch({"a": {"b": 1, "c": 2}}, {"a": {"b": None, "d": 3}}) == {"a": {"c": 2, "d": 3}}
+    assert json_patch({"l": [1, 2]}, [{"op": "add", "path": "/l/-", "value": 3}, {"op": "remove", "path": "/l/0"}]) \
+        == {"l": [2, 3]}
+
+
+def test_label_and_field_selectors(cs):
+    pods = cs.core_v1().pods("default")
+    pods.create(pod("a", {"TrainingJobName": "j1", "role": "x"}, node="gpu-0"))
+    pods.create(pod("b", {"TrainingJobName": "j1"}))
+    pods.create(pod("c", {"TrainingJobName": "j2"}))
+    assert [p["metadata"]["name"] for p in pods.list("TrainingJobName=j1")["items"]] == ["a", "b"]
+    assert [p["metadata"]["name"] for p in pods.list("TrainingJobName=j1,role=x")["items"]] == ["a"]
+    assert [p["metadata"]["name"] for p in pods.list(field_selector="spec.nodeName=gpu-0")["items"]] == ["a"]
+    assert len(cs.core_v1().pods("").list()["items"]) == 3
+    pods.delete_collection("TrainingJobName=j1")
+    left = {p["metadata"]["name"]: p for p in pods.list()["items"]}
+    assert sorted(left) == ["a", "c"]                     # "a" is bound + live: graceful, waits for the agent
+    assert left["a"]["metadata"]["deletionTimestamp"] and "deletionTimestamp" not in left["c"]["metadata"]
+
+
+def test_owner_reference_cascade(cs):
+    jobs = cs.elasticdeeplearning_v1().aitrainingjobs("default")
+    j = jobs.create(AITrainingJob.from_dict(example()))
+    ref = {"apiVersion": C.API_VERSION, "kind": C.KIND, "name": j.name, "uid": j.uid, "controller": True}
+    cs.core_v1().pods("default").create(pod("p0", owner=ref))
+    cs.core_v1().services("default").create({"kind": "Service", "metadata": {"name": "s0", "ownerReferences": [ref]},
+                                             "spec": {"clusterIP": "None"}})
+    cs.core_v1().pods("default").create(pod("stranger"))
+    jobs.delete(j.name)
+    assert [p["metadata"]["name"] for p in cs.core_v1().pods("default").list()["items"]] == ["stranger"]
+    assert cs.core_v1().services("default").list()["items"] == []
+
+
+def test_graceful_pod_delete_needs_agent_confirmation(cs):
+    pods = cs.core_v1().pods("default")
+    pods.create(pod("run", node="gpu-1", phase="Running"))
+    d = pods.delete("run")
+    assert d["metadata"]["deletionTimestamp"] and d["metadata"]["deletionGracePeriodSeconds"] == 30
+    assert pods.get("run")["metadata"]["deletionTimestamp"]      # still there until the agent confirms
+    pods.delete("run", grace_period_seconds=0)
+    with pytest.raises(APIError):
+        pods.get("run")
+    pods.create(pod("done", node="gpu-1", phase="Succeeded"))
+    pods.delete("done")                                         # finished pods go at once
+    with pytest.raises(APIError):
+        pods.get("done")
+    pods.create(pod("unbound"))
+    pods.delete("unbound")
+    with pytest.raises(APIError):
+        pods.get("unbound")
+
+
+def test_watch_stream_from_resource_version(cs):
+    pods = cs.core_v1().pods("default")
+    pods.create(pod("a"))
+    rv = pods.list()["metadata"]["resourceVersion"]
+    events = []
+    w = pods.watch(resource_version=rv, timeout=5)
+
+    def consume():
+        for ev in w:
+            events.append((ev["type"], ev["object"]["metadata"]["name"]))
+            if len(events) == 3:
+                break
+        w.close()
+
+    t = threading.Thread(target=consume)
+    t.start()
+    time.sleep(0.1)
+    b = pods.create(pod("b"))
+    b["metadata"]["labels"] = {"x": "y"}
+    pods.update(b)
+    pods.delete("b")
+    t.join(5)
+    assert events == [("ADDED", "b"), ("MODIFIED", "b"), ("DELETED", "b")]
+
+
+def test_http_discovery_health_metrics_and_yaml_body():
+    api = APIServer()
+    srv = APIHTTPServer(api).start()
+    try:
+        get = lambda p: urllib.request.urlopen(srv.url + p, timeout=5).read().decode()  # noqa: E731
+        assert get("/healthz") == "ok"
+        assert "v1.13.5" in get("/version")
+        groups = json.loads(get("/apis"))
+        assert any(g["name"] == C.GROUP_NAME for g in groups["groups"])
+        res = json.loads(get(f"/apis/{C.GROUP_NAME}/v1"))
+        assert res["resources"][0]["name"] == "aitrainingjobs" and res["resources"][0]["shortNames"] == ["aitj"]
+        req = urllib.request.Request(srv.url + R.AITRAININGJOB.path("default"), data=yaml.safe_dump(example()).encode(),
+                                     headers={"Content-Type": "application/yaml"}, method="POST")
+        created = json.loads(urllib.request.urlopen(req, timeout=5).read())
+        assert created["metadata"]["name"] == "paddle-mnist"
+        assert "aitj_apiserver_objects{kind=\"AITrainingJob\"} 1" in get("/metrics")
+        with pytest.raises(urllib.error.HTTPError) as ei:
+            urllib.request.urlopen(srv.url + "/apis/nope/v1/things", timeout=5)
+        assert ei.value.code == 404
+    finally:
+        srv.stop()
+
+
+def test_wal_survives_restart(tmp_path):
+    wal = str(tmp_path / "s.wal")
+    api = APIServer(wal)
+    cs1 = new_for_config(server=api)
+    j = cs1.elasticdeeplearning_v1().aitrainingjobs("default").create(AITrainingJob.from_dict(example()))
+    del api, cs1
+    cs2 = new_for_config(server=APIServer(wal))
+    again = cs2.elasticdeeplearning_v1().aitrainingjobs("default").get("paddle-mnist")
+    assert again.uid == j.uid and again.resource_version == j.resource_version

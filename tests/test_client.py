@@ -1,0 +1,169 @@
+"""Client machinery: fake clientset, informers/listers, event recorder, leader election (C8f, C9, C10, upstream)."""
+import threading
+import time
+
+import pytest
+
+from trainingjob_operator_b200.api import constants as C
+from trainingjob_operator_b200.api.types import AITrainingJob
+from trainingjob_operator_b200.client.clientset import new_for_config
+from trainingjob_operator_b200.client.fake import new_simple_clientset
+from trainingjob_operator_b200.client.informers import DeletedFinalStateUnknown, SharedInformerFactory
+from trainingjob_operator_b200.client.leaderelection import LEADER_ANNOTATION, LeaderElectionConfig, LeaderElector
+from trainingjob_operator_b200.client.record import EventRecorder, FakeRecorder, events_for
+from trainingjob_operator_b200.store.apiserver import APIError, APIServer
+
+from test_api import example
+
+
+def wait_until(fn, timeout=5.0):
+    deadline = time.time() + timeout
+    while time.time() < deadline:
+        if fn():
+            return True
+        time.sleep(0.01)
+    return False
+
+
+def test_fake_clientset_tracks_actions_and_reactors():
+    seed = example()
+    seed["metadata"]["namespace"] = "default"
+    cs = new_simple_clientset(seed)
+    jobs = cs.elasticdeeplearning_v1().aitrainingjobs("default")
+    assert jobs.get("paddle-mnist").name == "paddle-mnist"
+    j = jobs.get("paddle-mnist")
+    j.status.phase = "Running"
+    jobs.update(j)
+    verbs = [(a.verb, a.resource) for a in cs.actions()]
+    assert verbs == [("get", "aitrainingjobs"), ("get", "aitrainingjobs"), ("update", "aitrainingjobs")]
+    cs.prepend_reactor("update", "aitrainingjobs", lambda a: (True, APIError(500, "InternalError", "boom")))
+    with pytest.raises(APIError):
+        jobs.update(jobs.get("paddle-mnist"))
+    cs.prepend_reactor("create", "pods", lambda a: (True, {"metadata": {"name": "intercepted"}}))
+    assert cs.core_v1().pods("default").create({"metadata": {"name": "p"}})["metadata"]["name"] == "intercepted"
+    assert cs.core_v1().pods("default").list()["items"] == []     # the reactor swallowed the create
+
+
+def test_informer_cache_handlers_lister_and_resync():
+    api = APIServer()
+    cs = new_for_config(server=api)
+    jobs = cs.elasticdeeplearning_v1().aitrainingjobs("default")
+    jobs.create(AITrainingJob.from_dict(example()))           # exists before the informer starts
+    stop = threading.Event()
+    factory = SharedInformerFactory(cs, default_resync=0.2)
+    typed = factory.elasticdeeplearning().v1().aitrainingjobs()
+    events = []
+    typed.informer().add_event_handler(add=lambda o: events.append(("add", o["metadata"]["name"])),
+                                       update=lambda a, b: events.append(("update", a["metadata"]["resourceVersion"],
+                                                                          b["metadata"]["resourceVersion"])),
+                                       delete=lambda o: events.append(("delete",)))
+    assert factory.elasticdeeplearning().v1().aitrainingjobs().informer() is typed.informer()   # shared
+    factory.start(stop)
+    assert factory.wait_for_cache_sync(stop) == {"AITrainingJob": True}
+    lister = typed.lister()
+    assert lister.aitrainingjobs("default").get("paddle-mnist").name == "paddle-mnist"
+    with pytest.raises(APIError):
+        lister.aitrainingjobs("default").get("nope")
+    # listers hand out copies: mutating one must not touch the cache (fixes reference quirk Q6)
+    a = lister.aitrainingjobs("default").get("paddle-mnist")
+    a.status.phase = "Hacked"
+    assert lister.aitrainingjobs("default").get("paddle-mnist").status.phase == ""
+    j = jobs.get("paddle-mnist")
+    j.status.phase = "Pending"
+    jobs.update(j)
+    assert wait_until(lambda: lister.aitrainingjobs("default").get("paddle-mnist").status.phase == "Pending")
+    assert wait_until(lambda: any(e[0] == "update" and e[1] == e[2] for e in events))   # resync: same rv twice
+    jobs.delete("paddle-mnist")
+    assert wait_until(lambda: ("delete",) in events)
+    assert events[0] == ("add", "paddle-mnist")
+    assert lister.list() == []
+    stop.set()
+
+
+def test_informer_namespace_scope_and_selector():
+    api = APIServer()
+    cs = new_for_config(server=api)
+    for ns, name, lbl in (("a", "p1", {"k": "1"}), ("a", "p2", {"k": "2"}), ("b", "p3", {"k": "1"})):
+        cs.core_v1().pods(ns).create({"metadata": {"name": name, "labels": lbl}, "spec": {}})
+    stop = threading.Event()
+    f = SharedInformerFactory(cs, 0, namespace="a")
+    pods = f.core().v1().pods()
+    pods.informer()
+    f.start(stop)
+    f.wait_for_cache_sync(stop)
+    assert sorted(p["metadata"]["name"] for p in pods.lister().list()) == ["p1", "p2"]
+    assert [p["metadata"]["name"] for p in pods.lister().namespaced("a").list({"k": "2"})] == ["p2"]
+    stop.set()
+
+
+def test_event_recorder_writes_and_aggregates_events():
+    api = APIServer()
+    cs = new_for_config(server=api)
+    job = cs.elasticdeeplearning_v1().aitrainingjobs("default").create(AITrainingJob.from_dict(example()))
+    rec = EventRecorder(cs, C.CONTROLLER_NAME, log=False)
+    rec.eventf(job, "Normal", "SuccessfulCreatePod", "Created pod: %s", "paddle-mnist-trainer-0")
+    rec.eventf(job, "Warning", "FailedCreatePod", "Error creating: %s", "x")
+    rec.eventf(job, "Warning", "FailedCreatePod", "Error creating: %s", "x")
+    evs = events_for(cs, job)
+    assert [(e["reason"], e["count"]) for e in evs] == [("SuccessfulCreatePod", 1), ("FailedCreatePod", 2)]
+    assert evs[0]["source"]["component"] == "TrainingJobOperator" and evs[0]["involvedObject"]["uid"] == job.uid
+    fr = FakeRecorder()
+    fr.eventf(job, "Normal", "R", "m %d", 1)
+    assert fr.events == ["Normal R m 1"]
+
+
+def _elector(cs, ident, started, stopped, lease=0.6, renew=0.4, retry=0.1):
+    cfg = LeaderElectionConfig(identity=ident, lease_duration=lease, renew_deadline=renew, retry_period=retry)
+    return LeaderElector(cs, cfg, lambda stop: (started.append(ident), stop.wait()), lambda: stopped.append(ident))
+
+
+def test_leader_election_single_leader_then_failover():
+    api = APIServer()
+    cs = new_for_config(server=api)
+    started, stopped = [], []
+    stop_a, stop_b = threading.Event(), threading.Event()
+    a = _elector(cs, "a", started, stopped)
+    b = _elector(cs, "b", started, stopped)
+    ta = threading.Thread(target=a.run, args=(stop_a,), daemon=True)
+    ta.start()
+    assert wait_until(lambda: started == ["a"])
+    tb = threading.Thread(target=b.run, args=(stop_b,), daemon=True)
+    tb.start()
+    time.sleep(0.5)
+    assert started == ["a"] and b.get_leader() == "a"           # standby observes the holder, does not lead
+    lock = cs.core_v1().endpoints("kube-system").get("trainingjob-operator")
+    assert '"holderIdentity": "a"' in lock["metadata"]["annotations"][LEADER_ANNOTATION]
+    # kill the leader without releasing (crash): b must take over after the lease expires
+    a._client = lambda: (_ for _ in ()).throw(APIError(503, "ServiceUnavailable", "partitioned"))
+    assert wait_until(lambda: "a" in stopped, 5)
+    assert wait_until(lambda: started == ["a", "b"], 5)
+    rec = cs.core_v1().endpoints("kube-system").get("trainingjob-operator")["metadata"]["annotations"][LEADER_ANNOTATION]
+    assert '"holderIdentity": "b"' in rec and '"leaderTransitions": 1' in rec
+    stop_a.set(); stop_b.set()
+    tb.join(3)
+    assert "b" in stopped
+
+
+def test_leader_election_release_on_clean_stop_and_config_validation():
+    api = APIServer()
+    cs = new_for_config(server=api)
+    started, stopped = [], []
+    stop = threading.Event()
+    a = _elector(cs, "a", started, stopped)
+    t = threading.Thread(target=a.run, args=(stop,), daemon=True)
+    t.start()
+    assert wait_until(lambda: started == ["a"])
+    stop.set()
+    t.join(3)
+    b = _elector(cs, "b", started, stopped, lease=30, renew=20, retry=0.05)
+    assert b.try_acquire_or_renew()                              # released lock is taken at once
+    with pytest.raises(ValueError):
+        LeaderElector(cs, LeaderElectionConfig(lease_duration=1, renew_deadline=2, retry_period=0.1), None, None)
+
+
+def test_leases_lock_type_also_works():
+    cs = new_for_config(server=APIServer())
+    cfg = LeaderElectionConfig(lock_type="leases", identity="x", lease_duration=1, renew_deadline=0.5, retry_period=0.1)
+    e = LeaderElector(cs, cfg, lambda s: None, lambda: None)
+    assert e.try_acquire_or_renew() and e.try_acquire_or_renew()
+    assert cs.coordination_v1().leases("kube-system").get("trainingjob-operator")

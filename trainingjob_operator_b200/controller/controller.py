@@ -99,6 +99,9 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
         self._workers: List[threading.Thread] = []
         self.gc: Optional[GarbageCollector] = None
         self.sync_count = 0
+        # resourceVersion of our own last write per job: a cached copy older than that must not be acted on
+        self._written_rv: Dict[str, int] = {}
+        self._written_lock = threading.Lock()
 
     # ------------------------------------------------------------------ identity helpers
     def gen_owner_reference(self, job: AITrainingJob) -> dict:
@@ -187,6 +190,11 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
                 self._forget_job(key)
                 return True
             raise
+        if self._cache_is_stale(key, job):
+            # our own status write has not reached the informer cache yet: acting on the old phase could e.g.
+            # re-create pods of a job we just terminated (pods vanish faster here than under a kubelet)
+            self.work_queue.add_after(key, 0.005)
+            return True
         need_sync = self.satisfied_expectations(job)
         set_defaults_aitrainingjob(job)  # on our private copy (lister returns copies)
         self.sync_count += 1
@@ -197,6 +205,29 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
 
     def _forget_job(self, key: str) -> None:
         self.forget_rendezvous(key)
+        with self._written_lock:
+            self._written_rv.pop(key, None)
+
+    def _cache_is_stale(self, key: str, job: AITrainingJob) -> bool:
+        with self._written_lock:
+            rec = self._written_rv.get(key)
+        if rec is None:
+            return False
+        uid, rv = rec
+        if uid != job.uid:
+            return False
+        try:
+            return int(job.resource_version or 0) < rv
+        except ValueError:
+            return False
+
+    def _remember_write(self, key: str, updated: AITrainingJob) -> None:
+        try:
+            rv = int(updated.resource_version or 0)
+        except ValueError:
+            return
+        with self._written_lock:
+            self._written_rv[key] = (updated.uid, rv)
 
     def reconcile_training_jobs(self, job: AITrainingJob) -> None:
         klog.V(4).info("Reconcile training job: %s/%s", job.namespace, job.name)
@@ -241,7 +272,9 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
             or job.spec.to_dict() != old_spec
         if changed:
             job.status.last_reconcile_time = M.format_time()
-            self.update_training_job_phase(job)
+            updated = self.update_training_job_phase(job)
+            if updated is not None:
+                self._remember_write(job.key(), updated)
 
     def satisfied_expectations(self, job: AITrainingJob) -> bool:
         """Expectations gate (controller.go:390-404).  The reference ORs over every role's pod and service

@@ -68,70 +68,137 @@ __device__ __forceinline__ WorkItem decode_work(const GemmArgs& a, int w) {
   return wi;
 }
 
-template <int kBlockN>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& a, const uint32_t (&r)[32], int row, int col0) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+// ---- epilogue helpers -----------------------------------------------------------------------
+// Apply the fused epilogue to 8 consecutive columns of one row (x[] are the fp32 accumulators).
+__device__ __forceinline__ void epilogue_math8(const GemmArgs& a, float* x, size_t off, int col, bool row_ok,
+                                               uint4& pre_out) {
   const int flags = a.flags;
-  const size_t off = static_cast<size_t>(row) * a.ldc + col0;
+  if (flags & EPI_BIAS) {
+    uint4 b = *reinterpret_cast<const uint4*>(a.bias + col);
+    float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+    x[0] += b0.x; x[1] += b0.y; x[2] += b1.x; x[3] += b1.y;
+    x[4] += b2.x; x[5] += b2.y; x[6] += b3.x; x[7] += b3.y;
+  }
+  if (flags & EPI_SAVE_PRE) {
+    pre_out.x = pack_bf16x2(x[0], x[1]); pre_out.y = pack_bf16x2(x[2], x[3]);
+    pre_out.z = pack_bf16x2(x[4], x[5]); pre_out.w = pack_bf16x2(x[6], x[7]);
+  }
+  if (flags & EPI_GELU) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (col0 + q * 8 >= a.N) break;
-    float* x = v + q * 8;
-    if (flags & EPI_BIAS) {
-      uint4 b = *reinterpret_cast<const uint4*>(a.bias + col0 + q * 8);
-      float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
-      x[0] += b0.x; x[1] += b0.y; x[2] += b1.x; x[3] += b1.y;
-      x[4] += b2.x; x[5] += b2.y; x[6] += b3.x; x[7] += b3.y;
-    }
-    if (flags & EPI_SAVE_PRE) {
-      uint4 o;
-      o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-      o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-      *reinterpret_cast<uint4*>(a.aux + off + q * 8) = o;
-    }
-    if (flags & EPI_GELU) {
+    for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
+  }
+  if ((flags & EPI_DGELU) && row_ok) {
+    uint4 h = *reinterpret_cast<const uint4*>(a.aux + off);
+    float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y), h2 = unpack_bf16x2(h.z), h3 = unpack_bf16x2(h.w);
+    x[0] *= gelu_tanh_grad(h0.x); x[1] *= gelu_tanh_grad(h0.y);
+    x[2] *= gelu_tanh_grad(h1.x); x[3] *= gelu_tanh_grad(h1.y);
+    x[4] *= gelu_tanh_grad(h2.x); x[5] *= gelu_tanh_grad(h2.y);
+    x[6] *= gelu_tanh_grad(h3.x); x[7] *= gelu_tanh_grad(h3.y);
+  }
+  if ((flags & EPI_RESIDUAL) && row_ok) {
+    uint4 h = *reinterpret_cast<const uint4*>(a.residual + off);
+    float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y), h2 = unpack_bf16x2(h.z), h3 = unpack_bf16x2(h.w);
+    x[0] += h0.x; x[1] += h0.y; x[2] += h1.x; x[3] += h1.y;
+    x[4] += h2.x; x[5] += h2.y; x[6] += h3.x; x[7] += h3.y;
+  }
+}
+
+// One warp's staging buffers: 2 x (32 rows x 128 B), written in the TMA 128B-swizzle pattern
+// (16-byte chunk c of row r lives at chunk c ^ (r & 7)), so the st.shared.v4 of a quarter warp hit
+// 32 distinct banks and the tile leaves through one coalesced TMA store (or reduce-add) per chunk.
+struct StageCtx {
+  uint8_t* buf;   // this warp's 8 KB
+  int sel;        // next buffer
+};
+template <int kMaxPending = 1>
+__device__ __forceinline__ uint8_t* stage_acquire(StageCtx& sc, int lane) {
+  if (lane == 0) tma_store_wait_read<kMaxPending>();
+  __syncwarp();
+  uint8_t* b = sc.buf + sc.sel * 4096;
+  sc.sel ^= 1;
+  return b;
+}
+__device__ __forceinline__ void stage_write16(uint8_t* b, int lane, int chunk, const uint4& v) {
+  *reinterpret_cast<uint4*>(b + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
+}
+__device__ __forceinline__ void stage_commit(const CUtensorMap* tm, uint8_t* b, int col0, int row0, int lane,
+                                             bool reduce_add) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (reduce_add) tma_reduce_add_2d(tm, b, col0, row0);
+    else tma_store_2d(tm, b, col0, row0);
+    tma_store_commit();
+  }
+}
+
+// Drain one accumulator tile slice (32 rows x kBlockN columns) owned by this warp.
+template <int kBlockN>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
+                                              uint32_t tmem_acc, int row0, int n0, StageCtx& sc, int lane) {
+  const int flags = a.flags;
+  const int row = row0 + lane;
+  const bool row_ok = row < a.M;
+  if (flags & (EPI_OUT_F32 | EPI_ACCUM)) {
+    // fp32 output: 32 columns (128 B) per staged chunk; raw accumulators (+bias)
+#pragma unroll 1
+    for (int c = 0; c < kBlockN / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= a.N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + c * 32, r);
+      tmem_ld_wait();
+      uint8_t* b = stage_acquire(sc, lane);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
+      for (int q = 0; q < 8; ++q) {
+        uint4 v = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        stage_write16(b, lane, q, v);
+      }
+      stage_commit(tm_out, b, col0, row0, lane, (flags & EPI_ACCUM) != 0);
     }
-    if (flags & EPI_DGELU) {
-      uint4 h = *reinterpret_cast<const uint4*>(a.aux + off + q * 8);
-      float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y), h2 = unpack_bf16x2(h.z), h3 = unpack_bf16x2(h.w);
-      x[0] *= gelu_tanh_grad(h0.x); x[1] *= gelu_tanh_grad(h0.y);
-      x[2] *= gelu_tanh_grad(h1.x); x[3] *= gelu_tanh_grad(h1.y);
-      x[4] *= gelu_tanh_grad(h2.x); x[5] *= gelu_tanh_grad(h2.y);
-      x[6] *= gelu_tanh_grad(h3.x); x[7] *= gelu_tanh_grad(h3.y);
+    return;
+  }
+  // bf16 output: 64 columns (128 B) per staged chunk
+#pragma unroll 1
+  for (int c = 0; c < kBlockN / 64; ++c) {
+    const int col0 = n0 + c * 64;
+    if (col0 >= a.N) break;
+    // with SAVE_PRE two stores leave per chunk, so both buffers must be drained before reuse
+    uint8_t* b = (flags & EPI_SAVE_PRE) ? stage_acquire<0>(sc, lane) : stage_acquire<1>(sc, lane);
+    uint8_t* bpre = nullptr;
+    if (flags & EPI_SAVE_PRE) bpre = stage_acquire<0>(sc, lane);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int colh = col0 + h * 32;
+      if (colh >= a.N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + c * 64 + h * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int col = colh + q * 8;
+        if (col >= a.N) break;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(r[q * 8 + j]);
+        uint4 pre;
+        epilogue_math8(a, x, static_cast<size_t>(row) * a.ldc + col, col, row_ok, pre);
+        uint4 o;
+        o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+        o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+        stage_write16(b, lane, h * 4 + q, o);
+        if (flags & EPI_SAVE_PRE) stage_write16(bpre, lane, h * 4 + q, pre);
+      }
     }
-    if (flags & EPI_RESIDUAL) {
-      uint4 h = *reinterpret_cast<const uint4*>(a.residual + off + q * 8);
-      float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y), h2 = unpack_bf16x2(h.z), h3 = unpack_bf16x2(h.w);
-      x[0] += h0.x; x[1] += h0.y; x[2] += h1.x; x[3] += h1.y;
-      x[4] += h2.x; x[5] += h2.y; x[6] += h3.x; x[7] += h3.y;
-    }
-    if (flags & EPI_ACCUM) {
-      float* o = reinterpret_cast<float*>(a.out) + off + q * 8;
-      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3])
-                   : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + 4), "f"(x[4]), "f"(x[5]), "f"(x[6]),
-                   "f"(x[7])
-                   : "memory");
-    } else if (flags & EPI_OUT_F32) {
-      float* o = reinterpret_cast<float*>(a.out) + off + q * 8;
-      *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
-    } else {
-      uint4 o;
-      o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-      o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + off + q * 8) = o;
-    }
+    if (flags & EPI_SAVE_PRE) stage_commit(tm_aux, bpre, col0, row0, lane, false);
+    stage_commit(tm_out, b, col0, row0, lane, false);
   }
 }
 
 template <int kBlockN, bool kAMN, bool kBMN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                          const GemmArgs args) {
   constexpr int kStageA = BLOCK_M * BLOCK_K * 2;
   constexpr int kStageB = kBlockN * BLOCK_K * 2;
@@ -144,7 +211,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  constexpr int kStagingBytes = 4 * 2 * 4096;  // 4 epilogue warps x double-buffered 32x128B chunk
+  uint8_t* staging = smem + kStages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -156,6 +225,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (args.flags & EPI_SAVE_PRE) tma_prefetch_desc(&tmap_aux);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -241,26 +312,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int lg = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    StageCtx sc;
+    sc.buf = staging + (warp - 2) * 8192;
+    sc.sel = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const WorkItem wi = decode_work(args, w);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = wi.m_blk * BLOCK_M + lg * 32 + lane;
-      const bool has_k = wi.kb1 > wi.kb0;
-#pragma unroll 1
-      for (int c = 0; c < kBlockN / 32; ++c) {
-        const int col0 = wi.n_blk * kBlockN + c * 32;
-        if (col0 >= args.N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + acc * kBlockN + c * 32 + (static_cast<uint32_t>(lg * 32) << 16), r);
-        tmem_ld_wait();
-        if (row < args.M && has_k) epilogue_chunk<kBlockN>(args, r, row, col0);
+      if (wi.kb1 > wi.kb0) {
+        epilogue_tile<kBlockN>(args, &tmap_out, &tmap_aux,
+                               tmem_base + acc * kBlockN + (static_cast<uint32_t>(lg * 32) << 16),
+                               wi.m_blk * BLOCK_M + lg * 32, wi.n_blk * kBlockN, sc, lane);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -285,16 +354,17 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row stride `ld` elements.
-static int encode_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                          uint32_t box_inner, uint32_t box_outer) {
+// 2-D tensor map (128B swizzle): `inner` contiguous elements per row, `outer` rows, row stride `ld` elements.
+static int encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -10;
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (f32 ? 4u : 2u)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
@@ -311,11 +381,11 @@ static int num_sms() {
 }
 
 template <int kBlockN, bool kAMN, bool kBMN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int max_ctas,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                       const GemmArgs& args, int max_ctas, cudaStream_t stream) {
   constexpr int kStages = (kBlockN == 256) ? 4 : 6;
   constexpr int kStageBytes = BLOCK_M * BLOCK_K * 2 + kBlockN * BLOCK_K * 2;
-  constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  constexpr int kSmem = kStages * kStageBytes + 4 * 2 * 4096 + 1024 + 256;
   static bool configured = false;
   auto kern = gemm_bf16_tcgen05_kernel<kBlockN, kAMN, kBMN>;
   if (!configured) {
@@ -326,7 +396,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   const int num_work = args.tiles_m * args.tiles_n * args.split_k;
   int grid = num_work < num_sms() ? num_work : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, kGemmThreads, kSmem, stream>>>(ta, tb, args);
+  kern<<<grid, kGemmThreads, kSmem, stream>>>(ta, tb, to, tx, args);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
 }
 
@@ -342,6 +412,7 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   using namespace aitj;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((N & 7) || (ldc & 7) || (lda & 7) || (ldb & 7)) return -1;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || ((flags & EPI_SAVE_PRE) && (reinterpret_cast<uintptr_t>(aux) & 15))) return -4;
   if (split_k > 1 && !(flags & EPI_ACCUM)) return -2;
   if (block_n == 0) block_n = (N > 128) ? 256 : 128;
   if (block_n != 128 && block_n != 256) return -3;
@@ -363,18 +434,27 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
 
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn) rc = encode_bf16_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
-  else       rc = encode_bf16_2d(&ta, A, M, K, lda, 64, BLOCK_K);
+  if (!a_mn) rc = encode_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
+  else       rc = encode_2d(&ta, A, M, K, lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b_mn) rc = encode_bf16_2d(&tb, B, K, N, ldb, BLOCK_K, block_n);
-  else       rc = encode_bf16_2d(&tb, B, N, K, ldb, 64, BLOCK_K);
+  if (!b_mn) rc = encode_2d(&tb, B, K, N, ldb, BLOCK_K, block_n);
+  else       rc = encode_2d(&tb, B, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc - 1000;
+  CUtensorMap to, tx;
+  const bool out_f32 = (flags & (EPI_OUT_F32 | EPI_ACCUM)) != 0;
+  rc = encode_2d(&to, out, N, M, ldc, out_f32 ? 32 : 64, 32, out_f32);
+  if (rc) return rc - 2000;
+  tx = to;
+  if (flags & EPI_SAVE_PRE) {
+    rc = encode_2d(&tx, aux, N, M, ldc, 64, 32, false);
+    if (rc) return rc - 3000;
+  }
 
 #define AITJ_DISPATCH(BN)                                                                     \
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, args, max_ctas, stream);   \
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ta, tb, args, max_ctas, stream);     \
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ta, tb, args, max_ctas, stream);     \
-  return launch_gemm<BN, true, true>(ta, tb, args, max_ctas, stream);
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, to, tx, args, max_ctas, stream);   \
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ta, tb, to, tx, args, max_ctas, stream);     \
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ta, tb, to, tx, args, max_ctas, stream);     \
+  return launch_gemm<BN, true, true>(ta, tb, to, tx, args, max_ctas, stream);
   if (block_n == 256) { AITJ_DISPATCH(256) }
   AITJ_DISPATCH(128)
 #undef AITJ_DISPATCH
