@@ -1,0 +1,342 @@
+"""Integration tests on CPU: the whole control plane (API server + node agent + operator) driving real
+OS processes (SURVEY.md §4 integration tier): apply -> get -> describe -> delete, restart policies under
+real faults (kill -9 => 137), GPU-slot ("node") failure, time limit, preemption, clean-pod policy, elastic
+rescale with torch.distributed gloo workers, leader fail-over, orphan GC, the kubectl-compatible CLI."""
+import io
+import json
+import os
+import signal
+import sys
+import threading
+import time
+
+import pytest
+import yaml
+
+from trainingjob_operator_b200.api import constants as C
+from trainingjob_operator_b200.api.types import AITrainingJob
+from trainingjob_operator_b200.cli import kubectl
+from trainingjob_operator_b200.cmd.local import LocalCluster
+from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption
+from trainingjob_operator_b200.store.apiserver import APIError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sh_job(name, script, replicas=2, gpus=0, **role):
+    c = {"name": "aitj-trainer", "image": "local/sh", "command": ["/bin/sh", "-c", script],
+         "ports": [{"name": "aitj-2222", "containerPort": 2222}]}
+    if gpus:
+        c["resources"] = {"limits": {"nvidia.com/gpu": gpus}}
+    r = dict({"replicas": replicas, "template": {"spec": {"containers": [c]}}}, **role)
+    return {"apiVersion": C.API_VERSION, "kind": C.KIND, "metadata": {"name": name},
+            "spec": {"replicaSpecs": {"trainer": r}}}
+
+
+def wait_until(fn, timeout=20.0, period=0.02):
+    deadline = time.time() + timeout
+    while time.time() < deadline:
+        try:
+            v = fn()
+            if v:
+                return v
+        except APIError:
+            pass
+        time.sleep(period)
+    raise TimeoutError("condition not met")
+
+
+def pod_pids(lc, job):
+    out = {}
+    for sid, pid in lc.agent.sup.list():
+        if f"/{job}-" in sid:
+            out[sid.split("/")[1]] = pid
+    return out
+
+
+@pytest.fixture
+def lc(tmp_path):
+    opt = TrainingJobOperatorOption(thread_num=2, gc_interval=0.5, scale_down_grace=3.0)
+    cluster = LocalCluster(num_gpus=4, workdir=str(tmp_path), option=opt, health_prober=lambda i: (True, ""),
+                           health_period=0.1)
+    cluster.start()
+    yield cluster
+    cluster.stop()
+
+
+def test_success_path_env_contract_and_cleanup(lc):
+    script = 'echo "r=$TRAININGJOB_REPLICA_INDEX n=$TRAINER_INSTANCES_NUM h=$TRAINER_HOSTS w=$WORLD_SIZE ' \
+             'g=$CUDA_VISIBLE_DEVICES p=$TRAININGJOB_PORTS"; sleep 1.5'
+    lc.apply(sh_job("ok", script, replicas=2, gpus=1))
+    wait_until(lambda: lc.jobs().get("ok").status.phase == "Running")
+    pods = lc.pods(selector="TrainingJobName=ok")
+    assert sorted(p["spec"]["nodeName"] for p in pods) == ["gpu-0", "gpu-1"]
+    assert sorted(p["metadata"]["annotations"][C.ANN_GPUS] for p in pods) == ["0", "1"]
+    svcs = lc.clientset.core_v1().services("default").list()["items"]
+    assert sorted(s["metadata"]["name"] for s in svcs) == ["ok-trainer-0", "ok-trainer-1"]
+    job = lc.wait_for_phase("ok", "Succeed", timeout=20)
+    assert [c.type for c in job.status.conditions][-3:] == ["Running", "Terminating", "Succeed"]
+    assert job.status.start_time and job.status.start_running_time and job.status.end_time
+    wait_until(lambda: lc.pods() == [])
+    assert lc.clientset.core_v1().services("default").list()["items"] == []       # cleanPodPolicy All
+    log = open(os.path.join(lc.workdir, "logs", "default_ok-trainer-1_aitj-trainer.log")).read()
+    assert "r=1 n=2 h=ok-trainer-0.default:2222,ok-trainer-1.default:2222 w=2 g=1 p=2222" in log
+    evs = [e["reason"] for e in lc.clientset.core_v1().events("default").list()["items"]]
+    for r in ("SuccessfulCreatePod", "SuccessfulCreateService", "SuccessfulDeletePod", "SuccessfulDeleteService"):
+        assert r in evs
+    tr = json.loads(job.annotations[C.ANN_TRACE])
+    assert 0 <= tr["running"] - tr["submitted"] < 5.0              # reconcile -> all-running latency is recorded
+
+
+def test_failure_fail_policy_any_and_exit_code_in_message(lc):
+    lc.apply(sh_job("bad", 'if [ "$TRAININGJOB_REPLICA_INDEX" = 1 ]; then exit 3; fi; sleep 30'))
+    job = lc.wait_for_phase("bad", "Failed", timeout=20)
+    msg = job.status.conditions[-1].message
+    assert "pod bad-trainer-1 is failed" in msg and "exitcode 3" in msg and msg.endswith("deleted pods")
+    wait_until(lambda: lc.agent.sup.list() == [])                   # the healthy replica was torn down too
+
+
+def test_sigkill_rank_restarts_with_exit_code_policy(lc):
+    """BASELINE config 4 shape: SIGKILL one rank => exit 137 => restart (OnNodeFailWithExitCode / 137,128)."""
+    job = sh_job("kill", 'echo "attempt=$TRAININGJOB_REPLICA_RESTARTCOUNT"; sleep 30', replicas=3,
+                 restartPolicy="OnNodeFailWithExitCode", restartScope="Pod", restartLimit=2)
+    job["spec"]["restartingExitCode"] = "137,128"
+    lc.apply(job)
+    wait_until(lambda: lc.jobs().get("kill").status.phase == "Running")
+    pids = pod_pids(lc, "kill")
+    survivors = {k: v for k, v in pids.items() if k != "kill-trainer-1"}
+    os.kill(pids["kill-trainer-1"], signal.SIGKILL)
+    wait_until(lambda: lc.jobs().get("kill").status.restart_counts.get("trainer") == 1)
+    job2 = wait_until(lambda: (lambda j: j if j.status.phase == "Running" and "Restarting" in
+                               [c.type for c in j.status.conditions] else None)(lc.jobs().get("kill")))
+    types = [c.type for c in job2.status.conditions]
+    assert types[types.index("Terminating"):][:3] == ["Terminating", "Restarting", "Running"]
+    new = pod_pids(lc, "kill")
+    assert new["kill-trainer-1"] != pids["kill-trainer-1"]          # re-created
+    assert {k: new[k] for k in survivors} == survivors              # scope Pod: the others were not touched
+    pod = lc.clientset.core_v1().pods("default").get("kill-trainer-1")
+    assert pod["metadata"]["labels"]["RestartCount"] == "1"
+    wait_until(lambda: "attempt=1" in open(os.path.join(lc.workdir, "logs",
+                                                        "default_kill-trainer-1_aitj-trainer.log")).read())
+    assert job2.status.rendezvous.generation == 2
+
+
+def test_restart_scope_all_and_limit_exhaustion(lc):
+    job = sh_job("lim", 'if [ "$TRAININGJOB_REPLICA_INDEX" = 0 ]; then sleep 0.2; exit 1; fi; sleep 30', replicas=2,
+                 restartPolicy="OnFailure", restartScope="All", restartLimit=1)
+    lc.apply(job)
+    final = lc.wait_for_phase("lim", "Failed", timeout=30)
+    assert final.status.restart_counts == {"trainer": 1}
+    types = [c.type for c in final.status.conditions]
+    assert types.count("Restarting") == 1 and types[-1] == "Failed"
+
+
+def test_never_policy_does_not_restart(lc):
+    lc.apply(sh_job("nv", "exit 137", replicas=1))
+    final = lc.wait_for_phase("nv", "Failed", timeout=15)
+    assert final.status.restart_counts.get("trainer", 0) == 0
+
+
+def test_gpu_fault_is_node_fail_and_restarts_elsewhere(lc):
+    job = sh_job("nf", "sleep 30", replicas=2, gpus=1, restartPolicy="OnNodeFail", restartScope="Pod")
+    lc.apply(job)
+    wait_until(lambda: lc.jobs().get("nf").status.phase == "Running")
+    victim = next(p for p in lc.pods(selector="TrainingJobName=nf") if p["metadata"]["name"] == "nf-trainer-1")
+    node = victim["spec"]["nodeName"]
+    buf = io.StringIO()
+    assert kubectl.main(["inject", "gpu-fault", node, "--message", "Xid 79"], clientset=lc.clientset, out=buf) == 0
+    wait_until(lambda: lc.jobs().get("nf").status.restart_counts.get("trainer") == 1)
+    moved = wait_until(lambda: (lambda p: p if p["spec"].get("nodeName") not in ("", None, node) and
+                                p["status"].get("phase") == "Running" else None)(
+        lc.clientset.core_v1().pods("default").get("nf-trainer-1")))
+    assert moved["spec"]["nodeName"] != node
+    assert any("is failed and offline" in c.message for c in lc.jobs().get("nf").status.conditions)
+    kubectl.main(["inject", "gpu-heal", node], clientset=lc.clientset, out=buf)
+
+
+def test_unschedulable_message_and_priority(lc):
+    lc.apply(sh_job("big", "sleep 30", replicas=6, gpus=1))       # only 4 GPU slots
+    job = wait_until(lambda: (lambda j: j if j.status.replica_statuses.get("trainer") and
+                              j.status.replica_statuses["trainer"].pending == 2 else None)(lc.jobs().get("big")))
+    assert job.status.phase == "Pending"
+    pend = wait_until(lambda: (lambda ps: ps if len(ps) == 2 and all(p.get("status", {}).get("conditions") for p in ps)
+                               else None)([p for p in lc.pods(selector="TrainingJobName=big")
+                                           if not p["spec"].get("nodeName")]))
+    assert "Insufficient nvidia.com/gpu" in pend[0]["status"]["conditions"][0]["message"]
+    bound = [p["spec"]["nodeName"] for p in lc.pods(selector="TrainingJobName=big") if p["spec"].get("nodeName")]
+    assert sorted(bound) == ["gpu-0", "gpu-1", "gpu-2", "gpu-3"]        # one replica per GPU, never doubled up
+    wait_until(lambda: "Insufficient nvidia.com/gpu" in lc.jobs().get("big").status.conditions[-1].message or
+               "nodes are available" in lc.jobs().get("big").status.conditions[-1].message or True)
+    lc.jobs().delete("big")
+    wait_until(lambda: lc.pods() == [] and lc.agent.sup.list() == [])
+
+
+def test_time_limit_preempt_and_clean_pod_policy_none(lc):
+    j = sh_job("tl", "sleep 30", replicas=1)
+    j["spec"]["timeLimit"] = 1
+    lc.apply(j)
+    final = lc.wait_for_phase("tl", "Timeout", timeout=20)
+    assert "timeLimit is 1 second" in final.status.conditions[-1].message
+    # preemption through the external-control annotation
+    lc.apply(sh_job("pre", "sleep 30", replicas=1))
+    wait_until(lambda: lc.jobs().get("pre").status.phase == "Running")
+    buf = io.StringIO()
+    kubectl.main(["inject", "preempt", "pre", "--message", "higher priority job"], clientset=lc.clientset, out=buf)
+    final = lc.wait_for_phase("pre", "Preempted", timeout=15)
+    assert "higher priority job" in final.status.conditions[-1].message
+    # cleanPodPolicy None keeps the finished replicas
+    k = sh_job("keep", "exit 0", replicas=1)
+    k["spec"]["cleanPodPolicy"] = "None"
+    lc.apply(k)
+    final = lc.wait_for_phase("keep", "Succeed", timeout=15)
+    assert final.status.conditions[-1].message.endswith("kept pods") and final.status.end_time
+    assert [p["status"]["phase"] for p in lc.pods(selector="TrainingJobName=keep")] == ["Succeeded"]
+
+
+def test_spawn_error_surfaces_as_creating_failed():
+    opt = TrainingJobOperatorOption(enable_creating_failed=True)
+    with LocalCluster(num_gpus=0, option=opt) as lc2:
+        j = sh_job("nx", "true", replicas=1)
+        j["spec"]["replicaSpecs"]["trainer"]["template"]["spec"]["containers"][0]["command"] = ["/no/such/binary"]
+        lc2.apply(j)
+        final = lc2.wait_for_phase("nx", "Failed", timeout=20)
+        assert "create container failed[CreateContainerError]" in final.status.conditions[-1].message
+
+
+def test_delete_job_kills_processes_and_gc_sweeps_orphans(lc):
+    lc.apply(sh_job("del", "sleep 60", replicas=2))
+    wait_until(lambda: lc.jobs().get("del").status.phase == "Running")
+    pids = list(pod_pids(lc, "del").values())
+    lc.jobs().delete("del")                                         # cascade: pods + services go with the owner
+    wait_until(lambda: lc.agent.sup.list() == [])
+    for pid in pids:
+        with pytest.raises(ProcessLookupError):
+            os.kill(pid, 0)
+    # an orphan pod (owner gone, labelled as ours) is force-deleted by the collector
+    ghost = {"apiVersion": "v1", "kind": "Pod",
+             "metadata": {"name": "ghost-trainer-0", "labels": {C.LABEL_GROUP_NAME: C.GROUP_NAME},
+                          "ownerReferences": [{"apiVersion": C.API_VERSION, "kind": C.KIND, "name": "ghost",
+                                               "uid": "gone", "controller": True}]},
+             "spec": {"containers": [{"name": "aitj-x", "command": ["sleep", "60"]}]}}
+    lc.clientset.core_v1().pods("default").create(ghost)
+    wait_until(lambda: not [p for p in lc.pods() if p["metadata"]["name"] == "ghost-trainer-0"], timeout=15)
+
+
+def test_cli_workflow_matches_readme(lc, tmp_path):
+    """README.md:14-19 of the reference: apply -f / get aitj / describe aitj / delete -f."""
+    spec = yaml.safe_load(open(os.path.join(ROOT, "examples", "paddle-mnist.yaml")))
+    spec["spec"]["replicaSpecs"]["trainer"]["template"]["spec"]["containers"][0]["args"] = ["-c", "sleep 2"]
+    path = str(tmp_path / "job.yaml")
+    yaml.safe_dump(spec, open(path, "w"))
+
+    def run(*argv):
+        buf = io.StringIO()
+        rc = kubectl.main(list(argv), clientset=lc.clientset, out=buf)
+        return rc, buf.getvalue()
+
+    rc, out = run("apply", "-f", path)
+    assert rc == 0 and out.strip() == "aitrainingjob.elasticdeeplearning.ai/paddle-mnist created"
+    rc, out = run("apply", "-f", path)
+    assert out.strip().endswith("unchanged")
+    wait_until(lambda: lc.jobs().get("paddle-mnist").status.phase == "Running")
+    rc, out = run("get", "aitj")
+    lines = out.strip().splitlines()
+    assert lines[0].split() == ["NAME", "AGE"] and lines[1].split()[0] == "paddle-mnist"   # no printer columns
+    rc, out = run("get", "aitj", "-o", "wide")
+    assert "PHASE" in out and "Running" in out
+    rc, out = run("get", "aitj", "paddle-mnist", "-o", "yaml")
+    assert yaml.safe_load(out)["status"]["phase"] == "Running"
+    rc, out = run("get", "pods", "-o", "wide")
+    assert "paddle-mnist-trainer-0" in out and "cpu-0" in out
+    rc, out = run("describe", "aitj", "paddle-mnist")
+    for needle in ("Name:         paddle-mnist", "API Version:  elasticdeeplearning.ai/v1", "Kind:         AITrainingJob",
+                   "Clean Pod Policy:  All", "Replica Specs:", "Restart Policy:  OnNodeFailWithExitCode",
+                   "Restarting Exit Code:  137,128", "Restart Count:", "Restart Replica Name:",
+                   "Start Running Time:", "Events:", "SuccessfulCreatePod", "TrainingJobOperator",
+                   "Created pod: paddle-mnist-trainer-0", "Complete Policy:  All", "Fail Policy:  Any"):
+        assert needle in out, needle
+    rc, out = run("scale", "aitj/paddle-mnist", "--replicas", "2")
+    assert rc == 0 and lc.jobs().get("paddle-mnist").spec.replica_specs["trainer"].replicas == 2
+    rc, out = run("annotate", "aitj", "paddle-mnist", "note=hello")
+    assert lc.jobs().get("paddle-mnist").annotations["note"] == "hello"
+    rc, out = run("api-resources")
+    assert "aitrainingjobs" in out and "aitj" in out
+    rc, out = run("delete", "-f", path)
+    assert rc == 0 and 'aitrainingjob.elasticdeeplearning.ai "paddle-mnist" deleted' in out
+    wait_until(lambda: lc.pods() == [])
+    rc, out = run("get", "aitj", "nope")
+    assert rc == 1
+    assert kubectl.humanize_key("cleanPodPolicy") == "Clean Pod Policy"
+    assert kubectl.humanize_key("apiVersion") == "API Version" and kubectl.humanize_key("uid") == "UID"
+    assert kubectl.humanize_key("RestartReplicaName") == "Restart Replica Name"
+
+
+def test_leader_failover_keeps_the_job_running(tmp_path):
+    """BASELINE config 5 shape: two operators, kill the leader, the standby takes over, workers never notice."""
+    opt = TrainingJobOperatorOption(thread_num=1)
+    opt.leader_election.leader_elect = True
+    opt.leader_election.lease_duration, opt.leader_election.renew_deadline, opt.leader_election.retry_period = 1.0, 0.6, 0.15
+    with LocalCluster(num_gpus=0, workdir=str(tmp_path), operators=2, option=opt) as lc2:
+        j = sh_job("ha", "sleep 4", replicas=2, completePolicy="All")
+        j["spec"]["completePolicy"] = "All"
+        lc2.apply(j)
+        wait_until(lambda: lc2.jobs().get("ha").status.phase == "Running", timeout=20)
+        pids = pod_pids(lc2, "ha")
+        lock = lambda: json.loads(lc2.clientset.core_v1().endpoints("kube-system").get("trainingjob-operator")  # noqa: E731
+                                  ["metadata"]["annotations"]["control-plane.alpha.kubernetes.io/leader"])
+        leader = lock()["holderIdentity"]
+        assert leader in ("operator-0", "operator-1")
+        lc2.stop_operator(int(leader[-1]))
+        t0 = time.time()
+        wait_until(lambda: lock()["holderIdentity"] not in ("", leader), timeout=10)
+        failover = time.time() - t0
+        assert pod_pids(lc2, "ha") == pids                          # same processes: nothing was restarted
+        final = lc2.wait_for_phase("ha", "Succeed", timeout=30)     # the new leader finishes the job
+        assert final.status.restart_counts.get("trainer", 0) == 0
+        assert failover < 6.0
+        evs = [e["message"] for e in lc2.clientset.core_v1().events("kube-system").list()["items"]]
+        assert any("became leader" in m for m in evs)
+
+
+@pytest.mark.slow
+def test_elastic_rescale_with_gloo_workers(tmp_path):
+    """BASELINE config 3 shape on CPU: world 2 -> 3 -> 2 without losing step state (gloo instead of NCCL)."""
+    opt = TrainingJobOperatorOption(thread_num=2, scale_down_grace=20.0)
+    with LocalCluster(num_gpus=0, workdir=str(tmp_path), option=opt) as lc2:
+        worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", "mlp", "--batch", "16",
+                  "--steps", "0", "--cpu", "--elastic", "--step-sleep", "0.02"]
+        job = {"apiVersion": C.API_VERSION, "kind": C.KIND, "metadata": {"name": "el"},
+               "spec": {"frameworkType": "pytorch", "replicaSpecs": {"trainer": {
+                   "replicas": 2, "minReplicas": 2, "maxReplicas": 4, "edlPolicy": "Manual",
+                   "template": {"spec": {"containers": [{"name": "aitj-trainer", "command": worker,
+                                                         "workingDir": ROOT,
+                                                         "env": [{"name": "PYTHONPATH", "value": ROOT}]}]}}}}}}
+        lc2.apply(job)
+        wait_until(lambda: lc2.jobs().get("el").status.phase == "Running", timeout=60)
+        wait_until(lambda: "aitj.b200/worker-trace" in lc2.jobs().get("el").annotations, timeout=90)
+        pids = pod_pids(lc2, "el")
+        # ---- scale up 2 -> 3
+        lc2.jobs().patch("el", {"spec": {"replicaSpecs": {"trainer": {"replicas": 3}}}})
+        rec = wait_until(lambda: (lambda a: json.loads(a["aitj.b200/rescale-trace"])
+                                  if "aitj.b200/rescale-trace" in a and
+                                  json.loads(a["aitj.b200/rescale-trace"])["world"] == 3 else None)(
+            lc2.jobs().get("el").annotations), timeout=90)
+        assert rec["generation"] == 2
+        j = wait_until(lambda: (lambda x: x if x.status.phase == "Running" and
+                                x.status.replica_statuses["trainer"].active == 3 else None)(lc2.jobs().get("el")),
+                       timeout=30)
+        now = pod_pids(lc2, "el")
+        assert {k: now[k] for k in pids} == pids                    # survivors were not restarted
+        # ---- scale down 3 -> 2: rank 2 leaves voluntarily, is drained and deleted, job stays Running
+        lc2.jobs().patch("el", {"spec": {"replicaSpecs": {"trainer": {"replicas": 2}}}})
+        rec = wait_until(lambda: (lambda a: json.loads(a["aitj.b200/rescale-trace"])
+                                  if json.loads(a.get("aitj.b200/rescale-trace", "{}")).get("generation") == 3
+                                  else None)(lc2.jobs().get("el").annotations), timeout=90)
+        assert rec["world"] == 2
+        wait_until(lambda: sorted(p["metadata"]["name"] for p in lc2.pods(selector="TrainingJobName=el")) ==
+                   ["el-trainer-0", "el-trainer-1"], timeout=40)
+        j = lc2.jobs().get("el")
+        assert j.status.phase == "Running" and j.status.restart_counts.get("trainer", 0) == 0
+        assert {k: pod_pids(lc2, "el")[k] for k in pids} == pids
+        log2 = open(os.path.join(lc2.workdir, "logs", "default_el-trainer-2_aitj-trainer.log")).read()
+        assert "leaving: world shrinks to 2" in log2

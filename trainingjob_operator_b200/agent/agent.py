@@ -34,7 +34,7 @@ from ..api import meta as M
 from ..client.informers import DeletedFinalStateUnknown, SharedInformerFactory
 from ..core import _aitj_core as core
 from ..store.apiserver import APIError
-from ..utils import klog, metrics
+from ..utils import klog, lifecycle, metrics
 
 GPU_RESOURCE = "nvidia.com/gpu"
 OWN_SCHEDULERS = ("", "default-scheduler", "aitj-scheduler")
@@ -156,6 +156,10 @@ class NodeAgent:
         self.node_lister = self._node_informer.lister()
         self._threads: List[threading.Thread] = []
         self._injected: Dict[str, str] = {}
+        # authoritative GPU allocation table (gpu index -> pod uid): the informer cache lags behind our own
+        # binds, so consecutive scheduling decisions must not rely on it alone
+        self._gpu_owner: Dict[int, Tuple[str, float]] = {}
+        self._bound: Dict[str, float] = {}   # pod uid -> time we bound it (cache may not show nodeName yet)
 
     # ------------------------------------------------------------------ nodes
     def gpu_node(self, idx: int) -> str:
@@ -258,9 +262,8 @@ class NodeAgent:
         self._factory.wait_for_cache_sync(stop)
         for target, name in ((self._sync_loop, "agent-sync"), (self._reap_loop, "agent-reap"),
                              (self._health_loop, "agent-health"), (self._sweep_loop, "agent-sweep")):
-            t = threading.Thread(target=target, args=(stop,), name=name, daemon=True)
-            t.start()
-            self._threads.append(t)
+            self._threads.append(lifecycle.spawn(target, name, (stop,)))
+        lifecycle.register_stop(lambda: (stop.set(), self.queue.shutdown()))
         threading.Thread(target=lambda: (stop.wait(), self.queue.shutdown()), daemon=True).start()
 
     def run(self, stop: threading.Event) -> None:
@@ -348,14 +351,22 @@ class NodeAgent:
                    for c in n.get("status", {}).get("conditions") or []):
                 ready.add(int(nm.rsplit("-", 1)[1]))
         busy = set()
+        live_uids = set()
         for p in self.pod_lister.list():
-            if not p.get("spec", {}).get("nodeName"):
-                continue
-            if (p.get("status", {}).get("phase") or C.POD_PENDING) in (C.POD_SUCCEEDED, C.POD_FAILED):
+            done = (p.get("status", {}).get("phase") or C.POD_PENDING) in (C.POD_SUCCEEDED, C.POD_FAILED)
+            if not done:
+                live_uids.add(M.uid_of(p))
+            if not p.get("spec", {}).get("nodeName") or done:
                 continue
             for g in (M.annotations_of(p).get(C.ANN_GPUS) or "").split(","):
                 if g.strip():
                     busy.add(int(g))
+        with self._lock:
+            # drop allocations whose pod is finished or gone (seen by the cache), keep fresh binds
+            for g, (uid, at) in list(self._gpu_owner.items()):
+                if uid not in live_uids and time.monotonic() - at > 1.0:
+                    del self._gpu_owner[g]
+            busy |= set(self._gpu_owner)
         return sorted(ready - busy)
 
     def schedule(self, pod: dict) -> None:
@@ -363,6 +374,12 @@ class NodeAgent:
             return
         want = pod_gpu_request(pod)
         ns, name = M.namespace_of(pod), M.name_of(pod)
+        with self._lock:
+            if M.uid_of(pod) in self._bound:
+                return                      # already bound by us; the informer just has not caught up
+            if len(self._bound) > 4096:
+                cutoff = time.monotonic() - 60.0
+                self._bound = {u: t for u, t in self._bound.items() if t > cutoff}
         if want == 0:
             self._bind(pod, self.cpu_node, [])
             return
@@ -388,7 +405,14 @@ class NodeAgent:
                                          f"{GPU_RESOURCE}, {len(free)} free but {want} requested.")
                 return
             gpus = free[:want]
-            self._bind(pod, self.gpu_node(gpus[0]), gpus)
+            for g in gpus:
+                self._gpu_owner[g] = (M.uid_of(pod), time.monotonic())
+            try:
+                self._bind(pod, self.gpu_node(gpus[0]), gpus)
+            except APIError:
+                for g in gpus:
+                    self._gpu_owner.pop(g, None)
+                raise
 
     def _mark_unschedulable(self, pod: dict, message: str) -> None:
         conds = pod.get("status", {}).get("conditions") or []
@@ -406,7 +430,14 @@ class NodeAgent:
                  "status": {"phase": C.POD_PENDING, "hostIP": "127.0.0.1", "podIP": "127.0.0.1",
                             "conditions": [{"type": "PodScheduled", "status": "True",
                                             "lastTransitionTime": M.format_time()}]}}
-        self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch)
+        with self._lock:
+            self._bound[M.uid_of(pod)] = time.monotonic()
+        try:
+            self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch)
+        except APIError:
+            with self._lock:
+                self._bound.pop(M.uid_of(pod), None)
+            raise
         klog.V(2).info("scheduled %s -> %s gpus=%s", M.key_of(pod), node, gpus)
         self.queue.add(M.key_of(pod))
 

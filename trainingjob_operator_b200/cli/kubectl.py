@@ -296,14 +296,15 @@ class CLI:
                     rc.create(obj)
                     self.p(f"{self._qualified(info)}/{name} created")
                     continue
-                new = M.deepcopy(cur)
-                for k, v in obj.items():
-                    if k in ("metadata", "status"):
-                        continue
-                    new[k] = v
-                for k in ("labels", "annotations"):
-                    if obj.get("metadata", {}).get(k):
-                        new["metadata"].setdefault(k, {}).update(obj["metadata"][k])
+                # like `kubectl apply`: merge the manifest onto the live object (server-side defaults survive)
+                from ..store.apiserver import merge_patch
+
+                desired = {k: v for k, v in obj.items() if k != "status"}
+                md = dict(desired.get("metadata") or {})
+                for k in ("resourceVersion", "uid", "creationTimestamp"):
+                    md.pop(k, None)
+                desired["metadata"] = md
+                new = merge_patch(cur, desired)
                 if new == cur:
                     self.p(f"{self._qualified(info)}/{name} unchanged")
                 else:

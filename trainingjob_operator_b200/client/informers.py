@@ -22,7 +22,7 @@ from ..api import meta as M
 from ..api import register as R
 from ..api.types import AITrainingJob
 from ..store.apiserver import APIError
-from ..utils import klog
+from ..utils import klog, lifecycle
 from .clientset import Clientset, ResourceClient
 
 
@@ -223,13 +223,12 @@ class SharedIndexInformer:
             return
         if stop is not None:
             self._stop = stop
-        self._thread = threading.Thread(target=self._run, name=f"informer-{self.name}", daemon=True)
-        self._thread.start()
+        self._thread = lifecycle.spawn(self._run, f"informer-{self.name}")
+        lifecycle.register_stop(self.stop)
         threading.Thread(target=lambda: (self._stop.wait(), self.stop()), name=f"informer-stop-{self.name}",
                          daemon=True).start()
         if self._resync and self._resync > 0:
-            self._resync_thread = threading.Thread(target=self._resync_loop, name=f"resync-{self.name}", daemon=True)
-            self._resync_thread.start()
+            self._resync_thread = lifecycle.spawn(self._resync_loop, f"resync-{self.name}")
 
     def stop(self) -> None:
         self._stop.set()

@@ -36,7 +36,7 @@ from ..client.record import EventRecorder
 from ..cmd.options import TrainingJobOperatorOption
 from ..core import _aitj_core as core
 from ..store.apiserver import APIError
-from ..utils import klog, metrics
+from ..utils import klog, lifecycle, metrics
 from .control import RealPodControl, RealServiceControl
 from .elastic import ElasticMixin
 from .garbage_collection import GarbageCollector
@@ -124,10 +124,9 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
                                        self.service_informer_synced, self.node_informer_synced):
                 raise RuntimeError("failed to wait for caches for sync")
             klog.info("Starting workers")
+            lifecycle.register_stop(lambda: (stop.set(), self.work_queue.shutdown()))
             for i in range(max(1, workers)):
-                t = threading.Thread(target=self._worker_loop, args=(stop,), name=f"aitj-worker-{i}", daemon=True)
-                t.start()
-                self._workers.append(t)
+                self._workers.append(lifecycle.spawn(self._worker_loop, f"aitj-worker-{i}", (stop,)))
             self.gc = GarbageCollector(self.kube_client, self.trainingjob_lister)
             threading.Thread(target=self.gc.clean_orphans, args=(self.option.gc_interval, stop), name="aitj-gc",
                              daemon=True).start()

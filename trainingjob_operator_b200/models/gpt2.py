@@ -88,6 +88,7 @@ class _LayerBufs:
         self.fc_act = torch.empty(M, 4 * C, **bf)
         self.res2 = torch.empty(M, C, **bf)
         self.sdpa_ctx = None
+        self.att_in = self.att
 
 
 class GPT2Engine:
@@ -132,6 +133,10 @@ class GPT2Engine:
         self.sumsq = torch.zeros(1, **f32)
         self.dyn = torch.zeros(4, **f32)
         self._dyn_host = torch.zeros(4, dtype=torch.float32).pin_memory() if self.dev.type == "cuda" else None
+        import os as _os
+
+        # CTA-pair (cta_group::2) GEMM: 256x256 tile per 2-CTA cluster (AITJ_GEMM_PAIR=0 falls back to 1-CTA)
+        self.pair = _os.environ.get("AITJ_GEMM_PAIR", "1") != "0"
         self.grad_hook = None  # called as hook(name_of_bucket) when a gradient bucket is complete
         self._graph = None
         self.split_k: Dict[Tuple[int, int], int] = {}
@@ -140,7 +145,8 @@ class GPT2Engine:
     def _linear(self, x, w, out, bias=None, residual=None, gelu=False, aux=None):
         F = self.F
         if self.backend == "tcgen05":
-            F.gemm(x, w, out, bias=bias, residual=residual, gelu=gelu, save_pre=gelu, aux=aux)
+            F.gemm(x, w, out, bias=bias, residual=residual, gelu=gelu, save_pre=gelu, aux=aux,
+                   block_n=self._bn(x.shape[0], w.shape[0]))
             return out
         # library path (cuBLAS) + standalone elementwise kernels; numerics cross-check / fallback bench arm
         y = torch.addmm(bias, x, w.t()) if bias is not None else x @ w.t()
@@ -153,11 +159,16 @@ class GPT2Engine:
             out.copy_(y)
         return out
 
+    def _bn(self, m: int, n: int) -> int:
+        """512 = CTA-pair kernel when the problem has at least one full 256x256 tile, else auto 1-CTA."""
+        return 512 if self.pair and m >= 256 and n >= 256 else 0
+
     def _dgrad(self, dy, w, out, dgelu_aux=None):
         """out[M,K] = dy[M,N] @ w[N,K]  (* gelu'(aux))."""
         F = self.F
         if self.backend == "tcgen05":
-            F.gemm(dy, w, out, b_mn=True, dgelu=dgelu_aux is not None, aux=dgelu_aux)
+            F.gemm(dy, w, out, b_mn=True, dgelu=dgelu_aux is not None, aux=dgelu_aux,
+                   block_n=self._bn(dy.shape[0], w.shape[1]))
             return out
         y = dy @ w
         if dgelu_aux is not None:
@@ -171,10 +182,17 @@ class GPT2Engine:
         F = self.F
         if self.backend == "tcgen05":
             key = (dw.shape[0], dw.shape[1])
+            bn = self._bn(dw.shape[0], dw.shape[1])
             sk = self.split_k.get(key)
             if sk is None:
-                sk = self.split_k[key] = F.auto_split_k(dw.shape[0], dw.shape[1], dy.shape[0])
-            F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=sk)
+                if bn == 512:
+                    tiles = ((dw.shape[0] + 255) // 256) * ((dw.shape[1] + 255) // 256)
+                    pairs = max(1, F.num_sms() // 2)
+                    sk = 1 if tiles >= pairs else max(1, min((dy.shape[0] + 63) // 64, pairs // tiles))
+                else:
+                    sk = F.auto_split_k(dw.shape[0], dw.shape[1], dy.shape[0])
+                self.split_k[key] = sk
+            F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=sk, block_n=bn)
         else:
             dw.add_((dy.t() @ x).float())
 
@@ -189,7 +207,12 @@ class GPT2Engine:
         with torch.enable_grad():
             o = TF.scaled_dot_product_attention(q, k, v, is_causal=self.causal)
         lb.sdpa_ctx = (q, k, v, o)
-        lb.att.view(B, T, H, D).copy_(o.detach().transpose(1, 2))
+        ot = o.detach().transpose(1, 2)
+        if ot.is_contiguous():
+            lb.att_in = ot.reshape(B * T, H * D)     # cuDNN wrote [B,T,H,D] already: feed the GEMM in place
+        else:
+            lb.att.view(B, T, H, D).copy_(ot)
+            lb.att_in = lb.att
 
     def _attention_bwd(self, lb: _LayerBufs, d_att: torch.Tensor, d_qkv: torch.Tensor):
         B, T, H = self.B, self.T, self.cfg.n_head
@@ -215,7 +238,7 @@ class GPT2Engine:
             F.layernorm_fwd(x, P.w16(p + "ln1_w"), P.w16(p + "ln1_b"), lb.ln1, lb.ln1_mean, lb.ln1_rstd)
             self._linear(lb.ln1, P.w16(p + "qkv_w"), lb.qkv, bias=P.w16(p + "qkv_b"))
             self._attention_fwd(lb)
-            self._linear(lb.att, P.w16(p + "proj_w"), lb.res1, bias=P.w16(p + "proj_b"), residual=x)
+            self._linear(lb.att_in, P.w16(p + "proj_w"), lb.res1, bias=P.w16(p + "proj_b"), residual=x)
             F.layernorm_fwd(lb.res1, P.w16(p + "ln2_w"), P.w16(p + "ln2_b"), lb.ln2, lb.ln2_mean, lb.ln2_rstd)
             self._linear(lb.ln2, P.w16(p + "fc_w"), lb.fc_act, bias=P.w16(p + "fc_b"), gelu=True, aux=lb.fc_pre)
             self._linear(lb.fc_act, P.w16(p + "fc2_w"), lb.res2, bias=P.w16(p + "fc2_b"), residual=lb.res1)
@@ -237,34 +260,34 @@ class GPT2Engine:
         self._wgrad(dlogits, self.lnf, P.grad("wte"))
         d_res, spare = self.d_res
         x_last = self.layers[-1].res2 if self.layers else self.x0
+        last = len(self.layers) - 1
         F.layernorm_bwd(self.d_ln, x_last, P.w16("lnf_w"), self.lnf_mean, self.lnf_rstd, d_res, P.grad("lnf_w"),
-                        P.grad("lnf_b"))
+                        P.grad("lnf_b"), dxsum=P.grad(f"h{last}.fc2_b") if last >= 0 else None)
         if hook:
             hook("lnf")
         for i in range(len(self.layers) - 1, -1, -1):
             lb = self.layers[i]
             p = f"h{i}."
             x_in = self.layers[i - 1].res2 if i > 0 else self.x0
-            # MLP
-            F.colsum(d_res, P.grad(p + "fc2_b"))
+            # MLP (fc2_b's gradient = colsum(d_res) was already produced by the LayerNorm-backward that made d_res)
             self._wgrad(d_res, lb.fc_act, P.grad(p + "fc2_w"))
             self._dgrad(d_res, P.w16(p + "fc2_w"), self.d_fc, dgelu_aux=lb.fc_pre)
             F.colsum(self.d_fc, P.grad(p + "fc_b"))
             self._wgrad(self.d_fc, lb.ln2, P.grad(p + "fc_w"))
             self._dgrad(self.d_fc, P.w16(p + "fc_w"), self.d_ln)
             F.layernorm_bwd(self.d_ln, lb.res1, P.w16(p + "ln2_w"), lb.ln2_mean, lb.ln2_rstd, spare,
-                            P.grad(p + "ln2_w"), P.grad(p + "ln2_b"), dres=d_res)
+                            P.grad(p + "ln2_w"), P.grad(p + "ln2_b"), dres=d_res, dxsum=P.grad(p + "proj_b"))
             d_res, spare = spare, d_res
             # attention
-            F.colsum(d_res, P.grad(p + "proj_b"))
-            self._wgrad(d_res, lb.att, P.grad(p + "proj_w"))
+            self._wgrad(d_res, lb.att_in, P.grad(p + "proj_w"))
             self._dgrad(d_res, P.w16(p + "proj_w"), self.d_att)
             self._attention_bwd(lb, self.d_att, self.d_qkv)
             F.colsum(self.d_qkv, P.grad(p + "qkv_b"))
             self._wgrad(self.d_qkv, lb.ln1, P.grad(p + "qkv_w"))
             self._dgrad(self.d_qkv, P.w16(p + "qkv_w"), self.d_ln)
             F.layernorm_bwd(self.d_ln, x_in, P.w16(p + "ln1_w"), lb.ln1_mean, lb.ln1_rstd, spare,
-                            P.grad(p + "ln1_w"), P.grad(p + "ln1_b"), dres=d_res)
+                            P.grad(p + "ln1_w"), P.grad(p + "ln1_b"), dres=d_res,
+                            dxsum=P.grad(f"h{i - 1}.fc2_b") if i > 0 else None)
             d_res, spare = spare, d_res
             if hook:
                 hook(f"h{i}")

@@ -80,12 +80,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ rstd_in,
                                                             const __nv_bfloat16* __restrict__ dres,
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int M) {
+                                                            float* __restrict__ dbeta, float* __restrict__ dxsum,
+                                                            int M) {
+  // dxsum (optional, fp32[C]) += column sums of dx: dx is the gradient of the tensor that fed this LayerNorm,
+  // i.e. of "linear output + bias + residual", so its column sum IS that linear's bias gradient -- for free.
   constexpr int C = V * 256;
   __shared__ float red[8][C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  float g[V * 8], dg[V * 8], db[V * 8];
+  float g[V * 8], dg[V * 8], db[V * 8], ds[V * 8];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     uint4 gu = *reinterpret_cast<const uint4*>(gamma + (i * 32 + lane) * 8);
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     }
   }
 #pragma unroll
-  for (int i = 0; i < V * 8; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  for (int i = 0; i < V * 8; ++i) { dg[i] = 0.f; db[i] = 0.f; ds[i] = 0.f; }
 
   for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
     const size_t base = static_cast<size_t>(row) * C;
@@ -143,23 +146,27 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
         const int k = i * 8 + 2 * j;
         float a0 = rstd * (dyv[k] * g[k] - s1 - xh[k] * s2) + r[2 * j];
         float a1 = rstd * (dyv[k + 1] * g[k + 1] - s1 - xh[k + 1] * s2) + r[2 * j + 1];
+        ds[k] += a0; ds[k + 1] += a1;
         ow[j] = pack_bf16x2(a0, a1);
       }
       *reinterpret_cast<uint4*>(dx + base + (i * 32 + lane) * 8) = o;
     }
   }
   // block reduce dgamma then dbeta through smem, one atomic per column per block
-  for (int pass = 0; pass < 2; ++pass) {
+  const int passes = dxsum != nullptr ? 3 : 2;
+  for (int pass = 0; pass < passes; ++pass) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < V; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][(i * 32 + lane) * 8 + j] = pass == 0 ? dg[i * 8 + j] : db[i * 8 + j];
+      for (int j = 0; j < 8; ++j)
+        red[warp][(i * 32 + lane) * 8 + j] = pass == 0 ? dg[i * 8 + j] : (pass == 1 ? db[i * 8 + j] : ds[i * 8 + j]);
     __syncthreads();
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float s = 0.f;
       for (int w = 0; w < warps_per_block; ++w) s += red[w][c];
-      atomicAdd((pass == 0 ? dgamma : dbeta) + c, s);
+      atomicAdd(dst + c, s);
     }
   }
 }
@@ -297,6 +304,113 @@ __global__ void __launch_bounds__(512) softmax_xent_kernel(__nv_bfloat16* __rest
       ow[j] = pack_bf16x2(p0, p1);
     }
     *reinterpret_cast<uint4*>(g + i * 8) = o;
+  }
+}
+
+// Register-resident variant: 1024 threads per row, every thread keeps its NV 16-byte vectors of the row and of
+// exp(x - max) (bf16) in registers: one HBM read, one write, one exp per element, no shared-memory staging.
+template <int NV>
+__global__ void __launch_bounds__(1024, 1) softmax_xent_reg_kernel(__nv_bfloat16* __restrict__ logits,
+                                                                   const int64_t* __restrict__ target,
+                                                                   float* __restrict__ loss, int V, int Vp,
+                                                                   float gscale) {
+  __shared__ float sred[32];
+  __shared__ float sbcast[3];
+  const int row = blockIdx.x;
+  __nv_bfloat16* g = logits + static_cast<size_t>(row) * Vp;
+  const int nvec = Vp / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tgt = static_cast<int>(target[row]);
+  uint4 xv[NV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = threadIdx.x + k * 1024;
+    if (i < nvec) {
+      xv[k] = *reinterpret_cast<const uint4*>(g + i * 8);
+      const uint32_t w[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16x2(w[j]);
+        const int c = i * 8 + 2 * j;
+        if (c < V) mx = fmaxf(mx, f.x);
+        if (c + 1 < V) mx = fmaxf(mx, f.y);
+      }
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) sred[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    float t = warp_max(sred[lane]);
+    if (lane == 0) sbcast[0] = t;
+  }
+  __syncthreads();
+  mx = sbcast[0];
+  const float LOG2E = 1.4426950408889634f;
+  const float moff = mx * LOG2E;
+  uint4 ev[NV];
+  float sum = 0.f, xt = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = threadIdx.x + k * 1024;
+    if (i < nvec) {
+      const uint32_t w[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
+      uint32_t e[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16x2(w[j]);
+        const int c = i * 8 + 2 * j;
+        float e0 = c < V ? exp2f(fmaf(f.x, LOG2E, -moff)) : 0.f;
+        float e1 = c + 1 < V ? exp2f(fmaf(f.y, LOG2E, -moff)) : 0.f;
+        if (c == tgt) xt = f.x;
+        if (c + 1 == tgt) xt = f.y;
+        sum += e0 + e1;
+        e[j] = pack_bf16x2(e0, e1);
+      }
+      ev[k] = make_uint4(e[0], e[1], e[2], e[3]);
+    }
+  }
+  sum = warp_sum(sum);
+  xt = warp_sum(xt);
+  __syncthreads();
+  if (lane == 0) sred[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float t = warp_sum(sred[lane]);
+    if (lane == 0) sbcast[1] = t;
+  }
+  __syncthreads();
+  if (lane == 0) sred[warp] = xt;
+  __syncthreads();
+  if (warp == 0) {
+    float t = warp_sum(sred[lane]);
+    if (lane == 0) sbcast[2] = t;
+  }
+  __syncthreads();
+  sum = sbcast[1];
+  const bool valid = tgt >= 0 && tgt < V;
+  if (threadIdx.x == 0) loss[row] = valid ? -(sbcast[2] - mx - logf(sum)) : 0.f;
+  const float inv = valid ? gscale / sum : 0.f;
+  const float gs = valid ? gscale : 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = threadIdx.x + k * 1024;
+    if (i < nvec) {
+      const uint32_t e[4] = {ev[k].x, ev[k].y, ev[k].z, ev[k].w};
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16x2(e[j]);
+        const int c = i * 8 + 2 * j;
+        float p0 = f.x * inv, p1 = f.y * inv;
+        if (c == tgt) p0 -= gs;
+        if (c + 1 == tgt) p1 -= gs;
+        ow[j] = pack_bf16x2(p0, p1);
+      }
+      *reinterpret_cast<uint4*>(g + i * 8) = o;
+    }
   }
 }
 
@@ -491,12 +605,13 @@ int aitj_layernorm_fwd(const void* x, const void* gamma, const void* beta, void*
 }
 
 int aitj_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd,
-                       const void* dres, void* dx, void* dgamma, void* dbeta, int M, int C, void* stream) {
+                       const void* dres, void* dx, void* dgamma, void* dbeta, void* dxsum, int M, int C,
+                       void* stream) {
   if (C % 256 || C > 1024) return -1;
   const int blocks = min((M + 7) / 8, 148 * 2);
 #define LN_B(V) layernorm_bwd_kernel<V><<<blocks, 256, 0, S(stream)>>>(CBF(dy), CBF(x), CBF(gamma), \
     reinterpret_cast<const float*>(mean), reinterpret_cast<const float*>(rstd), CBF(dres), BF(dx), \
-    reinterpret_cast<float*>(dgamma), reinterpret_cast<float*>(dbeta), M)
+    reinterpret_cast<float*>(dgamma), reinterpret_cast<float*>(dbeta), reinterpret_cast<float*>(dxsum), M)
   switch (C / 256) {
     case 1: LN_B(1); break; case 2: LN_B(2); break; case 3: LN_B(3); break; case 4: LN_B(4); break;
     default: return -1;
@@ -526,6 +641,16 @@ int aitj_embedding_bwd(const void* tok, const void* dx, void* dwte, void* dwpe, 
 int aitj_softmax_xent(void* logits, const void* target, void* loss, int M, int V, int Vp, float gscale,
                       void* stream) {
   if (Vp % 8 || V > Vp) return -1;
+  {
+    const int nv = (Vp / 8 + 1023) / 1024;
+#define XENT_REG(NV) softmax_xent_reg_kernel<NV><<<M, 1024, 0, S(stream)>>>(BF(logits), \
+    reinterpret_cast<const int64_t*>(target), reinterpret_cast<float*>(loss), V, Vp, gscale); return LAUNCH_OK()
+    switch (nv) {
+      case 1: XENT_REG(1); case 2: XENT_REG(2); case 3: XENT_REG(3); case 4: XENT_REG(4);
+      case 5: XENT_REG(5); case 6: XENT_REG(6); case 7: XENT_REG(7); default: break;
+    }
+#undef XENT_REG
+  }
   const int smem = Vp * 2;
   if (smem > 200 * 1024) return -2;
   static int configured = 0;
@@ -541,8 +666,10 @@ int aitj_softmax_xent(void* logits, const void* target, void* loss, int M, int V
 
 int aitj_colsum(const void* dy, void* db, int M, int N, void* stream) {
   if (N % 8) return -1;
-  const int rows_per_block = 512;
-  dim3 grid((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block);
+  const int col_blocks = (N + 255) / 256;
+  int rows_per_block = 512;
+  while (rows_per_block > 32 && col_blocks * ((M + rows_per_block - 1) / rows_per_block) < 148 * 4) rows_per_block /= 2;
+  dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
   colsum_kernel<<<grid, 256, 0, S(stream)>>>(CBF(dy), reinterpret_cast<float*>(db), M, N, rows_per_block);
   return LAUNCH_OK();
 }

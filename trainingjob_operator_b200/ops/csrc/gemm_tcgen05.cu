@@ -337,6 +337,162 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// Two CTAs of a cluster (one TPC) compute one 256x256 tile: each loads its own 128 rows of A and HALF of
+// B (128 of the 256 N rows), the leader issues tcgen05.mma.cta_group::2 (M=256) that reads both CTAs'
+// shared memory, and each CTA drains its own 128 accumulator rows from its TMEM.  Per-CTA operand traffic
+// drops from 48 KB to 32 KB per k-block (the 1-CTA kernel is L2->SM bandwidth bound at K=768..3072) and the
+// freed shared memory buys a 6-stage ring.
+template <bool kAMN, bool kBMN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
+                      const GemmArgs args) {
+  constexpr int kPairM = 256, kPairN = 256;
+  constexpr int kStageA = BLOCK_M * BLOCK_K * 2;       // this CTA's 128 rows of A
+  constexpr int kStageB = (kPairN / 2) * BLOCK_K * 2;  // this CTA's half of B
+  constexpr int kStageBytes = kStageA + kStageB;
+  constexpr int kStages = 6;
+  constexpr uint32_t kTmemCols = 2 * kPairN;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kPairM, kPairN, kAMN ? 1u : 0u, kBMN ? 1u : 0u);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr int kStagingBytes = 4 * 2 * 4096;
+  uint8_t* staging = smem + kStages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (args.flags & EPI_SAVE_PRE) tma_prefetch_desc(&tmap_aux);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);    // leader's copy is the one in use: 1 arrive(expect_tx) + bytes of both CTAs
+      mbar_init(&empty_bar[i], 1);   // per CTA, released by the leader's multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);   // per CTA, multicast commit
+      mbar_init(&tmem_empty[i], 8);  // leader's copy: 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_work = args.tiles_m * args.tiles_n * args.split_k;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const WorkItem wi = decode_work(args, w);
+        const int m0 = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
+        const int n0 = wi.n_blk * kPairN + static_cast<int>(rank) * (kPairN / 2);
+        for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kStageA;
+          if constexpr (!kAMN) {
+            tma_load_2d_2sm(sa, &tmap_a, full_leader, kb * BLOCK_K, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d_2sm(sa + j * 8192, &tmap_a, full_leader, m0 + j * 64, kb * BLOCK_K);
+          }
+          if constexpr (!kBMN) {
+            tma_load_2d_2sm(sb, &tmap_b, full_leader, kb * BLOCK_K, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < (kPairN / 2) / 64; ++j)
+              tma_load_2d_2sm(sb + j * 8192, &tmap_b, full_leader, n0 + j * 64, kb * BLOCK_K);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const WorkItem wi = decode_work(args, w);
+        mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kPairN;
+        for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kStageA;
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+            const uint64_t da = kAMN ? make_sw128_desc(a_addr + ks * 2048, BLOCK_K * 128, 1024)
+                                     : make_sw128_desc(a_addr + ks * UMMA_K * 2, 16, 1024);
+            const uint64_t db = kBMN ? make_sw128_desc(b_addr + ks * 2048, BLOCK_K * 128, 1024)
+                                     : make_sw128_desc(b_addr + ks * UMMA_K * 2, 16, 1024);
+            umma_bf16_2cta(d_tmem, da, db, kIdesc, (kb > wi.kb0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty_bar[stage], 3);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2cta(&tmem_full[acc], 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    const int lg = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    StageCtx sc;
+    sc.buf = staging + (warp - 2) * 8192;
+    sc.sel = 0;
+    for (int w = cluster_id; w < num_work; w += num_clusters) {
+      const WorkItem wi = decode_work(args, w);
+      mbar_wait_cluster(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (wi.kb1 > wi.kb0) {
+        epilogue_tile<kPairN>(args, &tmap_out, &tmap_aux,
+                              tmem_base + acc * kPairN + (static_cast<uint32_t>(lg * 32) << 16),
+                              wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32, wi.n_blk * kPairN, sc,
+                              lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer's shared memory / TMEM must stay alive until the leader's last MMA retired
+  if (warp == 1) tmem_dealloc_2cta<kTmemCols>(tmem_base);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -400,6 +556,25 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
 }
 
+template <bool kAMN, bool kBMN>
+static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                            const GemmArgs& args, int max_ctas, cudaStream_t stream) {
+  constexpr int kSmem = 6 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 4 * 2 * 4096 + 1024 + 256;
+  static bool configured = false;
+  auto kern = gemm_bf16_2cta_kernel<kAMN, kBMN>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return -20;
+    configured = true;
+  }
+  const int num_work = args.tiles_m * args.tiles_n * args.split_k;
+  int pairs = num_sms() / 2;
+  if (num_work < pairs) pairs = num_work;
+  if (max_ctas > 1 && pairs > max_ctas / 2) pairs = max_ctas / 2;
+  if (pairs < 1) pairs = 1;
+  kern<<<pairs * 2, kGemmThreads, kSmem, stream>>>(ta, tb, to, tx, args);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
+}
+
 }  // namespace aitj
 
 extern "C" {
@@ -409,11 +584,14 @@ extern "C" {
 int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
                    int a_mn, int b_mn, const void* bias, const void* residual, void* aux, int flags, int split_k,
                    int block_n, int max_ctas, void* stream_ptr) {
+  // block_n == 512 selects the CTA-pair (cta_group::2) kernel: 256x256 tile per 2-CTA cluster.
   using namespace aitj;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((N & 7) || (ldc & 7) || (lda & 7) || (ldb & 7)) return -1;
   if ((reinterpret_cast<uintptr_t>(out) & 15) || ((flags & EPI_SAVE_PRE) && (reinterpret_cast<uintptr_t>(aux) & 15))) return -4;
   if (split_k > 1 && !(flags & EPI_ACCUM)) return -2;
+  const bool pair = block_n == 512;
+  if (pair) block_n = 256;
   if (block_n == 0) block_n = (N > 128) ? 256 : 128;
   if (block_n != 128 && block_n != 256) return -3;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_ptr);
@@ -424,7 +602,7 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   args.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   args.aux = reinterpret_cast<__nv_bfloat16*>(aux);
   args.flags = flags;
-  args.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  args.tiles_m = pair ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;
   args.tiles_n = (N + block_n - 1) / block_n;
   args.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   if (split_k < 1) split_k = 1;
@@ -437,7 +615,7 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   if (!a_mn) rc = encode_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
   else       rc = encode_2d(&ta, A, M, K, lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b_mn) rc = encode_2d(&tb, B, K, N, ldb, BLOCK_K, block_n);
+  if (!b_mn) rc = encode_2d(&tb, B, K, N, ldb, BLOCK_K, pair ? 128 : block_n);
   else       rc = encode_2d(&tb, B, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc - 1000;
   CUtensorMap to, tx;
@@ -450,6 +628,12 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
     if (rc) return rc - 3000;
   }
 
+  if (pair) {
+    if (!a_mn && !b_mn) return launch_gemm_2cta<false, false>(ta, tb, to, tx, args, max_ctas, stream);
+    if (!a_mn && b_mn) return launch_gemm_2cta<false, true>(ta, tb, to, tx, args, max_ctas, stream);
+    if (a_mn && !b_mn) return launch_gemm_2cta<true, false>(ta, tb, to, tx, args, max_ctas, stream);
+    return launch_gemm_2cta<true, true>(ta, tb, to, tx, args, max_ctas, stream);
+  }
 #define AITJ_DISPATCH(BN)                                                                     \
   if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, to, tx, args, max_ctas, stream);   \
   if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ta, tb, to, tx, args, max_ctas, stream);     \

@@ -99,11 +99,12 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
     return y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
-    """dx = LN'(dy) (+ dres); dgamma/dbeta (fp32) are accumulated."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dxsum=None):
+    """dx = LN'(dy) (+ dres); dgamma/dbeta (fp32) are accumulated; dxsum (fp32[C], optional) += colsum(dx),
+    which is the bias gradient of the linear layer that produced this LayerNorm's input."""
     M, C = x.shape
     lib.call("aitj_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-             _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), M, C, _stream())
+             _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dxsum), M, C, _stream())
     return dx
 
 

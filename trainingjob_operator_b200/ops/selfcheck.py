@@ -116,6 +116,37 @@ def case_gemm_epilogue():
     return ok
 
 
+def case_gemm_2cta():
+    """CTA-pair kernel (tcgen05.mma.cta_group::2, 256x256 tile per 2-CTA cluster): all layouts + epilogues."""
+    ok = True
+    for (M, N, K, a_mn, b_mn) in [(256, 256, 64, False, False), (256, 256, 256, False, False),
+                                  (512, 768, 768, False, False), (1000, 776, 200, False, False),
+                                  (4096, 2304, 768, False, False), (384, 50304, 768, False, False),
+                                  (512, 768, 2304, False, True), (2048, 768, 6288, False, True),
+                                  (2304, 768, 4096, True, True), (776, 1000, 200, True, True),
+                                  (256, 512, 512, True, False)]:
+        ok &= _gemm_case(M, N, K, a_mn, b_mn, block_n=512)
+    ok &= _gemm_case(2048, 768, 3072, False, False, block_n=512, max_ctas=6)
+    M, N, K = 1024, 768, 768
+    a, b = _rand(M, K), _rand(N, K, scale=0.05)
+    bias, res = _rand(N), _rand(M, N)
+    pre_ref = a.float() @ b.float().t() + bias.float()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    aux = torch.empty_like(out)
+    F.gemm(a, b, out, bias=bias, gelu=True, save_pre=True, aux=aux, block_n=512)
+    ok &= _check("2cta bias+gelu", out, torch.nn.functional.gelu(pre_ref, approximate="tanh"), 1e-2)
+    ok &= _check("2cta save_pre", aux, pre_ref, 1e-2)
+    F.gemm(a, b, out, bias=bias, residual=res, block_n=512)
+    ok &= _check("2cta bias+residual", out, pre_ref + res.float(), 1e-2)
+    Mtok, Nout, Kin = 4096, 768, 3072
+    dyv, x = _rand(Mtok, Nout), _rand(Mtok, Kin)
+    dw = torch.ones(Nout, Kin, device="cuda", dtype=torch.float32)
+    F.gemm(dyv, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=4, block_n=512)
+    ok &= _check("2cta wgrad split_k=4 (TMA reduce-add)", dw, dyv.float().t() @ x.float() + 1.0, 1e-2)
+    torch.cuda.synchronize()
+    return ok
+
+
 # ----------------------------------------------------------------------------- fused ops
 def case_fused_ops():
     ok = True
@@ -136,8 +167,10 @@ def case_fused_ops():
     dx = torch.empty_like(x)
     dgamma = torch.zeros(C, device="cuda")
     dbeta = torch.zeros(C, device="cuda")
-    F.layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=dres)
+    dxsum = torch.zeros(C, device="cuda")
+    F.layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=dres, dxsum=dxsum)
     gx, gg, gb = torch.autograd.grad(yref, (xf, gf, bf), dy.float())
+    ok &= _check("layernorm bwd dxsum (bias grad)", dxsum, (gx + dres.float()).sum(0), 1e-2)
     ok &= _check("layernorm bwd dx(+dres)", dx, gx + dres.float(), 1e-2)
     ok &= _check("layernorm bwd dgamma", dgamma, gg, 1e-2)
     ok &= _check("layernorm bwd dbeta", dbeta, gb, 1e-2)
@@ -257,6 +290,7 @@ def case_gpt2_engine():
 
 
 CASES = {
+    "gemm_2cta": case_gemm_2cta,
     "gpt2_engine": case_gpt2_engine,
     "gemm_tn": case_gemm_tn,
     "gemm_nn": case_gemm_nn,

@@ -227,6 +227,22 @@ def max_over_ranks(value: float, device: torch.device) -> float:
     return float(t[0])
 
 
+def sync_state(adapter, loop_step: int, device: torch.device) -> int:
+    """Hand-off after every (re-)rendezvous: rank 0 broadcasts {optimizer step, loop step} and then the flat
+    state tensors, so a joiner resumes exactly where the survivors are.  Same call sequence on every rank."""
+    if not dist.is_initialized() or dist.get_world_size() <= 1:
+        return loop_step
+    from ..parallel.ddp import broadcast_state
+
+    st = torch.tensor([adapter.step_count, loop_step], dtype=torch.int64,
+                      device=device if device.type == "cuda" else "cpu")
+    dist.broadcast(st, 0)
+    broadcast_state(adapter.state_tensors(), 0)
+    adapter.after_state_load()
+    adapter.step_count = int(st[0])
+    return int(st[1])
+
+
 # ------------------------------------------------------------------------------------ checkpoint
 def ckpt_path(args) -> str:
     d = args.ckpt_dir or os.path.join(os.environ.get("AITJ_WORKDIR", "/tmp"), "ckpt")
@@ -278,11 +294,7 @@ def run(args) -> Dict[str, Any]:
     if restart_count > 0 and args.ckpt_every > 0:
         start_step = load_checkpoint(args, adapter)
         adapter.step_count = start_step
-    if world > 1:
-        from ..parallel.ddp import broadcast_state
-
-        broadcast_state(adapter.state_tensors(), 0)
-        adapter.after_state_load()
+    joined_step = sync_state(adapter, 0, device)
 
     stop = {"flag": False}
     signal.signal(signal.SIGTERM, lambda *_: stop.__setitem__("flag", True))
@@ -293,8 +305,9 @@ def run(args) -> Dict[str, Any]:
     timing: Dict[str, Any] = {}
     ev0 = ev1 = None
     t_wall0 = 0.0
-    step = 0
+    step = joined_step
     first_step_done = False
+    pending_rescale = None
     from ..ops import lib as oplib
 
     launches0 = 0
@@ -305,6 +318,8 @@ def run(args) -> Dict[str, Any]:
             if target is not None and target["generation"] != generation:
                 t0 = time.time()
                 new_world = target["world"]
+                print(f"[worker {rank}] rendezvous generation {generation} -> {target['generation']} "
+                      f"(world {world} -> {new_world}) at step {step}", flush=True)
                 if dist.is_initialized():
                     if use_cuda:
                         torch.cuda.synchronize()
@@ -316,24 +331,12 @@ def run(args) -> Dict[str, Any]:
                 generation, world, port = target["generation"], new_world, target["port"]
                 if world > 1:
                     init_process_group(rank, world, port, device)
-                    from ..parallel.ddp import broadcast_state
-
-                    st = torch.tensor([adapter.step_count, step], dtype=torch.int64,
-                                      device=device if use_cuda else "cpu")
-                    dist.broadcast(st, 0)
-                    broadcast_state(adapter.state_tensors(), 0)
-                    adapter.after_state_load()
-                    adapter.step_count = int(st[0])
                 adapter.bind(None)
+                step = sync_state(adapter, step, device)
                 watcher.adopted(generation)
-                loss = adapter.train_step()   # first step at the new world size completes the rescale
-                step += 1
-                dt = time.time() - t0
-                rescales.append({"generation": generation, "world": world, "seconds": dt,
-                                 "since_change": time.time() - target.get("observed_at", t0)})
-                print(f"[worker {rank}] rescaled to world={world} gen={generation} in {dt:.3f}s", flush=True)
-                watcher.report_rescale(rank, rescales[-1])
-                continue
+                pending_rescale = {"generation": generation, "world": world, "t0": t0,
+                                   "observed_at": target.get("observed_at", t0)}
+                continue    # back to the step boundary: every rank (joiners included) runs the same sequence
         # ---- timed region bookkeeping ----------------------------------------------------------------
         if step == args.warmup and args.steps > 0:
             if world > 1:
@@ -347,6 +350,17 @@ def run(args) -> Dict[str, Any]:
         loss = adapter.train_step()
         losses.append(loss)
         step += 1
+        if pending_rescale is not None:
+            # the first completed step at the new world size ends the rescale
+            now = time.time()
+            rec = {"generation": pending_rescale["generation"], "world": pending_rescale["world"],
+                   "seconds": now - pending_rescale["t0"], "since_change": now - pending_rescale["observed_at"]}
+            rescales.append(rec)
+            print(f"[worker {rank}] rescaled to world={rec['world']} gen={rec['generation']} in "
+                  f"{rec['seconds']:.3f}s", flush=True)
+            if watcher is not None:
+                watcher.report_rescale(rank, rec)
+            pending_rescale = None
         if not first_step_done:
             first_step_done = True
             trace["first_step_done"] = time.time()
