@@ -245,6 +245,7 @@ def main():
                    "params": res["describe"].get("params"), "gemm": res["describe"].get("gemm"),
                    "optimizer": "AdamW (fused flat sweep, fp32 master + bf16 compute copy), grad-clip 1.0",
                    "cuda_graph": res.get("cuda_graph"), "graph_error": res.get("graph_error"),
+                   "allreduce": res.get("allreduce"),
                    "l2": "working set (params+activations >> 126 MB L2) exceeds L2; inputs change every step",
                    "loss_first": res.get("loss_first"), "loss_last": res.get("loss_last")},
         "clocks": clocks,

@@ -57,6 +57,7 @@ class FlatParams:
                 mask[s.offset // ALIGN:(s.offset + s.padded) // ALIGN] = 1
         self.wd_mask = mask.to(self.device)
         self.by_name: Dict[str, ParamSpec] = {s.name: s for s in self.specs}
+        self.mc_base = 0
         self.init_parameters(seed)
 
     def init_parameters(self, seed: int = 0) -> None:
@@ -86,8 +87,25 @@ class FlatParams:
     def w32(self, name: str) -> torch.Tensor:
         return self._view(self.p32, name)
 
-    def grad(self, name: str) -> torch.Tensor:
+    def grad(self, name: str):
+        """Where gradient-producing kernels accumulate ``name``'s gradient: the local fp32 slice, or -- when a
+        symmetric buffer with an NVSwitch multicast alias is attached -- that alias (reduce-to-all-peers)."""
+        if self.mc_base:
+            from ..ops.functional import RawView
+
+            s = self.by_name[name]
+            return RawView(self.mc_base + 4 * s.offset, s.shape, torch.float32)
         return self._view(self.g32, name)
+
+    def local_grad(self, name: str) -> torch.Tensor:
+        return self._view(self.g32, name)
+
+    def attach_grad_buffer(self, buf: torch.Tensor, multicast_ptr: int = 0) -> None:
+        """Replace the gradient buffer (e.g. by a symmetric-memory allocation) and set its multicast alias."""
+        assert buf.numel() >= self.total and buf.dtype == torch.float32
+        self.g32 = buf[: self.total]
+        self.g32.zero_()
+        self.mc_base = int(multicast_ptr or 0)
 
     def range_of(self, first: str, last: str) -> Tuple[int, int]:
         a, b = self.by_name[first], self.by_name[last]

@@ -182,6 +182,13 @@ class GPT2Engine:
         F = self.F
         if self.backend == "tcgen05":
             key = (dw.shape[0], dw.shape[1])
+            if getattr(dw, "is_multicast", False):
+                # fused wgrad -> all-reduce: partial sums would each cross the switch, so no split-K; narrower tiles
+                # keep the SMs busy instead
+                tiles256 = ((dw.shape[0] + 127) // 128) * ((dw.shape[1] + 255) // 256)
+                F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=1,
+                       block_n=256 if tiles256 >= F.num_sms() else 128)
+                return
             bn = self._bn(dw.shape[0], dw.shape[1])
             sk = self.split_k.get(key)
             if sk is None:

@@ -4,6 +4,8 @@
 // grad-norm, casts.  All 16-byte vectorised; one HBM read + one write per tensor.
 // The reference operator ships no kernels; these serve the launched
 // DDP workers that BASELINE.json's samples/sec metric measures.
+#include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace aitj {
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ dres,
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, float* __restrict__ dxsum,
-                                                            int M) {
+                                                            int M, int mc) {
   // dxsum (optional, fp32[C]) += column sums of dx: dx is the gradient of the tensor that fed this LayerNorm,
   // i.e. of "linear output + bias + residual", so its column sum IS that linear's bias gradient -- for free.
   constexpr int C = V * 256;
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float s = 0.f;
       for (int w = 0; w < warps_per_block; ++w) s += red[w][c];
-      atomicAdd(dst + c, s);
+      grad_add_f32(dst + c, s, mc != 0);
     }
   }
 }
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __res
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __restrict__ tok,
                                                             const __nv_bfloat16* __restrict__ dx,
                                                             float* __restrict__ dwte, float* __restrict__ dwpe, int M,
-                                                            int T, int C) {
+                                                            int T, int C, int mc) {
   const int vec_per_row = C / 4;
   const size_t total = static_cast<size_t>(M) * vec_per_row;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -207,42 +209,43 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __res
     const int m = static_cast<int>(i / vec_per_row), c = static_cast<int>(i % vec_per_row) * 4;
     uint2 u = *reinterpret_cast<const uint2*>(dx + static_cast<size_t>(m) * C + c);
     float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
-    float* p = dwte + tok[m] * C + c;
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(f0.x), "f"(f0.y), "f"(f1.x), "f"(f1.y)
-                 : "memory");
-    if (dwpe) {
-      float* q = dwpe + static_cast<size_t>(m % T) * C + c;
-      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(q), "f"(f0.x), "f"(f0.y), "f"(f1.x), "f"(f1.y)
-                   : "memory");
-    }
+    grad_add_v4_f32(dwte + tok[m] * C + c, f0.x, f0.y, f1.x, f1.y, mc != 0);
+    if (dwpe) grad_add_v4_f32(dwpe + static_cast<size_t>(m % T) * C + c, f0.x, f0.y, f1.x, f1.y, mc != 0);
   }
 }
 
 // ------------------------------------------------------------------ softmax cross-entropy fwd+bwd
 // One block per row. The row (bf16, Vp padded columns, V real) is staged in smem once; the
 // kernel writes the per-row loss and overwrites the logits with dlogits = (p - onehot) * gscale.
-__global__ void __launch_bounds__(512) softmax_xent_kernel(__nv_bfloat16* __restrict__ logits,
-                                                           const int64_t* __restrict__ target,
-                                                           float* __restrict__ loss, int V, int Vp, float gscale) {
+__global__ void __launch_bounds__(512, 2) softmax_xent_kernel(__nv_bfloat16* __restrict__ logits,
+                                                              const int64_t* __restrict__ target,
+                                                              float* __restrict__ loss, int V, int Vp, float gscale) {
+  // Row staged once in shared memory (2 CTAs / SM so one row loads while the other computes); exp(x - max)
+  // overwrites the staged row (bf16), so each element costs one exp and the gradient pass is a scale.
   extern __shared__ uint4 srow4[];
   __shared__ float sred[16];
   __shared__ float sbcast[2];
-  __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(srow4);
   const int row = blockIdx.x;
   __nv_bfloat16* g = logits + static_cast<size_t>(row) * Vp;
-  const int nvec = Vp / 8;
+  const int nvec = Vp / 8, nfull = V / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int tgt = static_cast<int>(target[row]);
+  const bool valid = tgt >= 0 && tgt < V;
+  const float xt = valid ? __bfloat162float(g[tgt]) : 0.f;
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
     uint4 u = *reinterpret_cast<const uint4*>(g + i * 8);
     srow4[i] = u;
+    float f[8];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = unpack_bf16x2(w[j]);
-      const int c = i * 8 + 2 * j;
-      if (c < V) mx = fmaxf(mx, f.x);
-      if (c + 1 < V) mx = fmaxf(mx, f.y);
+    for (int j = 0; j < 4; ++j) { float2 t = unpack_bf16x2(w[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+    if (i < nfull) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (i * 8 + j < V) mx = fmaxf(mx, f[j]);
     }
   }
   mx = warp_max(mx);
@@ -256,17 +259,26 @@ __global__ void __launch_bounds__(512) softmax_xent_kernel(__nv_bfloat16* __rest
   __syncthreads();
   mx = sbcast[0];
   const float LOG2E = 1.4426950408889634f;
+  const float moff = mx * LOG2E;
   float sum = 0.f;
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
     uint4 u = srow4[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float e[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float2 f = unpack_bf16x2(w[j]);
-      const int c = i * 8 + 2 * j;
-      if (c < V) sum += exp2f((f.x - mx) * LOG2E);
-      if (c + 1 < V) sum += exp2f((f.y - mx) * LOG2E);
+      float2 t = unpack_bf16x2(w[j]);
+      e[2 * j] = exp2f(fmaf(t.x, LOG2E, -moff));
+      e[2 * j + 1] = exp2f(fmaf(t.y, LOG2E, -moff));
     }
+    if (i >= nfull) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (i * 8 + j >= V) e[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += e[j];
+    srow4[i] = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
+                          pack_bf16x2(e[6], e[7]));
   }
   sum = warp_sum(sum);
   __syncthreads();
@@ -279,31 +291,22 @@ __global__ void __launch_bounds__(512) softmax_xent_kernel(__nv_bfloat16* __rest
   }
   __syncthreads();
   sum = sbcast[1];
-  const int tgt = static_cast<int>(target[row]);
-  const bool valid = tgt >= 0 && tgt < V;
-  if (threadIdx.x == 0) {
-    float l = 0.f;
-    if (valid) l = -(__bfloat162float(srow[tgt]) - mx - logf(sum));
-    loss[row] = l;
-  }
+  if (threadIdx.x == 0) loss[row] = valid ? -(xt - mx - logf(sum)) : 0.f;
   const float inv = valid ? gscale / sum : 0.f;
   const float gs = valid ? gscale : 0.f;
+  const int tvec = valid ? (tgt >> 3) : -1;
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
     uint4 u = srow4[i];
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    uint4 o;
-    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+    const uint32_t e[4] = {u.x, u.y, u.z, u.w};
+    float p[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = unpack_bf16x2(w[j]);
-      const int c = i * 8 + 2 * j;
-      float p0 = c < V ? exp2f((f.x - mx) * LOG2E) * inv : 0.f;
-      float p1 = c + 1 < V ? exp2f((f.y - mx) * LOG2E) * inv : 0.f;
-      if (c == tgt) p0 -= gs;
-      if (c + 1 == tgt) p1 -= gs;
-      ow[j] = pack_bf16x2(p0, p1);
+    for (int j = 0; j < 4; ++j) { float2 t = unpack_bf16x2(e[j]); p[2 * j] = t.x * inv; p[2 * j + 1] = t.y * inv; }
+    if (i == tvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j == (tgt & 7)) p[j] -= gs;
     }
-    *reinterpret_cast<uint4*>(g + i * 8) = o;
+    *reinterpret_cast<uint4*>(g + i * 8) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
+                                                      pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
   }
 }
 
@@ -315,12 +318,15 @@ __global__ void __launch_bounds__(1024, 1) softmax_xent_reg_kernel(__nv_bfloat16
                                                                    float* __restrict__ loss, int V, int Vp,
                                                                    float gscale) {
   __shared__ float sred[32];
-  __shared__ float sbcast[3];
+  __shared__ float sbcast[2];
   const int row = blockIdx.x;
   __nv_bfloat16* g = logits + static_cast<size_t>(row) * Vp;
   const int nvec = Vp / 8;
+  const int nfull = V / 8;                       // vectors with all 8 columns < V
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tgt = static_cast<int>(target[row]);
+  const bool valid = tgt >= 0 && tgt < V;
+  const float xt = valid ? __bfloat162float(g[tgt]) : 0.f;   // read before anyone overwrites the row
   uint4 xv[NV];
   float mx = -INFINITY;
 #pragma unroll
@@ -328,13 +334,16 @@ __global__ void __launch_bounds__(1024, 1) softmax_xent_reg_kernel(__nv_bfloat16
     const int i = threadIdx.x + k * 1024;
     if (i < nvec) {
       xv[k] = *reinterpret_cast<const uint4*>(g + i * 8);
+      float f[8];
       const uint32_t w[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = unpack_bf16x2(w[j]);
-        const int c = i * 8 + 2 * j;
-        if (c < V) mx = fmaxf(mx, f.x);
-        if (c + 1 < V) mx = fmaxf(mx, f.y);
+      for (int j = 0; j < 4; ++j) { float2 t = unpack_bf16x2(w[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+      if (i < nfull) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (i * 8 + j < V) mx = fmaxf(mx, f[j]);
       }
     }
   }
@@ -349,30 +358,31 @@ __global__ void __launch_bounds__(1024, 1) softmax_xent_reg_kernel(__nv_bfloat16
   mx = sbcast[0];
   const float LOG2E = 1.4426950408889634f;
   const float moff = mx * LOG2E;
-  uint4 ev[NV];
-  float sum = 0.f, xt = 0.f;
+  float sum = 0.f;
+  // exp(x - max) replaces x in the registers (bf16): one exp per element, reused for the gradient
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int i = threadIdx.x + k * 1024;
     if (i < nvec) {
       const uint32_t w[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
-      uint32_t e[4];
+      float e[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 f = unpack_bf16x2(w[j]);
-        const int c = i * 8 + 2 * j;
-        float e0 = c < V ? exp2f(fmaf(f.x, LOG2E, -moff)) : 0.f;
-        float e1 = c + 1 < V ? exp2f(fmaf(f.y, LOG2E, -moff)) : 0.f;
-        if (c == tgt) xt = f.x;
-        if (c + 1 == tgt) xt = f.y;
-        sum += e0 + e1;
-        e[j] = pack_bf16x2(e0, e1);
+        float2 t = unpack_bf16x2(w[j]);
+        e[2 * j] = exp2f(fmaf(t.x, LOG2E, -moff));
+        e[2 * j + 1] = exp2f(fmaf(t.y, LOG2E, -moff));
       }
-      ev[k] = make_uint4(e[0], e[1], e[2], e[3]);
+      if (i >= nfull) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (i * 8 + j >= V) e[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += e[j];
+      xv[k] = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
+                         pack_bf16x2(e[6], e[7]));
     }
   }
   sum = warp_sum(sum);
-  xt = warp_sum(xt);
   __syncthreads();
   if (lane == 0) sred[warp] = sum;
   __syncthreads();
@@ -381,42 +391,32 @@ __global__ void __launch_bounds__(1024, 1) softmax_xent_reg_kernel(__nv_bfloat16
     if (lane == 0) sbcast[1] = t;
   }
   __syncthreads();
-  if (lane == 0) sred[warp] = xt;
-  __syncthreads();
-  if (warp == 0) {
-    float t = warp_sum(sred[lane]);
-    if (lane == 0) sbcast[2] = t;
-  }
-  __syncthreads();
   sum = sbcast[1];
-  const bool valid = tgt >= 0 && tgt < V;
-  if (threadIdx.x == 0) loss[row] = valid ? -(sbcast[2] - mx - logf(sum)) : 0.f;
+  if (threadIdx.x == 0) loss[row] = valid ? -(xt - mx - logf(sum)) : 0.f;
   const float inv = valid ? gscale / sum : 0.f;
   const float gs = valid ? gscale : 0.f;
+  const int tvec = valid ? (tgt >> 3) : -1;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int i = threadIdx.x + k * 1024;
     if (i < nvec) {
-      const uint32_t e[4] = {ev[k].x, ev[k].y, ev[k].z, ev[k].w};
-      uint4 o;
-      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      const uint32_t e[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
+      float p[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = unpack_bf16x2(e[j]);
-        const int c = i * 8 + 2 * j;
-        float p0 = f.x * inv, p1 = f.y * inv;
-        if (c == tgt) p0 -= gs;
-        if (c + 1 == tgt) p1 -= gs;
-        ow[j] = pack_bf16x2(p0, p1);
+      for (int j = 0; j < 4; ++j) { float2 t = unpack_bf16x2(e[j]); p[2 * j] = t.x * inv; p[2 * j + 1] = t.y * inv; }
+      if (i == tvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j == (tgt & 7)) p[j] -= gs;
       }
-      *reinterpret_cast<uint4*>(g + i * 8) = o;
+      *reinterpret_cast<uint4*>(g + i * 8) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
+                                                        pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
     }
   }
 }
 
 // ------------------------------------------------------------------ bias grad: db[N] += colsum(dy[M,N])
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
-                                                     int M, int N, int rows_per_block) {
+                                                     int M, int N, int rows_per_block, int mc) {
   // block = 32 column-groups(8 cols each => 256 cols) x 8 row lanes
   __shared__ float red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][c];
-    atomicAdd(db + blockIdx.x * 256 + c, s);
+    grad_add_f32(db + blockIdx.x * 256 + c, s, mc != 0);
   }
 }
 
@@ -605,13 +605,13 @@ int aitj_layernorm_fwd(const void* x, const void* gamma, const void* beta, void*
 }
 
 int aitj_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd,
-                       const void* dres, void* dx, void* dgamma, void* dbeta, void* dxsum, int M, int C,
+                       const void* dres, void* dx, void* dgamma, void* dbeta, void* dxsum, int M, int C, int mc,
                        void* stream) {
   if (C % 256 || C > 1024) return -1;
   const int blocks = min((M + 7) / 8, 148 * 2);
 #define LN_B(V) layernorm_bwd_kernel<V><<<blocks, 256, 0, S(stream)>>>(CBF(dy), CBF(x), CBF(gamma), \
     reinterpret_cast<const float*>(mean), reinterpret_cast<const float*>(rstd), CBF(dres), BF(dx), \
-    reinterpret_cast<float*>(dgamma), reinterpret_cast<float*>(dbeta), reinterpret_cast<float*>(dxsum), M)
+    reinterpret_cast<float*>(dgamma), reinterpret_cast<float*>(dbeta), reinterpret_cast<float*>(dxsum), M, mc)
   switch (C / 256) {
     case 1: LN_B(1); break; case 2: LN_B(2); break; case 3: LN_B(3); break; case 4: LN_B(4); break;
     default: return -1;
@@ -629,12 +629,13 @@ int aitj_embedding_fwd(const void* tok, const void* wte, const void* wpe, void* 
   return LAUNCH_OK();
 }
 
-int aitj_embedding_bwd(const void* tok, const void* dx, void* dwte, void* dwpe, int M, int T, int C, void* stream) {
+int aitj_embedding_bwd(const void* tok, const void* dx, void* dwte, void* dwpe, int M, int T, int C, int mc,
+                       void* stream) {
   if (C % 4) return -1;
   const size_t total = static_cast<size_t>(M) * (C / 4);
   embedding_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, S(stream)>>>(
       reinterpret_cast<const int64_t*>(tok), CBF(dx), reinterpret_cast<float*>(dwte), reinterpret_cast<float*>(dwpe),
-      M, T, C);
+      M, T, C, mc);
   return LAUNCH_OK();
 }
 
@@ -642,7 +643,10 @@ int aitj_softmax_xent(void* logits, const void* target, void* loss, int M, int V
                       void* stream) {
   if (Vp % 8 || V > Vp) return -1;
   {
-    const int nv = (Vp / 8 + 1023) / 1024;
+    // the register-resident variant measured slower on B200 (one 1024-thread CTA per SM cannot overlap a row's
+    // load with another row's math); kept for reference, selected only with AITJ_XENT_REG=1
+    static const bool use_reg = getenv("AITJ_XENT_REG") != nullptr;
+    const int nv = use_reg ? (Vp / 8 + 1023) / 1024 : 99;
 #define XENT_REG(NV) softmax_xent_reg_kernel<NV><<<M, 1024, 0, S(stream)>>>(BF(logits), \
     reinterpret_cast<const int64_t*>(target), reinterpret_cast<float*>(loss), V, Vp, gscale); return LAUNCH_OK()
     switch (nv) {
@@ -664,13 +668,13 @@ int aitj_softmax_xent(void* logits, const void* target, void* loss, int M, int V
   return LAUNCH_OK();
 }
 
-int aitj_colsum(const void* dy, void* db, int M, int N, void* stream) {
+int aitj_colsum(const void* dy, void* db, int M, int N, int mc, void* stream) {
   if (N % 8) return -1;
   const int col_blocks = (N + 255) / 256;
   int rows_per_block = 512;
   while (rows_per_block > 32 && col_blocks * ((M + rows_per_block - 1) / rows_per_block) < 148 * 4) rows_per_block /= 2;
   dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
-  colsum_kernel<<<grid, 256, 0, S(stream)>>>(CBF(dy), reinterpret_cast<float*>(db), M, N, rows_per_block);
+  colsum_kernel<<<grid, 256, 0, S(stream)>>>(CBF(dy), reinterpret_cast<float*>(db), M, N, rows_per_block, mc);
   return LAUNCH_OK();
 }
 

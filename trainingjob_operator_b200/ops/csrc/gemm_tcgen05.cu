@@ -8,8 +8,9 @@
 //     b_mn == 0 : B stored [N,K] row-major                               -> forward  (x @ W^T)
 //     b_mn == 1 : B stored [K,N] row-major                               -> dgrad    (dy @ W), wgrad
 //
-// Warp roles (192 threads, 1 CTA / SM):  warp0 = TMA producer, warp1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane group = warp_id % 4).
+// Warp roles (320 threads, 1 CTA / SM):  warp0 = TMA producer, warp1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane group = warp_id % 4; warps 2-5 drain the left half of the tile's columns,
+// warps 6-9 the right half, so every SM sub-partition has two epilogue warps to hide TMEM/LDG latency).
 //
 // The reference operator has no GPU code; this kernel belongs to the launched
 // workers' training step that BASELINE.json measures (samples/sec).
@@ -20,7 +21,8 @@ namespace aitj {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 per TMEM lane group)
+constexpr int kEpiWarps = 8;
 
 enum : int {
   EPI_BIAS = 1,       // + bias[N]
@@ -30,7 +32,7 @@ enum : int {
   EPI_DGELU = 16,     // * gelu'(aux[M,ldc])
   EPI_OUT_F32 = 32,   // out is fp32 (plain store)
   EPI_ACCUM = 64,     // out is fp32, red.global.add (split-K / grad accumulation)
-  EPI_BIAS_ROW = 128  // reserved
+  EPI_MC = 128        // with EPI_ACCUM: `out` is an NVSwitch multicast address; reduce with multimem.red (GEMM + all-reduce in one kernel)
 };
 
 struct GemmArgs {
@@ -69,54 +71,23 @@ __device__ __forceinline__ WorkItem decode_work(const GemmArgs& a, int w) {
 }
 
 // ---- epilogue helpers -----------------------------------------------------------------------
-// Apply the fused epilogue to 8 consecutive columns of one row (x[] are the fp32 accumulators).
-__device__ __forceinline__ void epilogue_math8(const GemmArgs& a, float* x, size_t off, int col, bool row_ok,
-                                               uint4& pre_out) {
-  const int flags = a.flags;
-  if (flags & EPI_BIAS) {
-    uint4 b = *reinterpret_cast<const uint4*>(a.bias + col);
-    float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
-    x[0] += b0.x; x[1] += b0.y; x[2] += b1.x; x[3] += b1.y;
-    x[4] += b2.x; x[5] += b2.y; x[6] += b3.x; x[7] += b3.y;
-  }
-  if (flags & EPI_SAVE_PRE) {
-    pre_out.x = pack_bf16x2(x[0], x[1]); pre_out.y = pack_bf16x2(x[2], x[3]);
-    pre_out.z = pack_bf16x2(x[4], x[5]); pre_out.w = pack_bf16x2(x[6], x[7]);
-  }
-  if (flags & EPI_GELU) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
-  }
-  if ((flags & EPI_DGELU) && row_ok) {
-    uint4 h = *reinterpret_cast<const uint4*>(a.aux + off);
-    float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y), h2 = unpack_bf16x2(h.z), h3 = unpack_bf16x2(h.w);
-    x[0] *= gelu_tanh_grad(h0.x); x[1] *= gelu_tanh_grad(h0.y);
-    x[2] *= gelu_tanh_grad(h1.x); x[3] *= gelu_tanh_grad(h1.y);
-    x[4] *= gelu_tanh_grad(h2.x); x[5] *= gelu_tanh_grad(h2.y);
-    x[6] *= gelu_tanh_grad(h3.x); x[7] *= gelu_tanh_grad(h3.y);
-  }
-  if ((flags & EPI_RESIDUAL) && row_ok) {
-    uint4 h = *reinterpret_cast<const uint4*>(a.residual + off);
-    float2 h0 = unpack_bf16x2(h.x), h1 = unpack_bf16x2(h.y), h2 = unpack_bf16x2(h.z), h3 = unpack_bf16x2(h.w);
-    x[0] += h0.x; x[1] += h0.y; x[2] += h1.x; x[3] += h1.y;
-    x[4] += h2.x; x[5] += h2.y; x[6] += h3.x; x[7] += h3.y;
-  }
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* x) {
+  uint4 o;
+  o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+  o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+  return o;
 }
 
-// One warp's staging buffers: 2 x (32 rows x 128 B), written in the TMA 128B-swizzle pattern
-// (16-byte chunk c of row r lives at chunk c ^ (r & 7)), so the st.shared.v4 of a quarter warp hit
-// 32 distinct banks and the tile leaves through one coalesced TMA store (or reduce-add) per chunk.
-struct StageCtx {
-  uint8_t* buf;   // this warp's 8 KB
-  int sel;        // next buffer
-};
-template <int kMaxPending = 1>
-__device__ __forceinline__ uint8_t* stage_acquire(StageCtx& sc, int lane) {
-  if (lane == 0) tma_store_wait_read<kMaxPending>();
+// One warp's staging buffer: 32 rows x 128 B, written in the TMA 128B-swizzle pattern (16-byte chunk c of
+// row r lives at chunk c ^ (r & 7)), so the st.shared.v4 of a quarter warp hit 32 distinct banks and the tile
+// leaves through one coalesced TMA store (or fp32 reduce-add) per chunk.
+__device__ __forceinline__ void stage_acquire(int lane) {
+  if (lane == 0) tma_store_wait_read<0>();
   __syncwarp();
-  uint8_t* b = sc.buf + sc.sel * 4096;
-  sc.sel ^= 1;
-  return b;
 }
 __device__ __forceinline__ void stage_write16(uint8_t* b, int lane, int chunk, const uint4& v) {
   *reinterpret_cast<uint4*>(b + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
@@ -132,67 +103,130 @@ __device__ __forceinline__ void stage_commit(const CUtensorMap* tm, uint8_t* b, 
   }
 }
 
-// Drain one accumulator tile slice (32 rows x kBlockN columns) owned by this warp.
-template <int kBlockN>
+// Drain this warp's share of one accumulator tile: 32 rows x kCols columns starting at tile column c_begin.
+// `sbias` holds the tile's bias row (bf16, staged once per tile by the epilogue warps).
+template <int kCols>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
-                                              uint32_t tmem_acc, int row0, int n0, StageCtx& sc, int lane) {
+                                              uint32_t tmem_acc, int row0, int n0, int c_begin,
+                                              const __nv_bfloat16* sbias, uint8_t* sbuf, int lane) {
   const int flags = a.flags;
   const int row = row0 + lane;
   const bool row_ok = row < a.M;
-  if (flags & (EPI_OUT_F32 | EPI_ACCUM)) {
-    // fp32 output: 32 columns (128 B) per staged chunk; raw accumulators (+bias)
+  if (flags & EPI_MC) {
+    // fused GEMM -> all-reduce: every accumulator goes straight from registers into ALL peers' gradient buffers
+    // through the switch (multimem.red); no staging, no separate collective kernel
+    float* obase = reinterpret_cast<float*>(a.out) + static_cast<size_t>(row) * a.ldc;
 #pragma unroll 1
-    for (int c = 0; c < kBlockN / 32; ++c) {
-      const int col0 = n0 + c * 32;
+    for (int c = 0; c < kCols / 32; ++c) {
+      const int col0 = n0 + c_begin + c * 32;
       if (col0 >= a.N) break;
       uint32_t r[32];
-      tmem_ld_32x32(tmem_acc + c * 32, r);
+      tmem_ld_32x32(tmem_acc + c_begin + c * 32, r);
       tmem_ld_wait();
-      uint8_t* b = stage_acquire(sc, lane);
+      if (row_ok) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint4 v = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
-        stage_write16(b, lane, q, v);
+        for (int q = 0; q < 8; ++q) {
+          if (col0 + q * 4 < a.N)
+            mc_red_add_v4_f32(obase + col0 + q * 4, __uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                              __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+        }
       }
-      stage_commit(tm_out, b, col0, row0, lane, (flags & EPI_ACCUM) != 0);
+    }
+    return;
+  }
+  if (flags & (EPI_OUT_F32 | EPI_ACCUM)) {
+    // fp32 output: 32 columns (128 B) per staged chunk; raw accumulators
+#pragma unroll 1
+    for (int c = 0; c < kCols / 32; ++c) {
+      const int col0 = n0 + c_begin + c * 32;
+      if (col0 >= a.N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + c_begin + c * 32, r);
+      tmem_ld_wait();
+      stage_acquire(lane);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) stage_write16(sbuf, lane, q, make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]));
+      stage_commit(tm_out, sbuf, col0, row0, lane, (flags & EPI_ACCUM) != 0);
     }
     return;
   }
   // bf16 output: 64 columns (128 B) per staged chunk
+  const bool need_side = (flags & (EPI_DGELU | EPI_RESIDUAL)) != 0;
+  const __nv_bfloat16* side = (flags & EPI_DGELU) ? a.aux : a.residual;
 #pragma unroll 1
-  for (int c = 0; c < kBlockN / 64; ++c) {
-    const int col0 = n0 + c * 64;
+  for (int c = 0; c < kCols / 64; ++c) {
+    const int ct = c_begin + c * 64;        // column inside the tile
+    const int col0 = n0 + ct;
     if (col0 >= a.N) break;
-    // with SAVE_PRE two stores leave per chunk, so both buffers must be drained before reuse
-    uint8_t* b = (flags & EPI_SAVE_PRE) ? stage_acquire<0>(sc, lane) : stage_acquire<1>(sc, lane);
-    uint8_t* bpre = nullptr;
-    if (flags & EPI_SAVE_PRE) bpre = stage_acquire<0>(sc, lane);
+    // issue the row-scattered side loads (residual / pre-GELU) and both TMEM loads before waiting on anything
+    uint4 sv[8];
+    if (need_side && row_ok) {
+      const __nv_bfloat16* sp = side + static_cast<size_t>(row) * a.ldc + col0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int colh = col0 + h * 32;
-      if (colh >= a.N) break;
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_acc + c * 64 + h * 32, r);
-      tmem_ld_wait();
+      for (int q = 0; q < 8; ++q)
+        sv[q] = (col0 + q * 8 < a.N) ? *reinterpret_cast<const uint4*>(sp + q * 8) : make_uint4(0, 0, 0, 0);
+    } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int col = colh + q * 8;
-        if (col >= a.N) break;
-        float x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(r[q * 8 + j]);
-        uint4 pre;
-        epilogue_math8(a, x, static_cast<size_t>(row) * a.ldc + col, col, row_ok, pre);
-        uint4 o;
-        o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-        o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-        stage_write16(b, lane, h * 4 + q, o);
-        if (flags & EPI_SAVE_PRE) stage_write16(bpre, lane, h * 4 + q, pre);
-      }
+      for (int q = 0; q < 8; ++q) sv[q] = make_uint4(0, 0, 0, 0);
     }
-    if (flags & EPI_SAVE_PRE) stage_commit(tm_aux, bpre, col0, row0, lane, false);
-    stage_commit(tm_out, b, col0, row0, lane, false);
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(tmem_acc + ct, r0);
+    tmem_ld_32x32(tmem_acc + ct + 32, r1);
+    tmem_ld_wait();
+    uint4 outv[8], prev[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(q < 4 ? r0[q * 8 + j] : r1[(q - 4) * 8 + j]);
+      if (flags & EPI_BIAS) {
+        float bv[8];
+        unpack8(*reinterpret_cast<const uint4*>(sbias + ct + q * 8), bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += bv[j];
+      }
+      if (flags & EPI_SAVE_PRE) prev[q] = pack8(x);
+      if (flags & EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
+      }
+      if (flags & EPI_DGELU) {
+        float h[8];
+        unpack8(sv[q], h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] *= gelu_tanh_grad(h[j]);
+      }
+      if (flags & EPI_RESIDUAL) {
+        float h[8];
+        unpack8(sv[q], h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += h[j];
+      }
+      outv[q] = pack8(x);
+    }
+    if (flags & EPI_SAVE_PRE) {
+      stage_acquire(lane);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) stage_write16(sbuf, lane, q, prev[q]);
+      stage_commit(tm_aux, sbuf, col0, row0, lane, false);
+    }
+    stage_acquire(lane);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) stage_write16(sbuf, lane, q, outv[q]);
+    stage_commit(tm_out, sbuf, col0, row0, lane, false);
   }
+}
+
+// Epilogue warps stage the tile's bias row (kBlockN bf16) into shared memory; 256 threads, named barrier 1.
+template <int kBlockN>
+__device__ __forceinline__ void stage_bias(const GemmArgs& a, __nv_bfloat16* sbias, int n0, int epi_tid) {
+  if (a.flags & EPI_BIAS) {
+    if (epi_tid < kBlockN) {
+      const int col = n0 + epi_tid;
+      sbias[epi_tid] = col < a.N ? a.bias[col] : __float2bfloat16(0.f);
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 template <int kBlockN, bool kAMN, bool kBMN>
@@ -211,9 +245,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  constexpr int kStagingBytes = 4 * 2 * 4096;  // 4 epilogue warps x double-buffered 32x128B chunk
+  constexpr int kStagingBytes = kEpiWarps * 4096;  // one 32x128B chunk per epilogue warp
   uint8_t* staging = smem + kStages * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  __nv_bfloat16* sbias = reinterpret_cast<__nv_bfloat16*>(staging + kStagingBytes);   // 2 x 256 bf16
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes + 1024);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -233,7 +268,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -308,21 +343,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int epi_tid = threadIdx.x - 64;
+    uint8_t* sbuf = staging + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
-    StageCtx sc;
-    sc.buf = staging + (warp - 2) * 8192;
-    sc.sel = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const WorkItem wi = decode_work(args, w);
+      stage_bias<kBlockN>(args, sbias + acc * 256, wi.n_blk * kBlockN, epi_tid);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (wi.kb1 > wi.kb0) {
-        epilogue_tile<kBlockN>(args, &tmap_out, &tmap_aux,
-                               tmem_base + acc * kBlockN + (static_cast<uint32_t>(lg * 32) << 16),
-                               wi.m_blk * BLOCK_M + lg * 32, wi.n_blk * kBlockN, sc, lane);
+        epilogue_tile<kBlockN / 2>(args, &tmap_out, &tmap_aux,
+                                   tmem_base + acc * kBlockN + (static_cast<uint32_t>(lg * 32) << 16),
+                                   wi.m_blk * BLOCK_M + lg * 32, wi.n_blk * kBlockN, half * (kBlockN / 2),
+                                   sbias + acc * 256, sbuf, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -359,9 +396,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  constexpr int kStagingBytes = 4 * 2 * 4096;
+  constexpr int kStagingBytes = kEpiWarps * 4096;
   uint8_t* staging = smem + kStages * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  __nv_bfloat16* sbias = reinterpret_cast<__nv_bfloat16*>(staging + kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes + 1024);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -383,7 +421,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);   // per CTA, multicast commit
-      mbar_init(&tmem_empty[i], 8);  // leader's copy: 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);  // leader's copy: 8 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -463,22 +501,23 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    // ------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int epi_tid = threadIdx.x - 64;
+    uint8_t* sbuf = staging + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
-    StageCtx sc;
-    sc.buf = staging + (warp - 2) * 8192;
-    sc.sel = 0;
     for (int w = cluster_id; w < num_work; w += num_clusters) {
       const WorkItem wi = decode_work(args, w);
+      stage_bias<kPairN>(args, sbias + acc * 256, wi.n_blk * kPairN, epi_tid);
       mbar_wait_cluster(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (wi.kb1 > wi.kb0) {
-        epilogue_tile<kPairN>(args, &tmap_out, &tmap_aux,
-                              tmem_base + acc * kPairN + (static_cast<uint32_t>(lg * 32) << 16),
-                              wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32, wi.n_blk * kPairN, sc,
-                              lane);
+        epilogue_tile<kPairN / 2>(args, &tmap_out, &tmap_aux,
+                                  tmem_base + acc * kPairN + (static_cast<uint32_t>(lg * 32) << 16),
+                                  wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32, wi.n_blk * kPairN,
+                                  half * (kPairN / 2), sbias + acc * 256, sbuf, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -541,7 +580,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                        const GemmArgs& args, int max_ctas, cudaStream_t stream) {
   constexpr int kStages = (kBlockN == 256) ? 4 : 6;
   constexpr int kStageBytes = BLOCK_M * BLOCK_K * 2 + kBlockN * BLOCK_K * 2;
-  constexpr int kSmem = kStages * kStageBytes + 4 * 2 * 4096 + 1024 + 256;
+  constexpr int kSmem = kStages * kStageBytes + kEpiWarps * 4096 + 1024 + 1024 + 256;
   static bool configured = false;
   auto kern = gemm_bf16_tcgen05_kernel<kBlockN, kAMN, kBMN>;
   if (!configured) {
@@ -559,7 +598,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 template <bool kAMN, bool kBMN>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                             const GemmArgs& args, int max_ctas, cudaStream_t stream) {
-  constexpr int kSmem = 6 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 4 * 2 * 4096 + 1024 + 256;
+  constexpr int kSmem = 6 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + kEpiWarps * 4096 + 1024 + 1024 + 256;
   static bool configured = false;
   auto kern = gemm_bf16_2cta_kernel<kAMN, kBMN>;
   if (!configured) {
@@ -590,6 +629,7 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   if ((N & 7) || (ldc & 7) || (lda & 7) || (ldb & 7)) return -1;
   if ((reinterpret_cast<uintptr_t>(out) & 15) || ((flags & EPI_SAVE_PRE) && (reinterpret_cast<uintptr_t>(aux) & 15))) return -4;
   if (split_k > 1 && !(flags & EPI_ACCUM)) return -2;
+  if ((flags & EPI_MC) && !(flags & EPI_ACCUM)) return -5;
   const bool pair = block_n == 512;
   if (pair) block_n = 256;
   if (block_n == 0) block_n = (N > 128) ? 256 : 128;
@@ -620,8 +660,12 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   if (rc) return rc - 1000;
   CUtensorMap to, tx;
   const bool out_f32 = (flags & (EPI_OUT_F32 | EPI_ACCUM)) != 0;
-  rc = encode_2d(&to, out, N, M, ldc, out_f32 ? 32 : 64, 32, out_f32);
-  if (rc) return rc - 2000;
+  if (flags & EPI_MC) {
+    to = ta;   // the multicast path stores from registers; the tensor map is never dereferenced
+  } else {
+    rc = encode_2d(&to, out, N, M, ldc, out_f32 ? 32 : 64, 32, out_f32);
+    if (rc) return rc - 2000;
+  }
   tx = to;
   if (flags & EPI_SAVE_PRE) {
     rc = encode_2d(&tx, aux, N, M, ldc, 64, 32, false);

@@ -223,6 +223,27 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+// ---------------------------------------------------------------- NVSwitch multicast (NVLS) reductions
+// `p` is an address inside a multicast mapping: the NVSwitch applies the add to the same offset of every
+// peer's buffer.  Gradient producers use these instead of local atomics when the gradient buffer is symmetric,
+// which turns "compute then all-reduce" into one kernel (the reduction rides on the producer's stores).
+__device__ __forceinline__ void mc_red_add_f32(float* p, float v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_red_add_v4_f32(float* p, float a, float b, float c, float d) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void grad_add_f32(float* p, float v, bool mc) {
+  if (mc) mc_red_add_f32(p, v);
+  else atomicAdd(p, v);
+}
+__device__ __forceinline__ void grad_add_v4_f32(float* p, float a, float b, float c, float d, bool mc) {
+  if (mc) mc_red_add_v4_f32(p, a, b, c, d);
+  else asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- misc math / packing
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

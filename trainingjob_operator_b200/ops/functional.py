@@ -17,6 +17,33 @@ EPI_SAVE_PRE = 8
 EPI_DGELU = 16
 EPI_OUT_F32 = 32
 EPI_ACCUM = 64
+EPI_MC = 128
+
+
+class RawView:
+    """A (pointer, shape, dtype) triple standing in for a tensor: used to aim gradient-producing kernels at the
+    NVSwitch *multicast* alias of a symmetric buffer (an address torch has no tensor for)."""
+
+    is_multicast = True
+
+    def __init__(self, ptr: int, shape, dtype, row_stride=None):
+        self._ptr = int(ptr)
+        self.shape = tuple(shape)
+        self.dtype = dtype
+        self._rs = row_stride if row_stride is not None else (self.shape[-1] if len(self.shape) > 1 else 1)
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def stride(self, i: int) -> int:
+        return self._rs if (i == 0 and len(self.shape) > 1) else 1
+
+    def dim(self) -> int:
+        return len(self.shape)
+
+
+def _is_mc(t) -> int:
+    return 1 if getattr(t, "is_multicast", False) else 0
 
 _NUM_SMS = None
 
@@ -73,6 +100,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
         assert aux is not None and aux.stride(0) == out.stride(0)
     if out.dtype == torch.float32:
         flags |= EPI_ACCUM if accumulate else EPI_OUT_F32
+        if _is_mc(out):
+            assert accumulate, "multicast outputs are reduce-only"
+            flags |= EPI_MC
     else:
         assert out.dtype == torch.bfloat16 and not accumulate
     lib.call("aitj_gemm_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
@@ -104,7 +134,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dxsum=
     which is the bias gradient of the linear layer that produced this LayerNorm's input."""
     M, C = x.shape
     lib.call("aitj_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-             _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dxsum), M, C, _stream())
+             _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dxsum), M, C, _is_mc(dgamma),
+             _stream())
     return dx
 
 
@@ -116,7 +147,8 @@ def embedding_fwd(tok, wte, wpe, out, T):
 
 def embedding_bwd(tok, dx, dwte, dwpe, T):
     M, C = dx.shape
-    lib.call("aitj_embedding_bwd", tok.data_ptr(), dx.data_ptr(), dwte.data_ptr(), _ptr(dwpe), M, T, C, _stream())
+    lib.call("aitj_embedding_bwd", tok.data_ptr(), dx.data_ptr(), dwte.data_ptr(), _ptr(dwpe), M, T, C, _is_mc(dwte),
+             _stream())
 
 
 def softmax_xent(logits, target, loss, V, gscale):
@@ -128,7 +160,7 @@ def softmax_xent(logits, target, loss, V, gscale):
 
 def colsum(dy, db):
     M, N = dy.shape
-    lib.call("aitj_colsum", dy.data_ptr(), db.data_ptr(), M, N, _stream())
+    lib.call("aitj_colsum", dy.data_ptr(), db.data_ptr(), M, N, _is_mc(db), _stream())
 
 
 def sumsq(g, out):

@@ -60,8 +60,23 @@ class EngineTrainer:
         self.step_count = 0
         self.cuda = engine.dev.type == "cuda"
         backend = allreduce or os.environ.get("AITJ_ALLREDUCE", "nccl")
-        self.reducer = BucketAllReducer(engine.params.g32, engine.grad_buckets(), group, backend) \
-            if self.world > 1 else None
+        self.allreduce_backend = backend if self.world > 1 else "none"
+        self.symm = None
+        self.reducer = None
+        if self.world > 1 and backend == "mc" and self.cuda:
+            # fused GEMM -> all-reduce: gradients are reduced through the NVSwitch multicast alias by the kernels
+            # that produce them (parallel/symm.py); no gradient collective is launched at all
+            from ..parallel.symm import SymmetricGradBuffer
+
+            self.symm = SymmetricGradBuffer(engine.params.total, engine.dev, group)
+            if self.symm.available:
+                engine.params.attach_grad_buffer(self.symm.tensor, self.symm.multicast_ptr)
+            else:
+                self.allreduce_backend = f"nccl (mc unavailable: {self.symm.reason})"
+                self.symm = None
+                backend = "nccl"
+        if self.world > 1 and self.symm is None:
+            self.reducer = BucketAllReducer(engine.params.g32, engine.grad_buckets(), group, backend)
         engine.grad_hook = self.reducer.hook if self.reducer else None
         self.use_graph = use_graph and self.cuda
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -75,7 +90,11 @@ class EngineTrainer:
     def _device_step(self) -> None:
         e = self.engine
         e.forward()
+        if self.symm is not None:
+            self.symm.barrier()   # every peer finished zeroing its gradients (previous optimizer sweep)
         e.backward()
+        if self.symm is not None:
+            self.symm.barrier()   # every peer's multimem reductions of this step have landed
         if self.reducer:
             self.reducer.wait()
         e.optimizer_step(lr=self.lr, step=max(1, self.step_count), weight_decay=self.weight_decay,

@@ -398,6 +398,7 @@ def run(args) -> Dict[str, Any]:
             "describe": adapter.describe,
             "cuda_graph": bool(getattr(getattr(adapter, "trainer", None), "graph", None)),
             "graph_error": getattr(getattr(adapter, "trainer", None), "graph_error", None),
+            "allreduce": getattr(getattr(adapter, "trainer", None), "allreduce_backend", "nccl" if world > 1 else "none"),
         })
     if rank == 0 and args.result:
         os.makedirs(os.path.dirname(os.path.abspath(args.result)), exist_ok=True)
