@@ -1,0 +1,102 @@
+"""Worker-side pieces that run on CPU: flat parameter storage, bucketed all-reduce over gloo (2 processes),
+LR schedule, env parsing, the flat DDP wrapper (multi-process paths use gloo, world_size>1)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import torch
+
+from trainingjob_operator_b200.models.flat_params import FlatParams, ParamSpec
+from trainingjob_operator_b200.models.gpt2 import GPT2Config, flops_per_token, gpt2_param_specs
+from trainingjob_operator_b200.runtime.elastic import rendezvous_from_env
+from trainingjob_operator_b200.runtime.trainer import SyntheticTokens, cosine_lr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_flat_params_layout_and_masks():
+    fp = FlatParams([ParamSpec("w", (10, 30), True), ParamSpec("b", (30,), False, "zeros"),
+                     ParamSpec("g", (5,), False, "ones")], "cpu")
+    assert fp.total % 256 == 0 and fp.by_name["b"].offset == 512 and fp.by_name["g"].offset == 768
+    assert fp.w32("g").tolist() == [1.0] * 5 and float(fp.w32("b").abs().sum()) == 0
+    assert fp.wd_mask.tolist() == [1, 1, 0, 0]
+    assert fp.num_parameters() == 335
+    assert torch.equal(fp.w16("w").float(), fp.w32("w").bfloat16().float())
+    a, b = fp.range_of("w", "b")
+    assert (a, b) == (0, 768)
+    fp.grad("w").fill_(2.0)
+    assert float(fp.g32[:300].sum()) == 600.0
+    st = fp.state_dict()
+    fp2 = FlatParams([ParamSpec("w", (10, 30), True), ParamSpec("b", (30,), False, "zeros"),
+                      ParamSpec("g", (5,), False, "ones")], "cpu", seed=9)
+    fp2.load_state_dict(st)
+    assert torch.equal(fp2.p32, fp.p32)
+
+
+def test_gpt2_small_parameter_count_and_flops():
+    cfg = GPT2Config.small()
+    n = 0
+    for s in gpt2_param_specs(cfg):
+        k = 1
+        for d in s.shape:
+            k *= d
+        n += k
+    assert cfg.padded_vocab == 50304
+    assert n == 124_475_904                       # 124M (padded vocab), tied lm_head
+    assert 7.5e8 < flops_per_token(cfg, 1024) < 9.5e8
+
+
+def test_lr_schedule_and_synthetic_tokens(monkeypatch):
+    assert cosine_lr(0, 1.0, warmup=10) == 0.1 and cosine_lr(9, 1.0, warmup=10) == 1.0
+    assert abs(cosine_lr(10_000, 1.0, warmup=10, total=10_000) - 0.1) < 1e-9
+    d = SyntheticTokens(100, 2, 8, n_batches=2, pin=False)
+    tok, tgt = d.next()
+    assert tok.shape == (16,) and torch.equal(tgt, torch.roll(tok, -1)) and d.bytes_per_step == 2 * 16 * 8
+    monkeypatch.setenv("WORLD_SIZE", "4"); monkeypatch.setenv("MASTER_PORT", "1234")
+    monkeypatch.setenv("AITJ_RENDEZVOUS_GENERATION", "3")
+    assert rendezvous_from_env() == {"world": 4, "port": 1234, "generation": 3}
+
+
+def test_bucket_allreduce_and_flat_ddp_over_gloo():
+    script = textwrap.dedent("""
+        import os, sys, torch, torch.distributed as dist
+        sys.path.insert(0, %r)
+        from trainingjob_operator_b200.parallel.ddp import BucketAllReducer, broadcast_state
+        from trainingjob_operator_b200.parallel.flat_ddp import FlatDDP
+        from trainingjob_operator_b200.models.mnist_cnn import MLP
+        rank = int(os.environ["RANK"]); dist.init_process_group("gloo")
+        flat = torch.full((1024,), float(rank + 1))
+        r = BucketAllReducer(flat, [("a", 512, 1024), ("b", 256, 512), ("c", 0, 256)], backend="gloo", min_bucket_bytes=0)
+        for name in ("a", "b", "c"):
+            r.hook(name)
+        r.wait()
+        assert torch.all(flat == 3.0), flat[:4]
+        torch.manual_seed(0)
+        m = MLP()
+        ddp = FlatDDP(m, bucket_bytes=1 << 12, backend="gloo", lr=0.1, optimizer="sgd")
+        broadcast_state(ddp.state_tensors(), 0)
+        torch.manual_seed(10 + rank)
+        x, y = torch.randn(8, 64), torch.randint(0, 10, (8,))
+        before = ddp.p32.clone()
+        loss = torch.nn.functional.cross_entropy(m(x), y); loss.backward()
+        ddp.finish_backward()
+        g = ddp.g32.clone()
+        ddp.step()
+        gl = [torch.zeros_like(g) for _ in range(2)]
+        dist.all_gather(gl, g)
+        assert torch.allclose(gl[0], gl[1])                 # both ranks hold the same (summed) gradient
+        pl = [torch.zeros_like(ddp.p32) for _ in range(2)]
+        dist.all_gather(pl, ddp.p32)
+        assert torch.allclose(pl[0], pl[1]) and not torch.allclose(pl[0], before)
+        assert float(ddp.g32.abs().sum()) == 0.0            # grads zeroed by the optimizer sweep
+        print("OK", rank)
+    """ % ROOT)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29733")
+        procs.append(subprocess.Popen([sys.executable, "-c", script], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("OK" in o for o in outs)
