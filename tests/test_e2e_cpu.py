@@ -218,7 +218,13 @@ def test_delete_job_kills_processes_and_gc_sweeps_orphans(lc):
                           "ownerReferences": [{"apiVersion": C.API_VERSION, "kind": C.KIND, "name": "ghost",
                                                "uid": "gone", "controller": True}]},
              "spec": {"containers": [{"name": "aitj-x", "command": ["sleep", "60"]}]}}
-    lc.clientset.core_v1().pods("default").create(ghost)
+    # the API server refuses dependents of a missing owner (eager GC), so plant the orphan below it
+    import json as _json
+    ghost["metadata"].update({"namespace": "default", "uid": "ghost-uid", "creationTimestamp": "2026-01-01T00:00:00Z"})
+    lc.api._store.create("Pod", "default", "ghost-trainer-0", "ghost-uid", _json.dumps(ghost).encode(),
+                         ghost["metadata"]["labels"], ["gone"])
+    with pytest.raises(APIError):
+        lc.clientset.core_v1().pods("default").create(dict(ghost, metadata=dict(ghost["metadata"], name="ghost2")))
     wait_until(lambda: not [p for p in lc.pods() if p["metadata"]["name"] == "ghost-trainer-0"], timeout=15)
 
 

@@ -248,7 +248,7 @@ class NodeAgent:
     def _on_pod_delete(self, obj) -> None:
         pod = obj.obj if isinstance(obj, DeletedFinalStateUnknown) else obj
         self.queue.add(M.key_of(pod))
-        self._kick_pending()
+        self._release_gpus(M.uid_of(pod))
 
     def _kick_pending(self) -> None:
         for pod in self.pod_lister.list():
@@ -316,7 +316,9 @@ class NodeAgent:
         except APIError:
             self._kill_pod_processes(key, signal.SIGKILL)
             with self._lock:
-                self._states.pop(key, None)
+                gone = self._states.pop(key, None)
+            if gone is not None:
+                self._release_gpus(gone.uid)
             return
         st = self._states.get(key)
         if st is not None and st.uid != M.uid_of(pod):
@@ -362,7 +364,8 @@ class NodeAgent:
                 if g.strip():
                     busy.add(int(g))
         with self._lock:
-            # drop allocations whose pod is finished or gone (seen by the cache), keep fresh binds
+            # drop allocations whose pod is finished or gone (seen by the cache); keep binds the cache has not
+            # caught up with yet (younger than 1 s)
             for g, (uid, at) in list(self._gpu_owner.items()):
                 if uid not in live_uids and time.monotonic() - at > 1.0:
                     del self._gpu_owner[g]
@@ -414,7 +417,15 @@ class NodeAgent:
                     self._gpu_owner.pop(g, None)
                 raise
 
+    def _release_gpus(self, uid: str) -> None:
+        with self._lock:
+            for g in [g for g, (u, _t) in self._gpu_owner.items() if u == uid]:
+                del self._gpu_owner[g]
+            self._bound.pop(uid, None)
+        self._kick_pending()
+
     def _mark_unschedulable(self, pod: dict, message: str) -> None:
+        self.queue.add_after(M.key_of(pod), 1.0)   # safety net: retry even if no event announces a free GPU
         conds = pod.get("status", {}).get("conditions") or []
         cur = M.condition(conds, "PodScheduled")
         if cur is not None and cur.get("status") == "False" and cur.get("message") == message:
@@ -601,6 +612,8 @@ class NodeAgent:
         status: Dict[str, Any] = {"containerStatuses": statuses}
         if all(n in terms for n in want):
             status["phase"] = C.POD_SUCCEEDED if all(terms[n]["exitCode"] == 0 for n in want) else C.POD_FAILED
+        if "phase" in status:
+            self._release_gpus(st.uid)
         klog.V(2).info("pod %s container %s exited code=%d signal=%d", key, cname, code, sig)
         try:
             self.cs.core_v1().pods(ns).patch(name, {"status": status}, subresource="status")

@@ -166,6 +166,15 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
             forget = self.sync_handler(key)
             if forget:
                 self.work_queue.forget(key)
+        except APIError as e:
+            if e.reason == "NotFound":
+                # the job (or the owner of something we tried to create) vanished mid-pass: nothing left to do
+                klog.V(2).info("Sync %r: %s", key, e.message)
+                self.work_queue.forget(key)
+            else:
+                klog.error("Sync %r failed with %r", key, e)
+                metrics.inc("aitj_reconcile_errors_total")
+                self.work_queue.add_rate_limited(key)
         except Exception as e:  # noqa: BLE001 - utilruntime.HandleError + AddRateLimited
             klog.error("Sync %r failed with %r", key, e)
             metrics.inc("aitj_reconcile_errors_total")

@@ -207,6 +207,26 @@ class APIServer:
                 raise APIError(422, "Invalid", f"{C.KIND}.{C.GROUP_NAME} \"{M.name_of(obj)}\" is invalid: "
                                + "; ".join(errs))
 
+    def _check_owners(self, info: R.ResourceInfo, ns: str, obj: Dict[str, Any]) -> None:
+        """Garbage-collector semantics applied eagerly: a dependent whose controller owner no longer exists (same
+        kind/name/uid) would be collected by the Kubernetes GC right after creation; here it is refused, so a
+        reconcile pass racing with the deletion of its job cannot leave orphan replicas behind."""
+        for ref in obj.get("metadata", {}).get("ownerReferences") or []:
+            if not ref.get("controller") or not ref.get("uid"):
+                continue
+            try:
+                kind_info = R.by_kind(ref.get("kind", ""))
+            except KeyError:
+                continue
+            try:
+                owner = self._store.get(kind_info.kind, ns if kind_info.namespaced else "", ref.get("name", ""))
+                if owner["uid"] == ref["uid"]:
+                    continue
+            except core.StoreError:
+                pass
+            raise APIError(404, "NotFound", f"owner {ref.get('kind')} \"{ref.get('name')}\" (uid {ref['uid']}) of "
+                           f"{info.kind} \"{M.name_of(obj)}\" not found: refusing to create an orphan")
+
     # ------------------------------------------------------------------ verbs
     def create(self, info: R.ResourceInfo, namespace: str, obj: Dict[str, Any]) -> Dict[str, Any]:
         self.request_count += 1
@@ -226,6 +246,7 @@ class APIServer:
             else:
                 raise APIError(422, "Invalid", "metadata.name: Required value: name or generateName is required")
         self._admit(info, obj)
+        self._check_owners(info, ns, obj)
         md["uid"] = M.new_uid()
         md["creationTimestamp"] = M.format_time()
         md.setdefault("generation", 1)
