@@ -58,6 +58,8 @@ class FlatParams:
         self.wd_mask = mask.to(self.device)
         self.by_name: Dict[str, ParamSpec] = {s.name: s for s in self.specs}
         self.mc_base = 0
+        self.small_range = None
+        self.g_small = None
         self.init_parameters(seed)
 
     def init_parameters(self, seed: int = 0) -> None:
@@ -94,6 +96,10 @@ class FlatParams:
             from ..ops.functional import RawView
 
             s = self.by_name[name]
+            if len(s.shape) == 1 and self.small_range is not None:
+                # small 1-D params are accumulated locally (scalar atomics) and pushed once per step
+                a = s.offset - self.small_range[0]
+                return self.g_small[a:a + s.numel]
             return RawView(self.mc_base + 4 * s.offset, s.shape, torch.float32)
         return self._view(self.g32, name)
 
@@ -106,6 +112,24 @@ class FlatParams:
         self.g32 = buf[: self.total]
         self.g32.zero_()
         self.mc_base = int(multicast_ptr or 0)
+        self.small_range = None
+        if self.mc_base:
+            one_d = [s for s in self.specs if len(s.shape) == 1]
+            if one_d:
+                lo = min(s.offset for s in one_d)
+                hi = max(s.offset + s.padded for s in one_d)
+                # only valid when the 1-D parameters form one contiguous tail region of the layout
+                if all(len(s.shape) == 1 for s in self.specs if lo <= s.offset < hi):
+                    self.small_range = (lo, hi)
+                    self.g_small = torch.zeros(hi - lo, dtype=torch.float32, device=self.device)
+
+    def push_small_grads(self) -> None:
+        """Multicast mode: send the locally accumulated 1-D parameter gradients to every peer (one kernel)."""
+        if self.mc_base and self.small_range is not None:
+            from ..ops import functional as F
+
+            lo, hi = self.small_range
+            F.mc_push(self.mc_base + 4 * lo, self.g_small, hi - lo)
 
     def range_of(self, first: str, last: str) -> Tuple[int, int]:
         a, b = self.by_name[first], self.by_name[last]

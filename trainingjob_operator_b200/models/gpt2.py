@@ -46,19 +46,22 @@ class GPT2Config:
 
 
 def gpt2_param_specs(cfg: GPT2Config) -> List[ParamSpec]:
+    """Flat layout: embeddings, then each layer's four weight matrices, then ALL 1-D parameters (biases, LayerNorm)
+    in one tail region -- so a layer's matrices are one contiguous gradient bucket and the small parameters can be
+    reduced with a single kernel in multicast mode."""
     C, L = cfg.n_embd, cfg.n_layer
     specs = [ParamSpec("wte", (cfg.padded_vocab, C), True), ParamSpec("wpe", (cfg.block_size, C), True, std=0.01)]
     pstd = 0.02 / math.sqrt(2 * L)
     for i in range(L):
         p = f"h{i}."
-        specs += [
-            ParamSpec(p + "ln1_w", (C,), False, "ones"), ParamSpec(p + "ln1_b", (C,), False, "zeros"),
-            ParamSpec(p + "qkv_w", (3 * C, C), True), ParamSpec(p + "qkv_b", (3 * C,), False, "zeros"),
-            ParamSpec(p + "proj_w", (C, C), True, std=pstd), ParamSpec(p + "proj_b", (C,), False, "zeros"),
-            ParamSpec(p + "ln2_w", (C,), False, "ones"), ParamSpec(p + "ln2_b", (C,), False, "zeros"),
-            ParamSpec(p + "fc_w", (4 * C, C), True), ParamSpec(p + "fc_b", (4 * C,), False, "zeros"),
-            ParamSpec(p + "fc2_w", (C, 4 * C), True, std=pstd), ParamSpec(p + "fc2_b", (C,), False, "zeros"),
-        ]
+        specs += [ParamSpec(p + "qkv_w", (3 * C, C), True), ParamSpec(p + "proj_w", (C, C), True, std=pstd),
+                  ParamSpec(p + "fc_w", (4 * C, C), True), ParamSpec(p + "fc2_w", (C, 4 * C), True, std=pstd)]
+    for i in range(L):
+        p = f"h{i}."
+        specs += [ParamSpec(p + "ln1_w", (C,), False, "ones"), ParamSpec(p + "ln1_b", (C,), False, "zeros"),
+                  ParamSpec(p + "qkv_b", (3 * C,), False, "zeros"), ParamSpec(p + "proj_b", (C,), False, "zeros"),
+                  ParamSpec(p + "ln2_w", (C,), False, "ones"), ParamSpec(p + "ln2_b", (C,), False, "zeros"),
+                  ParamSpec(p + "fc_b", (4 * C,), False, "zeros"), ParamSpec(p + "fc2_b", (C,), False, "zeros")]
     specs += [ParamSpec("lnf_w", (C,), False, "ones"), ParamSpec("lnf_b", (C,), False, "zeros")]
     return specs
 
@@ -192,12 +195,7 @@ class GPT2Engine:
             bn = self._bn(dw.shape[0], dw.shape[1])
             sk = self.split_k.get(key)
             if sk is None:
-                if bn == 512:
-                    tiles = ((dw.shape[0] + 255) // 256) * ((dw.shape[1] + 255) // 256)
-                    pairs = max(1, F.num_sms() // 2)
-                    sk = 1 if tiles >= pairs else max(1, min((dy.shape[0] + 63) // 64, pairs // tiles))
-                else:
-                    sk = F.auto_split_k(dw.shape[0], dw.shape[1], dy.shape[0])
+                sk = F.auto_split_k(dw.shape[0], dw.shape[1], dy.shape[0], pair=(bn == 512))
                 self.split_k[key] = sk
             F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=sk, block_n=bn)
         else:
@@ -270,8 +268,6 @@ class GPT2Engine:
         last = len(self.layers) - 1
         F.layernorm_bwd(self.d_ln, x_last, P.w16("lnf_w"), self.lnf_mean, self.lnf_rstd, d_res, P.grad("lnf_w"),
                         P.grad("lnf_b"), dxsum=P.grad(f"h{last}.fc2_b") if last >= 0 else None)
-        if hook:
-            hook("lnf")
         for i in range(len(self.layers) - 1, -1, -1):
             lb = self.layers[i]
             p = f"h{i}."
@@ -299,8 +295,10 @@ class GPT2Engine:
             if hook:
                 hook(f"h{i}")
         F.embedding_bwd(self.tok, d_res, P.grad("wte"), P.grad("wpe"), self.T)
+        P.push_small_grads()
         if hook:
             hook("emb")
+            hook("small")
 
     # ------------------------------------------------------------------ optimizer
     def set_step_scalars(self, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.95) -> None:
@@ -328,10 +326,12 @@ class GPT2Engine:
     def grad_buckets(self) -> List[Tuple[str, int, int]]:
         """(name, start, end) slices of the flat gradient buffer in the order backward completes them."""
         P = self.params
-        out = [("lnf",) + P.range_of("lnf_w", "lnf_b")]
+        out = []
         for i in range(self.cfg.n_layer - 1, -1, -1):
-            out.append((f"h{i}",) + P.range_of(f"h{i}.ln1_w", f"h{i}.fc2_b"))
+            out.append((f"h{i}",) + P.range_of(f"h{i}.qkv_w", f"h{i}.fc2_w"))
         out.append(("emb",) + P.range_of("wte", "wpe"))
+        first_small = "h0.ln1_w" if self.cfg.n_layer > 0 else "lnf_w"
+        out.append(("small",) + P.range_of(first_small, "lnf_b"))
         return out
 
     def num_parameters(self) -> int:

@@ -523,6 +523,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
   }
 }
 
+// Push a locally accumulated fp32 gradient segment into every peer's buffer through the switch and clear it:
+// dst_mc[i] (+)= src[i]; src[i] = 0.  Used for the small 1-D parameters (biases, LayerNorm) whose gradients are
+// built from many scalar atomics that would be wasteful to send over NVLink one by one.
+__global__ void __launch_bounds__(256) mc_push_kernel(float* __restrict__ dst_mc, float* __restrict__ src, size_t n) {
+  const size_t nvec = n / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(src)[i];
+    mc_red_add_v4_f32(dst_mc + i * 4, v.x, v.y, v.z, v.w);
+    reinterpret_cast<float4*>(src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in,
                                                             __nv_bfloat16* __restrict__ out, size_t n) {
   const size_t nvec = n / 4;
@@ -698,6 +711,13 @@ int aitj_adamw(void* p, void* g, void* m, void* v, void* p16, const void* wd_mas
       reinterpret_cast<float*>(p), reinterpret_cast<float*>(g), reinterpret_cast<float*>(m),
       reinterpret_cast<float*>(v), BF(p16), reinterpret_cast<const uint8_t*>(wd_mask),
       reinterpret_cast<const float*>(sumsq), reinterpret_cast<const float*>(dyn), static_cast<size_t>(n), a);
+  return LAUNCH_OK();
+}
+
+int aitj_mc_push(void* dst_mc, void* src, long long n, void* stream) {
+  if (n % 4) return -1;
+  mc_push_kernel<<<grid_for(static_cast<size_t>(n) / 4, 256, 148 * 2), 256, 0, S(stream)>>>(
+      reinterpret_cast<float*>(dst_mc), reinterpret_cast<float*>(src), static_cast<size_t>(n));
   return LAUNCH_OK();
 }
 

@@ -113,9 +113,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorM
   const int row = row0 + lane;
   const bool row_ok = row < a.M;
   if (flags & EPI_MC) {
-    // fused GEMM -> all-reduce: every accumulator goes straight from registers into ALL peers' gradient buffers
-    // through the switch (multimem.red); no staging, no separate collective kernel
-    float* obase = reinterpret_cast<float*>(a.out) + static_cast<size_t>(row) * a.ldc;
+    // fused GEMM -> all-reduce: the accumulators are reduced into ALL peers' gradient buffers through the
+    // NVSwitch (multimem.red).  The 32x32 fp32 chunk is transposed through the staging buffer so that each warp
+    // instruction covers 4 rows x 128 contiguous bytes (full lines on NVLink) instead of 32 rows x 16 bytes.
+    float* obase = reinterpret_cast<float*>(a.out);
 #pragma unroll 1
     for (int c = 0; c < kCols / 32; ++c) {
       const int col0 = n0 + c_begin + c * 32;
@@ -123,12 +124,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorM
       uint32_t r[32];
       tmem_ld_32x32(tmem_acc + c_begin + c * 32, r);
       tmem_ld_wait();
-      if (row_ok) {
+      __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (col0 + q * 4 < a.N)
-            mc_red_add_v4_f32(obase + col0 + q * 4, __uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
-                              __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+      for (int q = 0; q < 8; ++q) stage_write16(sbuf, lane, q, make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]));
+      __syncwarp();
+      const int chunk = lane & 7;
+      if (col0 + chunk * 4 < a.N) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const int grow = row0 + rr;
+          if (grow < a.M) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sbuf + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+            mc_red_add_v4_f32(obase + static_cast<size_t>(grow) * a.ldc + col0 + chunk * 4, __uint_as_float(v.x),
+                              __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+          }
         }
       }
     }

@@ -111,15 +111,28 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
     return out
 
 
-def auto_split_k(M: int, N: int, K: int, block_n: int = 0) -> int:
-    """Split-K factor that fills the SMs for a weight-gradient shaped GEMM (small MxN, huge K)."""
-    bn = block_n or (256 if N > 128 else 128)
-    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
-    sms = num_sms()
-    if tiles >= sms:
+def auto_split_k(M: int, N: int, K: int, block_n: int = 0, pair: bool = False) -> int:
+    """Split-K factor for a weight-gradient shaped GEMM (small MxN, huge K): the split that best fills whole
+    waves of SMs (or SM pairs), keeping at least 16 k-blocks per split; ties go to the smaller split."""
+    if pair:
+        tiles = ((M + 255) // 256) * ((N + 255) // 256)
+        slots = max(1, num_sms() // 2)
+    else:
+        bn = block_n or (256 if N > 128 else 128)
+        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+        slots = num_sms()
+    if tiles >= slots:
         return 1
     kb = (K + 63) // 64
-    return max(1, min(kb, sms // tiles))
+    best, best_eff = 1, 0.0
+    for s in range(1, 33):
+        if s > 1 and kb // s < 16:
+            break
+        work = tiles * s
+        eff = work / (((work + slots - 1) // slots) * slots)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
 
 
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
@@ -174,6 +187,11 @@ def adamw(p, g, m, v, p16, wd_mask, *, lr, beta1=0.9, beta2=0.95, eps=1e-8, weig
     lib.call("aitj_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p16.data_ptr(), wd_mask.data_ptr(),
              _ptr(sumsq_buf), _ptr(dyn), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
              int(step), float(max_norm), float(grad_div), int(bool(zero_grad)), _stream())
+
+
+def mc_push(dst_mc_ptr: int, src, n: int):
+    """dst_mc[0:n] (+)= src[0:n] through the NVSwitch multicast alias; src is cleared."""
+    lib.call("aitj_mc_push", int(dst_mc_ptr), src.data_ptr(), int(n), _stream())
 
 
 def cast_f32_bf16(src, dst):

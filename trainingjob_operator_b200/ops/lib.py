@@ -67,6 +67,7 @@ _SIGS = {
     "aitj_sumsq": [_P, _L, _P, _P],
     "aitj_adamw": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
     "aitj_cast_f32_bf16": [_P, _P, _L, _P],
+    "aitj_mc_push": [_P, _P, _L, _P],
     "aitj_gelu_fwd": [_P, _P, _L, _P],
     "aitj_gelu_bwd": [_P, _P, _P, _L, _P],
 }

@@ -78,7 +78,9 @@ class EngineTrainer:
         if self.world > 1 and self.symm is None:
             self.reducer = BucketAllReducer(engine.params.g32, engine.grad_buckets(), group, backend)
         engine.grad_hook = self.reducer.hook if self.reducer else None
-        self.use_graph = use_graph and self.cuda
+        # the multicast path has no collectives and is captured as one CUDA graph; library collectives (NCCL) on
+        # the side stream are launched eagerly -- capturing them deadlocked on the 2-GPU box
+        self.use_graph = use_graph and self.cuda and self.reducer is None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss_host = torch.zeros(1, dtype=torch.float32)
         if self.cuda:
