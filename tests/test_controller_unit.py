@@ -455,6 +455,20 @@ def test_restart_scopes_and_barrier(h, scope, expected_deleted, counts):
     assert job.status.phase == "Running"
 
 
+def test_fault_tolerant_elastic_job_replaces_only_the_lost_replica(h):
+    job = h.add_job(job_dict(roles={"trainer": {"restartPolicy": "OnFailure", "restartScope": "All",
+                                                "edlPolicy": "Manual", "minReplicas": 1, "maxReplicas": 4}},
+                             faultTolerant=True))
+    h.pod(job, "trainer", 0, node="gpu-0")
+    h.pod(job, "trainer", 1, phase="Failed", exit_codes=[137], node="gpu-1")
+    job = h.sync()
+    assert h.pc.deleted == ["job-trainer-1"]                       # scope All would have taken trainer-0 down too
+    assert job.status.restart_replica_name == "trainer"
+    h.pods_idx.delete({"metadata": {"name": "job-trainer-1", "namespace": "default"}})
+    job = h.sync()
+    assert job.status.phase == "Restarting" and job.status.restart_replica_name == ""   # barrier cleared per Pod scope
+
+
 def test_restart_limit_exhaustion_falls_through_to_fail_policy(h):
     job = h.add_job(job_dict(roles={"trainer": {"restartPolicy": "OnFailure", "restartScope": "Pod",
                                                 "restartLimit": 1}}))

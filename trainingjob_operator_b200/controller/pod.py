@@ -198,11 +198,14 @@ class PodReconciler:
                 if limit is None or job.status.restart_counts.get(rtype, 0) < limit:
                     S.update_restart_count(job, rtype)
                     msg = f"restart times is {job.status.restart_counts[rtype]}, {msg} "
-                    if spec.restart_scope == C.RESTART_SCOPE_POD:
+                    # faultTolerant (unused in the reference, types.go:47): an elastic job replaces only the lost
+                    # replica; survivors keep their state and re-rendezvous with the replacement
+                    scope = S.effective_restart_scope(job, rtype)
+                    if scope == C.RESTART_SCOPE_POD:
                         klog.warning("According to restartscope, need to restart the pod: %s.%s",
                                      M.namespace_of(pod), M.name_of(pod))
                         victims = [pod]
-                    elif spec.restart_scope == C.RESTART_SCOPE_REPLICA:
+                    elif scope == C.RESTART_SCOPE_REPLICA:
                         klog.warning("According to restartscope, need to restart all pods of the replica: %s", rtype)
                         victims = [p for sl in pod_slices for p in sl]
                     else:

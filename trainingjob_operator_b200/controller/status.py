@@ -91,7 +91,7 @@ def initialize_restart_counts(job: AITrainingJob, rtype: str) -> None:
 
 def update_restart_count(job: AITrainingJob, rtype: str) -> None:
     """status.go:322-330: scope All bumps every role."""
-    if job.spec.replica_specs[rtype].restart_scope == C.RESTART_SCOPE_ALL:
+    if effective_restart_scope(job, rtype) == C.RESTART_SCOPE_ALL:
         for r in job.spec.replica_specs:
             job.status.restart_counts[r] = job.status.restart_counts.get(r, 0) + 1
     else:
@@ -124,6 +124,14 @@ def update_replica_statuses(job: AITrainingJob, rtype: str, pods: List[dict]) ->
     job.status.replica_statuses[rtype] = rs
 
 
+def effective_restart_scope(job: AITrainingJob, rtype: str) -> str:
+    """``restartScope`` of a role; an elastic ``faultTolerant`` job replaces only the lost replica (scope Pod)."""
+    spec = job.spec.replica_specs[rtype]
+    if job.spec.fault_tolerant and spec.edl_policy in (C.EDL_POLICY_AUTO, C.EDL_POLICY_MANUAL):
+        return C.RESTART_SCOPE_POD
+    return spec.restart_scope
+
+
 def filter_pods_for_replica_type(pods: List[dict], rt_lower: str) -> List[dict]:
     return [p for p in pods if M.labels_of(p).get(C.LABEL_REPLICA_NAME) == rt_lower]
 
@@ -148,13 +156,14 @@ class StatusEngine:
                 return
             reason = C.TRAINING_JOB_REASON[C.PHASE_RESTARTING]
             replica_pods = filter_pods_for_replica_type(live_pods, rname.lower())
-            if spec.restart_scope == C.RESTART_SCOPE_ALL and not live_pods:
+            scope = effective_restart_scope(job, rname)
+            if scope == C.RESTART_SCOPE_ALL and not live_pods:
                 update_conditions(job, C.PHASE_RESTARTING, reason, "All pods are restarting now")
                 job.status.restart_replica_name = ""
-            elif spec.restart_scope == C.RESTART_SCOPE_REPLICA and not replica_pods:
+            elif scope == C.RESTART_SCOPE_REPLICA and not replica_pods:
                 update_conditions(job, C.PHASE_RESTARTING, reason, f"{rname.lower()} pods are restarting now")
                 job.status.restart_replica_name = ""
-            elif spec.restart_scope == C.RESTART_SCOPE_POD and len(replica_pods) < int(spec.replicas or 0):
+            elif scope == C.RESTART_SCOPE_POD and len(replica_pods) < int(spec.replicas or 0):
                 update_conditions(job, C.PHASE_RESTARTING, reason, "pod is restarting now")
                 job.status.restart_replica_name = ""
             return
