@@ -95,3 +95,17 @@ def test_e2e_job_on_gpu_through_the_control_plane(tmp_path):
         assert final.status.phase == "Succeed", logs
         m = json.loads(final.annotations["aitj.b200/metrics"])
         assert m["samples_per_sec"] > 0 and m["gpu_launches"] > 0
+
+
+@pytest.mark.gpu
+def test_fused_gemm_allreduce_matches_nccl_sum_on_two_gpus():
+    """GEMM->all-reduce fused through the NVSwitch multicast alias == local gradients + NCCL all-reduce."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(ROOT, "tools", "ddp_check.py")],
+                       cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout

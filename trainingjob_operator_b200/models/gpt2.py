@@ -258,47 +258,68 @@ class GPT2Engine:
     @torch.no_grad()
     def backward(self) -> None:
         """Accumulates into the flat fp32 gradient buffer (zeroed by the optimizer sweep)."""
-        F, P = self.F, self.params
         hook = self.grad_hook
+        for buckets, fn in self.backward_segments():
+            fn()
+            if hook:
+                for b in buckets:
+                    hook(b)
+
+    def backward_segments(self):
+        """Backward split at the points where a gradient bucket becomes final: [(finished buckets, callable)].
+        The trainer captures each callable as its own CUDA graph and launches the bucket's all-reduce between
+        replays, so library collectives stay outside the graphs while everything else is replayed."""
+        segs = [((), self._bwd_head)]
+        for i in range(len(self.layers) - 1, -1, -1):
+            segs.append(((f"h{i}",), (lambda i=i: self._bwd_layer(i))))
+        segs.append((("emb", "small"), self._bwd_tail))
+        return segs
+
+    @torch.no_grad()
+    def _bwd_head(self) -> None:
+        F, P = self.F, self.params
         dlogits = self.logits
         self._dgrad(dlogits, P.w16("wte"), self.d_ln)
         self._wgrad(dlogits, self.lnf, P.grad("wte"))
-        d_res, spare = self.d_res
+        self._d_cur, self._d_spare = self.d_res
         x_last = self.layers[-1].res2 if self.layers else self.x0
         last = len(self.layers) - 1
-        F.layernorm_bwd(self.d_ln, x_last, P.w16("lnf_w"), self.lnf_mean, self.lnf_rstd, d_res, P.grad("lnf_w"),
+        F.layernorm_bwd(self.d_ln, x_last, P.w16("lnf_w"), self.lnf_mean, self.lnf_rstd, self._d_cur, P.grad("lnf_w"),
                         P.grad("lnf_b"), dxsum=P.grad(f"h{last}.fc2_b") if last >= 0 else None)
-        for i in range(len(self.layers) - 1, -1, -1):
-            lb = self.layers[i]
-            p = f"h{i}."
-            x_in = self.layers[i - 1].res2 if i > 0 else self.x0
-            # MLP (fc2_b's gradient = colsum(d_res) was already produced by the LayerNorm-backward that made d_res)
-            self._wgrad(d_res, lb.fc_act, P.grad(p + "fc2_w"))
-            self._dgrad(d_res, P.w16(p + "fc2_w"), self.d_fc, dgelu_aux=lb.fc_pre)
-            F.colsum(self.d_fc, P.grad(p + "fc_b"))
-            self._wgrad(self.d_fc, lb.ln2, P.grad(p + "fc_w"))
-            self._dgrad(self.d_fc, P.w16(p + "fc_w"), self.d_ln)
-            F.layernorm_bwd(self.d_ln, lb.res1, P.w16(p + "ln2_w"), lb.ln2_mean, lb.ln2_rstd, spare,
-                            P.grad(p + "ln2_w"), P.grad(p + "ln2_b"), dres=d_res, dxsum=P.grad(p + "proj_b"))
-            d_res, spare = spare, d_res
-            # attention
-            self._wgrad(d_res, lb.att_in, P.grad(p + "proj_w"))
-            self._dgrad(d_res, P.w16(p + "proj_w"), self.d_att)
-            self._attention_bwd(lb, self.d_att, self.d_qkv)
-            F.colsum(self.d_qkv, P.grad(p + "qkv_b"))
-            self._wgrad(self.d_qkv, lb.ln1, P.grad(p + "qkv_w"))
-            self._dgrad(self.d_qkv, P.w16(p + "qkv_w"), self.d_ln)
-            F.layernorm_bwd(self.d_ln, x_in, P.w16(p + "ln1_w"), lb.ln1_mean, lb.ln1_rstd, spare,
-                            P.grad(p + "ln1_w"), P.grad(p + "ln1_b"), dres=d_res,
-                            dxsum=P.grad(f"h{i - 1}.fc2_b") if i > 0 else None)
-            d_res, spare = spare, d_res
-            if hook:
-                hook(f"h{i}")
-        F.embedding_bwd(self.tok, d_res, P.grad("wte"), P.grad("wpe"), self.T)
+
+    @torch.no_grad()
+    def _bwd_layer(self, i: int) -> None:
+        F, P = self.F, self.params
+        d_res, spare = self._d_cur, self._d_spare
+        lb = self.layers[i]
+        p = f"h{i}."
+        x_in = self.layers[i - 1].res2 if i > 0 else self.x0
+        # MLP (fc2_b's gradient = colsum(d_res) was already produced by the LayerNorm-backward that made d_res)
+        self._wgrad(d_res, lb.fc_act, P.grad(p + "fc2_w"))
+        self._dgrad(d_res, P.w16(p + "fc2_w"), self.d_fc, dgelu_aux=lb.fc_pre)
+        F.colsum(self.d_fc, P.grad(p + "fc_b"))
+        self._wgrad(self.d_fc, lb.ln2, P.grad(p + "fc_w"))
+        self._dgrad(self.d_fc, P.w16(p + "fc_w"), self.d_ln)
+        F.layernorm_bwd(self.d_ln, lb.res1, P.w16(p + "ln2_w"), lb.ln2_mean, lb.ln2_rstd, spare,
+                        P.grad(p + "ln2_w"), P.grad(p + "ln2_b"), dres=d_res, dxsum=P.grad(p + "proj_b"))
+        d_res, spare = spare, d_res
+        # attention
+        self._wgrad(d_res, lb.att_in, P.grad(p + "proj_w"))
+        self._dgrad(d_res, P.w16(p + "proj_w"), self.d_att)
+        self._attention_bwd(lb, self.d_att, self.d_qkv)
+        F.colsum(self.d_qkv, P.grad(p + "qkv_b"))
+        self._wgrad(self.d_qkv, lb.ln1, P.grad(p + "qkv_w"))
+        self._dgrad(self.d_qkv, P.w16(p + "qkv_w"), self.d_ln)
+        F.layernorm_bwd(self.d_ln, x_in, P.w16(p + "ln1_w"), lb.ln1_mean, lb.ln1_rstd, spare,
+                        P.grad(p + "ln1_w"), P.grad(p + "ln1_b"), dres=d_res,
+                        dxsum=P.grad(f"h{i - 1}.fc2_b") if i > 0 else None)
+        self._d_cur, self._d_spare = spare, d_res
+
+    @torch.no_grad()
+    def _bwd_tail(self) -> None:
+        F, P = self.F, self.params
+        F.embedding_bwd(self.tok, self._d_cur, P.grad("wte"), P.grad("wpe"), self.T)
         P.push_small_grads()
-        if hook:
-            hook("emb")
-            hook("small")
 
     # ------------------------------------------------------------------ optimizer
     def set_step_scalars(self, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.95) -> None:

@@ -78,9 +78,13 @@ class EngineTrainer:
         if self.world > 1 and self.symm is None:
             self.reducer = BucketAllReducer(engine.params.g32, engine.grad_buckets(), group, backend)
         engine.grad_hook = self.reducer.hook if self.reducer else None
-        # the multicast path has no collectives and is captured as one CUDA graph; library collectives (NCCL) on
-        # the side stream are launched eagerly -- capturing them deadlocked on the 2-GPU box
-        self.use_graph = use_graph and self.cuda and self.reducer is None
+        # Without library collectives (1 GPU, or the fused multicast path) the whole step is ONE CUDA graph.  With
+        # the NCCL reducer the step is a chain of graphs split where a gradient bucket becomes final; the bucket's
+        # all-reduce is launched between two replays on the side stream (capturing NCCL itself deadlocked on
+        # the 2-GPU box), so collectives overlap the next segment's math and nothing else is launched eagerly.
+        self.use_graph = use_graph and self.cuda
+        self.segmented = self.reducer is not None
+        self.seg_graphs = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss_host = torch.zeros(1, dtype=torch.float32)
         if self.cuda:
@@ -99,8 +103,54 @@ class EngineTrainer:
             self.symm.barrier()   # every peer's multimem reductions of this step have landed
         if self.reducer:
             self.reducer.wait()
-        e.optimizer_step(lr=self.lr, step=max(1, self.step_count), weight_decay=self.weight_decay,
-                         max_norm=self.max_norm, grad_div=float(self.world), use_dyn=True)
+        self._optimizer()
+
+    def _optimizer(self) -> None:
+        self.engine.optimizer_step(lr=self.lr, step=max(1, self.step_count), weight_decay=self.weight_decay,
+                                   max_norm=self.max_norm, grad_div=float(self.world), use_dyn=True)
+
+    def _capture_segments(self) -> None:
+        """NCCL mode: [forward] [bwd head] [layer L-1] ... [layer 0] [tail] [optimizer] as separate graphs."""
+        from ..ops import lib
+
+        e = self.engine
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._device_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        saved_hook, e.grad_hook = e.grad_hook, None
+        parts = [((), e.forward)] + list(e.backward_segments()) + [(None, self._optimizer)]
+        graphs = []
+        pool = None
+        before = lib.LAUNCHES
+        try:
+            for buckets, fn in parts:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    fn()
+                if pool is None:
+                    pool = g.pool()
+                graphs.append((buckets, g))
+            self.seg_graphs = graphs
+            self.launches_per_step = lib.LAUNCHES - before
+        except Exception as ex:  # noqa: BLE001
+            self.seg_graphs = None
+            self.use_graph = False
+            self.graph_error = f"{type(ex).__name__}: {ex}"
+            torch.cuda.synchronize()
+        finally:
+            e.grad_hook = saved_hook
+
+    def _replay_segments(self) -> None:
+        for buckets, g in self.seg_graphs:
+            if buckets is None:            # optimizer: every bucket must have been reduced
+                self.reducer.wait()
+            g.replay()
+            for b in buckets or ():
+                self.reducer.hook(b)
 
     def _capture(self) -> None:
         from ..ops import lib
@@ -140,7 +190,14 @@ class EngineTrainer:
         e.tok.copy_(tok_host, non_blocking=True)
         e.tgt.copy_(tgt_host, non_blocking=True)
         e.set_step_scalars(cosine_lr(self.step_count, self.lr), self.step_count)
-        if self.use_graph:
+        if self.use_graph and self.segmented:
+            if self.seg_graphs is None:
+                self._capture_segments()
+            if self.seg_graphs is not None:
+                self._replay_segments()
+            else:
+                self._device_step()
+        elif self.use_graph:
             if self.graph is None:
                 self._capture()
                 # the two warm-up passes + capture consumed optimizer steps on real data; that is fine for

@@ -396,7 +396,9 @@ def run(args) -> Dict[str, Any]:
             "loss_first": losses[0] if losses else None, "loss_last": losses[-1] if losses else None,
             "flops_per_step": getattr(adapter, "flops_per_step", 0.0),
             "describe": adapter.describe,
-            "cuda_graph": bool(getattr(getattr(adapter, "trainer", None), "graph", None)),
+            "cuda_graph": bool(getattr(getattr(adapter, "trainer", None), "graph", None)
+                               or getattr(getattr(adapter, "trainer", None), "seg_graphs", None)),
+            "graph_segments": len(getattr(getattr(adapter, "trainer", None), "seg_graphs", None) or []) or None,
             "graph_error": getattr(getattr(adapter, "trainer", None), "graph_error", None),
             "allreduce": getattr(getattr(adapter, "trainer", None), "allreduce_backend", "nccl" if world > 1 else "none"),
         })
