@@ -346,3 +346,40 @@ def test_elastic_rescale_with_gloo_workers(tmp_path):
         assert {k: pod_pids(lc2, "el")[k] for k in pids} == pids
         log2 = open(os.path.join(lc2.workdir, "logs", "default_el-trainer-2_aitj-trainer.log")).read()
         assert "leaving: world shrinks to 2" in log2
+
+
+def test_warm_pool_adopts_parked_interpreter(tmp_path):
+    """A `python script` container is started by a pre-warmed interpreter (same lifecycle, same exit-code path,
+    torch already imported) and the pool refills; non-python commands still spawn cold."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, time\n"
+        "print('warm', 'torch' in sys.modules, os.environ['TRAININGJOB_REPLICA_INDEX'], os.environ['WORLD_SIZE'],\n"
+        "      os.environ.get('AITJ_TEST_MARK'), sys.argv[1:], os.getpid(), flush=True)\n"
+        "time.sleep(0.3)\n"
+        "sys.exit(7 if os.environ['TRAININGJOB_REPLICA_INDEX'] == '1' else 0)\n")
+    with LocalCluster(num_gpus=0, workdir=str(tmp_path / "wd"), warm_pool=2) as lc2:
+        wait_until(lambda: lc2.agent.warm_ready() == 2, timeout=60, period=0.1)
+        parked = {pid for sid, pid in lc2.agent.sup.list() if sid.startswith("~zygote/")}
+        assert len(parked) == 2
+        j = sh_job("wp", "true", replicas=2)
+        c = j["spec"]["replicaSpecs"]["trainer"]["template"]["spec"]["containers"][0]
+        c["command"] = [sys.executable, "-u", str(script), "--flag", "x"]
+        c["env"] = [{"name": "AITJ_TEST_MARK", "value": "m1"}]
+        j["spec"]["replicaSpecs"]["trainer"]["failPolicy"] = "Any"
+        lc2.apply(j)
+        final = lc2.wait_for_phase("wp", "Failed", timeout=30)
+        assert "7" in final.status.conditions[-1].message          # the exit code travels the usual path
+        logs = [open(os.path.join(lc2.workdir, "logs", f"default_wp-trainer-{i}_aitj-trainer.log")).read() for i in (0, 1)]
+        for i, log in enumerate(logs):
+            assert f"warm True {i} 2 m1 ['--flag', 'x']" in log, log
+            assert int(log.split()[-1]) in parked              # the container IS the parked process
+        # the pool refills in the background; shell commands do not consume it
+        wait_until(lambda: lc2.agent.warm_ready() == 2, timeout=60, period=0.1)
+        lc2.apply(sh_job("cold", "sleep 0.2", replicas=1))
+        lc2.wait_for_phase("cold", "Succeed", timeout=20)
+        assert lc2.agent.warm_ready() == 2
+    # nothing is left behind
+    time.sleep(0.2)
+    for pid in parked:
+        assert not os.path.exists(f"/proc/{pid}") or open(f"/proc/{pid}/stat").read().split()[2] == "Z"

@@ -18,12 +18,18 @@ agent, which keeps the exact object contract the controller logic reads
   128+N); exec failures surface as ``CreateContainerError`` / ``CreateContainerConfigError`` waiting
   reasons (constants.go:46-56); graceful delete = SIGTERM, grace period, SIGKILL, then the pod object
   is removed; a vanished pod object kills its processes (orphan sweep, garbage_collection.go analogue).
+* **warm pool** (``warm_pool=N``): N parked interpreters with torch already imported (``runtime/zygote.py``);
+  a container whose command is ``python -m mod`` / ``python script`` adopts one instead of paying the
+  interpreter start + ``import torch`` (seconds) on the spawn -> Running path.
 """
 from __future__ import annotations
 
+import json
 import os
 import shlex
+import shutil
 import signal
+import sys
 import threading
 import time
 from dataclasses import dataclass, field
@@ -44,6 +50,8 @@ _PASS_ENV = ("PATH", "HOME", "USER", "LANG", "LC_ALL", "LD_LIBRARY_PATH", "VIRTU
              "GRAFT_REPO_ROOT", "HF_HOME", "TORCH_HOME", "XDG_CACHE_HOME")
 
 metrics.describe("aitj_spawn_seconds", "pod bound -> all containers started")
+metrics.describe("aitj_warm_adoptions_total", "containers started by adopting a pre-warmed interpreter")
+ZYGOTE_PREFIX = "~zygote/"     # supervisor ids of parked interpreters ('~' cannot start a namespace name)
 
 
 def detect_gpu_count() -> int:
@@ -131,7 +139,7 @@ class NodeAgent:
     def __init__(self, clientset, num_gpus: Optional[int] = None, workdir: str = "/tmp/aitj-agent",
                  health_prober: Optional[Callable[[int], Tuple[bool, str]]] = None, health_period: float = 2.0,
                  cpu_slots: int = 64, image_map: Optional[Dict[str, List[str]]] = None,
-                 supervisor=None, node_prefix: str = ""):
+                 supervisor=None, node_prefix: str = "", warm_pool: int = 0):
         self.cs = clientset
         self.num_gpus = detect_gpu_count() if num_gpus is None else int(num_gpus)
         self.workdir = workdir
@@ -160,6 +168,13 @@ class NodeAgent:
         # binds, so consecutive scheduling decisions must not rely on it alone
         self._gpu_owner: Dict[int, Tuple[str, float]] = {}
         self._bound: Dict[str, float] = {}   # pod uid -> time we bound it (cache may not show nodeName yet)
+        # warm pool of parked interpreters: supervisor id -> {"fifo": path, "spawned": monotonic}
+        self.warm_pool = max(0, int(warm_pool))
+        self._zygotes: Dict[str, Dict[str, Any]] = {}
+        self._zy_seq = 0
+        self._zy_failures = 0
+        self._zy_dir = os.path.join(workdir, "zygotes")
+        self._stopping = False
 
     # ------------------------------------------------------------------ nodes
     def gpu_node(self, idx: int) -> str:
@@ -263,8 +278,10 @@ class NodeAgent:
         for target, name in ((self._sync_loop, "agent-sync"), (self._reap_loop, "agent-reap"),
                              (self._health_loop, "agent-health"), (self._sweep_loop, "agent-sweep")):
             self._threads.append(lifecycle.spawn(target, name, (stop,)))
-        lifecycle.register_stop(lambda: (stop.set(), self.queue.shutdown()))
-        threading.Thread(target=lambda: (stop.wait(), self.queue.shutdown()), daemon=True).start()
+        lifecycle.register_stop(lambda: (stop.set(), self.queue.shutdown(), self._kill_zygotes()))
+        threading.Thread(target=lambda: (stop.wait(), self.queue.shutdown(), self._kill_zygotes()),
+                         daemon=True).start()
+        self._ensure_pool()
 
     def run(self, stop: threading.Event) -> None:
         self.start(stop)
@@ -272,6 +289,7 @@ class NodeAgent:
         self.shutdown()
 
     def shutdown(self, kill: bool = False) -> None:
+        self._kill_zygotes()
         if kill:
             for sid, _pid in self.sup.list():
                 self.sup.kill(sid, signal.SIGKILL, True)
@@ -299,7 +317,122 @@ class NodeAgent:
     def _reap_loop(self, stop: threading.Event) -> None:
         while not stop.is_set():
             for ev in self.sup.poll_exits(0.5):
-                self._on_exit(ev)
+                if ev["id"].startswith(ZYGOTE_PREFIX):
+                    self._on_zygote_exit(ev)
+                else:
+                    self._on_exit(ev)
+
+    # ------------------------------------------------------------------ warm pool
+    def _zygote_env(self) -> Dict[str, str]:
+        env = {k: os.environ[k] for k in _PASS_ENV if k in os.environ}
+        env["PYTHONUNBUFFERED"] = "1"
+        return env
+
+    def _ensure_pool(self) -> None:
+        """Top the pool up to ``warm_pool`` parked interpreters (no-op when disabled or shutting down)."""
+        if self.warm_pool <= 0 or self._stopping or self._zy_failures >= 3:
+            return
+        os.makedirs(self._zy_dir, exist_ok=True)
+        with self._lock:
+            while len(self._zygotes) < self.warm_pool:
+                self._zy_seq += 1
+                zid = f"{ZYGOTE_PREFIX}{os.getpid()}-{self._zy_seq}"
+                fifo = os.path.join(self._zy_dir, f"z{os.getpid()}-{self._zy_seq}.fifo")
+                for path in (fifo, fifo + ".ready"):
+                    try:
+                        os.unlink(path)
+                    except OSError:
+                        pass
+                try:
+                    os.mkfifo(fifo, 0o600)
+                    self.sup.spawn(zid, [sys.executable, "-m", "trainingjob_operator_b200.runtime.zygote", fifo],
+                                   self._zygote_env(), "", os.path.join(self.log_dir, "zygotes.log"), "", [])
+                except OSError as e:
+                    klog.warning("warm pool: cannot start an interpreter: %s", e)
+                    self._zy_failures += 1
+                    return
+                self._zygotes[zid] = {"fifo": fifo, "spawned": time.monotonic()}
+
+    def warm_ready(self) -> int:
+        """Number of parked interpreters that finished their imports."""
+        with self._lock:
+            return sum(1 for z in self._zygotes.values() if os.path.exists(z["fifo"] + ".ready"))
+
+    def _on_zygote_exit(self, ev: Dict[str, Any]) -> None:
+        with self._lock:
+            z = self._zygotes.pop(ev["id"], None)
+        if z is None:
+            return
+        for path in (z["fifo"], z["fifo"] + ".ready"):
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
+        if self._stopping:
+            return
+        if time.monotonic() - z["spawned"] < 5.0:
+            self._zy_failures += 1
+            klog.warning("warm pool: parked interpreter exited early (code %s)", ev.get("exit_code"))
+        self._ensure_pool()
+
+    def _kill_zygotes(self) -> None:
+        self._stopping = True
+        with self._lock:
+            ids = list(self._zygotes)
+        for zid in ids:
+            self.sup.kill(zid, signal.SIGKILL, True)
+
+    def _adopt_zygote(self, sid: str, argv: List[str], env: Dict[str, str], cwd: str, log: str,
+                      cpus: List[int]) -> bool:
+        """Start the container by handing it to a parked interpreter.  False => caller spawns it cold."""
+        if self.warm_pool <= 0 or self._stopping:
+            return False
+        from ..runtime.zygote import split_python_command
+
+        if split_python_command(argv) is None:
+            return False
+        exe = shutil.which(argv[0], path=env.get("PATH")) or argv[0]
+        try:
+            if os.path.realpath(exe) != os.path.realpath(sys.executable):
+                return False
+        except OSError:
+            return False
+        with self._lock:
+            zid = next((z for z, info in self._zygotes.items() if os.path.exists(info["fifo"] + ".ready")), None)
+            info = self._zygotes.pop(zid) if zid else None
+        if info is None:
+            return False
+        fd = -1
+        deadline = time.monotonic() + 0.25
+        while fd < 0:
+            try:
+                fd = os.open(info["fifo"], os.O_WRONLY | os.O_NONBLOCK)
+            except OSError:          # ENXIO: the reader has not reached open() yet
+                if time.monotonic() > deadline:
+                    break
+                time.sleep(0.002)
+        ok = fd >= 0 and self.sup.rename(zid, sid)
+        if ok:
+            msg = json.dumps({"argv": argv, "env": env, "cwd": cwd, "log": log, "cpus": cpus}) + "\n"
+            try:
+                os.write(fd, msg.encode())
+            except OSError:
+                ok = False
+                self.sup.kill(sid, signal.SIGKILL, True)
+        if fd >= 0:
+            os.close(fd)
+        if not ok:
+            self.sup.kill(zid, signal.SIGKILL, True)
+            for path in (info["fifo"], info["fifo"] + ".ready"):
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
+        else:
+            metrics.inc("aitj_warm_adoptions_total")
+            klog.V(2).info("container %s adopted parked interpreter %s", sid, zid)
+        threading.Thread(target=self._ensure_pool, daemon=True).start()
+        return ok
 
     def _sweep_loop(self, stop: threading.Event) -> None:
         while not stop.wait(5.0):
@@ -542,8 +675,10 @@ class NodeAgent:
             sid = f"{st.key}/{st.uid[:8]}/{c['name']}"
             try:
                 cwd = c.get("workingDir") or ""
-                self.sup.spawn(sid, argv, self._container_env(pod, c, gpus), cwd, self.log_path(pod, c["name"]), "",
-                               self._cpus_for(gpus))
+                env = self._container_env(pod, c, gpus)
+                log, cpus = self.log_path(pod, c["name"]), self._cpus_for(gpus)
+                if not self._adopt_zygote(sid, argv, env, cwd, log, cpus):
+                    self.sup.spawn(sid, argv, env, cwd, log, "", cpus)
                 st.containers[c["name"]] = sid
                 return ""
             except OSError as e:
@@ -661,6 +796,8 @@ class NodeAgent:
         """Kill supervised processes whose pod record is gone or was replaced (GC analogue)."""
         n = 0
         for sid, _pid in self.sup.list():
+            if sid.startswith(ZYGOTE_PREFIX):
+                continue
             key = "/".join(sid.split("/")[:2])
             uid8 = sid.split("/")[2] if sid.count("/") >= 3 else ""
             ns, name = M.split_key(key)

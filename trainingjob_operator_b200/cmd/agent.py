@@ -20,13 +20,18 @@ def main(argv=None) -> int:
     ap.add_argument("--workdir", default=os.path.expanduser("~/.aitj"))
     ap.add_argument("--image-map", action="append", default=[], help="image=command (repeatable)")
     ap.add_argument("--v", type=int, default=0)
+    ap.add_argument("--warm-pool", type=int, default=-1,
+                    help="parked pre-imported interpreters for fast replica start (-1 = one per GPU slot, 0 = off)")
     args = ap.parse_args(argv)
     klog.configure(args.v, True)
     master = resolve_master(TrainingJobOperatorOption(master_url=args.master, kubeconfig=args.kubeconfig))
     import shlex
 
     image_map = {kv.split("=", 1)[0]: shlex.split(kv.split("=", 1)[1]) for kv in args.image_map if "=" in kv}
-    agent = NodeAgent(new_for_config(master=master), num_gpus=args.gpus, workdir=args.workdir, image_map=image_map)
+    from .local import _auto_pool
+
+    agent = NodeAgent(new_for_config(master=master), num_gpus=args.gpus, workdir=args.workdir, image_map=image_map,
+                      warm_pool=_auto_pool(args.warm_pool, args.gpus))
     stop = setup_signal_handler()
     agent.start(stop)
     print(f"aitj-agent up: {agent.num_gpus} GPU slot(s), master {master}", flush=True)

@@ -31,7 +31,7 @@ class LocalCluster:
     def __init__(self, num_gpus: Optional[int] = None, workdir: Optional[str] = None, wal: bool = False,
                  operators: int = 1, leader_elect: bool = False, http: bool = True, port: int = 0,
                  option: Optional[options_mod.TrainingJobOperatorOption] = None, health_prober=None,
-                 health_period: float = 1.0, verbosity: int = 0):
+                 health_period: float = 1.0, verbosity: int = 0, warm_pool: int = 0):
         self.workdir = workdir or tempfile.mkdtemp(prefix="aitj-")
         os.makedirs(self.workdir, exist_ok=True)
         klog.configure(verbosity, True)
@@ -41,7 +41,7 @@ class LocalCluster:
         self.stop_event = threading.Event()
         self.clientset: Clientset = new_for_config(server=self.api)
         self.agent = NodeAgent(new_for_config(server=self.api), num_gpus=num_gpus, workdir=self.workdir,
-                               health_prober=health_prober, health_period=health_period)
+                               health_prober=health_prober, health_period=health_period, warm_pool=warm_pool)
         self.option = option or options_mod.TrainingJobOperatorOption()
         self.option.master_url = self.http.url if self.http else ""
         if leader_elect:
@@ -141,6 +141,15 @@ class LocalCluster:
         self.stop()
 
 
+def _auto_pool(requested: int, gpus: Optional[int]) -> int:
+    if requested >= 0:
+        return requested
+    from ..agent.agent import detect_gpu_count
+
+    n = detect_gpu_count() if gpus is None else gpus
+    return min(8, max(0, n))
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="aitj-local", description="single-box AITrainingJob control plane")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -152,6 +161,8 @@ def main(argv=None) -> int:
     up.add_argument("--leader-elect", action="store_true")
     up.add_argument("--no-wal", action="store_true")
     up.add_argument("--v", type=int, default=0)
+    up.add_argument("--warm-pool", type=int, default=-1,
+                    help="parked pre-imported interpreters for fast replica start (-1 = one per GPU slot, 0 = off)")
     options_group = up.add_argument_group("operator flags")
     options_group.add_argument("--thread-num", type=int, default=4)
     options_group.add_argument("--enable-creating-failed", action="store_true")
@@ -163,7 +174,7 @@ def main(argv=None) -> int:
     stop = setup_signal_handler()
     cluster = LocalCluster(num_gpus=args.gpus, workdir=args.workdir, wal=not args.no_wal, operators=args.operators,
                            leader_elect=args.leader_elect or args.operators > 1, port=args.port, option=opt,
-                           verbosity=args.v)
+                           verbosity=args.v, warm_pool=_auto_pool(args.warm_pool, args.gpus))
     cluster.start()
     cfg_dir = os.path.expanduser("~/.aitj")
     os.makedirs(cfg_dir, exist_ok=True)

@@ -168,6 +168,7 @@ PYBIND11_MODULE(_aitj_core, m) {
       .def("spawn", &Supervisor::spawn, py::arg("id"), py::arg("argv"), py::arg("env"), py::arg("cwd") = "",
            py::arg("stdout_path") = "", py::arg("stderr_path") = "", py::arg("cpus") = std::vector<int>{})
       .def("kill", &Supervisor::kill_proc, py::arg("id"), py::arg("sig") = 15, py::arg("group") = true)
+      .def("rename", &Supervisor::rename, py::arg("from_id"), py::arg("to_id"))
       .def("alive", &Supervisor::alive)
       .def("pid_of", &Supervisor::pid_of)
       .def("list", &Supervisor::list)

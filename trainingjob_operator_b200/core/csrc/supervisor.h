@@ -173,6 +173,23 @@ class Supervisor {
     return rc == 0;
   }
 
+  // Re-key a supervised process (a pre-warmed worker adopted as a pod's container).  The exit event of the
+  // process is reported under the new id.  False if `from` is gone or `to` is taken.
+  bool rename(const std::string& from, const std::string& to) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = procs_.find(from);
+      if (it == procs_.end() || procs_.count(to)) return false;
+      ProcInfo info = it->second;
+      info.id = to;
+      info.started = std::chrono::steady_clock::now();
+      procs_.erase(it);
+      procs_[to] = info;
+    }
+    wake();
+    return true;
+  }
+
   bool alive(const std::string& id) {
     std::lock_guard<std::mutex> lk(mu_);
     return procs_.count(id) > 0;

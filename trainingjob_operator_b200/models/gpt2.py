@@ -14,6 +14,7 @@ step is captured in one CUDA graph.  Only scaled-dot-product attention calls a l
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -21,6 +22,9 @@ import torch
 import torch.nn.functional as TF
 
 from .flat_params import FlatParams, ParamSpec
+
+
+_QKV_GATHER = os.environ.get("AITJ_QKV_GATHER", "1") != "0"
 
 
 @dataclass
@@ -219,16 +223,21 @@ class GPT2Engine:
             lb.att.view(B, T, H, D).copy_(ot)
             lb.att_in = lb.att
 
-    def _attention_bwd(self, lb: _LayerBufs, d_att: torch.Tensor, d_qkv: torch.Tensor):
+    def _attention_bwd(self, lb: _LayerBufs, d_att: torch.Tensor, d_qkv: torch.Tensor, d_bias: torch.Tensor):
+        """d_qkv <- SDPA backward; d_bias (the qkv bias gradient) += colsum(d_qkv), fused into the gather."""
         B, T, H = self.B, self.T, self.cfg.n_head
         D = self.cfg.n_embd // H
         q, k, v, o = lb.sdpa_ctx
         do = d_att.view(B, T, H, D).transpose(1, 2)
         dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
-        dst = d_qkv.view(B, T, 3, H, D)
-        dst[:, :, 0].copy_(dq.transpose(1, 2))
-        dst[:, :, 1].copy_(dk.transpose(1, 2))
-        dst[:, :, 2].copy_(dv.transpose(1, 2))
+        if _QKV_GATHER:
+            self.F.qkv_gather_colsum(dq, dk, dv, d_qkv, d_bias)
+        else:   # A/B arm: three strided copies + a separate column reduction
+            dst = d_qkv.view(B, T, 3, H, D)
+            dst[:, :, 0].copy_(dq.transpose(1, 2))
+            dst[:, :, 1].copy_(dk.transpose(1, 2))
+            dst[:, :, 2].copy_(dv.transpose(1, 2))
+            self.F.colsum(d_qkv, d_bias)
         lb.sdpa_ctx = None
 
     # ------------------------------------------------------------------ forward / backward
@@ -306,8 +315,7 @@ class GPT2Engine:
         # attention
         self._wgrad(d_res, lb.att_in, P.grad(p + "proj_w"))
         self._dgrad(d_res, P.w16(p + "proj_w"), self.d_att)
-        self._attention_bwd(lb, self.d_att, self.d_qkv)
-        F.colsum(self.d_qkv, P.grad(p + "qkv_b"))
+        self._attention_bwd(lb, self.d_att, self.d_qkv, P.grad(p + "qkv_b"))
         self._wgrad(self.d_qkv, lb.ln1, P.grad(p + "qkv_w"))
         self._dgrad(self.d_qkv, P.w16(p + "qkv_w"), self.d_ln)
         F.layernorm_bwd(self.d_ln, x_in, P.w16(p + "ln1_w"), lb.ln1_mean, lb.ln1_rstd, spare,

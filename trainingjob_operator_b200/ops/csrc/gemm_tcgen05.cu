@@ -46,7 +46,15 @@ struct GemmArgs {
   int split_k;
   int tiles_m, tiles_n;
   int k_blocks, k_per_split;
+  // optional per-CTA role timeline (8 x u64 per CTA, see aitj_gemm_set_trace): where each warp role waits
+  unsigned long long* trace;
 };
+
+// trace slots
+enum : int { TR_MMA_TOTAL = 0, TR_MMA_WAIT_FULL = 1, TR_MMA_WAIT_TMEM = 2, TR_TMA_WAIT_EMPTY = 3,
+             TR_EPI_WAIT_FULL = 4, TR_EPI_BUSY = 5, TR_EPI_TOTAL = 6, TR_TILES = 7 };
+#define TR_BEGIN(tr, t) long long t = (tr) ? clock64() : 0
+#define TR_ADD(tr, t, accv) do { if (tr) accv += clock64() - t; } while (0)
 
 struct WorkItem {
   int m_blk, n_blk, kb0, kb1;
@@ -103,15 +111,11 @@ __device__ __forceinline__ void stage_commit(const CUtensorMap* tm, uint8_t* b, 
   }
 }
 
-// Drain this warp's share of one accumulator tile: 32 rows x kCols columns starting at tile column c_begin.
-// `sbias` holds the tile's bias row (bf16, staged once per tile by the epilogue warps).
+// fp32 outputs (plain store, TMA reduce-add, or multimem reduction): raw accumulators, 32 columns per chunk.
 template <int kCols>
-__device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
-                                              uint32_t tmem_acc, int row0, int n0, int c_begin,
-                                              const __nv_bfloat16* sbias, uint8_t* sbuf, int lane) {
+__device__ __forceinline__ void epilogue_f32(const GemmArgs& a, const CUtensorMap* tm_out, uint32_t tmem_acc, int row0,
+                                             int n0, int c_begin, uint8_t* sbuf, int lane) {
   const int flags = a.flags;
-  const int row = row0 + lane;
-  const bool row_ok = row < a.M;
   if (flags & EPI_MC) {
     // fused GEMM -> all-reduce: the accumulators are reduced into ALL peers' gradient buffers through the
     // NVSwitch (multimem.red).  The 32x32 fp32 chunk is transposed through the staging buffer so that each warp
@@ -145,7 +149,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorM
     return;
   }
   if (flags & (EPI_OUT_F32 | EPI_ACCUM)) {
-    // fp32 output: 32 columns (128 B) per staged chunk; raw accumulators
 #pragma unroll 1
     for (int c = 0; c < kCols / 32; ++c) {
       const int col0 = n0 + c_begin + c * 32;
@@ -158,6 +161,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorM
       for (int q = 0; q < 8; ++q) stage_write16(sbuf, lane, q, make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]));
       stage_commit(tm_out, sbuf, col0, row0, lane, (flags & EPI_ACCUM) != 0);
     }
+  }
+}
+
+// Drain this warp's share of one accumulator tile: 32 rows x kCols columns starting at tile column c_begin.
+// `sbias` holds the tile's bias row (bf16, staged once per tile by the epilogue warps).
+template <int kCols>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
+                                              uint32_t tmem_acc, int row0, int n0, int c_begin,
+                                              const __nv_bfloat16* sbias, uint8_t* sbuf, int lane) {
+  const int flags = a.flags;
+  const int row = row0 + lane;
+  const bool row_ok = row < a.M;
+  if (flags & (EPI_MC | EPI_OUT_F32 | EPI_ACCUM)) {
+    epilogue_f32<kCols>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane);
     return;
   }
   // bf16 output: 64 columns (128 B) per staged chunk
@@ -227,8 +244,95 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorM
   }
 }
 
+// 16-warp variant of the drain: this warp owns 32 rows x 64 columns (tile columns c_begin .. c_begin+63).  The
+// bf16 path works in two 32-column halves so that at most one TMEM load + one side load are live per thread
+// (<= 112 registers at 576 threads per CTA); with four epilogue warps per SM sub-partition the TMEM / global /
+// TMA-store latencies of one warp are covered by the other three.
+__device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
+                                                uint32_t tmem_acc, int row0, int n0, int c_begin,
+                                                const __nv_bfloat16* sbias, uint8_t* sbuf, int lane) {
+  const int flags = a.flags;
+  if (flags & (EPI_MC | EPI_OUT_F32 | EPI_ACCUM)) {
+    epilogue_f32<64>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane);
+    return;
+  }
+  const int col0 = n0 + c_begin;
+  if (col0 >= a.N) return;
+  const int row = row0 + lane;
+  const bool row_ok = row < a.M;
+  const bool need_side = (flags & (EPI_DGELU | EPI_RESIDUAL)) != 0;
+  const __nv_bfloat16* side = (flags & EPI_DGELU) ? a.aux : a.residual;
+  const __nv_bfloat16* sp = side + static_cast<size_t>(row) * a.ldc + col0;
+  if (flags & EPI_SAVE_PRE) {
+    // pass 1: the pre-activation (acc + bias) goes out through the aux tensor map
+    stage_acquire(lane);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + c_begin + h * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float x[8], bv[8];
+        unpack8(*reinterpret_cast<const uint4*>(sbias + c_begin + h * 32 + q * 8), bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(r[q * 8 + j]) + ((flags & EPI_BIAS) ? bv[j] : 0.f);
+        stage_write16(sbuf, lane, h * 4 + q, pack8(x));
+      }
+    }
+    stage_commit(tm_aux, sbuf, col0, row0, lane, false);
+  }
+  stage_acquire(lane);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    uint4 sv[4];
+    if (need_side && row_ok) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        sv[q] = (col0 + h * 32 + q * 8 < a.N) ? *reinterpret_cast<const uint4*>(sp + h * 32 + q * 8)
+                                             : make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sv[q] = make_uint4(0, 0, 0, 0);
+    }
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_acc + c_begin + h * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(r[q * 8 + j]);
+      if (flags & EPI_BIAS) {
+        float bv[8];
+        unpack8(*reinterpret_cast<const uint4*>(sbias + c_begin + h * 32 + q * 8), bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += bv[j];
+      }
+      if (flags & EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
+      }
+      if (flags & EPI_DGELU) {
+        float hh[8];
+        unpack8(sv[q], hh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] *= gelu_tanh_grad(hh[j]);
+      }
+      if (flags & EPI_RESIDUAL) {
+        float hh[8];
+        unpack8(sv[q], hh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += hh[j];
+      }
+      stage_write16(sbuf, lane, h * 4 + q, pack8(x));
+    }
+  }
+  stage_commit(tm_out, sbuf, col0, row0, lane, false);
+}
+
 // Epilogue warps stage the tile's bias row (kBlockN bf16) into shared memory; 256 threads, named barrier 1.
-template <int kBlockN>
+template <int kBlockN, int kEpiThreads = 256>
 __device__ __forceinline__ void stage_bias(const GemmArgs& a, __nv_bfloat16* sbias, int n0, int epi_tid) {
   if (a.flags & EPI_BIAS) {
     if (epi_tid < kBlockN) {
@@ -236,7 +340,7 @@ __device__ __forceinline__ void stage_bias(const GemmArgs& a, __nv_bfloat16* sbi
       sbias[epi_tid] = col < a.N ? a.bias[col] : __float2bfloat16(0.f);
     }
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
 template <int kBlockN, bool kAMN, bool kBMN>
@@ -390,8 +494,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // shared memory, and each CTA drains its own 128 accumulator rows from its TMEM.  Per-CTA operand traffic
 // drops from 48 KB to 32 KB per k-block (the 1-CTA kernel is L2->SM bandwidth bound at K=768..3072) and the
 // freed shared memory buys a 6-stage ring.
-template <bool kAMN, bool kBMN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <bool kAMN, bool kBMN, int kEpiW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiW, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                       const GemmArgs args) {
@@ -399,14 +503,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   constexpr int kStageA = BLOCK_M * BLOCK_K * 2;       // this CTA's 128 rows of A
   constexpr int kStageB = (kPairN / 2) * BLOCK_K * 2;  // this CTA's half of B
   constexpr int kStageBytes = kStageA + kStageB;
-  constexpr int kStages = 6;
+  constexpr int kStages = kEpiW == 16 ? 5 : 6;   // 16 staging buffers cost one ring stage
   constexpr uint32_t kTmemCols = 2 * kPairN;
   constexpr uint32_t kIdesc = make_idesc_bf16(kPairM, kPairN, kAMN ? 1u : 0u, kBMN ? 1u : 0u);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  constexpr int kStagingBytes = kEpiWarps * 4096;
+  constexpr int kStagingBytes = kEpiW * 4096;
   uint8_t* staging = smem + kStages * kStageBytes;
   __nv_bfloat16* sbias = reinterpret_cast<__nv_bfloat16*>(staging + kStagingBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes + 1024);
@@ -431,7 +535,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);   // per CTA, multicast commit
-      mbar_init(&tmem_empty[i], 2 * kEpiWarps);  // leader's copy: 8 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[i], 2 * kEpiW);  // leader's copy: all epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -450,12 +554,15 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long tr_wait = 0;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
         const WorkItem wi = decode_work(args, w);
         const int m0 = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
         const int n0 = wi.n_blk * kPairN + static_cast<int>(rank) * (kPairN / 2);
         for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+          TR_BEGIN(args.trace, t0);
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          TR_ADD(args.trace, t0, tr_wait);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -477,6 +584,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (args.trace) args.trace[blockIdx.x * 8 + TR_TMA_WAIT_EMPTY] = tr_wait;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -485,13 +593,20 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long tr_full = 0, tr_tmem = 0, tr_tiles = 0;
+      TR_BEGIN(args.trace, tr_start);
       for (int w = cluster_id; w < num_work; w += num_clusters) {
         const WorkItem wi = decode_work(args, w);
+        TR_BEGIN(args.trace, t0);
         mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);
+        TR_ADD(args.trace, t0, tr_tmem);
+        ++tr_tiles;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kPairN;
         for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+          TR_BEGIN(args.trace, t1);
           mbar_wait_cluster(&full_bar[stage], phase);
+          TR_ADD(args.trace, t1, tr_full);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
           const uint32_t b_addr = a_addr + kStageA;
@@ -509,32 +624,56 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         umma_commit_2cta(&tmem_full[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+      if (args.trace) {
+        unsigned long long* tr = args.trace + blockIdx.x * 8;
+        tr[TR_MMA_TOTAL] = clock64() - tr_start;
+        tr[TR_MMA_WAIT_FULL] = tr_full;
+        tr[TR_MMA_WAIT_TMEM] = tr_tmem;
+        tr[TR_TILES] = tr_tiles;
+      }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    // ------------------------------------------------------------ epilogue (warps 2.., both CTAs)
     const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;     // column slice: halves (8 warps) or quarters (16 warps)
     const int epi_tid = threadIdx.x - 64;
     uint8_t* sbuf = staging + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long tr_wait = 0, tr_busy = 0;
+    TR_BEGIN(args.trace, tr_start);
     for (int w = cluster_id; w < num_work; w += num_clusters) {
       const WorkItem wi = decode_work(args, w);
-      stage_bias<kPairN>(args, sbias + acc * 256, wi.n_blk * kPairN, epi_tid);
+      stage_bias<kPairN, 32 * kEpiW>(args, sbias + acc * 256, wi.n_blk * kPairN, epi_tid);
+      TR_BEGIN(args.trace, t0);
       mbar_wait_cluster(&tmem_full[acc], acc_phase);
+      TR_ADD(args.trace, t0, tr_wait);
+      TR_BEGIN(args.trace, t1);
       tc_fence_after();
       if (wi.kb1 > wi.kb0) {
-        epilogue_tile<kPairN / 2>(args, &tmap_out, &tmap_aux,
-                                  tmem_base + acc * kPairN + (static_cast<uint32_t>(lg * 32) << 16),
-                                  wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32, wi.n_blk * kPairN,
-                                  half * (kPairN / 2), sbias + acc * 256, sbuf, lane);
+        const uint32_t t_acc = tmem_base + acc * kPairN + (static_cast<uint32_t>(lg * 32) << 16);
+        const int row0 = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32;
+        if constexpr (kEpiW == 16) {
+          epilogue_cols64(args, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * 64, sbias + acc * 256,
+                          sbuf, lane);
+        } else {
+          epilogue_tile<kPairN / 2>(args, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * (kPairN / 2),
+                                    sbias + acc * 256, sbuf, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+      TR_ADD(args.trace, t1, tr_busy);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait<0>();
+    if (args.trace && warp == 2 && lane == 0) {
+      unsigned long long* tr = args.trace + blockIdx.x * 8;
+      tr[TR_EPI_WAIT_FULL] = tr_wait;
+      tr[TR_EPI_BUSY] = tr_busy;
+      tr[TR_EPI_TOTAL] = clock64() - tr_start;
+    }
   }
 
   tc_fence_before();
@@ -605,12 +744,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
 }
 
-template <bool kAMN, bool kBMN>
+static int pair_epilogue_warps() {
+  // 16 (default): four epilogue warps per SM sub-partition, 5-stage ring.  8: two per sub-partition, 6 stages.
+  static int w = 0;
+  if (!w) {
+    const char* e = getenv("AITJ_GEMM_EPI_WARPS");
+    w = (e && atoi(e) == 8) ? 8 : 16;
+  }
+  return w;
+}
+
+template <bool kAMN, bool kBMN, int kEpiW>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                             const GemmArgs& args, int max_ctas, cudaStream_t stream) {
-  constexpr int kSmem = 6 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + kEpiWarps * 4096 + 1024 + 1024 + 256;
+  constexpr int kSmem = (kEpiW == 16 ? 5 : 6) * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + kEpiW * 4096 + 1024 +
+                        1024 + 256;
   static bool configured = false;
-  auto kern = gemm_bf16_2cta_kernel<kAMN, kBMN>;
+  auto kern = gemm_bf16_2cta_kernel<kAMN, kBMN, kEpiW>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return -20;
     configured = true;
@@ -620,13 +770,19 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   if (num_work < pairs) pairs = num_work;
   if (max_ctas > 1 && pairs > max_ctas / 2) pairs = max_ctas / 2;
   if (pairs < 1) pairs = 1;
-  kern<<<pairs * 2, kGemmThreads, kSmem, stream>>>(ta, tb, to, tx, args);
+  kern<<<pairs * 2, 64 + 32 * kEpiW, kSmem, stream>>>(ta, tb, to, tx, args);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
 }
 
 }  // namespace aitj
 
+static unsigned long long* g_gemm_trace = nullptr;
+
 extern "C" {
+
+// Debug/profiling: when non-null, the CTA-pair kernel writes 8 x u64 per CTA (TR_* slots, clock64 cycles) showing
+// where the MMA issuer, the TMA producer and epilogue warp 2 waited.  The buffer needs 8*8*num_SMs bytes.
+int aitj_gemm_set_trace(void* buf) { g_gemm_trace = reinterpret_cast<unsigned long long*>(buf); return 0; }
 
 // Returns 0 on success. See file header for operand conventions. lda/ldb/ldc in elements.
 // block_n: 128 or 256 (0 = auto). split_k > 1 requires EPI_ACCUM. max_ctas: 0 = all SMs.
@@ -652,6 +808,7 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   args.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   args.aux = reinterpret_cast<__nv_bfloat16*>(aux);
   args.flags = flags;
+  args.trace = g_gemm_trace;
   args.tiles_m = pair ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;
   args.tiles_n = (N + block_n - 1) / block_n;
   args.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
@@ -683,10 +840,14 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   }
 
   if (pair) {
-    if (!a_mn && !b_mn) return launch_gemm_2cta<false, false>(ta, tb, to, tx, args, max_ctas, stream);
-    if (!a_mn && b_mn) return launch_gemm_2cta<false, true>(ta, tb, to, tx, args, max_ctas, stream);
-    if (a_mn && !b_mn) return launch_gemm_2cta<true, false>(ta, tb, to, tx, args, max_ctas, stream);
-    return launch_gemm_2cta<true, true>(ta, tb, to, tx, args, max_ctas, stream);
+#define AITJ_PAIR(W)                                                                                  \
+    if (!a_mn && !b_mn) return launch_gemm_2cta<false, false, W>(ta, tb, to, tx, args, max_ctas, stream); \
+    if (!a_mn && b_mn) return launch_gemm_2cta<false, true, W>(ta, tb, to, tx, args, max_ctas, stream);   \
+    if (a_mn && !b_mn) return launch_gemm_2cta<true, false, W>(ta, tb, to, tx, args, max_ctas, stream);   \
+    return launch_gemm_2cta<true, true, W>(ta, tb, to, tx, args, max_ctas, stream);
+    if (pair_epilogue_warps() == 16) { AITJ_PAIR(16) }
+    AITJ_PAIR(8)
+#undef AITJ_PAIR
   }
 #define AITJ_DISPATCH(BN)                                                                     \
   if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, to, tx, args, max_ctas, stream);   \

@@ -176,6 +176,21 @@ def colsum(dy, db):
     lib.call("aitj_colsum", dy.data_ptr(), db.data_ptr(), M, N, _is_mc(db), _stream())
 
 
+def qkv_gather_colsum(dq, dk, dv, d_qkv, db):
+    """d_qkv[B*T, 3*H*D] <- (dq, dk, dv), each logically [B,H,T,D] with any B/H/T strides; db[3*H*D] += colsum."""
+    import ctypes
+
+    B, H, T, D = dq.shape
+    st = []
+    for t in (dq, dk, dv):
+        if t.stride(3) != 1 or tuple(t.shape) != (B, H, T, D):
+            raise ValueError("qkv_gather_colsum: need [B,H,T,D] tensors with unit D stride")
+        st += [t.stride(0), t.stride(1), t.stride(2)]
+    arr = (ctypes.c_longlong * 9)(*st)
+    lib.call("aitj_qkv_gather_colsum", dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ctypes.addressof(arr),
+             d_qkv.data_ptr(), db.data_ptr(), B, T, H, D, _is_mc(db), _stream())
+
+
 def sumsq(g, out):
     lib.call("aitj_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), _stream())
 

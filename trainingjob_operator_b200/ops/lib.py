@@ -58,12 +58,14 @@ _F = ctypes.c_float
 _SIGS = {
     "aitj_gemm_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "aitj_num_sms": [],
+    "aitj_gemm_set_trace": [_P],
     "aitj_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
     "aitj_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "aitj_embedding_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "aitj_embedding_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "aitj_softmax_xent": [_P, _P, _P, _I, _I, _I, _F, _P],
     "aitj_colsum": [_P, _P, _I, _I, _I, _P],
+    "aitj_qkv_gather_colsum": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "aitj_sumsq": [_P, _L, _P, _P],
     "aitj_adamw": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
     "aitj_cast_f32_bf16": [_P, _P, _L, _P],

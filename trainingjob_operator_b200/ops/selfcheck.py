@@ -212,6 +212,20 @@ def case_fused_ops():
     F.colsum(dyc, db)
     ok &= _check("colsum", db, dyc.float().sum(0), 1e-3)
 
+    # attention-backward gather fused with the qkv bias gradient (both source layouts cuDNN may return)
+    Bq, Hq, Tq, Dq = 3, 12, 100, 64
+    for layout in ("bhtd", "bthd"):
+        if layout == "bhtd":
+            srcs = [_rand(Bq, Hq, Tq, Dq) for _ in range(3)]
+        else:
+            srcs = [_rand(Bq, Tq, Hq, Dq).transpose(1, 2) for _ in range(3)]
+        outq = torch.empty(Bq * Tq, 3 * Hq * Dq, device="cuda", dtype=torch.bfloat16)
+        dbq = torch.zeros(3 * Hq * Dq, device="cuda")
+        F.qkv_gather_colsum(srcs[0], srcs[1], srcs[2], outq, dbq)
+        refq = torch.stack([t.transpose(1, 2) for t in srcs], dim=2).reshape(Bq * Tq, 3 * Hq * Dq)
+        ok &= bool((outq == refq).all())
+        ok &= _check(f"qkv_gather_colsum {layout}", dbq, refq.float().sum(0), 1e-3)
+
     # adamw vs torch.optim.AdamW, two steps, with decay mask
     n = 256 * 40
     p0 = torch.randn(n, device="cuda")
