@@ -63,7 +63,8 @@ def main():
         ("square 8192", 8192, 8192, 8192, False, False),
         ("square 4096", 4096, 4096, 4096, False, False),
     ]
-    for name, m, n, k, a_mn, b_mn in shapes:
+    mem_only = "--mem-only" in sys.argv
+    for name, m, n, k, a_mn, b_mn in ([] if mem_only else shapes):
         a = torch.randn(m, k, device="cuda").bfloat16()
         b = (torch.randn(k, n, device="cuda") if b_mn else torch.randn(n, k, device="cuda")).bfloat16()
         out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
@@ -77,8 +78,8 @@ def main():
         rows.append({"kernel": f"cublas  {name}", "M": m, "N": n, "K": k, "ms_med": med, "ms_best": best,
                      "tflops": flops / med / 1e9, "frac_of_measured_peak": flops / med / 1e9 / PEAK_TF})
     # wgrad (split-K, fp32 red.add)
-    for name, nout, kin in [("qkv wgrad", 3 * C, C), ("fc wgrad", 4 * C, C), ("fc2 wgrad", C, 4 * C),
-                            ("proj wgrad", C, C), ("lm_head wgrad", 50304, C)]:
+    for name, nout, kin in ([] if mem_only else [("qkv wgrad", 3 * C, C), ("fc wgrad", 4 * C, C), ("fc2 wgrad", C, 4 * C),
+                                                 ("proj wgrad", C, C), ("lm_head wgrad", 50304, C)]):
         dy = torch.randn(M, nout, device="cuda").bfloat16()
         x = torch.randn(M, kin, device="cuda").bfloat16()
         dw = torch.zeros(nout, kin, device="cuda")

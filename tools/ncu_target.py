@@ -13,13 +13,16 @@ M = B * T
 if what.startswith("gemm"):
     shapes = {"gemm_fc": (M, 4 * C, C, False, False), "gemm_square": (8192, 8192, 8192, False, False),
               "gemm_fc2_dgrad": (M, 4 * C, C, False, True), "gemm_wgrad": (4 * C, C, M, True, True)}
+    shapes.update({"gemm_qkv_pair": (M, 3 * C, C, False, False), "gemm_square_pair": (8192, 8192, 8192, False, False),
+                   "gemm_fcwgrad_pair": (4 * C, C, M, True, True)})
     m, n, k, a_mn, b_mn = shapes[what]
+    bn = 512 if what.endswith("_pair") else 0
     a = (torch.randn(k, m, device="cuda") if a_mn else torch.randn(m, k, device="cuda")).bfloat16()
     b = (torch.randn(k, n, device="cuda") if b_mn else torch.randn(n, k, device="cuda")).bfloat16()
     acc = a_mn
     out = torch.zeros(m, n, device="cuda", dtype=torch.float32 if acc else torch.bfloat16)
     for _ in range(6):
-        F.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, accumulate=acc, split_k=2 if acc else 1)
+        F.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, accumulate=acc, split_k=2 if acc else 1, block_n=bn)
 elif what == "xent":
     logits = torch.randn(M, 50304, device="cuda").bfloat16()
     tgt = torch.randint(0, 50257, (M,), device="cuda")

@@ -71,106 +71,133 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
   }
 }
 
+// Block reduction of one per-thread partial (V*8 columns per lane) to one atomic per column: the upper half of
+// the warps hand their partials to the lower half through shared memory, which then publish the partial sums.
+constexpr int kLnBwdWarps = 12;
+template <int V>
+__device__ __forceinline__ void ln_bwd_block_reduce(const float (&acc)[V * 8], float (*red)[V * 256], float* dst, int warp,
+                                                    int lane, int mc) {
+  constexpr int C = V * 256;
+  constexpr int H = kLnBwdWarps / 2;
+  __syncthreads();
+  if (warp >= H) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float* d = &red[warp - H][(i * 32 + lane) * 8];
+      *reinterpret_cast<float4*>(d) = make_float4(acc[i * 8], acc[i * 8 + 1], acc[i * 8 + 2], acc[i * 8 + 3]);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(acc[i * 8 + 4], acc[i * 8 + 5], acc[i * 8 + 6], acc[i * 8 + 7]);
+    }
+  }
+  __syncthreads();
+  if (warp < H) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float* d = &red[warp][(i * 32 + lane) * 8];
+      const float4 p0 = *reinterpret_cast<const float4*>(d), p1 = *reinterpret_cast<const float4*>(d + 4);
+      *reinterpret_cast<float4*>(d) = make_float4(acc[i * 8] + p0.x, acc[i * 8 + 1] + p0.y, acc[i * 8 + 2] + p0.z,
+                                                  acc[i * 8 + 3] + p0.w);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(acc[i * 8 + 4] + p1.x, acc[i * 8 + 5] + p1.y,
+                                                      acc[i * 8 + 6] + p1.z, acc[i * 8 + 7] + p1.w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < H; ++w) t += red[w][c];
+    grad_add_f32(dst + c, t, mc != 0);
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm backward
 // dx (bf16), dgamma/dbeta accumulated (fp32 atomics) into flat grad buffer. If `dres` != null
 // the incoming residual-stream gradient is added to dx (fuses the residual branch add).
 template <int V>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                            const __nv_bfloat16* __restrict__ x,
-                                                            const __nv_bfloat16* __restrict__ gamma,
-                                                            const float* __restrict__ mean_in,
-                                                            const float* __restrict__ rstd_in,
-                                                            const __nv_bfloat16* __restrict__ dres,
-                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, float* __restrict__ dxsum,
-                                                            int M, int mc) {
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 1) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ x,
+                                                               const __nv_bfloat16* __restrict__ gamma,
+                                                               const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in,
+                                                               const __nv_bfloat16* __restrict__ dres,
+                                                               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, float* __restrict__ dxsum,
+                                                               int M, int mc) {
   // dxsum (optional, fp32[C]) += column sums of dx: dx is the gradient of the tensor that fed this LayerNorm,
   // i.e. of "linear output + bias + residual", so its column sum IS that linear's bias gradient -- for free.
+  //
+  // One warp per row, 12 warps per SM.  The kernel is a pure HBM stream (3 reads + 1 write per element), so what
+  // matters is bytes in flight: per-thread state is kept under 168 registers (x / dy / dres stay packed bf16, gamma
+  // lives in shared memory) so that 12 warps fit, and all three inputs of a row are requested before any math.
   constexpr int C = V * 256;
-  __shared__ float red[8][C];
+  __shared__ float red[kLnBwdWarps / 2][C];
+  __shared__ float sgamma[C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  float g[V * 8], dg[V * 8], db[V * 8], ds[V * 8];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    uint4 gu = *reinterpret_cast<const uint4*>(gamma + (i * 32 + lane) * 8);
-    const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 gf = unpack_bf16x2(gw[j]);
-      g[i * 8 + 2 * j] = gf.x; g[i * 8 + 2 * j + 1] = gf.y;
-    }
-  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sgamma[c] = __bfloat162float(gamma[c]);
+  __syncthreads();
+  float dg[V * 8], db[V * 8], ds[V * 8];
 #pragma unroll
   for (int i = 0; i < V * 8; ++i) { dg[i] = 0.f; db[i] = 0.f; ds[i] = 0.f; }
+  const bool has_res = dres != nullptr;
 
   for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
     const size_t base = static_cast<size_t>(row) * C;
+    uint4 xu[V], du[V], ru[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      xu[i] = *reinterpret_cast<const uint4*>(x + base + (i * 32 + lane) * 8);
+      du[i] = *reinterpret_cast<const uint4*>(dy + base + (i * 32 + lane) * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      ru[i] = has_res ? *reinterpret_cast<const uint4*>(dres + base + (i * 32 + lane) * 8) : make_uint4(0, 0, 0, 0);
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[V * 8], dyv[V * 8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      uint4 xu = *reinterpret_cast<const uint4*>(x + base + (i * 32 + lane) * 8);
-      uint4 du = *reinterpret_cast<const uint4*>(dy + base + (i * 32 + lane) * 8);
-      const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w}, dw[4] = {du.x, du.y, du.z, du.w};
+      const uint32_t xw[4] = {xu[i].x, xu[i].y, xu[i].z, xu[i].w}, dw[4] = {du[i].x, du[i].y, du[i].z, du[i].w};
+      const float4 g0 = *reinterpret_cast<const float4*>(sgamma + (i * 32 + lane) * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(sgamma + (i * 32 + lane) * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]);
+        const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]);
         const int k = i * 8 + 2 * j;
-        xh[k] = (xf.x - mean) * rstd; xh[k + 1] = (xf.y - mean) * rstd;
-        dyv[k] = df.x; dyv[k + 1] = df.y;
-        dg[k] += df.x * xh[k]; dg[k + 1] += df.y * xh[k + 1];
+        const float h0 = (xf.x - mean) * rstd, h1 = (xf.y - mean) * rstd;
+        dg[k] += df.x * h0; dg[k + 1] += df.y * h1;
         db[k] += df.x; db[k + 1] += df.y;
-        const float a0 = df.x * g[k], a1 = df.y * g[k + 1];
+        const float a0 = df.x * gg[2 * j], a1 = df.y * gg[2 * j + 1];
         s1 += a0 + a1;
-        s2 += a0 * xh[k] + a1 * xh[k + 1];
+        s2 += a0 * h0 + a1 * h1;
       }
     }
     s1 = warp_sum(s1) * (1.0f / C);
     s2 = warp_sum(s2) * (1.0f / C);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float r[8];
-      if (dres != nullptr) {
-        uint4 ru = *reinterpret_cast<const uint4*>(dres + base + (i * 32 + lane) * 8);
-        const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 f = unpack_bf16x2(rw[j]); r[2 * j] = f.x; r[2 * j + 1] = f.y; }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = 0.f;
-      }
+      const uint32_t xw[4] = {xu[i].x, xu[i].y, xu[i].z, xu[i].w}, dw[4] = {du[i].x, du[i].y, du[i].z, du[i].w};
+      const uint32_t rw[4] = {ru[i].x, ru[i].y, ru[i].z, ru[i].w};
+      const float4 g0 = *reinterpret_cast<const float4*>(sgamma + (i * 32 + lane) * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(sgamma + (i * 32 + lane) * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       uint4 o;
       uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16x2(xw[j]), df = unpack_bf16x2(dw[j]), rf = unpack_bf16x2(rw[j]);
         const int k = i * 8 + 2 * j;
-        float a0 = rstd * (dyv[k] * g[k] - s1 - xh[k] * s2) + r[2 * j];
-        float a1 = rstd * (dyv[k + 1] * g[k + 1] - s1 - xh[k + 1] * s2) + r[2 * j + 1];
+        const float h0 = (xf.x - mean) * rstd, h1 = (xf.y - mean) * rstd;
+        const float a0 = rstd * (df.x * gg[2 * j] - s1 - h0 * s2) + rf.x;
+        const float a1 = rstd * (df.y * gg[2 * j + 1] - s1 - h1 * s2) + rf.y;
         ds[k] += a0; ds[k + 1] += a1;
         ow[j] = pack_bf16x2(a0, a1);
       }
       *reinterpret_cast<uint4*>(dx + base + (i * 32 + lane) * 8) = o;
     }
   }
-  // block reduce dgamma then dbeta through smem, one atomic per column per block
-  const int passes = dxsum != nullptr ? 3 : 2;
-  for (int pass = 0; pass < passes; ++pass) {
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < V; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        red[warp][(i * 32 + lane) * 8 + j] = pass == 0 ? dg[i * 8 + j] : (pass == 1 ? db[i * 8 + j] : ds[i * 8 + j]);
-    __syncthreads();
-    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s = 0.f;
-      for (int w = 0; w < warps_per_block; ++w) s += red[w][c];
-      grad_add_f32(dst + c, s, mc != 0);
-    }
-  }
+  ln_bwd_block_reduce<V>(dg, red, dgamma, warp, lane, mc);
+  ln_bwd_block_reduce<V>(db, red, dbeta, warp, lane, mc);
+  if (dxsum != nullptr) ln_bwd_block_reduce<V>(ds, red, dxsum, warp, lane, mc);
 }
 
 // ------------------------------------------------------------------ embedding
@@ -685,8 +712,8 @@ int aitj_layernorm_bwd(const void* dy, const void* x, const void* gamma, const v
                        const void* dres, void* dx, void* dgamma, void* dbeta, void* dxsum, int M, int C, int mc,
                        void* stream) {
   if (C % 256 || C > 1024) return -1;
-  const int blocks = min((M + 7) / 8, 148 * 2);
-#define LN_B(V) layernorm_bwd_kernel<V><<<blocks, 256, 0, S(stream)>>>(CBF(dy), CBF(x), CBF(gamma), \
+  const int blocks = min((M + kLnBwdWarps - 1) / kLnBwdWarps, 148);
+#define LN_B(V) layernorm_bwd_kernel<V><<<blocks, kLnBwdWarps * 32, 0, S(stream)>>>(CBF(dy), CBF(x), CBF(gamma), \
     reinterpret_cast<const float*>(mean), reinterpret_cast<const float*>(rstd), CBF(dres), BF(dx), \
     reinterpret_cast<float*>(dgamma), reinterpret_cast<float*>(dbeta), reinterpret_cast<float*>(dxsum), M, mc)
   switch (C / 256) {
