@@ -40,7 +40,7 @@ def run(name, fn, iters=3):
     allc = t[t[:, 6] > 0]
     us = e0.elapsed_time(e1) * 1000 / iters
     tiles = lead[:, 7].mean().item()
-    print(f"{name:34s} {us:7.1f} us | tiles/cluster {tiles:4.1f} | MMA total {lead[:,0].mean():8.0f} "
+    print(f"{name:44s} {us:7.1f} us | tiles/cluster {tiles:4.1f} | MMA total {lead[:,0].mean():8.0f} "
           f"wait_full(TMA) {lead[:,1].mean():8.0f} wait_tmem(epi) {lead[:,2].mean():8.0f} | "
           f"TMA wait_empty {t[:,3][t[:,6]>0].mean():8.0f} | EPI total {allc[:,6].mean():8.0f} "
           f"wait_full {allc[:,4].mean():8.0f} busy {allc[:,5].mean():8.0f} (per tile {allc[:,5].mean()/max(tiles,1):6.0f})",
@@ -66,6 +66,9 @@ BN = 512
 
 run("qkv fwd  (bias)", lambda: F.gemm(x, w_qkv, o3, bias=b_qkv, block_n=BN))
 run("qkv fwd  (no epilogue math)", lambda: F.gemm(x, w_qkv, o3, block_n=BN))
+run("qkv fwd  (epilogue skipped: main loop only)", lambda: F.gemm(x, w_qkv, o3, block_n=BN, _debug_skip_epilogue=True))
+run("fc fwd   (epilogue skipped)", lambda: F.gemm(x, w_fc, o4, block_n=BN, _debug_skip_epilogue=True))
+run("fc dgrad (epilogue skipped)", lambda: F.gemm(x4, w_fc, o1, b_mn=True, block_n=BN, _debug_skip_epilogue=True))
 run("proj fwd (bias+residual)", lambda: F.gemm(x, w_proj, o1, bias=b_proj, residual=res, block_n=BN))
 run("fc fwd   (bias+gelu+save_pre)", lambda: F.gemm(x, w_fc, o4, bias=b_fc, gelu=True, save_pre=True, aux=pre4, block_n=BN))
 run("fc fwd   (bias only)", lambda: F.gemm(x, w_fc, o4, bias=b_fc, block_n=BN))
@@ -81,3 +84,4 @@ run("fc2 wgrad sk=4", lambda: F.gemm(x, x4, g42, a_mn=True, b_mn=True, accumulat
 big_a, big_b = r(8192, 8192), r(8192, 8192)
 big_o = torch.empty(8192, 8192, device=dev, dtype=torch.bfloat16)
 run("square 8192", lambda: F.gemm(big_a, big_b, big_o, block_n=BN))
+run("square 8192 (epilogue skipped)", lambda: F.gemm(big_a, big_b, big_o, block_n=BN, _debug_skip_epilogue=True))

@@ -32,7 +32,10 @@ enum : int {
   EPI_DGELU = 16,     // * gelu'(aux[M,ldc])
   EPI_OUT_F32 = 32,   // out is fp32 (plain store)
   EPI_ACCUM = 64,     // out is fp32, red.global.add (split-K / grad accumulation)
-  EPI_MC = 128        // with EPI_ACCUM: `out` is an NVSwitch multicast address; reduce with multimem.red (GEMM + all-reduce in one kernel)
+  EPI_MC = 128,       // with EPI_ACCUM: `out` is an NVSwitch multicast address; reduce with multimem.red (GEMM + all-reduce in one kernel)
+  EPI_DEBUG_SKIP = 256, // profiling only: the epilogue releases the accumulator without draining it (main loop in isolation)
+  EPI_DIRECT = 512      // bf16 outputs leave through st.global from registers (one 128-byte row segment per thread)
+                        // instead of the shared-memory staging + TMA store
 };
 
 struct GemmArgs {
@@ -263,9 +266,12 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
   const bool need_side = (flags & (EPI_DGELU | EPI_RESIDUAL)) != 0;
   const __nv_bfloat16* side = (flags & EPI_DGELU) ? a.aux : a.residual;
   const __nv_bfloat16* sp = side + static_cast<size_t>(row) * a.ldc + col0;
+  const bool direct = (flags & EPI_DIRECT) != 0;
+  __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(row) * a.ldc + col0;
   if (flags & EPI_SAVE_PRE) {
     // pass 1: the pre-activation (acc + bias) goes out through the aux tensor map
-    stage_acquire(lane);
+    __nv_bfloat16* arow = a.aux + static_cast<size_t>(row) * a.ldc + col0;
+    if (!direct) stage_acquire(lane);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       uint32_t r[32];
@@ -277,12 +283,16 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
         unpack8(*reinterpret_cast<const uint4*>(sbias + c_begin + h * 32 + q * 8), bv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(r[q * 8 + j]) + ((flags & EPI_BIAS) ? bv[j] : 0.f);
-        stage_write16(sbuf, lane, h * 4 + q, pack8(x));
+        if (direct) {
+          if (row_ok && col0 + h * 32 + q * 8 < a.N) *reinterpret_cast<uint4*>(arow + h * 32 + q * 8) = pack8(x);
+        } else {
+          stage_write16(sbuf, lane, h * 4 + q, pack8(x));
+        }
       }
     }
-    stage_commit(tm_aux, sbuf, col0, row0, lane, false);
+    if (!direct) stage_commit(tm_aux, sbuf, col0, row0, lane, false);
   }
-  stage_acquire(lane);
+  if (!direct) stage_acquire(lane);
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     uint4 sv[4];
@@ -325,10 +335,14 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] += hh[j];
       }
-      stage_write16(sbuf, lane, h * 4 + q, pack8(x));
+      if (direct) {
+        if (row_ok && col0 + h * 32 + q * 8 < a.N) *reinterpret_cast<uint4*>(orow + h * 32 + q * 8) = pack8(x);
+      } else {
+        stage_write16(sbuf, lane, h * 4 + q, pack8(x));
+      }
     }
   }
-  stage_commit(tm_out, sbuf, col0, row0, lane, false);
+  if (!direct) stage_commit(tm_out, sbuf, col0, row0, lane, false);
 }
 
 // Epilogue warps stage the tile's bias row (kBlockN bf16) into shared memory; 256 threads, named barrier 1.
@@ -650,7 +664,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       TR_ADD(args.trace, t0, tr_wait);
       TR_BEGIN(args.trace, t1);
       tc_fence_after();
-      if (wi.kb1 > wi.kb0) {
+      if (wi.kb1 > wi.kb0 && !(args.flags & EPI_DEBUG_SKIP)) {
         const uint32_t t_acc = tmem_base + acc * kPairN + (static_cast<uint32_t>(lg * 32) << 16);
         const int row0 = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32;
         if constexpr (kEpiW == 16) {
@@ -807,6 +821,10 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   args.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   args.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   args.aux = reinterpret_cast<__nv_bfloat16*>(aux);
+  {
+    static const bool direct_store = getenv("AITJ_GEMM_DIRECT_STORE") && atoi(getenv("AITJ_GEMM_DIRECT_STORE")) != 0;
+    if (direct_store && !(flags & (EPI_OUT_F32 | EPI_ACCUM))) flags |= EPI_DIRECT;
+  }
   args.flags = flags;
   args.trace = g_gemm_trace;
   args.tiles_m = pair ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;

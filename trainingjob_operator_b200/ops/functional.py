@@ -64,7 +64,7 @@ def _ptr(t):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, gelu=False, dgelu=False,
-         save_pre=False, accumulate=False, split_k=1, block_n=0, max_ctas=0):
+         save_pre=False, accumulate=False, split_k=1, block_n=0, max_ctas=0, _debug_skip_epilogue=False):
     """out[M,N] (+)= opA[M,K] @ opB[N,K]^T on tcgen05 tensor cores (bf16 in, fp32 accumulate).
 
     a_mn=False: ``a`` is [M,K]; a_mn=True: ``a`` is [K,M] (its transpose is used).
@@ -105,6 +105,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
             flags |= EPI_MC
     else:
         assert out.dtype == torch.bfloat16 and not accumulate
+    if _debug_skip_epilogue:
+        flags |= 256
     lib.call("aitj_gemm_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
              out.stride(0), int(a_mn), int(b_mn), _ptr(bias), _ptr(residual), _ptr(aux), flags, int(split_k),
              int(block_n), int(max_ctas), _stream())
