@@ -335,6 +335,13 @@ class NodeAgent:
         os.makedirs(self._zy_dir, exist_ok=True)
         with self._lock:
             while len(self._zygotes) < self.warm_pool:
+                # GPU box: one parked interpreter per GPU slot, CUDA context included; CPU-only box: generic ones
+                gpu = None
+                if self.num_gpus > 0:
+                    taken = {z["gpu"] for z in self._zygotes.values()}
+                    gpu = next((g for g in range(min(self.num_gpus, self.warm_pool)) if g not in taken), None)
+                    if gpu is None:
+                        return
                 self._zy_seq += 1
                 zid = f"{ZYGOTE_PREFIX}{os.getpid()}-{self._zy_seq}"
                 fifo = os.path.join(self._zy_dir, f"z{os.getpid()}-{self._zy_seq}.fifo")
@@ -345,13 +352,19 @@ class NodeAgent:
                         pass
                 try:
                     os.mkfifo(fifo, 0o600)
-                    self.sup.spawn(zid, [sys.executable, "-m", "trainingjob_operator_b200.runtime.zygote", fifo],
-                                   self._zygote_env(), "", os.path.join(self.log_dir, "zygotes.log"), "", [])
+                    env = self._zygote_env()
+                    cmd = [sys.executable, "-m", "trainingjob_operator_b200.runtime.zygote", fifo]
+                    if gpu is not None:
+                        env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+                        env["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
+                        cmd.append("--cuda")
+                    self.sup.spawn(zid, cmd, env, "", os.path.join(self.log_dir, "zygotes.log"), "",
+                                   self._cpus_for([gpu]) if gpu is not None else [])
                 except OSError as e:
                     klog.warning("warm pool: cannot start an interpreter: %s", e)
                     self._zy_failures += 1
                     return
-                self._zygotes[zid] = {"fifo": fifo, "spawned": time.monotonic()}
+                self._zygotes[zid] = {"fifo": fifo, "spawned": time.monotonic(), "gpu": gpu}
 
     def warm_ready(self) -> int:
         """Number of parked interpreters that finished their imports."""
@@ -397,8 +410,15 @@ class NodeAgent:
                 return False
         except OSError:
             return False
+        want_gpu: Optional[int] = None
+        if self.num_gpus > 0:
+            vis = env.get("CUDA_VISIBLE_DEVICES", "")
+            if not vis.isdigit():
+                return False          # CPU-only or multi-GPU container: parked interpreters are pinned to one slot each
+            want_gpu = int(vis)
         with self._lock:
-            zid = next((z for z, info in self._zygotes.items() if os.path.exists(info["fifo"] + ".ready")), None)
+            zid = next((z for z, info in self._zygotes.items()
+                        if info["gpu"] == want_gpu and os.path.exists(info["fifo"] + ".ready")), None)
             info = self._zygotes.pop(zid) if zid else None
         if info is None:
             return False

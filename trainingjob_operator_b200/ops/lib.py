@@ -12,7 +12,10 @@ from pathlib import Path
 
 _LIB = None
 _LOCK = threading.Lock()
-LIB_PATH = Path(__file__).resolve().parent / "libaitj_kernels.so"
+import os
+
+# AITJ_KERNEL_LIB points at an alternative build of the same kernels (A/B experiments on one box)
+LIB_PATH = Path(os.environ.get("AITJ_KERNEL_LIB") or Path(__file__).resolve().parent / "libaitj_kernels.so")
 
 # launch counter: every successful launch through `call` increments it; bench.py reports the
 # delta over the timed region as "gpu_launches".

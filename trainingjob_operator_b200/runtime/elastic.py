@@ -23,6 +23,7 @@ import torch.distributed as dist
 ANN_METRICS = "aitj.b200/metrics"
 ANN_WORKER_TRACE = "aitj.b200/worker-trace"
 ANN_RESCALE = "aitj.b200/rescale-trace"
+ANN_READY_PREFIX = "aitj.b200/ready-r"     # + rank: the generation that rank has finished its local set-up for
 
 
 def env_int(name: str, default: int = 0) -> int:
@@ -38,7 +39,8 @@ def rendezvous_from_env() -> Dict[str, int]:
 
 
 class ElasticWatcher:
-    def __init__(self, master: str, namespace: str, job: str, role: str, generation: int, poll: float = 0.1):
+    def __init__(self, master: str, namespace: str, job: str, role: str, generation: int, poll: float = 0.1,
+                 world: int = 0):
         from ..api import register as R
         from ..store.transport import HTTPTransport
 
@@ -46,6 +48,12 @@ class ElasticWatcher:
         self._info = R.AITRAININGJOB
         self.ns, self.job, self.role = namespace, job, role
         self.generation = generation
+        # world size this worker currently runs at: ranks >= it in a newer, larger generation are joiners, and the
+        # generation is only adopted once every joiner announced that its local set-up (CUDA context, model build,
+        # warm-up step) is done -- survivors keep training meanwhile instead of idling in the rendezvous
+        self.world = world or env_int("WORLD_SIZE", 1)
+        self.ready_timeout = float(os.environ.get("AITJ_JOIN_READY_TIMEOUT", "90"))
+        self._first_seen: Dict[int, float] = {}
         self.poll = poll
         self._latest: Optional[Dict[str, Any]] = None
         self._lock = threading.Lock()
@@ -62,7 +70,7 @@ class ElasticWatcher:
         if not master or not job:
             return None
         return cls(master, os.environ.get("TRAININGJOB_NAMESPACE", "default"), job,
-                   os.environ.get("TRAININGJOB_REPLICA_NAME", "trainer"), generation)
+                   os.environ.get("TRAININGJOB_REPLICA_NAME", "trainer"), generation, world=env_int("WORLD_SIZE", 1))
 
     # ------------------------------------------------------------------ polling thread
     def _fetch(self) -> Optional[Dict[str, Any]]:
@@ -80,16 +88,35 @@ class ElasticWatcher:
                 world = int(v)
         if world is None:
             return None
-        return {"generation": int(rdv.get("generation", 0)), "world": world, "port": int(rdv.get("masterPort", 0))}
+        ann = (obj.get("metadata") or {}).get("annotations") or {}
+        ready = {}
+        for k, v in ann.items():
+            if k.startswith(ANN_READY_PREFIX):
+                try:
+                    ready[int(k[len(ANN_READY_PREFIX):])] = int(json.loads(v))
+                except (TypeError, ValueError):
+                    pass
+        return {"generation": int(rdv.get("generation", 0)), "world": world, "port": int(rdv.get("masterPort", 0)),
+                "ready": ready}
+
+    def _joiners_ready(self, r: Dict[str, Any]) -> bool:
+        gen = r["generation"]
+        first = self._first_seen.setdefault(gen, time.time())
+        missing = [j for j in range(self.world, r["world"]) if r["ready"].get(j, -1) < gen]
+        if not missing:
+            return True
+        return time.time() - first > self.ready_timeout      # a joiner that never shows up must not block forever
 
     def _loop(self) -> None:
         while not self._stop.wait(self.poll):
             r = self._fetch()
             if r is None:
                 continue
+            if r["generation"] > self.generation and not self._joiners_ready(r):
+                continue
             with self._lock:
                 if self._latest is None or r["generation"] > self._latest["generation"]:
-                    r["observed_at"] = time.time()
+                    r["observed_at"] = self._first_seen.get(r["generation"], time.time())
                     self._latest = r
 
     def _wait_for(self, generation: int, timeout: float = 30.0) -> Optional[Dict[str, Any]]:
@@ -118,8 +145,14 @@ class ElasticWatcher:
             return None
         return self._wait_for(newest)
 
-    def adopted(self, generation: int) -> None:
+    def adopted(self, generation: int, world: int = 0) -> None:
         self.generation = generation
+        if world:
+            self.world = world
+
+    def announce_ready(self, rank: int, generation: int) -> None:
+        """A joiner finished everything it can do alone; survivors may now switch to ``generation``."""
+        self._annotate(f"{ANN_READY_PREFIX}{rank}", generation)
 
     # ------------------------------------------------------------------ reporting
     def _annotate(self, key: str, value: Any) -> None:

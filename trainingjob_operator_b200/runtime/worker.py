@@ -280,14 +280,30 @@ def run(args) -> Dict[str, Any]:
     if use_cuda:
         torch.cuda.set_device(device)
     trace = {"process_start": t_proc, "torch_imported": time.time()}
-    if world > 1:
-        init_process_group(rank, world, port, device)
-    trace["rendezvous_done"] = time.time()
-    adapter = build_adapter(args, device)
-    adapter.bind(None)
     watcher = ElasticWatcher.from_env(generation)
     if watcher is not None and not args.elastic:
         watcher.poll = 5.0  # reporting only
+    adapter = build_adapter(args, device)
+    trace["model_built"] = time.time()
+    if args.elastic and watcher is not None and generation > 1 and world > 1:
+        # Joining a running job: do everything that needs no peer first -- CUDA context, model build, two throw-away
+        # steps (kernel loading, cuDNN plans, allocator growth; the state is overwritten by rank 0's broadcast
+        # anyway) -- and only then tell the survivors, who keep training until this rank is ready to rendezvous.
+        adapter.bind(None)
+        for _ in range(2):
+            adapter.train_step()
+        if use_cuda:
+            torch.cuda.synchronize()
+        trace["prewarmed"] = time.time()
+        watcher.announce_ready(rank, generation)
+        print(f"[worker {rank}] joiner ready for generation {generation} after "
+              f"{trace['prewarmed'] - t_proc:.2f}s of local set-up (model build "
+              f"{trace['model_built'] - t_proc:.2f}s, warm-up steps {trace['prewarmed'] - trace['model_built']:.2f}s)",
+              flush=True)
+    if world > 1:
+        init_process_group(rank, world, port, device)
+    trace["rendezvous_done"] = time.time()
+    adapter.bind(None)
 
     restart_count = env_int("TRAININGJOB_REPLICA_RESTARTCOUNT", 0)
     start_step = 0
@@ -329,13 +345,16 @@ def run(args) -> Dict[str, Any]:
                           flush=True)
                     return {"left": True, "generation": target["generation"], "step": step}
                 generation, world, port = target["generation"], new_world, target["port"]
+                t1 = time.time()
                 if world > 1:
                     init_process_group(rank, world, port, device)
+                t2 = time.time()
                 adapter.bind(None)
                 step = sync_state(adapter, step, device)
-                watcher.adopted(generation)
+                watcher.adopted(generation, world)
                 pending_rescale = {"generation": generation, "world": world, "t0": t0,
-                                   "observed_at": target.get("observed_at", t0)}
+                                   "observed_at": target.get("observed_at", t0),
+                                   "teardown_s": t1 - t0, "init_pg_s": t2 - t1, "sync_state_s": time.time() - t2}
                 continue    # back to the step boundary: every rank (joiners included) runs the same sequence
         # ---- timed region bookkeeping ----------------------------------------------------------------
         if step == args.warmup and args.steps > 0:
@@ -354,7 +373,11 @@ def run(args) -> Dict[str, Any]:
             # the first completed step at the new world size ends the rescale
             now = time.time()
             rec = {"generation": pending_rescale["generation"], "world": pending_rescale["world"],
-                   "seconds": now - pending_rescale["t0"], "since_change": now - pending_rescale["observed_at"]}
+                   "seconds": now - pending_rescale["t0"], "since_change": now - pending_rescale["observed_at"],
+                   "teardown_s": round(pending_rescale["teardown_s"], 4),
+                   "init_pg_s": round(pending_rescale["init_pg_s"], 4),
+                   "sync_state_s": round(pending_rescale["sync_state_s"], 4)}
+            rec["first_step_s"] = round(rec["seconds"] - rec["teardown_s"] - rec["init_pg_s"] - rec["sync_state_s"], 4)
             rescales.append(rec)
             print(f"[worker {rank}] rescaled to world={rec['world']} gen={rec['generation']} in "
                   f"{rec['seconds']:.3f}s", flush=True)

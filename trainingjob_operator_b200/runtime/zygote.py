@@ -2,8 +2,11 @@
 
 Spawn -> Running of a replica is dominated by the interpreter start and ``import torch`` (seconds), not by the
 control plane (milliseconds; SURVEY.md §7.3 item 1 "warm worker pool").  The node agent therefore keeps a few of
-these processes parked: interpreter up, torch / torch.distributed / the worker runtime imported, **no CUDA context**
-(``CUDA_VISIBLE_DEVICES`` is only known at assignment).  When a pod whose container command is
+these processes parked: interpreter up, torch / torch.distributed / the worker runtime imported.  On a GPU box each
+parked interpreter is pinned to one GPU slot (``CUDA_VISIBLE_DEVICES`` set when it is spawned, ``--cuda``) and also
+holds a live CUDA context with the cuBLAS / cuDNN handles created; it is only handed to a container scheduled onto
+that slot.  Without ``--cuda`` no CUDA call is made (the device is only known at assignment).  When a pod whose
+container command is
 ``python -m <module> ...`` (or ``python <script> ...``) is started, the agent re-keys one parked process as that
 container and sends it the assignment -- argv, environment, cwd, log file, CPU set -- over a FIFO.  The process
 then *becomes* the container: same PID, supervised by the same C++ supervisor, exit status reported the usual way.
@@ -11,7 +14,7 @@ then *becomes* the container: same PID, supervised by the same C++ supervisor, e
 The reference has no counterpart: kubelet always starts a fresh container (pkg/controller/pod.go:528 builds the
 env once at pod creation); this only removes start-up latency, the observable pod lifecycle is unchanged.
 
-Protocol: ``python -m trainingjob_operator_b200.runtime.zygote <fifo>``; after the imports the zygote creates
+Protocol: ``python -m trainingjob_operator_b200.runtime.zygote <fifo> [--cuda]``; after the imports the zygote creates
 ``<fifo>.ready`` and blocks opening the FIFO.  One JSON object arrives:
 ``{"argv": [...], "env": {...}, "cwd": "", "log": "/path", "cpus": [..]}``.
 """
@@ -23,8 +26,9 @@ import runpy
 import sys
 
 
-def _preload() -> None:
-    # everything a training worker imports before touching the GPU; never initialises CUDA
+def _preload(cuda: bool = False) -> None:
+    # everything a training worker imports before touching the GPU; CUDA is initialised only when this
+    # interpreter was pinned to a GPU slot at spawn time
     import numpy  # noqa: F401
     import torch  # noqa: F401
     import torch.distributed  # noqa: F401
@@ -36,6 +40,17 @@ def _preload() -> None:
         try:
             __import__(mod)
         except Exception:  # noqa: BLE001 - optional pieces must not keep the pool from warming
+            pass
+    if cuda and torch.cuda.is_available():
+        try:
+            dev = torch.device("cuda", 0)
+            a = torch.randn(64, 64, device=dev, dtype=torch.bfloat16)
+            (a @ a).sum().item()                                           # context + cuBLAS handle
+            x = torch.randn(1, 8, 16, 16, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            torch.nn.functional.conv2d(x, torch.randn(8, 8, 3, 3, device=dev, dtype=torch.bfloat16), padding=1).sum().item()
+            del a, x
+            torch.cuda.empty_cache()
+        except Exception:  # noqa: BLE001
             pass
 
 
@@ -101,7 +116,7 @@ def become(assign: dict) -> None:
 
 def main() -> int:
     fifo = sys.argv[1]
-    _preload()
+    _preload(cuda="--cuda" in sys.argv[2:])
     with open(fifo + ".ready", "w") as f:
         f.write(str(os.getpid()))
     with open(fifo, "r") as f:          # blocks until the agent opens the write end
