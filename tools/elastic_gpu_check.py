@@ -17,12 +17,13 @@ from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption  # n
 model = sys.argv[1] if len(sys.argv) > 1 else "resnet50"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else torch.cuda.device_count()
 pool = int(sys.argv[3]) if len(sys.argv) > 3 else 0        # agent warm pool size (0 = cold interpreter starts)
+start = 2 if n >= 4 else 1                                  # BASELINE config 3: min=2 max=8, 2 -> 8 -> 4
 batch = {"resnet50": 64, "gpt2-tiny": 4, "mnist": 256, "gpt2": 8}.get(model, 8)
 worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", model, "--batch", str(batch),
           "--seq", "256", "--steps", "0", "--elastic"]
 job = {"apiVersion": "elasticdeeplearning.ai/v1", "kind": "AITrainingJob", "metadata": {"name": "elastic"},
        "spec": {"frameworkType": "pytorch", "replicaSpecs": {"trainer": {
-           "replicas": 1, "minReplicas": 1, "maxReplicas": n, "edlPolicy": "Manual",
+           "replicas": start, "minReplicas": start, "maxReplicas": n, "edlPolicy": "Manual",
            "template": {"spec": {"containers": [{"name": "aitj-trainer", "command": worker, "workingDir": ROOT,
                                                  "env": [{"name": "PYTHONPATH", "value": ROOT}] + [
                                                      {"name": kv.split("=", 1)[0], "value": kv.split("=", 1)[1]}
@@ -58,12 +59,12 @@ with LocalCluster(num_gpus=n, option=opt, workdir=f"/tmp/aitj-elastic-{pool}", w
     out["submit_to_first_step_s"] = round(time.time() - t_submit, 3)
     base = pids(lc)
     gen = 1
-    for target in [n, max(1, n // 2)]:
+    for target in [n, max(start, n // 2)]:
         if target == lc.jobs().get("elastic").spec.replica_specs["trainer"].replicas:
             continue
         gen += 1
         if pool:
-            wait(lambda: lc.agent.warm_ready() >= min(pool, max(0, target - 1)), 120)
+            wait(lambda: lc.agent.warm_ready() >= min(pool, max(0, target - start)), 120)
         t0 = time.time()
         lc.jobs().patch("elastic", {"spec": {"replicaSpecs": {"trainer": {"replicas": target}}}})
         rec = wait(lambda: (lambda a: json.loads(a["aitj.b200/rescale-trace"])

@@ -112,6 +112,9 @@ class GPT2Engine:
         self.M = batch_size * seq_len
         self.dev = torch.device(device)
         self.backend = gemm_backend
+        # backward GEMMs may leave a few SMs to the gradient all-reduce kernels that run next to them (DDP): a
+        # persistent grid of exactly #SMs CTAs needs a second wave as soon as a collective holds some SMs
+        self.bwd_max_ctas = 0
         self.causal = causal
         self.params = FlatParams(gpt2_param_specs(cfg), self.dev, seed=seed)
         C, M, Vp = cfg.n_embd, self.M, cfg.padded_vocab
@@ -175,7 +178,7 @@ class GPT2Engine:
         F = self.F
         if self.backend == "tcgen05":
             F.gemm(dy, w, out, b_mn=True, dgelu=dgelu_aux is not None, aux=dgelu_aux,
-                   block_n=self._bn(dy.shape[0], w.shape[1]))
+                   block_n=self._bn(dy.shape[0], w.shape[1]), max_ctas=self.bwd_max_ctas)
             return out
         y = dy @ w
         if dgelu_aux is not None:
@@ -201,7 +204,8 @@ class GPT2Engine:
             if sk is None:
                 sk = F.auto_split_k(dw.shape[0], dw.shape[1], dy.shape[0], pair=(bn == 512))
                 self.split_k[key] = sk
-            F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=sk, block_n=bn)
+            F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=sk, block_n=bn,
+                   max_ctas=self.bwd_max_ctas)
         else:
             dw.add_((dy.t() @ x).float())
 

@@ -78,6 +78,13 @@ class EngineTrainer:
         if self.world > 1 and self.symm is None:
             self.reducer = BucketAllReducer(engine.params.g32, engine.grad_buckets(), group, backend)
         engine.grad_hook = self.reducer.hook if self.reducer else None
+        if self.reducer is not None and hasattr(engine, "bwd_max_ctas"):
+            reserve = int(os.environ.get("AITJ_DDP_RESERVE_SMS", "0"))
+            if reserve > 0:
+                from ..ops import functional as F
+
+                engine.bwd_max_ctas = max(2, (F.num_sms() - reserve) // 2 * 2)
+                engine.split_k.clear() if hasattr(engine, "split_k") else None
         # Without library collectives (1 GPU, or the fused multicast path) the whole step is ONE CUDA graph.  With
         # the NCCL reducer the step is a chain of graphs split where a gradient bucket becomes final; the bucket's
         # all-reduce is launched between two replays on the side stream (capturing NCCL itself deadlocked on
