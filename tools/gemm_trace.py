@@ -67,6 +67,8 @@ BN = 512
 run("qkv fwd  (bias)", lambda: F.gemm(x, w_qkv, o3, bias=b_qkv, block_n=BN))
 run("qkv fwd  (no epilogue math)", lambda: F.gemm(x, w_qkv, o3, block_n=BN))
 run("qkv fwd  (epilogue skipped: main loop only)", lambda: F.gemm(x, w_qkv, o3, block_n=BN, _debug_skip_epilogue=True))
+run("qkv fwd  (tcgen05.ld only)", lambda: F.gemm(x, w_qkv, o3, block_n=BN, _debug_skip_epilogue="ldonly"))
+run("qkv fwd  (ld + staging, no TMA store)", lambda: F.gemm(x, w_qkv, o3, block_n=BN, _debug_skip_epilogue="notma"))
 run("fc fwd   (epilogue skipped)", lambda: F.gemm(x, w_fc, o4, block_n=BN, _debug_skip_epilogue=True))
 run("fc dgrad (epilogue skipped)", lambda: F.gemm(x4, w_fc, o1, b_mn=True, block_n=BN, _debug_skip_epilogue=True))
 run("proj fwd (bias+residual)", lambda: F.gemm(x, w_proj, o1, bias=b_proj, residual=res, block_n=BN))

@@ -34,8 +34,9 @@ enum : int {
   EPI_ACCUM = 64,     // out is fp32, red.global.add (split-K / grad accumulation)
   EPI_MC = 128,       // with EPI_ACCUM: `out` is an NVSwitch multicast address; reduce with multimem.red (GEMM + all-reduce in one kernel)
   EPI_DEBUG_SKIP = 256, // profiling only: the epilogue releases the accumulator without draining it (main loop in isolation)
-  EPI_DIRECT = 512      // bf16 outputs leave through st.global from registers (one 128-byte row segment per thread)
-                        // instead of the shared-memory staging + TMA store
+  EPI_DEBUG_NOTMA = 1024,  // profiling only: stage the tile in shared memory but do not issue the TMA store
+  EPI_DEBUG_LDONLY = 2048, // profiling only: read the accumulators (tcgen05.ld) and drop them
+  EPI_GROUP_STORE = 4096   // CTA-pair kernel, bf16 outputs: one 128x64 TMA store per column quarter instead of four 32x64
 };
 
 struct GemmArgs {
@@ -249,29 +250,64 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorM
 
 // 16-warp variant of the drain: this warp owns 32 rows x 64 columns (tile columns c_begin .. c_begin+63).  The
 // bf16 path works in two 32-column halves so that at most one TMEM load + one side load are live per thread
-// (<= 112 registers at 576 threads per CTA); with four epilogue warps per SM sub-partition the TMEM / global /
+// (<= 96 registers at 576 threads per CTA); with four epilogue warps per SM sub-partition the TMEM / global /
 // TMA-store latencies of one warp are covered by the other three.
+//
+// Stores: the four warps that share a column quarter (TMEM lane groups 0..3 => CTA rows 0..127) stage into one
+// contiguous 16 KB buffer -- warp lg at rows lg*32.., which keeps the 128B-swizzle pattern of a 128-row box -- and ONE
+// thread issues ONE 128x64 TMA store for all four (EPI_GROUP_STORE; named barrier 2+quarter, 128 threads).  The TMA
+// stores of a K=768 GEMM cost ~10 us next to the operand ring (profiles/ncu_gemm_v2.md); fewer, larger stores did
+// not change that (it is bytes, not store count), so the per-warp 4 KB stores stay the default.
+struct StoreGroup {
+  uint8_t* buf;      // 16 KB staging of the group; this warp's rows start at buf + lg * 4096
+  int bar_id;        // named barrier of the group
+  int row0_cta;      // first output row of this CTA's 128-row slab
+  bool issuer;       // the one thread that talks to the TMA unit
+  bool grouped;
+};
+
+__device__ __forceinline__ void group_acquire(const StoreGroup& g, int lane) {
+  if (g.grouped) {
+    if (g.issuer) tma_store_wait_read<0>();
+    asm volatile("bar.sync %0, 128;" ::"r"(g.bar_id) : "memory");
+  } else {
+    stage_acquire(lane);
+  }
+}
+__device__ __forceinline__ void group_commit(const StoreGroup& g, const CUtensorMap* tm32, const CUtensorMap* tm128,
+                                             uint8_t* wbuf, int col0, int row0, int lane) {
+  if (g.grouped) {
+    fence_proxy_async_smem();
+    asm volatile("bar.sync %0, 128;" ::"r"(g.bar_id) : "memory");
+    if (g.issuer) {
+      tma_store_2d(tm128, g.buf, col0, g.row0_cta);
+      tma_store_commit();
+    }
+  } else {
+    stage_commit(tm32, wbuf, col0, row0, lane, false);
+  }
+}
+
 __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
+                                                const CUtensorMap* tm_out128, const CUtensorMap* tm_aux128,
                                                 uint32_t tmem_acc, int row0, int n0, int c_begin,
-                                                const __nv_bfloat16* sbias, uint8_t* sbuf, int lane) {
+                                                const __nv_bfloat16* sbias, const StoreGroup& g, int lg, int lane) {
   const int flags = a.flags;
+  uint8_t* sbuf = g.buf + lg * 4096;
   if (flags & (EPI_MC | EPI_OUT_F32 | EPI_ACCUM)) {
     epilogue_f32<64>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane);
     return;
   }
   const int col0 = n0 + c_begin;
-  if (col0 >= a.N) return;
+  if (col0 >= a.N) return;          // uniform over the store group
   const int row = row0 + lane;
   const bool row_ok = row < a.M;
   const bool need_side = (flags & (EPI_DGELU | EPI_RESIDUAL)) != 0;
   const __nv_bfloat16* side = (flags & EPI_DGELU) ? a.aux : a.residual;
   const __nv_bfloat16* sp = side + static_cast<size_t>(row) * a.ldc + col0;
-  const bool direct = (flags & EPI_DIRECT) != 0;
-  __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(row) * a.ldc + col0;
   if (flags & EPI_SAVE_PRE) {
     // pass 1: the pre-activation (acc + bias) goes out through the aux tensor map
-    __nv_bfloat16* arow = a.aux + static_cast<size_t>(row) * a.ldc + col0;
-    if (!direct) stage_acquire(lane);
+    group_acquire(g, lane);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       uint32_t r[32];
@@ -283,16 +319,12 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
         unpack8(*reinterpret_cast<const uint4*>(sbias + c_begin + h * 32 + q * 8), bv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(r[q * 8 + j]) + ((flags & EPI_BIAS) ? bv[j] : 0.f);
-        if (direct) {
-          if (row_ok && col0 + h * 32 + q * 8 < a.N) *reinterpret_cast<uint4*>(arow + h * 32 + q * 8) = pack8(x);
-        } else {
-          stage_write16(sbuf, lane, h * 4 + q, pack8(x));
-        }
+        stage_write16(sbuf, lane, h * 4 + q, pack8(x));
       }
     }
-    if (!direct) stage_commit(tm_aux, sbuf, col0, row0, lane, false);
+    group_commit(g, tm_aux, tm_aux128, sbuf, col0, row0, lane);
   }
-  if (!direct) stage_acquire(lane);
+  group_acquire(g, lane);
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     uint4 sv[4];
@@ -335,14 +367,20 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] += hh[j];
       }
-      if (direct) {
-        if (row_ok && col0 + h * 32 + q * 8 < a.N) *reinterpret_cast<uint4*>(orow + h * 32 + q * 8) = pack8(x);
+      if (flags & EPI_DEBUG_LDONLY) {
+        if (x[0] == 1.2345e30f) sbuf[0] = 1;       // keep the loads alive
       } else {
         stage_write16(sbuf, lane, h * 4 + q, pack8(x));
       }
     }
   }
-  if (!direct) stage_commit(tm_out, sbuf, col0, row0, lane, false);
+  if (flags & (EPI_DEBUG_NOTMA | EPI_DEBUG_LDONLY)) {
+    if (g.grouped) {   // keep the barrier sequence of the group balanced
+      asm volatile("bar.sync %0, 128;" ::"r"(g.bar_id) : "memory");
+    }
+    return;
+  }
+  group_commit(g, tm_out, tm_out128, sbuf, col0, row0, lane);
 }
 
 // Epilogue warps stage the tile's bias row (kBlockN bf16) into shared memory; 256 threads, named barrier 1.
@@ -512,6 +550,7 @@ template <bool kAMN, bool kBMN, int kEpiW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiW, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
+                      const __grid_constant__ CUtensorMap tmap_out128, const __grid_constant__ CUtensorMap tmap_aux128,
                       const GemmArgs args) {
   constexpr int kPairM = 256, kPairN = 256;
   constexpr int kStageA = BLOCK_M * BLOCK_K * 2;       // this CTA's 128 rows of A
@@ -651,7 +690,13 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;     // column slice: halves (8 warps) or quarters (16 warps)
     const int epi_tid = threadIdx.x - 64;
-    uint8_t* sbuf = staging + (warp - 2) * 4096;
+    // staging: warps of one column slice are contiguous in TMEM-lane-group order (rows 0..127 of the CTA's slab)
+    uint8_t* sbuf = kEpiW == 16 ? staging + (half * 4 + lg) * 4096 : staging + (warp - 2) * 4096;
+    StoreGroup sg;
+    sg.buf = staging + half * 16384;
+    sg.bar_id = 2 + half;
+    sg.issuer = lg == 0 && lane == 0;
+    sg.grouped = kEpiW == 16 && (args.flags & EPI_GROUP_STORE) != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     long long tr_wait = 0, tr_busy = 0;
@@ -668,8 +713,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const uint32_t t_acc = tmem_base + acc * kPairN + (static_cast<uint32_t>(lg * 32) << 16);
         const int row0 = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32;
         if constexpr (kEpiW == 16) {
-          epilogue_cols64(args, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * 64, sbias + acc * 256,
-                          sbuf, lane);
+          sg.row0_cta = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
+          epilogue_cols64(args, &tmap_out, &tmap_aux, &tmap_out128, &tmap_aux128, t_acc, row0, wi.n_blk * kPairN,
+                          half * 64, sbias + acc * 256, sg, lg, lane);
         } else {
           epilogue_tile<kPairN / 2>(args, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * (kPairN / 2),
                                     sbias + acc * 256, sbuf, lane);
@@ -770,7 +816,8 @@ static int pair_epilogue_warps() {
 
 template <bool kAMN, bool kBMN, int kEpiW>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
-                            const GemmArgs& args, int max_ctas, cudaStream_t stream) {
+                            const CUtensorMap& to128, const CUtensorMap& tx128, const GemmArgs& args, int max_ctas,
+                            cudaStream_t stream) {
   constexpr int kSmem = (kEpiW == 16 ? 5 : 6) * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + kEpiW * 4096 + 1024 +
                         1024 + 256;
   static bool configured = false;
@@ -784,7 +831,7 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   if (num_work < pairs) pairs = num_work;
   if (max_ctas > 1 && pairs > max_ctas / 2) pairs = max_ctas / 2;
   if (pairs < 1) pairs = 1;
-  kern<<<pairs * 2, 64 + 32 * kEpiW, kSmem, stream>>>(ta, tb, to, tx, args);
+  kern<<<pairs * 2, 64 + 32 * kEpiW, kSmem, stream>>>(ta, tb, to, tx, to128, tx128, args);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
 }
 
@@ -822,8 +869,9 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   args.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   args.aux = reinterpret_cast<__nv_bfloat16*>(aux);
   {
-    static const bool direct_store = getenv("AITJ_GEMM_DIRECT_STORE") && atoi(getenv("AITJ_GEMM_DIRECT_STORE")) != 0;
-    if (direct_store && !(flags & (EPI_OUT_F32 | EPI_ACCUM))) flags |= EPI_DIRECT;
+    // measured: no gain for plain epilogues, slower for the dGELU one (profiles/ncu_gemm_v2.md) -> opt-in only
+    static const bool group_store = getenv("AITJ_GEMM_GROUP_STORE") && atoi(getenv("AITJ_GEMM_GROUP_STORE")) != 0;
+    if (group_store && pair && !(flags & (EPI_OUT_F32 | EPI_ACCUM))) flags |= EPI_GROUP_STORE;
   }
   args.flags = flags;
   args.trace = g_gemm_trace;
@@ -858,11 +906,21 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   }
 
   if (pair) {
+    CUtensorMap to128 = to, tx128 = tx;
+    if (flags & EPI_GROUP_STORE) {
+      rc = encode_2d(&to128, out, N, M, ldc, 64, 128, false);
+      if (rc) return rc - 4000;
+      tx128 = to128;
+      if (flags & EPI_SAVE_PRE) {
+        rc = encode_2d(&tx128, aux, N, M, ldc, 64, 128, false);
+        if (rc) return rc - 5000;
+      }
+    }
 #define AITJ_PAIR(W)                                                                                  \
-    if (!a_mn && !b_mn) return launch_gemm_2cta<false, false, W>(ta, tb, to, tx, args, max_ctas, stream); \
-    if (!a_mn && b_mn) return launch_gemm_2cta<false, true, W>(ta, tb, to, tx, args, max_ctas, stream);   \
-    if (a_mn && !b_mn) return launch_gemm_2cta<true, false, W>(ta, tb, to, tx, args, max_ctas, stream);   \
-    return launch_gemm_2cta<true, true, W>(ta, tb, to, tx, args, max_ctas, stream);
+    if (!a_mn && !b_mn) return launch_gemm_2cta<false, false, W>(ta, tb, to, tx, to128, tx128, args, max_ctas, stream); \
+    if (!a_mn && b_mn) return launch_gemm_2cta<false, true, W>(ta, tb, to, tx, to128, tx128, args, max_ctas, stream);   \
+    if (a_mn && !b_mn) return launch_gemm_2cta<true, false, W>(ta, tb, to, tx, to128, tx128, args, max_ctas, stream);   \
+    return launch_gemm_2cta<true, true, W>(ta, tb, to, tx, to128, tx128, args, max_ctas, stream);
     if (pair_epilogue_warps() == 16) { AITJ_PAIR(16) }
     AITJ_PAIR(8)
 #undef AITJ_PAIR

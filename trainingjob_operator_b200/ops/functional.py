@@ -106,7 +106,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
     else:
         assert out.dtype == torch.bfloat16 and not accumulate
     if _debug_skip_epilogue:
-        flags |= 256
+        flags |= {True: 256, "notma": 1024, "ldonly": 2048}[_debug_skip_epilogue]
     lib.call("aitj_gemm_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
              out.stride(0), int(a_mn), int(b_mn), _ptr(bias), _ptr(residual), _ptr(aux), flags, int(split_k),
              int(block_n), int(max_ctas), _stream())
