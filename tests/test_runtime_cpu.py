@@ -100,3 +100,74 @@ def test_bucket_allreduce_and_flat_ddp_over_gloo():
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("OK" in o for o in outs)
+
+
+def test_staged_join_gates_scale_up_until_joiners_announce(monkeypatch):
+    """Survivors adopt a larger world only after every joiner announced readiness for that generation (or the
+    timeout passed); scale-down and same-size generations are adopted at once."""
+    import json
+    import time
+
+    from trainingjob_operator_b200.runtime import elastic as E
+
+    state = {"gen": 1, "world": 2, "ann": {}}
+
+    class FakeTransport:
+        def __init__(self, *a, **k):
+            self.patches = []
+
+        def get(self, info, ns, name):
+            return {"metadata": {"annotations": dict(state["ann"])},
+                    "status": {"rendezvous": {"generation": state["gen"], "worldSizes": {"trainer": state["world"]},
+                                              "masterPort": 1234}}}
+
+        def patch(self, info, ns, name, body):
+            self.patches.append(body)
+            state["ann"].update(body["metadata"]["annotations"])
+
+    import trainingjob_operator_b200.store.transport as T
+
+    monkeypatch.setattr(T, "HTTPTransport", FakeTransport)
+    w = E.ElasticWatcher("http://x", "default", "job", "trainer", generation=1, poll=0.01, world=2)
+    try:
+        dev = torch.device("cpu")
+        time.sleep(0.05)
+        assert w.agree(dev) is None                       # nothing new
+        state.update(gen=2, world=4)                      # scale up 2 -> 4: ranks 2 and 3 are joiners
+        time.sleep(0.1)
+        assert w.agree(dev) is None                       # gated: nobody announced yet
+        state["ann"][E.ANN_READY_PREFIX + "2"] = json.dumps(2)
+        time.sleep(0.1)
+        assert w.agree(dev) is None                       # rank 3 still missing
+        state["ann"][E.ANN_READY_PREFIX + "3"] = json.dumps(1)   # stale announcement of an older generation
+        time.sleep(0.1)
+        assert w.agree(dev) is None
+        w.announce_ready(3, 2)                            # what the joiner calls; goes through the same annotation
+        time.sleep(0.1)
+        t = w.agree(dev)
+        assert t is not None and t["generation"] == 2 and t["world"] == 4 and t["port"] == 1234
+        assert t["observed_at"] <= time.time() - 0.3      # latency is counted from when the change was first seen
+        w.adopted(2, 4)
+        state.update(gen=3, world=2)                      # scale down: no joiners, adopted at once
+        time.sleep(0.1)
+        t = w.agree(dev)
+        assert t is not None and t["generation"] == 3 and t["world"] == 2
+        w.adopted(3, 2)
+        w.ready_timeout = 0.15
+        state.update(gen=4, world=3)                      # a joiner that never shows up cannot block forever
+        time.sleep(0.05)
+        assert w.agree(dev) is None
+        time.sleep(0.3)
+        assert w.agree(dev)["generation"] == 4
+    finally:
+        w.stop()
+
+
+def test_zygote_command_parsing():
+    from trainingjob_operator_b200.runtime.zygote import split_python_command as sp
+
+    assert sp(["python", "-m", "pkg.mod", "--a", "1"]) == ("module", "pkg.mod", ["--a", "1"])
+    assert sp(["/usr/bin/python3", "-u", "train.py", "x"]) == ("script", "train.py", ["x"])
+    assert sp(["python", "-c", "print(1)"]) is None
+    assert sp(["/bin/sh", "-c", "true"]) is None
+    assert sp(["python"]) is None and sp([]) is None
