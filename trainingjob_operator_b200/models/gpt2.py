@@ -25,6 +25,8 @@ from .flat_params import FlatParams, ParamSpec
 
 
 _QKV_GATHER = os.environ.get("AITJ_QKV_GATHER", "1") != "0"
+_FUSE_COLSUM = os.environ.get("AITJ_FUSE_COLSUM", "1") != "0" and os.environ.get("AITJ_GEMM_EPI_WARPS", "16") != "8" \
+    and os.environ.get("AITJ_GEMM_GROUP_STORE", "0") == "0"
 
 
 @dataclass
@@ -173,18 +175,24 @@ class GPT2Engine:
         """512 = CTA-pair kernel when the problem has at least one full 256x256 tile, else auto 1-CTA."""
         return 512 if self.pair and m >= 256 and n >= 256 else 0
 
-    def _dgrad(self, dy, w, out, dgelu_aux=None):
-        """out[M,K] = dy[M,N] @ w[N,K]  (* gelu'(aux))."""
+    def _dgrad(self, dy, w, out, dgelu_aux=None, colsum=None):
+        """out[M,K] = dy[M,N] @ w[N,K]  (* gelu'(aux)); colsum (fp32[K], optional) += column sums of out."""
         F = self.F
         if self.backend == "tcgen05":
+            bn = self._bn(dy.shape[0], w.shape[1])
+            fused = colsum is not None and bn == 512 and _FUSE_COLSUM
             F.gemm(dy, w, out, b_mn=True, dgelu=dgelu_aux is not None, aux=dgelu_aux,
-                   block_n=self._bn(dy.shape[0], w.shape[1]), max_ctas=self.bwd_max_ctas)
+                   block_n=bn, max_ctas=self.bwd_max_ctas, colsum=colsum if fused else None)
+            if colsum is not None and not fused:
+                F.colsum(out, colsum)
             return out
         y = dy @ w
         if dgelu_aux is not None:
             F.gelu_bwd(dgelu_aux, y, out)
         else:
             out.copy_(y)
+        if colsum is not None:
+            F.colsum(out, colsum)
         return out
 
     def _wgrad(self, dy, x, dw):
@@ -309,8 +317,7 @@ class GPT2Engine:
         x_in = self.layers[i - 1].res2 if i > 0 else self.x0
         # MLP (fc2_b's gradient = colsum(d_res) was already produced by the LayerNorm-backward that made d_res)
         self._wgrad(d_res, lb.fc_act, P.grad(p + "fc2_w"))
-        self._dgrad(d_res, P.w16(p + "fc2_w"), self.d_fc, dgelu_aux=lb.fc_pre)
-        F.colsum(self.d_fc, P.grad(p + "fc_b"))
+        self._dgrad(d_res, P.w16(p + "fc2_w"), self.d_fc, dgelu_aux=lb.fc_pre, colsum=P.grad(p + "fc_b"))
         self._wgrad(self.d_fc, lb.ln2, P.grad(p + "fc_w"))
         self._dgrad(self.d_fc, P.w16(p + "fc_w"), self.d_ln)
         F.layernorm_bwd(self.d_ln, lb.res1, P.w16(p + "ln2_w"), lb.ln2_mean, lb.ln2_rstd, spare,

@@ -50,6 +50,9 @@ struct GemmArgs {
   int split_k;
   int tiles_m, tiles_n;
   int k_blocks, k_per_split;
+  // optional (CTA-pair kernel, bf16 output): colsum[N] += column sums of the stored output, i.e. the bias gradient of
+  // the layer whose input gradient this GEMM produces, taken from the staged tile while it waits for its TMA store
+  float* colsum;
   // optional per-CTA role timeline (8 x u64 per CTA, see aitj_gemm_set_trace): where each warp role waits
   unsigned long long* trace;
 };
@@ -381,6 +384,22 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
     return;
   }
   group_commit(g, tm_out, tm_out128, sbuf, col0, row0, lane);
+  if (a.colsum != nullptr) {
+    // lane l sums columns 2l, 2l+1 of this warp's 32 staged rows (bf16, exactly what was stored); one row of the
+    // swizzled buffer is read by the 32 lanes as 32 distinct words -> conflict free
+    __syncwarp();
+    const int rows = min(32, a.M - row0);
+    const int chunk = lane >> 2, within = (lane & 3) << 2;
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+      const float2 f = unpack_bf16x2(w);
+      s0 += f.x; s1 += f.y;
+    }
+    const int c = col0 + 2 * lane;
+    if (c < a.N) atomicAdd(a.colsum + c, s0);
+    if (c + 1 < a.N) atomicAdd(a.colsum + c + 1, s1);
+  }
 }
 
 // Epilogue warps stage the tile's bias row (kBlockN bf16) into shared memory; 256 threads, named barrier 1.
@@ -838,12 +857,17 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
 }  // namespace aitj
 
 static unsigned long long* g_gemm_trace = nullptr;
+static float* g_gemm_colsum = nullptr;   // consumed by the next aitj_gemm_bf16 call
 
 extern "C" {
 
 // Debug/profiling: when non-null, the CTA-pair kernel writes 8 x u64 per CTA (TR_* slots, clock64 cycles) showing
 // where the MMA issuer, the TMA producer and epilogue warp 2 waited.  The buffer needs 8*8*num_SMs bytes.
 int aitj_gemm_set_trace(void* buf) { g_gemm_trace = reinterpret_cast<unsigned long long*>(buf); return 0; }
+
+// The next aitj_gemm_bf16 call (CTA-pair kernel, bf16 output, 16 epilogue warps) also accumulates the column sums of
+// its output into buf[N] (fp32).  One-shot: cleared by that call.
+int aitj_gemm_set_colsum(void* buf) { g_gemm_colsum = reinterpret_cast<float*>(buf); return 0; }
 
 // Returns 0 on success. See file header for operand conventions. lda/ldb/ldc in elements.
 // block_n: 128 or 256 (0 = auto). split_k > 1 requires EPI_ACCUM. max_ctas: 0 = all SMs.
@@ -874,6 +898,10 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
     if (group_store && pair && !(flags & (EPI_OUT_F32 | EPI_ACCUM))) flags |= EPI_GROUP_STORE;
   }
   args.flags = flags;
+  args.colsum = g_gemm_colsum;
+  g_gemm_colsum = nullptr;
+  if (args.colsum && !(pair && pair_epilogue_warps() == 16 && !(flags & (EPI_OUT_F32 | EPI_ACCUM | EPI_GROUP_STORE))))
+    return -6;   // only the 16-warp CTA-pair bf16 epilogue implements it
   args.trace = g_gemm_trace;
   args.tiles_m = pair ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;
   args.tiles_n = (N + block_n - 1) / block_n;

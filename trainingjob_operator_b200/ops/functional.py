@@ -64,13 +64,15 @@ def _ptr(t):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, gelu=False, dgelu=False,
-         save_pre=False, accumulate=False, split_k=1, block_n=0, max_ctas=0, _debug_skip_epilogue=False):
+         save_pre=False, accumulate=False, split_k=1, block_n=0, max_ctas=0, colsum=None,
+         _debug_skip_epilogue=False):
     """out[M,N] (+)= opA[M,K] @ opB[N,K]^T on tcgen05 tensor cores (bf16 in, fp32 accumulate).
 
     a_mn=False: ``a`` is [M,K]; a_mn=True: ``a`` is [K,M] (its transpose is used).
     b_mn=False: ``b`` is [N,K]; b_mn=True: ``b`` is [K,N].
     ``out`` bf16 -> plain store; fp32 -> store, or red.add when ``accumulate`` (needed for split_k>1).
     Epilogue: +bias[N] -> (aux<-pre) -> gelu -> *gelu'(aux) -> +residual[M,N].
+    ``colsum`` (fp32[N], CTA-pair kernel with bf16 output only): += column sums of the stored output.
     """
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
@@ -105,6 +107,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
             flags |= EPI_MC
     else:
         assert out.dtype == torch.bfloat16 and not accumulate
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == N and block_n == 512
+        lib.load().aitj_gemm_set_colsum(colsum.data_ptr())
     if _debug_skip_epilogue:
         flags |= {True: 256, "notma": 1024, "ldonly": 2048}[_debug_skip_epilogue]
     lib.call("aitj_gemm_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),

@@ -143,6 +143,16 @@ def case_gemm_2cta():
     dw = torch.ones(Nout, Kin, device="cuda", dtype=torch.float32)
     F.gemm(dyv, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=4, block_n=512)
     ok &= _check("2cta wgrad split_k=4 (TMA reduce-add)", dw, dyv.float().t() @ x.float() + 1.0, 1e-2)
+    # dgrad + dGELU with the bias gradient (column sums of the stored bf16 output) fused into the epilogue; M tail
+    Md, Nd, Kd = 1000, 3072, 768
+    dyd, wd, pre = _rand(Md, Kd), _rand(Kd, Nd, scale=0.05), _rand(Md, Nd)
+    outd = torch.empty(Md, Nd, device="cuda", dtype=torch.bfloat16)
+    cs = torch.full((Nd,), 2.0, device="cuda")
+    F.gemm(dyd, wd, outd, b_mn=True, dgelu=True, aux=pre, block_n=512, colsum=cs)
+    pf = pre.float().requires_grad_(True)
+    (gp,) = torch.autograd.grad(torch.nn.functional.gelu(pf, approximate="tanh").sum(), pf)
+    ok &= _check("2cta dgrad*dgelu", outd, (dyd.float() @ wd.float()) * gp, 2e-2)
+    ok &= _check("2cta fused colsum (bias grad)", cs, outd.float().sum(0) + 2.0, 1e-3)
     torch.cuda.synchronize()
     return ok
 
