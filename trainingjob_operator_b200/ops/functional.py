@@ -183,6 +183,17 @@ def colsum(dy, db):
     lib.call("aitj_colsum", dy.data_ptr(), db.data_ptr(), M, N, _is_mc(db), _stream())
 
 
+def attention_fwd(qkv, out, lse, B, T, H, causal=True, scale=0.0):
+    """Flash attention forward on tcgen05 (head dim 64): qkv bf16 [B*T, 3*H*64] packed q|k|v -> out bf16 [B*T, H*64],
+    lse fp32 [B, H, T] (natural-log sum-exp of the scaled scores).  T % 128 == 0."""
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and lse.dtype == torch.float32
+    assert qkv.is_contiguous() and out.is_contiguous() and lse.is_contiguous()
+    assert qkv.shape == (B * T, 3 * H * 64) and out.shape == (B * T, H * 64) and lse.numel() == B * H * T
+    lib.call("aitj_attn_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, H, int(causal), float(scale),
+             _stream())
+    return out
+
+
 def qkv_gather_colsum(dq, dk, dv, d_qkv, db):
     """d_qkv[B*T, 3*H*D] <- (dq, dk, dv), each logically [B,H,T,D] with any B/H/T strides; db[3*H*D] += colsum."""
     import ctypes

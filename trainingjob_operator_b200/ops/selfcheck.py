@@ -313,7 +313,63 @@ def case_gpt2_engine():
     return ok
 
 
+# ----------------------------------------------------------------------------- attention
+def case_attention():
+    """tcgen05 flash-attention forward vs. an fp32 PyTorch reference (causal and full), plus its device time next to
+    the cuDNN SDPA kernel PyTorch dispatches to."""
+    ok = True
+    for (B, T, H, causal) in [(2, 256, 3, True), (1, 128, 2, True), (2, 384, 2, False), (2, 1024, 12, True),
+                              (1, 512, 2, "ramp"), (1, 512, 2, "ramp-full")]:
+        C = H * 64
+        qkv = _rand(B * T, 3 * C, scale=1.0)
+        if isinstance(causal, str):
+            # adversarial: later keys score enormously higher than earlier ones (logit blow-up), which forces the
+            # kernel's lagging softmax reference through its exact-redo path
+            qv = qkv.view(B, T, 3, H, 64)
+            ramp = torch.linspace(0.0, 40.0, T, device="cuda").view(1, T, 1, 1)
+            qv[:, :, 1] = (qv[:, :, 1].float() + ramp * qv[:, :1, 0].float().sign()).bfloat16()
+            qv[:, :, 0] = qv[:, :1, 0].abs() * 4 + 0.0 * qv[:, :, 0]
+            causal = causal == "ramp"
+        out = torch.empty(B * T, C, device="cuda", dtype=torch.bfloat16)
+        lse = torch.empty(B, H, T, device="cuda")
+        F.attention_fwd(qkv, out, lse, B, T, H, causal=causal)
+        q, k, v = (qkv.view(B, T, 3, H, 64)[:, :, i].transpose(1, 2).float() for i in range(3))
+        s = (q @ k.transpose(-1, -2)) * 0.125
+        if causal:
+            s = s.masked_fill(torch.ones(T, T, device="cuda", dtype=torch.bool).triu(1), float("-inf"))
+        ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, C)
+        ok &= _check(f"attn fwd out B{B} T{T} H{H} causal={causal}", out, ref, 2e-2)
+        ok &= _check(f"attn fwd lse B{B} T{T} H{H} causal={causal}", lse, torch.logsumexp(s, -1), 1e-3)
+    # timing at the GPT-2 small shape
+    B, T, H = 16, 1024, 12
+    C = H * 64
+    qkv = _rand(B * T, 3 * C, scale=1.0)
+    out = torch.empty(B * T, C, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device="cuda")
+
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+
+    t_ours = timeit(lambda: F.attention_fwd(qkv, out, lse, B, T, H, causal=True))
+    q, k, v = (qkv.view(B, T, 3, H, 64)[:, :, i].transpose(1, 2) for i in range(3))
+    t_lib = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True))
+    flops = 4.0 * B * H * T * T * 64 / 2
+    print(f"  attention fwd B16 T1024 H12 causal: tcgen05 {t_ours:.1f} us ({flops / t_ours / 1e6:.0f} TFLOP/s)  "
+          f"cuDNN SDPA {t_lib:.1f} us ({flops / t_lib / 1e6:.0f} TFLOP/s)")
+    return ok
+
+
 CASES = {
+    "attention": case_attention,
     "gemm_2cta": case_gemm_2cta,
     "gpt2_engine": case_gpt2_engine,
     "gemm_tn": case_gemm_tn,
