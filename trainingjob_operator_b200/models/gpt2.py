@@ -98,6 +98,7 @@ class _LayerBufs:
         self.res2 = torch.empty(M, C, **bf)
         self.sdpa_ctx = None
         self.att_in = self.att
+        self.lse = None              # [B, H, T] fp32, only with the tcgen05 attention forward
 
 
 class GPT2Engine:
@@ -114,6 +115,12 @@ class GPT2Engine:
         self.M = batch_size * seq_len
         self.dev = torch.device(device)
         self.backend = gemm_backend
+        # attention forward: "cudnn" (PyTorch SDPA -> cuDNN flash kernel, the faster one today: 56 us per layer at
+        # B=16, T=1024) or "tcgen05" (our kernel, 71 us; AITJ_ATTN=tcgen05).  The backward is cuDNN's in both cases.
+        self.attn_impl = os.environ.get("AITJ_ATTN", "cudnn")
+        if self.attn_impl == "tcgen05" and (seq_len % 128 or cfg.n_embd // cfg.n_head != 64 or gemm_backend != "tcgen05"):
+            self.attn_impl = "cudnn"
+        self._philox = torch.zeros((), dtype=torch.int64, device=device)
         # backward GEMMs may leave a few SMs to the gradient all-reduce kernels that run next to them (DDP): a
         # persistent grid of exactly #SMs CTAs needs a second wave as soon as a collective holds some SMs
         self.bwd_max_ctas = 0
@@ -221,6 +228,14 @@ class GPT2Engine:
     def _attention_fwd(self, lb: _LayerBufs):
         B, T, H = self.B, self.T, self.cfg.n_head
         D = self.cfg.n_embd // H
+        if self.attn_impl == "tcgen05":
+            # hand-written flash-attention forward (ops/csrc/attention_tcgen05.cu): reads the packed qkv in place,
+            # writes [B*T, H*D] and the log-sum-exp the backward needs
+            if lb.lse is None:
+                lb.lse = torch.empty(B, H, T, device=self.dev, dtype=torch.float32)
+            self.F.attention_fwd(lb.qkv, lb.att, lb.lse, B, T, H, causal=self.causal)
+            lb.att_in = lb.att
+            return
         qkv = lb.qkv.view(B, T, 3, H, D)
         q = qkv[:, :, 0].transpose(1, 2).detach().requires_grad_(True)
         k = qkv[:, :, 1].transpose(1, 2).detach().requires_grad_(True)
@@ -239,9 +254,18 @@ class GPT2Engine:
         """d_qkv <- SDPA backward; d_bias (the qkv bias gradient) += colsum(d_qkv), fused into the gather."""
         B, T, H = self.B, self.T, self.cfg.n_head
         D = self.cfg.n_embd // H
-        q, k, v, o = lb.sdpa_ctx
         do = d_att.view(B, T, H, D).transpose(1, 2)
-        dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
+        if self.attn_impl == "tcgen05":
+            # cuDNN's SDPA backward accepts our forward's output and log-sum-exp ([B,H,T,1], natural log)
+            qkv5 = lb.qkv.view(B, T, 3, H, D)
+            q, k, v = (qkv5[:, :, i].transpose(1, 2) for i in range(3))
+            o4 = lb.att.view(B, T, H, D).transpose(1, 2)
+            dq, dk, dv = torch.ops.aten._scaled_dot_product_cudnn_attention_backward(
+                do, q, k, v, o4, lb.lse.view(B, H, T, 1), self._philox, self._philox, None, None, None, T, T, 0.0,
+                self.causal)
+        else:
+            q, k, v, o = lb.sdpa_ctx
+            dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
         if _QKV_GATHER:
             self.F.qkv_gather_colsum(dq, dk, dv, d_qkv, d_bias)
         else:   # A/B arm: three strided copies + a separate column reduction

@@ -14,6 +14,9 @@
 //             a row's running maximum grew by more than 2^8, which after the first blocks is rare.
 //
 // The reference operator has no GPU code; this kernel belongs to the launched workers' step.
+#ifdef AITJ_ATTN_DEBUG
+#define AITJ_MBAR_DEBUG 1
+#endif
 #include "ptx.cuh"
 
 namespace aitj {
@@ -29,9 +32,69 @@ struct AttnArgs {
   float scale_log2;   // softmax scale * log2(e)
   float* lse;         // [B, H, T] natural-log sum-exp of the scaled scores (what the backward needs)
   unsigned long long* trace;   // optional: 8 x u64 per CTA, clock64 spent by softmax warp 2 lane 0 in each phase
+  int stagger_cycles;          // start delay of the second CTA of every SM
+  unsigned int* sm_arrivals;   // [#SMs] never-reset arrival counters: odd arrival on an SM == its second CTA
 };
 #define ATR_BEGIN(t) long long t = kTrace ? clock64() : 0
 #define ATR_ADD(t, accv) do { if (kTrace) accv += clock64() - t; } while (0)
+
+// One 32-column chunk of the exponential pass for one row: p = 2^(min(x*sl2 - R, 64)), row-sum and row-max partials,
+// bf16 P into the swizzled A tile.  Written in 8-wide stages -- arguments, then 8 independent MUFU.EX2, then a tree
+// sum -- so that eight exponentials are always in flight (ptxas otherwise rotates three registers through
+// MUFU -> FSEL and every exponential pays the MUFU latency).  Masked (key > query) entries get argument -1e30 BEFORE
+// the exponential, so there is no select behind the MUFU, and only the diagonal block instantiates that code.
+template <bool kDiag>
+__device__ __forceinline__ void attn_exp_chunk(const uint32_t (&cur)[32], int c, int row, float sl2, float R, float& sum,
+                                               float& bmx, uint8_t* prow) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float x[8], t[8], e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      x[k] = __uint_as_float(cur[q * 8 + k]);
+      t[k] = fminf(fmaf(x[k], sl2, -R), 64.f);
+      if (kDiag && c * 32 + q * 8 + k > row) { t[k] = -1.0e30f; x[k] = -1.0e30f; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = fast_exp2(t[k]);
+    bmx = fmaxf(bmx, fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]))));
+    sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+    asm volatile("" : "+f"(sum), "+f"(bmx));    // keep the partial reductions here: ptxas otherwise defers all 128 adds
+                                                // to the end of the block and spills the exponentials it needs for them
+    const int chunk = (c & 1) * 4 + q;
+    *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
+        make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+  }
+}
+
+template <bool B>
+struct BoolTag { static constexpr bool value = B; };
+
+struct AttnTile {
+  int qt, b, h, row0, n_blocks;
+};
+__device__ __forceinline__ AttnTile attn_tile(const AttnArgs& a, int t) {
+  // tiles are enumerated heaviest first (causal: the last query tile of every (b,h) sees the most key blocks), so the
+  // static round-robin over persistent CTAs is a longest-processing-time-first schedule
+  const int BH = a.B * a.H, n_qt = a.T / ATT_BM;
+  AttnTile x;
+  const int w = t / BH, bh = t - w * BH;
+  x.qt = a.causal ? n_qt - 1 - w : w;
+  x.b = bh / a.H;
+  x.h = bh - x.b * a.H;
+  x.row0 = x.b * a.T + x.qt * ATT_BM;
+  x.n_blocks = a.causal ? x.qt + 1 : a.T / ATT_BN;
+  return x;
+}
+
+// Static schedule of the persistent CTAs: round r of the heaviest-first tile list is dealt out forward for even r and
+// backward for odd r ("snake"), which pairs heavy with light tiles: per-CTA load 21..24 key blocks instead of 19..27 for
+// plain round-robin at B=16, H=12, T=1024 on 296 CTAs.
+__device__ __forceinline__ int attn_first_tile() { return blockIdx.x; }
+__device__ __forceinline__ int attn_next_tile(int, int round) {
+  const int n = gridDim.x;
+  return round * n + ((round & 1) ? n - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x));
+}
 
 template <bool kTrace>
 __global__ void __launch_bounds__(kAttThreads, 2)
@@ -40,40 +103,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                 // 128 x 64 bf16 (reused as the output staging tile)
+  uint8_t* sQ = smem;                 // 128 x 64 bf16
   uint8_t* sK = sQ + 16384;           // 2 stages of 128 x 64
   uint8_t* sV = sK + 32768;           // 128 keys x 64
-  uint8_t* sP = sV + 16384;           // 128 x 128 bf16 as two K-major 64-key atoms
+  uint8_t* sP = sV + 16384;           // 128 x 128 bf16 as two K-major 64-key atoms; atom 0 doubles as output staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;        // [2]
-  uint64_t* k_empty = bars + 3;       // [2]
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 6;
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_ready = bars + 8;
-  uint64_t* o_full = bars + 9;        // P.V of block j has been added into O (TMEM columns 128..191)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;        // [2]
+  uint64_t* k_empty = bars + 4;       // [2]
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 8;
+  uint64_t* p_ready = bars + 9;
+  uint64_t* o_full = bars + 10;       // [2] P.V of block g has been added into O (TMEM columns 128..191): o_full[g & 1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int C = args.H * ATT_D;
-  const int n_qt = args.T / ATT_BM;
-  const int qt = args.causal ? (n_qt - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);  // heavy tiles first
-  const int b = blockIdx.y / args.H, h = blockIdx.y - b * args.H;
-  const int row0 = b * args.T + qt * ATT_BM;
-  const int n_blocks = args.causal ? qt + 1 : args.T / ATT_BN;
+  const int n_tiles = args.B * args.H * (args.T / ATT_BM);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_out);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
-    mbar_init(o_full, 1);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -81,21 +143,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The two CTAs of an SM are launched together and would run in lock step -- both in their exponential phase (each at
+  // half MUFU rate), then both waiting for their next S.  Starting the second one half a block period late makes them
+  // alternate instead: one CTA's exponentials overlap the other's MMA round trip.
+  if (args.stagger_cycles > 0) {
+    __shared__ unsigned int s_second;
+    if (threadIdx.x == 0) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_second = atomicAdd(args.sm_arrivals + smid, 1u) & 1u;
+    }
+    __syncthreads();
+    if (s_second) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < args.stagger_cycles) {}
+    }
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 16384);
-      tma_load_2d(sQ, &tmap_qkv, q_full, h * ATT_D, row0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int s = j & 1;
-        const int krow = b * args.T + j * ATT_BN;
-        mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1u);
-        mbar_arrive_expect_tx(&k_full[s], 16384);
-        tma_load_2d(sK + s * 16384, &tmap_qkv, &k_full[s], C + h * ATT_D, krow);
-        mbar_wait(v_empty, (j & 1) ^ 1u);
-        mbar_arrive_expect_tx(v_full, 16384);
-        tma_load_2d(sV, &tmap_qkv, v_full, 2 * C + h * ATT_D, krow);
+      int g = 0, ti = 0;
+      for (int t = attn_first_tile(); t < n_tiles; t = attn_next_tile(t, ++ti)) {
+        const AttnTile x = attn_tile(args, t);
+        mbar_wait(q_empty, (ti & 1) ^ 1u, 1);            // the previous tile's last S = Q K^T retired
+        mbar_arrive_expect_tx(q_full, 16384);
+        tma_load_2d(sQ, &tmap_qkv, q_full, x.h * ATT_D, x.row0);
+        for (int j = 0; j < x.n_blocks; ++j, ++g) {
+          const int s = g & 1;
+          const int krow = x.b * args.T + j * ATT_BN;
+          mbar_wait(&k_empty[s], ((g >> 1) & 1) ^ 1u, 2);
+          mbar_arrive_expect_tx(&k_full[s], 16384);
+          tma_load_2d(sK + s * 16384, &tmap_qkv, &k_full[s], C + x.h * ATT_D, krow);
+          mbar_wait(v_empty, (g & 1) ^ 1u, 3);
+          mbar_arrive_expect_tx(v_full, 16384);
+          tma_load_2d(sV, &tmap_qkv, v_full, 2 * C + x.h * ATT_D, krow);
+        }
       }
     }
   } else if (warp == 1) {
@@ -105,9 +188,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       constexpr uint32_t kIdescO = make_idesc_bf16(ATT_BM, ATT_D, 0u, 1u);    // P (K-major) x V (MN-major)
       const uint32_t t_S = tmem_base, t_O = tmem_base + ATT_BN;
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), v_addr = smem_u32(sV);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&k_full[s], (j >> 1) & 1);
+      auto issue_s = [&](int gg) {
+        const int s = gg & 1;
+        mbar_wait(&k_full[s], (gg >> 1) & 1, 4);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + s * 16384);
 #pragma unroll
@@ -117,40 +200,50 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         umma_commit(&k_empty[s]);
         umma_commit(s_full);
       };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < n_blocks; ++j) {
-        mbar_wait(p_ready, j & 1);            // P[j] is in smem and S[j] has been read out of TMEM
-        tc_fence_after();
-        if (j + 1 < n_blocks) issue_s(j + 1);
-        mbar_wait(v_full, j & 1);
-        tc_fence_after();
+      int g = 0, ti = 0;
+      for (int t = attn_first_tile(); t < n_tiles; t = attn_next_tile(t, ++ti)) {
+        const AttnTile x = attn_tile(args, t);
+        mbar_wait(q_full, ti & 1, 5);
+        issue_s(g);
+        for (int j = 0; j < x.n_blocks; ++j) {
+          mbar_wait(p_ready, (g + j) & 1, 6);      // P[j] is in smem and S[j] has been read out of TMEM
+          tc_fence_after();
+          if (j + 1 < x.n_blocks) issue_s(g + j + 1);
+          else umma_commit(q_empty);            // no more S for this tile: Q may be overwritten once they retired
+          mbar_wait(v_full, (g + j) & 1, 7);
+          tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < ATT_BN / 16; ++ks)
-          umma_bf16(t_O, make_sw128_desc(p_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                    make_sw128_desc(v_addr + ks * 2048, 16384, 1024), kIdescO, (j > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(v_empty);
-        umma_commit(o_full);
+          for (int ks = 0; ks < ATT_BN / 16; ++ks)
+            umma_bf16(t_O, make_sw128_desc(p_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                      make_sw128_desc(v_addr + ks * 2048, 16384, 1024), kIdescO, (j > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(v_empty);
+          umma_commit(&o_full[(g + j) & 1]);
+        }
+        g += x.n_blocks;
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax / accumulate (warps 2..5, thread = row)
+    // ------------------------------------------------------------ softmax (warps 2..5, thread = row)
     const int lg = warp & 3;
     const int row = lg * 32 + lane;                       // row inside the tile == TMEM lane
     const uint32_t t_S = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
     const uint32_t t_O = t_S + ATT_BN;
     const float sl2 = args.scale_log2;
-    // (l, O) are kept relative to the reference `ref` (log2 domain, already scaled); pend > 0 is a reference move that
-    // still has to be applied to them (decided at the end of a block, applied once that block's P.V has retired)
-    float ref = 0.f, l = 0.f, pend_ref = 0.f;
-    bool pend = false;
-    long long tr_ws = 0, tr_p1 = 0, tr_p2 = 0, tr_wo = 0, tr_acc = 0;
+    const bool issuer = warp == 2 && lane == 0;           // the one thread that talks to the TMA unit for stores
+    long long tr_ws = 0, tr_p1 = 0, tr_p2 = 0, tr_wo = 0, tr_acc = 0, tr_blocks = 0;
     ATR_BEGIN(tr_start);
-
-    // rescale this thread's row of O in TMEM by `a` (after P.V of block jb retired) -- the rare path
-    auto rescale_o = [&](int jb, float a) {
+    // P.V completions alternate between two barriers and every one is waited for, in order, at the latest two blocks
+    // late: by then it has happened (the tensor pipe retires in order) and the same barrier cannot have completed
+    // again (its next P.V needs this thread's p_ready), so the parity test can neither block nor alias.  With a single
+    // barrier a waiter two phases behind sees the parity it is waiting for as "not yet" and deadlocks.
+    int o_waited = 0;
+    auto wait_o_until = [&](int k) {
+      while (o_waited <= k) { mbar_wait(&o_full[o_waited & 1], (o_waited >> 1) & 1, 8); ++o_waited; }
+    };
+    // rescale this thread's row of O in TMEM by `a` once P.V of global block gb retired -- the rare path
+    auto rescale_o = [&](int gb, float a) {
       ATR_BEGIN(t3);
-      mbar_wait(o_full, jb & 1);
+      wait_o_until(gb);
       ATR_ADD(t3, tr_wo);
       ATR_BEGIN(t4);
       tc_fence_after();
@@ -167,129 +260,135 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       ATR_ADD(t4, tr_acc);
     };
 
-    for (int j = 0; j < n_blocks; ++j) {
-      const bool diag = args.causal && j == n_blocks - 1;   // key block == query tile: mask key > query
-      ATR_BEGIN(t0);
-      mbar_wait(s_full, j & 1);
-      ATR_ADD(t0, tr_ws);
-      ATR_BEGIN(t1);
+    int g = 0, ti = 0;
+    for (int t = attn_first_tile(); t < n_tiles; t = attn_next_tile(t, ++ti)) {
+      const AttnTile x = attn_tile(args, t);
+      if (ti > 0) {
+        // the previous tile's output was staged in sP: its TMA store must have read it before P is written again
+        if (issuer) tma_store_wait_read<0>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      // (l, O) are kept relative to the reference `ref` (log2 domain, scaled); pend = a reference move decided at the
+      // end of a block and applied once that block's P.V has retired
+      float ref = 0.f, l = 0.f, pend_ref = 0.f;
+      bool pend = false;
+      // the block body exists twice -- plain, and with the key > query mask of the diagonal block (the last one of
+      // a causal tile) -- as separate code regions, so that the plain path carries no mask instructions at all
+      auto block = [&](int j, auto diag_tag) {
+        constexpr bool diag = decltype(diag_tag)::value;
+        const int gj = g + j;
+        ATR_BEGIN(t0);
+        mbar_wait(s_full, gj & 1, 9);
+        ATR_ADD(t0, tr_ws);
+        ATR_BEGIN(t1);
+        tc_fence_after();
+        if (gj >= 2) wait_o_until(gj - 2);
+        if (j == 0) {
+          // first block: exact row maximum as the reference (one extra sweep over TMEM)
+          float mx = -1.0e30f;
+#pragma unroll 1
+          for (int c = 0; c < ATT_BN / 64; ++c) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(t_S + c * 64, r0);
+            tmem_ld_32x32(t_S + c * 64 + 32, r1);
+            tmem_ld_wait();
+            if (diag) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (c * 64 + i <= row) mx = fmaxf(mx, __uint_as_float(r0[i]));
+                if (c * 64 + 32 + i <= row) mx = fmaxf(mx, __uint_as_float(r1[i]));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+            }
+          }
+          ref = mx * sl2;
+        } else if (__any_sync(0xffffffffu, pend)) {
+          // the previous block pushed some row's maximum more than 2^8 above the reference: move it now
+          const float a = pend ? fast_exp2(ref - pend_ref) : 1.f;
+          rescale_o(gj - 1, a);
+          l *= a;
+          if (pend) ref = pend_ref;
+          pend = false;
+        }
+        ATR_ADD(t1, tr_p1);
+        ATR_BEGIN(t2);
+        // p = 2^(s*scale - ref) (clamped at 2^64: bf16 and fp32 share the exponent range, so a stale reference costs
+        // no accuracy as long as nothing overflows), row sum, the block's own maximum, bf16 P into the swizzled A
+        // tile.  The TMEM load of the next 32 columns is in flight while the current 32 go through the MUFU pipe.
+        float sum, bmx;
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          const float R = ref;
+          sum = 0.f;
+          bmx = -1.0e30f;
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32(t_S, ra);
+#pragma unroll
+          for (int c = 0; c < ATT_BN / 32; ++c) {
+            tmem_ld_wait();
+            uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+            if (c + 1 < ATT_BN / 32) tmem_ld_32x32(t_S + (c + 1) * 32, (c & 1) ? ra : rb);
+            uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
+            attn_exp_chunk<diag>(cur, c, row, sl2, R, sum, bmx, prow);
+          }
+          if (!__any_sync(0xffffffffu, bmx * sl2 - R > 60.f)) break;
+          // some row outgrew its reference by more than 2^60 within this block (the clamp would bite): move the
+          // reference to the true maximum first -- (l, O) move with it -- and redo the block exactly
+          const float r2 = fmaxf(R, bmx * sl2);
+          const float a = fast_exp2(R - r2);
+          if (j > 0) rescale_o(gj - 1, a);
+          l *= a;
+          ref = r2;
+        }
+        l += sum;
+        if (bmx * sl2 - ref > 8.f) { pend = true; pend_ref = bmx * sl2; }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        ATR_ADD(t2, tr_p2);
+      };
+      for (int j = 0; j + 1 < x.n_blocks; ++j) block(j, BoolTag<false>{});
+      if (args.causal) block(x.n_blocks - 1, BoolTag<true>{});
+      else block(x.n_blocks - 1, BoolTag<false>{});
+      g += x.n_blocks;
+      tr_blocks += x.n_blocks;
+      // tile epilogue: O / l, log-sum-exp, bf16 tile staged in P's first atom, one TMA store (not waited for here)
+      wait_o_until(g - 1);
       tc_fence_after();
-      if (j == 0) {
-        // first block: exact row maximum as the reference (one extra sweep over TMEM)
-        float mx = -1.0e30f;
-#pragma unroll 1
-        for (int c = 0; c < ATT_BN / 64; ++c) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(t_S + c * 64, r0);
-          tmem_ld_32x32(t_S + c * 64 + 32, r1);
-          tmem_ld_wait();
-          if (diag) {
+      const float inv = 1.0f / l;
+      args.lse[(static_cast<size_t>(x.b) * args.H + x.h) * args.T + x.qt * ATT_BM + row] =
+          ref * 0.6931471805599453f + logf(l);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (c * 64 + i <= row) mx = fmaxf(mx, __uint_as_float(r0[i]));
-              if (c * 64 + 32 + i <= row) mx = fmaxf(mx, __uint_as_float(r1[i]));
-            }
-          } else {
+      for (int c = 0; c < ATT_D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_O + c * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-          }
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = c * 4 + q;
+          *reinterpret_cast<uint4*>(sP + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(pack_bf16x2(__uint_as_float(r[q * 8]) * inv, __uint_as_float(r[q * 8 + 1]) * inv),
+                         pack_bf16x2(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv),
+                         pack_bf16x2(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv),
+                         pack_bf16x2(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv));
         }
-        ref = mx * sl2;
-      } else if (__any_sync(0xffffffffu, pend)) {
-        // the previous block pushed some row's maximum more than 2^8 above the reference: move it now
-        const float a = pend ? fast_exp2(ref - pend_ref) : 1.f;
-        rescale_o(j - 1, a);
-        l *= a;
-        if (pend) ref = pend_ref;
-        pend = false;
       }
-      ATR_ADD(t1, tr_p1);
-      ATR_BEGIN(t2);
-      // p = 2^(s*scale - ref) (clamped at 2^64: bf16 and fp32 share the exponent range, so a stale reference costs no
-      // accuracy as long as nothing overflows), row sum, the block's own maximum, bf16 P into the swizzled A tile.
-      // The TMEM load of the next 32 columns is in flight while the current 32 go through the MUFU pipe.
-      float sum, bmx;
-#pragma unroll 1
-      for (int attempt = 0; attempt < 2; ++attempt) {
-        const float R = ref;
-        sum = 0.f;
-        bmx = -1.0e30f;
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(t_S, ra);
-#pragma unroll
-        for (int c = 0; c < ATT_BN / 32; ++c) {
-          tmem_ld_wait();
-          uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-          if (c + 1 < ATT_BN / 32) tmem_ld_32x32(t_S + (c + 1) * 32, (c & 1) ? ra : rb);
-          uint8_t* prow = sP + (c >> 1) * 16384 + row * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float e[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int i = q * 8 + k;
-              const float x = __uint_as_float(cur[i]);
-              float v = fast_exp2(fminf(fmaf(x, sl2, -R), 64.f));
-              if (diag && c * 32 + i > row) v = 0.f;
-              else bmx = fmaxf(bmx, x);
-              e[k] = v;
-              sum += v;
-            }
-            const int chunk = (c & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
-                           pack_bf16x2(e[6], e[7]));
-          }
-        }
-        if (!__any_sync(0xffffffffu, bmx * sl2 - R > 60.f)) break;
-        // some row outgrew its reference by more than 2^60 within this block (the clamp would bite): move the reference
-        // to the true maximum first -- (l, O) move with it -- and redo the block exactly
-        const float r2 = fmaxf(R, bmx * sl2);
-        const float a = fast_exp2(R - r2);
-        if (j > 0) rescale_o(j - 1, a);
-        l *= a;
-        ref = r2;
-      }
-      l += sum;
-      if (bmx * sl2 - ref > 8.f) { pend = true; pend_ref = bmx * sl2; }
       fence_proxy_async_smem();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
-      ATR_ADD(t2, tr_p2);
-    }
-    // epilogue: O / l, log-sum-exp, bf16 tile through the (now idle) Q buffer and one TMA store
-    mbar_wait(o_full, (n_blocks - 1) & 1);
-    tc_fence_after();
-    if (kTrace && warp == 2 && lane == 0) {
-      unsigned long long* tr = args.trace + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
-      tr[0] = clock64() - tr_start; tr[1] = tr_ws; tr[2] = tr_p1; tr[3] = tr_p2; tr[4] = tr_wo; tr[5] = tr_acc;
-      tr[6] = n_blocks;
-    }
-    const float inv = 1.0f / l;
-    args.lse[(static_cast<size_t>(b) * args.H + h) * args.T + qt * ATT_BM + row] = ref * 0.6931471805599453f + logf(l);
-#pragma unroll
-    for (int c = 0; c < ATT_D / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(t_O + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = c * 4 + q;
-        *reinterpret_cast<uint4*>(sQ + row * 128 + ((chunk ^ (row & 7)) << 4)) =
-            make_uint4(pack_bf16x2(__uint_as_float(r[q * 8]) * inv, __uint_as_float(r[q * 8 + 1]) * inv),
-                       pack_bf16x2(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv),
-                       pack_bf16x2(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv),
-                       pack_bf16x2(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv));
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+        tma_store_2d(&tmap_out, sP, x.h * ATT_D, x.row0);
+        tma_store_commit();
       }
     }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane == 0) {
-      tma_store_2d(&tmap_out, sQ, h * ATT_D, row0);
-      tma_store_commit();
-      tma_store_wait<0>();
+    if (issuer) tma_store_wait<0>();
+    if (kTrace && issuer) {
+      unsigned long long* tr = args.trace + static_cast<size_t>(blockIdx.x) * 8;
+      tr[0] = clock64() - tr_start; tr[1] = tr_ws; tr[2] = tr_p1; tr[3] = tr_p2; tr[4] = tr_wo; tr[5] = tr_acc;
+      tr[6] = tr_blocks;
     }
   }
 
@@ -357,7 +456,25 @@ int aitj_attn_fwd(const void* qkv, void* out, void* lse, int B, int T, int H, in
       return -20;
     configured = true;
   }
-  dim3 grid(T / ATT_BM, B * H);
+  static int n_sms = 0;
+  if (!n_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static const int stagger = getenv("AITJ_ATTN_STAGGER") ? atoi(getenv("AITJ_ATTN_STAGGER")) : 1500;
+  a.stagger_cycles = stagger;
+  static unsigned int* sm_arrivals = nullptr;
+  if (!sm_arrivals) {
+    if (cudaMalloc(&sm_arrivals, 1024 * sizeof(unsigned int)) != cudaSuccess) return -21;
+    cudaMemset(sm_arrivals, 0, 1024 * sizeof(unsigned int));
+  }
+  a.sm_arrivals = sm_arrivals;
+  const int n_tiles = B * H * (T / ATT_BM);
+  static const int max_ctas = getenv("AITJ_ATTN_MAX_CTAS") ? atoi(getenv("AITJ_ATTN_MAX_CTAS")) : 0;   // tests
+  int n_ctas = n_tiles < 2 * n_sms ? n_tiles : 2 * n_sms;
+  if (max_ctas > 0 && n_ctas > max_ctas) n_ctas = max_ctas;
+  dim3 grid(n_ctas);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_ptr);
   if (a.trace) attn_fwd_kernel<true><<<grid, kAttThreads, kSmem, st>>>(tq, to, a);
   else attn_fwd_kernel<false><<<grid, kAttThreads, kSmem, st>>>(tq, to, a);

@@ -283,8 +283,14 @@ def case_gpt2_engine():
     ok = True
     cfg = GPT2Config(vocab_size=1000, n_layer=2, n_head=4, n_embd=256, block_size=128, name="t")
     B, T = 4, 128
-    for backend in ("tcgen05", "cublas"):
+    import os
+
+    for backend, attn in (("tcgen05", "cudnn"), ("cublas", "cudnn"), ("tcgen05", "tcgen05")):
+        os.environ["AITJ_ATTN"] = attn
         eng = GPT2Engine(cfg, B, T, "cuda", seed=3, gemm_backend=backend)
+        os.environ.pop("AITJ_ATTN", None)
+        assert eng.attn_impl == attn
+        backend = backend if attn == "cudnn" else backend + "+attn"
         ref = GPT2Reference(cfg, eng.params).cuda()
         g = torch.Generator().manual_seed(5)
         tok = torch.randint(0, cfg.vocab_size, (B, T), generator=g).cuda()
