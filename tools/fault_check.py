@@ -1,0 +1,84 @@
+"""Restart-on-failure through the control plane (BASELINE config 4 shape): DDP job, SIGKILL one rank (exit 137),
+``restartPolicy: OnFailure`` + ``restartScope: All`` -> every replica is re-created, resumes from rank 0's checkpoint.
+Reports kill -> job Running again -> first training step after the restart.
+
+    python tools/fault_check.py [model] [n] [warm_pool] [--cpu]
+"""
+import json
+import os
+import signal
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from trainingjob_operator_b200.cmd.local import LocalCluster  # noqa: E402
+from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption  # noqa: E402
+
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+cpu = "--cpu" in sys.argv
+model = argv[0] if argv else ("mlp" if cpu else "bert")
+n = int(argv[1]) if len(argv) > 1 else 2
+pool = int(argv[2]) if len(argv) > 2 else 0
+victim = min(3, n - 1)
+batch = {"bert": 8, "mlp": 16, "gpt2": 4, "resnet50": 32}.get(model, 8)
+worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", model, "--batch", str(batch),
+          "--steps", "0", "--ckpt-every", "10"] + (["--cpu", "--step-sleep", "0.02"] if cpu else [])
+c = {"name": "aitj-trainer", "command": worker, "workingDir": ROOT, "env": [{"name": "PYTHONPATH", "value": ROOT}]}
+if not cpu:
+    c["resources"] = {"limits": {"nvidia.com/gpu": 1}}
+job = {"apiVersion": "elasticdeeplearning.ai/v1", "kind": "AITrainingJob", "metadata": {"name": "ft"},
+       "spec": {"frameworkType": "pytorch", "replicaSpecs": {"trainer": {
+           "replicas": n, "restartPolicy": "OnFailure", "restartScope": "All", "restartLimit": 3,
+           "template": {"spec": {"terminationGracePeriodSeconds": 1, "containers": [c]}}}}}}
+
+
+def wait(fn, timeout=240):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        try:
+            v = fn()
+            if v:
+                return v
+        except Exception:  # noqa: BLE001
+            pass
+        time.sleep(0.02)
+    raise TimeoutError
+
+
+def first_step_at(lc):
+    tr = json.loads(lc.jobs().get("ft").annotations.get("aitj.b200/worker-trace", "{}"))
+    return tr.get("first_step_done", 0.0)
+
+
+out = {"model": model, "replicas": n, "warm_pool": pool, "cpu": cpu, "victim_rank": victim}
+with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thread_num=2),
+                  workdir=f"/tmp/aitj-fault-{pool}", warm_pool=pool) as lc:
+    if pool:
+        wait(lambda: lc.agent.warm_ready() >= pool, 120)
+    t_submit = time.time()
+    lc.apply(job)
+    wait(lambda: first_step_at(lc) > 0)
+    out["submit_to_first_step_s"] = round(time.time() - t_submit, 3)
+    time.sleep(3.0 if not cpu else 1.0)               # let it train and write a checkpoint
+    if pool:
+        wait(lambda: lc.agent.warm_ready() >= min(pool, n), 120)
+    pid = next(p for sid, p in lc.agent.sup.list() if f"/ft-trainer-{victim}/" in sid)
+    t_kill = time.time()
+    os.kill(pid, signal.SIGKILL)
+    wait(lambda: (lambda j: j.status.phase == "Running" and j.status.restart_counts.get("trainer", 0) >= 1 and
+                  j.status.replica_statuses["trainer"].active == n)(lc.jobs().get("ft")))
+    out["kill_to_running_s"] = round(time.time() - t_kill, 3)
+    wait(lambda: first_step_at(lc) > t_kill)
+    out["kill_to_first_step_s"] = round(first_step_at(lc) - t_kill, 3)
+    j = lc.jobs().get("ft")
+    out["restart_counts"] = j.status.restart_counts
+    out["conditions"] = [c.type for c in j.status.conditions][-6:]
+    log0 = open(os.path.join(lc.workdir, "logs", "default_ft-trainer-0_aitj-trainer.log")).read()
+    out["resumed"] = [ln for ln in log0.splitlines() if "resumed from checkpoint" in ln][-1:]
+    lc.jobs().delete("ft")
+    time.sleep(0.5)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}.json", "w"), indent=1)
+print(json.dumps(out))
+sys.exit(0 if out["restart_counts"].get("trainer") == 1 and out["resumed"] else 1)

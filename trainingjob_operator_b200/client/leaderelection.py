@@ -40,6 +40,9 @@ class LeaderElectionConfig:
     lease_duration: float = 15.0
     renew_deadline: float = 5.0
     retry_period: float = 3.0
+    # hand the lease over on a clean stop (client-go ReleaseOnCancel); a callable lets a harness simulate a crash,
+    # after which the standby has to wait for the lease to expire -- the reference's behaviour on a killed leader
+    release_on_cancel: object = True
 
 
 class LeaderElector:
@@ -199,7 +202,8 @@ class LeaderElector:
         finally:
             self._leading.clear()
             lead_stop.set()
-            if stop.is_set():
+            roc = self.cfg.release_on_cancel
+            if stop.is_set() and (roc() if callable(roc) else roc):
                 self.release()
             self._on_stop()
 

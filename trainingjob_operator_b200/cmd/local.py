@@ -49,6 +49,7 @@ class LocalCluster:
         self._operators = operators
         self._op_threads: List[threading.Thread] = []
         self._op_stops: List[threading.Event] = []
+        self._op_opts: list = []
         self.operator_errors: List[BaseException] = []
 
     @property
@@ -79,10 +80,14 @@ class LocalCluster:
         t.start()
         self._op_threads.append(t)
         self._op_stops.append(op_stop)
+        self._op_opts.append(opt)
         return op_stop
 
-    def stop_operator(self, index: int) -> None:
-        """Simulates an operator crash / kill (leader fail-over tests)."""
+    def stop_operator(self, index: int, crash: bool = False) -> None:
+        """Stops one operator.  ``crash=True`` simulates kill -9: the lease is NOT handed over, so the standby has to
+        wait for it to expire (leader fail-over tests / tools/failover_check.py)."""
+        if crash:
+            self._op_opts[index].crash_on_stop = True
         self._op_stops[index].set()
 
     # ------------------------------------------------------------------ convenience API

@@ -78,7 +78,8 @@ def run(opt: TrainingJobOperatorOption, stop: Optional[threading.Event] = None, 
     cfg = LeaderElectionConfig(lock_type=le.resource_lock, lock_namespace="kube-system",
                                lock_name="trainingjob-operator", identity=opt.identity or default_identity(),
                                lease_duration=le.lease_duration, renew_deadline=le.renew_deadline,
-                               retry_period=le.retry_period)
+                               retry_period=le.retry_period,
+                               release_on_cancel=lambda: not getattr(opt, "crash_on_stop", False))
     lost = threading.Event()
 
     def on_stopped() -> None:

@@ -310,7 +310,8 @@ def run(args) -> Dict[str, Any]:
     if restart_count > 0 and args.ckpt_every > 0:
         start_step = load_checkpoint(args, adapter)
         adapter.step_count = start_step
-    joined_step = sync_state(adapter, 0, device)
+        print(f"[worker {rank}] restart #{restart_count}: resumed from checkpoint at step {start_step}", flush=True)
+    joined_step = sync_state(adapter, start_step, device)
 
     stop = {"flag": False}
     signal.signal(signal.SIGTERM, lambda *_: stop.__setitem__("flag", True))
