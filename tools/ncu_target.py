@@ -29,6 +29,21 @@ elif what == "xent":
     loss = torch.empty(M, device="cuda")
     for _ in range(4):
         F.softmax_xent(logits, tgt, loss, 50257, 1.0 / M)
+elif what == "attn":
+    H = 12
+    qkv = torch.randn(M, 3 * C, device="cuda").bfloat16()
+    out = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device="cuda")
+    for _ in range(6):
+        F.attention_fwd(qkv, out, lse, B, T, H, causal=True)
+elif what == "ln_bwd":
+    x = torch.randn(M, C, device="cuda").bfloat16()
+    dy = torch.randn(M, C, device="cuda").bfloat16()
+    g = torch.ones(C, device="cuda").bfloat16()
+    mean = torch.zeros(M, device="cuda"); rstd = torch.ones(M, device="cuda")
+    dx = torch.empty_like(x); dg = torch.zeros(C, device="cuda"); db = torch.zeros(C, device="cuda")
+    for _ in range(6):
+        F.layernorm_bwd(dy, x, g, mean, rstd, dx, dg, db, dres=x)
 elif what == "adamw":
     n = 124_475_904 // 256 * 256
     p = torch.randn(n, device="cuda"); g = torch.randn(n, device="cuda")
