@@ -282,7 +282,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         ATR_ADD(t0, tr_ws);
         ATR_BEGIN(t1);
         tc_fence_after();
-        if (gj >= 2) wait_o_until(gj - 2);
         if (j == 0) {
           // first block: exact row maximum as the reference (one extra sweep over TMEM)
           float mx = -1.0e30f;
@@ -325,6 +324,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           bmx = -1.0e30f;
           uint32_t ra[32], rb[32];
           tmem_ld_32x32(t_S, ra);
+          // P[gj-1] is still being read by its P.V MMA (issued after this block's S, so S-ready does not imply it has
+          // retired): it must have before the first store into the P tile.  The wait hides behind the TMEM load.
+          if (gj >= 1) wait_o_until(gj - 1);
 #pragma unroll
           for (int c = 0; c < ATT_BN / 32; ++c) {
             tmem_ld_wait();
