@@ -383,3 +383,38 @@ def test_warm_pool_adopts_parked_interpreter(tmp_path):
     time.sleep(0.2)
     for pid in parked:
         assert not os.path.exists(f"/proc/{pid}") or open(f"/proc/{pid}/stat").read().split()[2] == "Z"
+
+
+def test_crashed_leader_lease_must_expire_before_takeover(tmp_path):
+    """A leader that dies without handing its lease over (kill -9) is only replaced once the lease ran out -- the
+    reference's behaviour -- while a clean stop releases it at once."""
+    opt = TrainingJobOperatorOption(thread_num=1)
+    opt.leader_election.leader_elect = True
+    opt.leader_election.lease_duration, opt.leader_election.renew_deadline, opt.leader_election.retry_period = 1.5, 1.0, 0.2
+    with LocalCluster(num_gpus=0, workdir=str(tmp_path), operators=2, option=opt) as lc2:
+        lock = lambda: json.loads(lc2.clientset.core_v1().endpoints("kube-system").get("trainingjob-operator")  # noqa: E731
+                                  ["metadata"]["annotations"]["control-plane.alpha.kubernetes.io/leader"])
+        leader = wait_until(lambda: lock()["holderIdentity"], timeout=10)
+        lc2.stop_operator(int(leader[-1]), crash=True)
+        t0 = time.time()
+        time.sleep(0.6)
+        assert lock()["holderIdentity"] == leader                   # still the dead leader's lease
+        wait_until(lambda: lock()["holderIdentity"] not in ("", leader), timeout=10)
+        assert 1.0 < time.time() - t0 < 6.0
+        lc2.apply(sh_job("after", "true", replicas=1))               # the new leader reconciles
+        lc2.wait_for_phase("after", "Succeed", timeout=20)
+
+
+@pytest.mark.slow
+def test_restart_scope_all_resumes_ddp_job_from_checkpoint(tmp_path):
+    """BASELINE config 4 shape on CPU: SIGKILL one rank of a gloo DDP job, restartPolicy OnFailure + restartScope All
+    re-creates every replica and rank 0 resumes from its checkpoint (tools/fault_check.py runs the same on GPUs)."""
+    import subprocess
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fault_check.py"), "mlp", "2", "0", "--cpu"],
+                       cwd=str(tmp_path), capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["restart_counts"] == {"trainer": 1} and out["resumed"]
+    assert out["conditions"][-3:] == ["Terminating", "Restarting", "Running"]
+    assert out["kill_to_first_step_s"] < 60

@@ -4,12 +4,13 @@ The reference wires N identical ``trainer`` replicas together (env contract, pod
 leaves data parallelism to the framework inside the containers; here the launched
 workers' DDP is part of the product.  Gradients live in one flat fp32 buffer
 (``models.flat_params``), so a bucket is a slice: no flatten/unflatten copies.  Buckets are reduced
-on a side stream as soon as backward finishes them (event fork/join, capturable in the step's CUDA
-graph) and the optimizer sweep divides by the world size while it reads the sum.
+on a side stream as soon as backward finishes them (event fork/join; with CUDA graphs the collectives
+are launched between graph segments, ``runtime.trainer``) and the optimizer sweep divides by the world
+size while it reads the sum.
 
-Backends: ``nccl`` (torch.distributed: ring/tree/NVLS chosen by NCCL) and ``nvls`` -- our own
-two-shot multimem kernel over the NVSwitch multicast address (``parallel.nvls``), selected with
-``AITJ_ALLREDUCE=nvls``; ``gloo`` keeps the same code path testable on CPU.
+Backends: ``nccl`` (torch.distributed: ring/tree/NVLS chosen by NCCL); ``gloo`` keeps the same code path
+testable on CPU.  The alternative without any collective kernel -- gradients reduced through the NVSwitch
+multicast alias by the GEMM epilogues that produce them -- lives in ``parallel.symm`` (``AITJ_ALLREDUCE=mc``).
 """
 from __future__ import annotations
 
@@ -42,11 +43,6 @@ class BucketAllReducer:
         self.trigger: Dict[str, Tuple[int, int]] = {m[3]: (m[1], m[2]) for m in merged}
         self.comm_stream = torch.cuda.Stream() if self.cuda else None
         self._works: List = []
-        self._nvls = None
-        if backend == "nvls" and self.world > 1:
-            from .nvls import NvlsAllReduce
-
-            self._nvls = NvlsAllReduce(flat_grad, group)
 
     def hook(self, name: str) -> None:
         """Called by the engine when bucket ``name`` is final: reduce its slice asynchronously."""
@@ -62,10 +58,7 @@ class BucketAllReducer:
         ev.record(main)
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
-            if self._nvls is not None:
-                self._nvls.all_reduce_slice(a, b)
-            else:
-                self._works.append(dist.all_reduce(view, group=self.group, async_op=True))
+            self._works.append(dist.all_reduce(view, group=self.group, async_op=True))
 
     def wait(self) -> None:
         """Join: the current stream waits for every outstanding bucket reduction."""
