@@ -133,6 +133,9 @@ class _PodState:
     bound_at: float = 0.0
     spawn_failures: int = 0
     next_retry: float = 0.0
+    # serialises "containers started -> status Running" against the exit handler: a command that exits at once must not
+    # have its terminated status overwritten by the (later) Running patch
+    status_lock: threading.Lock = field(default_factory=threading.Lock)
 
 
 class NodeAgent:
@@ -561,6 +564,16 @@ class NodeAgent:
                                          f"{GPU_RESOURCE}, {len(free)} free but {want} requested.")
                 return
             gpus = free[:want]
+            if want == 1:
+                # rank i prefers GPU slot i when it is free: replicas are created in parallel, so arrival order is not
+                # rank order, and a stable rank -> GPU mapping is what the pinned warm pool and a human reading
+                # nvidia-smi both expect
+                try:
+                    pref = int(M.labels_of(pod).get(C.LABEL_REPLICA_INDEX, "")) % max(1, self.num_gpus)
+                    if pref in free:
+                        gpus = [pref]
+                except ValueError:
+                    pass
             for g in gpus:
                 self._gpu_owner[g] = (M.uid_of(pod), time.monotonic())
             try:
@@ -655,6 +668,10 @@ class NodeAgent:
                 st = self._states[key] = _PodState(key=key, uid=M.uid_of(pod), bound_at=time.monotonic())
             if st.started or time.monotonic() < st.next_retry:
                 return
+        with st.status_lock:
+            self._start_pod_locked(pod, st)
+
+    def _start_pod_locked(self, pod: dict, st: _PodState) -> None:
         spec = pod.get("spec", {})
         gpus = [int(g) for g in (M.annotations_of(pod).get(C.ANN_GPUS) or "").split(",") if g.strip()]
         inits = spec.get("initContainers") or []
@@ -726,8 +743,14 @@ class NodeAgent:
         cname = sid.split("/")[-1]
         with self._lock:
             st = self._states.get(key)
-        if st is None or st.containers.get(cname) != sid:
+        if st is None:
             return
+        with st.status_lock:      # the start path holds it across spawn + bookkeeping: a process that exits at once
+            if st.containers.get(cname) != sid:          # is only looked up after its id has been recorded
+                return
+            self._on_exit_locked(ev, st, key, cname)
+
+    def _on_exit_locked(self, ev: Dict[str, Any], st: _PodState, key: str, cname: str) -> None:
         ns, name = M.split_key(key)
         try:
             pod = self.cs.core_v1().pods(ns).get(name)
