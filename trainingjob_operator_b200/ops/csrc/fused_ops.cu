@@ -34,13 +34,29 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
       b[i * 8 + 2 * j] = bf.x; b[i * 8 + 2 * j + 1] = bf.y;
     }
   }
-  for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
-    const __nv_bfloat16* xr = x + static_cast<size_t>(row) * C;
+  // persistent warps (2 blocks per SM), one row at a time with the NEXT row's loads already in flight: the kernel is a
+  // pure stream, so bytes in flight per SM are what sets its bandwidth
+  const int stride = gridDim.x * warps_per_block;
+  int row = blockIdx.x * warps_per_block + warp;
+  uint4 nxt[V];
+  if (row < M) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) nxt[i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * C + (i * 32 + lane) * 8);
+  }
+  for (; row < M; row += stride) {
+    uint4 cur[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) cur[i] = nxt[i];
+    if (row + stride < M) {
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        nxt[i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row + stride) * C + (i * 32 + lane) * 8);
+    }
     float v[V * 8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      uint4 u = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+      const uint4 u = cur[i];
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -337,110 +353,6 @@ __global__ void __launch_bounds__(512, 2) softmax_xent_kernel(__nv_bfloat16* __r
   }
 }
 
-// Register-resident variant: 1024 threads per row, every thread keeps its NV 16-byte vectors of the row and of
-// exp(x - max) (bf16) in registers: one HBM read, one write, one exp per element, no shared-memory staging.
-template <int NV>
-__global__ void __launch_bounds__(1024, 1) softmax_xent_reg_kernel(__nv_bfloat16* __restrict__ logits,
-                                                                   const int64_t* __restrict__ target,
-                                                                   float* __restrict__ loss, int V, int Vp,
-                                                                   float gscale) {
-  __shared__ float sred[32];
-  __shared__ float sbcast[2];
-  const int row = blockIdx.x;
-  __nv_bfloat16* g = logits + static_cast<size_t>(row) * Vp;
-  const int nvec = Vp / 8;
-  const int nfull = V / 8;                       // vectors with all 8 columns < V
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tgt = static_cast<int>(target[row]);
-  const bool valid = tgt >= 0 && tgt < V;
-  const float xt = valid ? __bfloat162float(g[tgt]) : 0.f;   // read before anyone overwrites the row
-  uint4 xv[NV];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int i = threadIdx.x + k * 1024;
-    if (i < nvec) {
-      xv[k] = *reinterpret_cast<const uint4*>(g + i * 8);
-      float f[8];
-      const uint32_t w[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { float2 t = unpack_bf16x2(w[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
-      if (i < nfull) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (i * 8 + j < V) mx = fmaxf(mx, f[j]);
-      }
-    }
-  }
-  mx = warp_max(mx);
-  if (lane == 0) sred[warp] = mx;
-  __syncthreads();
-  if (warp == 0) {
-    float t = warp_max(sred[lane]);
-    if (lane == 0) sbcast[0] = t;
-  }
-  __syncthreads();
-  mx = sbcast[0];
-  const float LOG2E = 1.4426950408889634f;
-  const float moff = mx * LOG2E;
-  float sum = 0.f;
-  // exp(x - max) replaces x in the registers (bf16): one exp per element, reused for the gradient
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int i = threadIdx.x + k * 1024;
-    if (i < nvec) {
-      const uint32_t w[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
-      float e[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 t = unpack_bf16x2(w[j]);
-        e[2 * j] = exp2f(fmaf(t.x, LOG2E, -moff));
-        e[2 * j + 1] = exp2f(fmaf(t.y, LOG2E, -moff));
-      }
-      if (i >= nfull) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (i * 8 + j >= V) e[j] = 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += e[j];
-      xv[k] = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
-                         pack_bf16x2(e[6], e[7]));
-    }
-  }
-  sum = warp_sum(sum);
-  __syncthreads();
-  if (lane == 0) sred[warp] = sum;
-  __syncthreads();
-  if (warp == 0) {
-    float t = warp_sum(sred[lane]);
-    if (lane == 0) sbcast[1] = t;
-  }
-  __syncthreads();
-  sum = sbcast[1];
-  if (threadIdx.x == 0) loss[row] = valid ? -(xt - mx - logf(sum)) : 0.f;
-  const float inv = valid ? gscale / sum : 0.f;
-  const float gs = valid ? gscale : 0.f;
-  const int tvec = valid ? (tgt >> 3) : -1;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int i = threadIdx.x + k * 1024;
-    if (i < nvec) {
-      const uint32_t e[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
-      float p[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { float2 t = unpack_bf16x2(e[j]); p[2 * j] = t.x * inv; p[2 * j + 1] = t.y * inv; }
-      if (i == tvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (j == (tgt & 7)) p[j] -= gs;
-      }
-      *reinterpret_cast<uint4*>(g + i * 8) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
-                                                        pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-    }
-  }
-}
-
 // ------------------------------------------------------------------ bias grad: db[N] += colsum(dy[M,N])
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
                                                      int M, int N, int rows_per_block, int mc) {
@@ -474,114 +386,6 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
     for (int w = 0; w < 8; ++w) s += red[w][c];
     grad_add_f32(db + blockIdx.x * 256 + c, s, mc != 0);
   }
-}
-
-// Cluster variant: the two CTAs of a cluster each hold HALF of one row (50 KB of shared memory instead of 100 KB), so
-// four CTAs are resident per SM and three phases (row load / exp / gradient store) of different rows overlap instead
-// of two.  Row maximum and sum are exchanged through distributed shared memory.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 4)
-softmax_xent_cluster_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
-                            float* __restrict__ loss, int V, int Vp, float gscale) {
-  extern __shared__ uint4 srow4[];
-  __shared__ float sred[8];
-  __shared__ float xchg[2];          // [0] this CTA's max, [1] this CTA's sum: read by the peer
-  __shared__ float sbcast[2];
-  const uint32_t half = cluster_ctarank();
-  const int row = blockIdx.x >> 1;
-  __nv_bfloat16* g = logits + static_cast<size_t>(row) * Vp;
-  const int nvec = Vp / 8, nfull = V / 8;
-  const int v0 = half == 0 ? 0 : nvec / 2, v1 = half == 0 ? nvec / 2 : nvec;
-  const int nloc = v1 - v0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tgt = static_cast<int>(target[row]);
-  const bool valid = tgt >= 0 && tgt < V;
-  const float xt = valid ? __bfloat162float(g[tgt]) : 0.f;
-  const uint32_t peer_xchg = mapa_u32(smem_u32(xchg), half ^ 1u);
-
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
-    const int gi = v0 + i;
-    uint4 u = *reinterpret_cast<const uint4*>(g + gi * 8);
-    srow4[i] = u;
-    float f[8];
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { float2 t = unpack_bf16x2(w[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
-    if (gi < nfull) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (gi * 8 + j < V) mx = fmaxf(mx, f[j]);
-    }
-  }
-  mx = warp_max(mx);
-  if (lane == 0) sred[warp] = mx;
-  __syncthreads();
-  if (warp == 0) {
-    float t = lane < 8 ? sred[lane] : -INFINITY;
-    t = warp_max(t);
-    if (lane == 0) xchg[0] = t;
-  }
-  cluster_sync_all();                                   // both halves published their maximum
-  if (threadIdx.x == 0) sbcast[0] = fmaxf(xchg[0], ld_shared_cluster_f32(peer_xchg));
-  __syncthreads();
-  mx = sbcast[0];
-  const float LOG2E = 1.4426950408889634f;
-  const float moff = mx * LOG2E;
-  float sum = 0.f;
-  for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
-    const int gi = v0 + i;
-    uint4 u = srow4[i];
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float e[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 t = unpack_bf16x2(w[j]);
-      e[2 * j] = exp2f(fmaf(t.x, LOG2E, -moff));
-      e[2 * j + 1] = exp2f(fmaf(t.y, LOG2E, -moff));
-    }
-    if (gi >= nfull) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (gi * 8 + j >= V) e[j] = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sum += e[j];
-    srow4[i] = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
-                          pack_bf16x2(e[6], e[7]));
-  }
-  sum = warp_sum(sum);
-  __syncthreads();
-  if (lane == 0) sred[warp] = sum;
-  __syncthreads();
-  if (warp == 0) {
-    float t = lane < 8 ? sred[lane] : 0.f;
-    t = warp_sum(t);
-    if (lane == 0) xchg[1] = t;
-  }
-  cluster_sync_all();                                   // both halves published their partial sum
-  if (threadIdx.x == 0) sbcast[1] = xchg[1] + ld_shared_cluster_f32(peer_xchg + 4);
-  __syncthreads();
-  sum = sbcast[1];
-  if (threadIdx.x == 0 && half == 0) loss[row] = valid ? -(xt - mx - logf(sum)) : 0.f;
-  const float inv = valid ? gscale / sum : 0.f;
-  const float gs = valid ? gscale : 0.f;
-  const int tvec = valid ? (tgt >> 3) : -1;
-  for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
-    const int gi = v0 + i;
-    uint4 u = srow4[i];
-    const uint32_t e[4] = {u.x, u.y, u.z, u.w};
-    float p[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { float2 t = unpack_bf16x2(e[j]); p[2 * j] = t.x * inv; p[2 * j + 1] = t.y * inv; }
-    if (gi == tvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (j == (tgt & 7)) p[j] -= gs;
-    }
-    *reinterpret_cast<uint4*>(g + gi * 8) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
-                                                       pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-  }
-  cluster_sync_all();                                   // the peer may still be reading this CTA's xchg[]
 }
 
 // ------------------------------------------------------------------ attention backward epilogue:
@@ -805,7 +609,7 @@ using namespace aitj;
 int aitj_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, void* mean, void* rstd, int M,
                        int C, float eps, void* stream) {
   if (C % 256 || C > 2048) return -1;
-  const int blocks = min((M + 7) / 8, 148 * 8);
+  const int blocks = min((M + 7) / 8, 148 * 2);
 #define LN_F(V) layernorm_fwd_kernel<V><<<blocks, 256, 0, S(stream)>>>(CBF(x), CBF(gamma), CBF(beta), BF(y), \
     reinterpret_cast<float*>(mean), reinterpret_cast<float*>(rstd), M, eps)
   switch (C / 256) {
@@ -854,38 +658,10 @@ int aitj_embedding_bwd(const void* tok, const void* dx, void* dwte, void* dwpe, 
 int aitj_softmax_xent(void* logits, const void* target, void* loss, int M, int V, int Vp, float gscale,
                       void* stream) {
   if (Vp % 8 || V > Vp) return -1;
-  {
-    // the register-resident variant measured slower on B200 (one 1024-thread CTA per SM cannot overlap a row's
-    // load with another row's math); kept for reference, selected only with AITJ_XENT_REG=1
-    static const bool use_reg = getenv("AITJ_XENT_REG") != nullptr;
-    const int nv = use_reg ? (Vp / 8 + 1023) / 1024 : 99;
-#define XENT_REG(NV) softmax_xent_reg_kernel<NV><<<M, 1024, 0, S(stream)>>>(BF(logits), \
-    reinterpret_cast<const int64_t*>(target), reinterpret_cast<float*>(loss), V, Vp, gscale); return LAUNCH_OK()
-    switch (nv) {
-      case 1: XENT_REG(1); case 2: XENT_REG(2); case 3: XENT_REG(3); case 4: XENT_REG(4);
-      case 5: XENT_REG(5); case 6: XENT_REG(6); case 7: XENT_REG(7); default: break;
-    }
-#undef XENT_REG
-  }
-  {
-    // cluster variant: half a row per CTA, 4 CTAs / SM.  Measured 0.89 ms against 0.84 ms for the one-CTA-per-row kernel
-    // at 16384 x 50304 (the two DSMEM exchanges cost more than the extra residency buys) -> opt-in (AITJ_XENT_CLUSTER=1)
-    static const bool use_cluster = getenv("AITJ_XENT_CLUSTER") && atoi(getenv("AITJ_XENT_CLUSTER")) != 0;
-    const int nvec = Vp / 8;
-    const int smem_half = (nvec - nvec / 2) * 16;
-    if (use_cluster && smem_half <= 56 * 1024) {
-      static int configured_c = 0;
-      if (configured_c < smem_half) {
-        if (cudaFuncSetAttribute(softmax_xent_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_half) !=
-            cudaSuccess)
-          return -21;
-        configured_c = smem_half;
-      }
-      softmax_xent_cluster_kernel<<<2 * M, 256, smem_half, S(stream)>>>(
-          BF(logits), reinterpret_cast<const int64_t*>(target), reinterpret_cast<float*>(loss), V, Vp, gscale);
-      return LAUNCH_OK();
-    }
-  }
+  // Three alternatives were measured slower at 16384 x 50304 and removed (profiles/README.md): the row held in registers
+  // by one 1024-thread CTA (1.99 ms: nothing overlaps a row's load), a 2-CTA cluster holding half a row each (0.89 ms:
+  // the DSMEM exchanges cost more than the extra residency buys) and a persistent 1024-thread CTA with bulk-async row
+  // prefetch / store (1.02 ms).  This kernel -- row staged in shared memory, two CTAs per SM -- takes 0.84 ms.
   const int smem = Vp * 2;
   if (smem > 200 * 1024) return -2;
   static int configured = 0;
