@@ -36,6 +36,7 @@ enum : int {
   EPI_DEBUG_SKIP = 256, // profiling only: the epilogue releases the accumulator without draining it (main loop in isolation)
   EPI_DEBUG_NOTMA = 1024,  // profiling only: stage the tile in shared memory but do not issue the TMA store
   EPI_DEBUG_LDONLY = 2048, // profiling only: read the accumulators (tcgen05.ld) and drop them
+  EPI_NO_SIDE_TMA = 8192,  // A/B switch: fetch the residual / pre-GELU tile with per-thread global loads again
   EPI_GROUP_STORE = 4096   // CTA-pair kernel, bf16 outputs: one 128x64 TMA store per column quarter instead of four 32x64
 };
 
@@ -294,7 +295,10 @@ __device__ __forceinline__ void group_commit(const StoreGroup& g, const CUtensor
 __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
                                                 const CUtensorMap* tm_out128, const CUtensorMap* tm_aux128,
                                                 uint32_t tmem_acc, int row0, int n0, int c_begin,
-                                                const __nv_bfloat16* sbias, const StoreGroup& g, int lg, int lane) {
+                                                const __nv_bfloat16* sbias, const StoreGroup& g, int lg, int lane,
+                                                uint64_t* side_bar = nullptr, uint32_t side_parity = 0) {
+  // side_bar != nullptr: the residual / pre-GELU tile of this warp was prefetched by TMA into its staging buffer
+  // (swizzled like the output); it is read from there and overwritten in place by the result
   const int flags = a.flags;
   uint8_t* sbuf = g.buf + lg * 4096;
   if (flags & (EPI_MC | EPI_OUT_F32 | EPI_ACCUM)) {
@@ -327,11 +331,19 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
     }
     group_commit(g, tm_aux, tm_aux128, sbuf, col0, row0, lane);
   }
-  group_acquire(g, lane);
+  if (side_bar != nullptr) {
+    mbar_wait(side_bar, side_parity);
+  } else {
+    group_acquire(g, lane);
+  }
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     uint4 sv[4];
-    if (need_side && row_ok) {
+    if (side_bar != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        sv[q] = *reinterpret_cast<const uint4*>(sbuf + lane * 128 + (((h * 4 + q) ^ (lane & 7)) << 4));
+    } else if (need_side && row_ok) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         sv[q] = (col0 + h * 32 + q * 8 < a.N) ? *reinterpret_cast<const uint4*>(sp + h * 32 + q * 8)
@@ -570,7 +582,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiW, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                       const __grid_constant__ CUtensorMap tmap_out128, const __grid_constant__ CUtensorMap tmap_aux128,
-                      const GemmArgs args) {
+                      const __grid_constant__ CUtensorMap tmap_side, const GemmArgs args) {
   constexpr int kPairM = 256, kPairN = 256;
   constexpr int kStageA = BLOCK_M * BLOCK_K * 2;       // this CTA's 128 rows of A
   constexpr int kStageB = (kPairN / 2) * BLOCK_K * 2;  // this CTA's half of B
@@ -590,6 +602,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* side_bar = tmem_empty + 3;          // [kEpiW] one per epilogue warp: its prefetched residual / pre-GELU tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -609,6 +622,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(&tmem_full[i], 1);   // per CTA, multicast commit
       mbar_init(&tmem_empty[i], 2 * kEpiW);  // leader's copy: all epilogue warps of both CTAs
     }
+    for (int i = 0; i < kEpiW; ++i) mbar_init(&side_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2cta<kTmemCols>(tmem_slot);
@@ -718,10 +732,31 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     sg.grouped = kEpiW == 16 && (args.flags & EPI_GROUP_STORE) != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // The residual / pre-GELU tile this warp's epilogue needs is fetched by TMA into the warp's staging buffer while
+    // the tile's MMAs are still running (the row-scattered 16-byte global loads it replaces cost the dGELU epilogue
+    // ~4000 cycles per tile, more than the K=768 main loop leaves).
+    const int side_kind = args.flags & (EPI_DGELU | EPI_RESIDUAL);
+    const bool side_tma = kEpiW == 16 && !sg.grouped &&
+                          !(args.flags & (EPI_SAVE_PRE | EPI_MC | EPI_OUT_F32 | EPI_ACCUM | EPI_NO_SIDE_TMA)) &&
+                          (side_kind == EPI_DGELU || side_kind == EPI_RESIDUAL);
+    uint64_t* my_side_bar = &side_bar[warp - 2];
+    uint32_t side_phase = 0;
     long long tr_wait = 0, tr_busy = 0;
     TR_BEGIN(args.trace, tr_start);
     for (int w = cluster_id; w < num_work; w += num_clusters) {
       const WorkItem wi = decode_work(args, w);
+      bool side_now = false;
+      if constexpr (kEpiW == 16) {
+        if (side_tma && wi.kb1 > wi.kb0 && wi.n_blk * kPairN + half * 64 < args.N) {
+          side_now = true;
+          stage_acquire(lane);             // the previous tile's TMA store has finished reading this buffer
+          if (lane == 0) {
+            mbar_arrive_expect_tx(my_side_bar, 4096);
+            tma_load_2d(sbuf, &tmap_side, my_side_bar, wi.n_blk * kPairN + half * 64,
+                        wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32);
+          }
+        }
+      }
       stage_bias<kPairN, 32 * kEpiW>(args, sbias + acc * 256, wi.n_blk * kPairN, epi_tid);
       TR_BEGIN(args.trace, t0);
       mbar_wait_cluster(&tmem_full[acc], acc_phase);
@@ -734,7 +769,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if constexpr (kEpiW == 16) {
           sg.row0_cta = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
           epilogue_cols64(args, &tmap_out, &tmap_aux, &tmap_out128, &tmap_aux128, t_acc, row0, wi.n_blk * kPairN,
-                          half * 64, sbias + acc * 256, sg, lg, lane);
+                          half * 64, sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase);
+          if (side_now) side_phase ^= 1u;
         } else {
           epilogue_tile<kPairN / 2>(args, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * (kPairN / 2),
                                     sbias + acc * 256, sbuf, lane);
@@ -835,8 +871,8 @@ static int pair_epilogue_warps() {
 
 template <bool kAMN, bool kBMN, int kEpiW>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
-                            const CUtensorMap& to128, const CUtensorMap& tx128, const GemmArgs& args, int max_ctas,
-                            cudaStream_t stream) {
+                            const CUtensorMap& to128, const CUtensorMap& tx128, const CUtensorMap& tside,
+                            const GemmArgs& args, int max_ctas, cudaStream_t stream) {
   constexpr int kSmem = (kEpiW == 16 ? 5 : 6) * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + kEpiW * 4096 + 1024 +
                         1024 + 256;
   static bool configured = false;
@@ -850,7 +886,7 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   if (num_work < pairs) pairs = num_work;
   if (max_ctas > 1 && pairs > max_ctas / 2) pairs = max_ctas / 2;
   if (pairs < 1) pairs = 1;
-  kern<<<pairs * 2, 64 + 32 * kEpiW, kSmem, stream>>>(ta, tb, to, tx, to128, tx128, args);
+  kern<<<pairs * 2, 64 + 32 * kEpiW, kSmem, stream>>>(ta, tb, to, tx, to128, tx128, tside, args);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
 }
 
@@ -896,6 +932,8 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
     // measured: no gain for plain epilogues, slower for the dGELU one (profiles/ncu_gemm_v2.md) -> opt-in only
     static const bool group_store = getenv("AITJ_GEMM_GROUP_STORE") && atoi(getenv("AITJ_GEMM_GROUP_STORE")) != 0;
     if (group_store && pair && !(flags & (EPI_OUT_F32 | EPI_ACCUM))) flags |= EPI_GROUP_STORE;
+    static const bool no_side_tma = getenv("AITJ_GEMM_SIDE_TMA") && atoi(getenv("AITJ_GEMM_SIDE_TMA")) == 0;
+    if (no_side_tma) flags |= EPI_NO_SIDE_TMA;
   }
   args.flags = flags;
   args.colsum = g_gemm_colsum;
@@ -944,11 +982,17 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
         if (rc) return rc - 5000;
       }
     }
+    CUtensorMap tside = to;
+    if (!(flags & (EPI_OUT_F32 | EPI_ACCUM)) && (flags & (EPI_DGELU | EPI_RESIDUAL))) {
+      const void* side_ptr = (flags & EPI_DGELU) ? static_cast<const void*>(aux) : residual;
+      rc = encode_2d(&tside, side_ptr, N, M, ldc, 64, 32, false);
+      if (rc) return rc - 6000;
+    }
 #define AITJ_PAIR(W)                                                                                  \
-    if (!a_mn && !b_mn) return launch_gemm_2cta<false, false, W>(ta, tb, to, tx, to128, tx128, args, max_ctas, stream); \
-    if (!a_mn && b_mn) return launch_gemm_2cta<false, true, W>(ta, tb, to, tx, to128, tx128, args, max_ctas, stream);   \
-    if (a_mn && !b_mn) return launch_gemm_2cta<true, false, W>(ta, tb, to, tx, to128, tx128, args, max_ctas, stream);   \
-    return launch_gemm_2cta<true, true, W>(ta, tb, to, tx, to128, tx128, args, max_ctas, stream);
+    if (!a_mn && !b_mn) return launch_gemm_2cta<false, false, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream); \
+    if (!a_mn && b_mn) return launch_gemm_2cta<false, true, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream);   \
+    if (a_mn && !b_mn) return launch_gemm_2cta<true, false, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream);   \
+    return launch_gemm_2cta<true, true, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream);
     if (pair_epilogue_warps() == 16) { AITJ_PAIR(16) }
     AITJ_PAIR(8)
 #undef AITJ_PAIR
