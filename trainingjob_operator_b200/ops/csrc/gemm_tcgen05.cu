@@ -1,6 +1,6 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring ->
 // tcgen05.mma (one elected thread) -> fp32 accumulators in TMEM (double buffered) ->
-// tcgen05.ld epilogue with fused bias / GELU / dGELU / residual / fp32 (split-K, red.add) output.
+// tcgen05.ld epilogue with fused bias / GELU / dGELU / residual / fp32 (split-K, TMA reduce-add) output.
 //
 //   out[M,N] (+)= opA[M,K] * opB[N,K]^T
 //     a_mn == 0 : A stored [M,K] row-major (K contiguous, "K-major")
@@ -8,9 +8,15 @@
 //     b_mn == 0 : B stored [N,K] row-major                               -> forward  (x @ W^T)
 //     b_mn == 1 : B stored [K,N] row-major                               -> dgrad    (dy @ W), wgrad
 //
-// Warp roles (320 threads, 1 CTA / SM):  warp0 = TMA producer, warp1 = TMEM owner + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane group = warp_id % 4; warps 2-5 drain the left half of the tile's columns,
-// warps 6-9 the right half, so every SM sub-partition has two epilogue warps to hide TMEM/LDG latency).
+// Two kernels:
+//  * gemm_bf16_tcgen05_kernel  -- one CTA per SM, 128 x {128,256} tiles, 320 threads: warp0 = TMA producer, warp1 = TMEM
+//    owner + MMA issuer, warps 2..9 = epilogue (TMEM lane group = warp_id % 4, two warps per SM sub-partition).
+//  * gemm_bf16_2cta_kernel     -- a 2-CTA cluster (one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2; each
+//    CTA loads its 128 rows of A and half of B.  576 threads: 16 epilogue warps (four per sub-partition, 32 rows x 64
+//    columns each), 5-stage ring; the residual / pre-GELU tile of an epilogue is prefetched by TMA, outputs leave
+//    through swizzled staging + TMA store, the dGELU variant can also emit the bias gradient (column sums).
+//    This is the kernel the training step uses for every GEMM with M, N >= 256 (block_n == 512).
+// Measurements behind these choices: profiles/ncu_gemm_v1.md, ncu_gemm_v2.md, gemm_role_trace_*.txt.
 //
 // The reference operator has no GPU code; this kernel belongs to the launched
 // workers' training step that BASELINE.json measures (samples/sec).
