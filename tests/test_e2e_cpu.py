@@ -418,3 +418,34 @@ def test_restart_scope_all_resumes_ddp_job_from_checkpoint(tmp_path):
     assert out["restart_counts"] == {"trainer": 1} and out["resumed"]
     assert out["conditions"][-3:] == ["Terminating", "Restarting", "Running"]
     assert out["kill_to_first_step_s"] < 60
+
+
+def test_hang_detection_and_exec_liveness_probe(lc):
+    """A worker that stops heart-beating for AITJ_HANG_TIMEOUT seconds is killed (exit 137) and restarted by the job's
+    policy; a failing ``livenessProbe.exec`` does the same (kubelet semantics the reference relies on)."""
+    # heartbeat: beats for ~1 s, then "hangs"
+    script = 'i=0; while [ $i -lt 10 ]; do touch "$AITJ_HEARTBEAT_FILE"; sleep 0.1; i=$((i+1)); done; sleep 60'
+    j = sh_job("hang", script, replicas=1, restartPolicy="OnFailure", restartScope="Pod", restartLimit=5)
+    j["spec"]["replicaSpecs"]["trainer"]["template"]["spec"]["containers"][0]["env"] = [
+        {"name": "AITJ_HANG_TIMEOUT", "value": "1"}]
+    lc.apply(j)
+    wait_until(lambda: lc.jobs().get("hang").status.restart_counts.get("trainer", 0) >= 1, timeout=30)
+    evs = [(e["reason"], e["message"]) for e in lc.clientset.core_v1().events("default").list()["items"]]
+    assert any(r == "Unhealthy" and "no heartbeat" in m for r, m in evs), evs
+    assert any(r == "Killing" for r, _ in evs)
+    job = lc.jobs().get("hang")
+    assert job.status.phase in ("Running", "Restarting", "Creating", "Pending")
+    lc.jobs().delete("hang")
+    # exec probe: passes while the marker file exists
+    marker = os.path.join(lc.workdir, "alive")
+    open(marker, "w").close()
+    k = sh_job("probe", "sleep 60", replicas=1, restartPolicy="Never")
+    k["spec"]["replicaSpecs"]["trainer"]["template"]["spec"]["containers"][0]["livenessProbe"] = {
+        "exec": {"command": ["test", "-f", marker]}, "periodSeconds": 0.2, "failureThreshold": 2}
+    lc.apply(k)
+    wait_until(lambda: lc.jobs().get("probe").status.phase == "Running")
+    time.sleep(1.0)
+    assert lc.jobs().get("probe").status.phase == "Running"            # healthy while the probe passes
+    os.remove(marker)
+    final = lc.wait_for_phase("probe", "Failed", timeout=20)
+    assert "137" in final.status.conditions[-1].message

@@ -2,7 +2,10 @@
 ``restartPolicy: OnFailure`` + ``restartScope: All`` -> every replica is re-created, resumes from rank 0's checkpoint.
 Reports kill -> job Running again -> first training step after the restart.
 
-    python tools/fault_check.py [model] [n] [warm_pool] [--cpu]
+    python tools/fault_check.py [model] [n] [warm_pool] [--cpu] [--scope Pod|All] [--hang SECONDS]
+
+``--scope Pod --hang S``: only the killed replica is re-created by the controller; the survivors, stuck in a collective
+with a dead peer, are caught by the agent's heartbeat-based hang detection after S seconds and restarted too.
 """
 import json
 import os
@@ -15,21 +18,29 @@ sys.path.insert(0, ROOT)
 from trainingjob_operator_b200.cmd.local import LocalCluster  # noqa: E402
 from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption  # noqa: E402
 
-argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+argv = [a for a in sys.argv[1:] if not a.startswith("--") and "=" not in a]
 cpu = "--cpu" in sys.argv
 model = argv[0] if argv else ("mlp" if cpu else "bert")
 n = int(argv[1]) if len(argv) > 1 else 2
 pool = int(argv[2]) if len(argv) > 2 else 0
+scope = sys.argv[sys.argv.index("--scope") + 1] if "--scope" in sys.argv else "All"
+hang = sys.argv[sys.argv.index("--hang") + 1] if "--hang" in sys.argv else ""
+argv = [a for a in argv if a not in (scope, hang)] if ("--scope" in sys.argv or "--hang" in sys.argv) else argv
 victim = min(3, n - 1)
 batch = {"bert": 8, "mlp": 16, "gpt2": 4, "resnet50": 32}.get(model, 8)
 worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", model, "--batch", str(batch),
           "--steps", "0", "--ckpt-every", "10"] + (["--cpu", "--step-sleep", "0.02"] if cpu else [])
 c = {"name": "aitj-trainer", "command": worker, "workingDir": ROOT, "env": [{"name": "PYTHONPATH", "value": ROOT}]}
+if hang:
+    c["env"].append({"name": "AITJ_HANG_TIMEOUT", "value": hang})
+for kv in sys.argv[1:]:
+    if "=" in kv and not kv.startswith("--"):
+        c["env"].append({"name": kv.split("=", 1)[0], "value": kv.split("=", 1)[1]})
 if not cpu:
     c["resources"] = {"limits": {"nvidia.com/gpu": 1}}
 job = {"apiVersion": "elasticdeeplearning.ai/v1", "kind": "AITrainingJob", "metadata": {"name": "ft"},
        "spec": {"frameworkType": "pytorch", "replicaSpecs": {"trainer": {
-           "replicas": n, "restartPolicy": "OnFailure", "restartScope": "All", "restartLimit": 3,
+           "replicas": n, "restartPolicy": "OnFailure", "restartScope": scope, "restartLimit": 6,
            "template": {"spec": {"terminationGracePeriodSeconds": 1, "containers": [c]}}}}}}
 
 
@@ -51,7 +62,8 @@ def first_step_at(lc):
     return tr.get("first_step_done", 0.0)
 
 
-out = {"model": model, "replicas": n, "warm_pool": pool, "cpu": cpu, "victim_rank": victim}
+out = {"model": model, "replicas": n, "warm_pool": pool, "cpu": cpu, "victim_rank": victim, "restart_scope": scope,
+       "hang_timeout_s": hang or None}
 with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thread_num=2),
                   workdir=f"/tmp/aitj-fault-{pool}", warm_pool=pool) as lc:
     if pool:
@@ -79,6 +91,6 @@ with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thr
     lc.jobs().delete("ft")
     time.sleep(0.5)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}.json", "w"), indent=1)
+json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_{scope.lower()}.json", "w"), indent=1)
 print(json.dumps(out))
-sys.exit(0 if out["restart_counts"].get("trainer") == 1 and out["resumed"] else 1)
+sys.exit(0 if out["restart_counts"].get("trainer", 0) >= 1 and out["resumed"] else 1)

@@ -18,6 +18,11 @@ agent, which keeps the exact object contract the controller logic reads
   128+N); exec failures surface as ``CreateContainerError`` / ``CreateContainerConfigError`` waiting
   reasons (constants.go:46-56); graceful delete = SIGTERM, grace period, SIGKILL, then the pod object
   is removed; a vanished pod object kills its processes (orphan sweep, garbage_collection.go analogue).
+* **liveness**: ``containers[].livenessProbe.exec`` is honoured (period / failureThreshold / initialDelay / timeout as
+  in Kubernetes), and a worker that stops touching ``$AITJ_HEARTBEAT_FILE`` for ``AITJ_HANG_TIMEOUT`` seconds (env of
+  the container) is treated the same way: event ``Unhealthy`` + ``Killing``, SIGKILL => exit 137 => the job's restart
+  policy takes over.  This is the hang detection the reference leaves to kubelet probes; a DDP rank
+  stuck in a collective because a peer died is the case it exists for.
 * **warm pool** (``warm_pool=N``): N parked interpreters with torch already imported (``runtime/zygote.py``);
   a container whose command is ``python -m mod`` / ``python script`` adopts one instead of paying the
   interpreter start + ``import torch`` (seconds) on the spawn -> Running path.
@@ -38,6 +43,7 @@ from typing import Any, Callable, Dict, List, Optional, Tuple
 from ..api import constants as C
 from ..api import meta as M
 from ..client.informers import DeletedFinalStateUnknown, SharedInformerFactory
+from ..client.record import EventRecorder
 from ..core import _aitj_core as core
 from ..store.apiserver import APIError
 from ..utils import klog, lifecycle, metrics
@@ -51,6 +57,7 @@ _PASS_ENV = ("PATH", "HOME", "USER", "LANG", "LC_ALL", "LD_LIBRARY_PATH", "VIRTU
 
 metrics.describe("aitj_spawn_seconds", "pod bound -> all containers started")
 metrics.describe("aitj_warm_adoptions_total", "containers started by adopting a pre-warmed interpreter")
+metrics.describe("aitj_liveness_kills_total", "containers killed by a failed liveness probe / missing heartbeat")
 ZYGOTE_PREFIX = "~zygote/"     # supervisor ids of parked interpreters ('~' cannot start a namespace name)
 
 
@@ -136,6 +143,9 @@ class _PodState:
     # serialises "containers started -> status Running" against the exit handler: a command that exits at once must not
     # have its terminated status overwritten by the (later) Running patch
     status_lock: threading.Lock = field(default_factory=threading.Lock)
+    started_at: float = 0.0
+    probe_next: Dict[str, float] = field(default_factory=dict)      # container -> next liveness check (monotonic)
+    probe_failures: Dict[str, int] = field(default_factory=dict)
 
 
 class NodeAgent:
@@ -167,6 +177,9 @@ class NodeAgent:
         self.node_lister = self._node_informer.lister()
         self._threads: List[threading.Thread] = []
         self._injected: Dict[str, str] = {}
+        self.recorder = EventRecorder(clientset, "aitj-agent", log=False)
+        self.heartbeat_dir = os.path.join(workdir, "heartbeats")
+        os.makedirs(self.heartbeat_dir, exist_ok=True)
         # authoritative GPU allocation table (gpu index -> pod uid): the informer cache lags behind our own
         # binds, so consecutive scheduling decisions must not rely on it alone
         self._gpu_owner: Dict[int, Tuple[str, float]] = {}
@@ -241,6 +254,84 @@ class NodeAgent:
         while not stop.wait(self.health_period):
             self.check_health_once()
 
+    # ------------------------------------------------------------------ liveness probes / hang detection
+    def _probe_loop(self, stop: threading.Event) -> None:
+        while not stop.wait(0.25):
+            try:
+                self.check_liveness_once()
+            except Exception as e:  # noqa: BLE001
+                klog.V(2).info("agent: liveness pass failed: %r", e)
+
+    def check_liveness_once(self) -> None:
+        now = time.monotonic()
+        with self._lock:
+            states = [st for st in self._states.values() if st.started and st.containers]
+        for st in states:
+            ns, name = M.split_key(st.key)
+            try:
+                pod = self.pod_lister.namespaced(ns).get(name)
+            except APIError:
+                continue
+            if M.uid_of(pod) != st.uid or pod.get("metadata", {}).get("deletionTimestamp") or \
+                    pod.get("status", {}).get("phase") != C.POD_RUNNING:
+                continue
+            for c in pod.get("spec", {}).get("containers") or []:
+                sid = st.containers.get(c["name"])
+                if not sid or not self.sup.alive(sid):
+                    continue
+                verdict = self._probe_container(pod, st, c, now)
+                if verdict:
+                    self.recorder.event(pod, "Warning", "Unhealthy", f"Liveness probe failed: {verdict}")
+                    self.recorder.event(pod, "Normal", "Killing",
+                                        f"Container {c['name']} failed liveness probe, will be restarted")
+                    klog.warning("pod %s container %s: liveness failed (%s), killing", st.key, c["name"], verdict)
+                    metrics.inc("aitj_liveness_kills_total")
+                    st.probe_failures.pop(c["name"], None)
+                    self.sup.kill(sid, signal.SIGKILL, True)
+
+    def _probe_container(self, pod: dict, st: _PodState, c: dict, now: float) -> str:
+        """'' while the container is considered alive, else the reason to kill it."""
+        cname = c["name"]
+        env = {str(e.get("name")): str(e.get("value", "")) for e in c.get("env") or [] if "name" in e}
+        # built-in hang detection: the worker touches its heartbeat file every step
+        try:
+            hang = float(env.get("AITJ_HANG_TIMEOUT", "0") or 0)
+        except ValueError:
+            hang = 0.0
+        if hang > 0:
+            try:
+                age = time.time() - os.stat(self.heartbeat_path(pod, cname)).st_mtime
+            except OSError:
+                age = now - st.started_at            # never written: count from container start
+            if age > hang:
+                return f"no heartbeat for {age:.1f}s (AITJ_HANG_TIMEOUT={hang:g}s)"
+        probe = (c.get("livenessProbe") or {})
+        cmd = (probe.get("exec") or {}).get("command")
+        if not cmd:
+            return ""
+        period = float(probe.get("periodSeconds", 10))
+        if now - st.started_at < float(probe.get("initialDelaySeconds", 0)) or now < st.probe_next.get(cname, 0.0):
+            return ""
+        st.probe_next[cname] = now + period
+        import subprocess
+
+        gpus = [int(g) for g in (M.annotations_of(pod).get(C.ANN_GPUS) or "").split(",") if g.strip()]
+        try:
+            r = subprocess.run([str(x) for x in cmd], env=self._container_env(pod, c, gpus), capture_output=True,
+                               timeout=float(probe.get("timeoutSeconds", 1)), cwd=c.get("workingDir") or None)
+            ok, why = r.returncode == 0, f"exit code {r.returncode}"
+        except subprocess.TimeoutExpired:
+            ok, why = False, "timed out"
+        except OSError as e:
+            ok, why = False, str(e)
+        if ok:
+            st.probe_failures[cname] = 0
+            return ""
+        st.probe_failures[cname] = st.probe_failures.get(cname, 0) + 1
+        if st.probe_failures[cname] >= int(probe.get("failureThreshold", 3)):
+            return f"exec {cmd!r}: {why} ({st.probe_failures[cname]} consecutive failures)"
+        return ""
+
     def check_health_once(self) -> None:
         for i in range(self.num_gpus):
             name = self.gpu_node(i)
@@ -279,7 +370,8 @@ class NodeAgent:
         self._factory.start(stop)
         self._factory.wait_for_cache_sync(stop)
         for target, name in ((self._sync_loop, "agent-sync"), (self._reap_loop, "agent-reap"),
-                             (self._health_loop, "agent-health"), (self._sweep_loop, "agent-sweep")):
+                             (self._health_loop, "agent-health"), (self._sweep_loop, "agent-sweep"),
+                             (self._probe_loop, "agent-liveness")):
             self._threads.append(lifecycle.spawn(target, name, (stop,)))
         lifecycle.register_stop(lambda: (stop.set(), self.queue.shutdown(), self._kill_zygotes()))
         threading.Thread(target=lambda: (stop.wait(), self.queue.shutdown(), self._kill_zygotes()),
@@ -642,6 +734,7 @@ class NodeAgent:
         env["AITJ_POD_UID"] = M.uid_of(pod)
         env["AITJ_NODE_NAME"] = pod.get("spec", {}).get("nodeName", "")
         env["AITJ_WORKDIR"] = self.workdir
+        env["AITJ_HEARTBEAT_FILE"] = self.heartbeat_path(pod, c.get("name", ""))
         env["PYTHONUNBUFFERED"] = "1"
         for e in c.get("env") or []:
             if "name" in e:
@@ -657,6 +750,9 @@ class NodeAgent:
         for g in gpus:
             out += list(range(g * per, (g + 1) * per))
         return out
+
+    def heartbeat_path(self, pod: dict, container: str) -> str:
+        return os.path.join(self.heartbeat_dir, f"{M.namespace_of(pod)}_{M.name_of(pod)}_{container}")
 
     def log_path(self, pod: dict, container: str) -> str:
         return os.path.join(self.log_dir, f"{M.namespace_of(pod)}_{M.name_of(pod)}_{container}.log")
@@ -694,6 +790,7 @@ class NodeAgent:
         if not ok:
             return
         st.started = True
+        st.started_at = time.monotonic()
         now = M.format_time()
         for c in mains:
             statuses.append({"name": c["name"], "image": c.get("image", ""), "ready": True, "restartCount": 0,
@@ -714,6 +811,11 @@ class NodeAgent:
                 cwd = c.get("workingDir") or ""
                 env = self._container_env(pod, c, gpus)
                 log, cpus = self.log_path(pod, c["name"]), self._cpus_for(gpus)
+                try:        # a fresh heartbeat: a restarted replica must not inherit its predecessor's stale one
+                    with open(env["AITJ_HEARTBEAT_FILE"], "w"):
+                        pass
+                except OSError:
+                    pass
                 if not self._adopt_zygote(sid, argv, env, cwd, log, cpus):
                     self.sup.spawn(sid, argv, env, cwd, log, "", cpus)
                 st.containers[c["name"]] = sid

@@ -99,6 +99,10 @@ class ElasticWatcher:
         return {"generation": int(rdv.get("generation", 0)), "world": world, "port": int(rdv.get("masterPort", 0)),
                 "ready": ready}
 
+    def fetch_now(self) -> Optional[Dict[str, Any]]:
+        """The job's current rendezvous record, read synchronously (no readiness gating): used while (re)joining."""
+        return self._fetch()
+
     def _joiners_ready(self, r: Dict[str, Any]) -> bool:
         gen = r["generation"]
         first = self._first_seen.setdefault(gen, time.time())

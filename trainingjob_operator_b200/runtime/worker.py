@@ -208,15 +208,83 @@ def build_adapter(args, device: torch.device):
 
 
 # ------------------------------------------------------------------------------------ process group
-def init_process_group(rank: int, world: int, port: int, device: torch.device, timeout_s: float = 120.0):
+def init_process_group(rank: int, world: int, port: int, device: torch.device, timeout_s: float = 120.0,
+                       attempt_timeout_s: float = 0.0):
+    """Rendezvous on the generation's loopback port.  With ``attempt_timeout_s`` the TCP-store phase (all ranks
+    present) is bounded separately and raises on expiry, so the caller can re-read the job's current rendezvous
+    generation and try again; ``timeout_s`` stays the collective timeout of the process group."""
     import datetime
 
     backend = "nccl" if device.type == "cuda" else "gloo"
     kw: Dict[str, Any] = {}
     if device.type == "cuda":
         kw["device_id"] = device
+    if attempt_timeout_s > 0:
+        store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0),
+                              timeout=datetime.timedelta(seconds=attempt_timeout_s), wait_for_workers=True)
+        store.set_timeout(datetime.timedelta(seconds=timeout_s))
+        dist.init_process_group(backend, store=store, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=timeout_s), **kw)
+        return
     dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                             timeout=datetime.timedelta(seconds=timeout_s), **kw)
+
+
+class _KeepBeating:
+    """Heart-beats from a side thread while the main thread is legitimately blocked in a *bounded* wait (waiting for
+    peers in a rendezvous attempt); a stuck training step still stops the heartbeat, which is the point of it."""
+
+    def __enter__(self):
+        import threading
+
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def _run(self):
+        while not self._stop.wait(1.0):
+            heartbeat(force=True)
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=2.0)
+        return False
+
+
+def rendezvous(rank: int, rdv: Dict[str, int], device: torch.device, watcher) -> Optional[Dict[str, int]]:
+    """Join the job's CURRENT rendezvous generation.  A replica created for generation g may find, while it waits for
+    its peers, that the controller has moved on (another replica failed and was re-created, the job was rescaled): the
+    attempt is bounded (``AITJ_RDV_ATTEMPT_TIMEOUT``, default 15 s), after which the newest generation / world / port
+    is read from the job and the rendezvous is retried there, so replicas created at different moments converge
+    instead of waiting for each other on different ports.  Returns the adopted record, or None when this rank is no
+    longer part of the world."""
+    attempt = float(os.environ.get("AITJ_RDV_ATTEMPT_TIMEOUT", "15"))
+    deadline = time.time() + float(os.environ.get("AITJ_RDV_TIMEOUT", "600"))
+    cur = dict(rdv)
+    while True:
+        latest = watcher.fetch_now() if watcher is not None else None
+        if latest is not None and latest["generation"] > cur["generation"]:
+            print(f"[worker {rank}] rendezvous: generation {cur['generation']} is stale, joining {latest['generation']} "
+                  f"(world {latest['world']})", flush=True)
+            cur = {"generation": latest["generation"], "world": latest["world"], "port": latest["port"]}
+        if rank >= cur["world"]:
+            return None
+        if cur["world"] <= 1:
+            return cur
+        try:
+            with _KeepBeating():
+                init_process_group(rank, cur["world"], cur["port"], device,
+                                   attempt_timeout_s=attempt if watcher is not None else 0.0)
+            return cur
+        except Exception as e:  # noqa: BLE001 - peers missing within the attempt window (or a stale port)
+            if dist.is_initialized():
+                dist.destroy_process_group()
+            if watcher is None or time.time() > deadline:
+                raise
+            print(f"[worker {rank}] rendezvous attempt on generation {cur['generation']} failed "
+                  f"({type(e).__name__}); re-reading the job", flush=True)
+            heartbeat(force=True)
 
 
 def max_over_ranks(value: float, device: torch.device) -> float:
@@ -268,6 +336,24 @@ def load_checkpoint(args, adapter) -> int:
     return int(ck["step"])
 
 
+_HB = {"path": os.environ.get("AITJ_HEARTBEAT_FILE", ""), "last": 0.0}
+
+
+def heartbeat(force: bool = False) -> None:
+    """Touch ``$AITJ_HEARTBEAT_FILE`` (at most once a second): the node agent kills a worker whose heartbeat is older
+    than the container's ``AITJ_HANG_TIMEOUT`` -- e.g. a rank stuck in a collective after a peer died."""
+    path = _HB["path"] or os.environ.get("AITJ_HEARTBEAT_FILE", "")
+    now = time.time()
+    if not path or (not force and now - _HB["last"] < 1.0):
+        return
+    _HB["last"] = now
+    try:
+        with open(path, "a"):
+            os.utime(path, None)
+    except OSError:
+        pass
+
+
 # ------------------------------------------------------------------------------------ main loop
 def run(args) -> Dict[str, Any]:
     t_proc = time.time()
@@ -280,11 +366,13 @@ def run(args) -> Dict[str, Any]:
     if use_cuda:
         torch.cuda.set_device(device)
     trace = {"process_start": t_proc, "torch_imported": time.time()}
+    heartbeat(force=True)
     watcher = ElasticWatcher.from_env(generation)
     if watcher is not None and not args.elastic:
         watcher.poll = 5.0  # reporting only
     adapter = build_adapter(args, device)
     trace["model_built"] = time.time()
+    heartbeat(force=True)
     if args.elastic and watcher is not None and generation > 1 and world > 1:
         # Joining a running job: do everything that needs no peer first -- CUDA context, model build, two throw-away
         # steps (kernel loading, cuDNN plans, allocator growth; the state is overwritten by rank 0's broadcast
@@ -301,8 +389,15 @@ def run(args) -> Dict[str, Any]:
               f"{trace['model_built'] - t_proc:.2f}s, warm-up steps {trace['prewarmed'] - trace['model_built']:.2f}s)",
               flush=True)
     if world > 1:
-        init_process_group(rank, world, port, device)
+        got = rendezvous(rank, {"generation": generation, "world": world, "port": port}, device, watcher)
+        if got is None:
+            print(f"[worker {rank}] not part of the current world any more, leaving", flush=True)
+            return {"left": True, "generation": generation, "step": 0}
+        generation, world, port = got["generation"], got["world"], got["port"]
+        if watcher is not None:
+            watcher.adopted(generation, world)
     trace["rendezvous_done"] = time.time()
+    heartbeat(force=True)
     adapter.bind(None)
 
     restart_count = env_int("TRAININGJOB_REPLICA_RESTARTCOUNT", 0)
@@ -348,10 +443,14 @@ def run(args) -> Dict[str, Any]:
                 generation, world, port = target["generation"], new_world, target["port"]
                 t1 = time.time()
                 if world > 1:
-                    init_process_group(rank, world, port, device)
+                    got = rendezvous(rank, {"generation": generation, "world": world, "port": port}, device, watcher)
+                    if got is None:
+                        return {"left": True, "generation": generation, "step": step}
+                    generation, world, port = got["generation"], got["world"], got["port"]
                 t2 = time.time()
                 adapter.bind(None)
                 step = sync_state(adapter, step, device)
+                heartbeat(force=True)
                 watcher.adopted(generation, world)
                 pending_rescale = {"generation": generation, "world": world, "t0": t0,
                                    "observed_at": target.get("observed_at", t0),
@@ -370,6 +469,7 @@ def run(args) -> Dict[str, Any]:
         loss = adapter.train_step()
         losses.append(loss)
         step += 1
+        heartbeat()
         if pending_rescale is not None:
             # the first completed step at the new world size ends the rescale
             now = time.time()
