@@ -255,11 +255,11 @@ class _KeepBeating:
 def rendezvous(rank: int, rdv: Dict[str, int], device: torch.device, watcher) -> Optional[Dict[str, int]]:
     """Join the job's CURRENT rendezvous generation.  A replica created for generation g may find, while it waits for
     its peers, that the controller has moved on (another replica failed and was re-created, the job was rescaled): the
-    attempt is bounded (``AITJ_RDV_ATTEMPT_TIMEOUT``, default 15 s), after which the newest generation / world / port
+    attempt is bounded (``AITJ_RDV_ATTEMPT_TIMEOUT``, default 30 s), after which the newest generation / world / port
     is read from the job and the rendezvous is retried there, so replicas created at different moments converge
     instead of waiting for each other on different ports.  Returns the adopted record, or None when this rank is no
     longer part of the world."""
-    attempt = float(os.environ.get("AITJ_RDV_ATTEMPT_TIMEOUT", "15"))
+    attempt = float(os.environ.get("AITJ_RDV_ATTEMPT_TIMEOUT", "30"))
     deadline = time.time() + float(os.environ.get("AITJ_RDV_TIMEOUT", "600"))
     cur = dict(rdv)
     while True:
