@@ -434,7 +434,7 @@ def test_hang_detection_and_exec_liveness_probe(lc):
     assert any(r == "Unhealthy" and "no heartbeat" in m for r, m in evs), evs
     assert any(r == "Killing" for r, _ in evs)
     job = lc.jobs().get("hang")
-    assert job.status.phase in ("Running", "Restarting", "Creating", "Pending")
+    assert job.status.phase in ("Running", "Terminating", "Restarting", "Creating", "Pending")   # being restarted, not failed
     lc.jobs().delete("hang")
     # exec probe: passes while the marker file exists
     marker = os.path.join(lc.workdir, "alive")
@@ -449,3 +449,36 @@ def test_hang_detection_and_exec_liveness_probe(lc):
     os.remove(marker)
     final = lc.wait_for_phase("probe", "Failed", timeout=20)
     assert "137" in final.status.conditions[-1].message
+
+
+def test_agent_restart_readopts_running_workers_and_fails_lost_ones(lc):
+    """a restarted agent re-adopts its predecessor's live workers (pid + start time from
+    ``containerID``), keeps supervising them to completion, and marks a pod whose process vanished as failed instead
+    of leaving it Running or spawning it twice."""
+    lc.apply(sh_job("keepon", 'sleep 3; echo 0 > "$AITJ_EXIT_FILE"', replicas=2, gpus=1))
+    lc.apply(sh_job("gone", "sleep 30", replicas=1, restartPolicy="Never"))
+    wait_until(lambda: lc.jobs().get("keepon").status.phase == "Running" and lc.jobs().get("gone").status.phase == "Running")
+    pods = {p["metadata"]["name"]: p for p in lc.pods()}
+    cid = pods["keepon-trainer-0"]["status"]["containerStatuses"][0]["containerID"]
+    assert cid.startswith("aitj://") and cid.count("/") == 3
+    before = pod_pids(lc, "keepon")
+    gone_pid = list(pod_pids(lc, "gone").values())[0]
+    old_agent = lc.agent
+    # "crash": stop the old agent's loops, then kill one worker behind its back before the new agent comes up
+    lc._agent_stop.set()
+    for t in old_agent._threads:
+        t.join(timeout=3)
+    os.kill(gone_pid, signal.SIGKILL)
+    wait_until(lambda: not os.path.exists(f"/proc/{gone_pid}") or
+               open(f"/proc/{gone_pid}/stat").read().split()[2] == "Z", timeout=5)
+    old_agent = None
+    summary = lc.restart_agent()
+    assert summary == {"adopted": 2, "lost": 1}
+    assert pod_pids(lc, "keepon") == before                       # same processes, nothing was spawned twice
+    final = lc.wait_for_phase("gone", "Failed", timeout=20)
+    assert "137" in final.status.conditions[-1].message
+    done = lc.wait_for_phase("keepon", "Succeed", timeout=30)      # adopted workers are supervised to completion
+    assert done.status.restart_counts.get("trainer", 0) == 0
+    # and their GPU slots were accounted for while adopted, released afterwards
+    lc.apply(sh_job("after", "true", replicas=4, gpus=1))
+    lc.wait_for_phase("after", "Succeed", timeout=30)

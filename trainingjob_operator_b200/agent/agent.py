@@ -18,6 +18,12 @@ agent, which keeps the exact object contract the controller logic reads
   128+N); exec failures surface as ``CreateContainerError`` / ``CreateContainerConfigError`` waiting
   reasons (constants.go:46-56); graceful delete = SIGTERM, grace period, SIGKILL, then the pod object
   is removed; a vanished pod object kills its processes (orphan sweep, garbage_collection.go analogue).
+* **restart recovery**: ``containerStatuses[].containerID`` records ``aitj://<pid>/<start-time>``; a restarted agent
+  re-adopts the workers of its predecessor that are still alive (identity = pid + kernel start time, exit observed
+  through a pidfd) and fails the ones that are gone with ``ContainerStatusUnknown`` / 137, instead of leaving their
+  pods ``Running`` forever or double-spawning them.  The exit status of an adopted (non-child)
+  process cannot be waited for: a container that wrote its exit code to ``$AITJ_EXIT_FILE`` (the bundled workers do)
+  is believed, any other is reported as ``ContainerStatusUnknown``.
 * **liveness**: ``containers[].livenessProbe.exec`` is honoured (period / failureThreshold / initialDelay / timeout as
   in Kubernetes), and a worker that stops touching ``$AITJ_HEARTBEAT_FILE`` for ``AITJ_HANG_TIMEOUT`` seconds (env of
   the container) is treated the same way: event ``Unhealthy`` + ``Killing``, SIGKILL => exit 137 => the job's restart
@@ -127,6 +133,29 @@ def pod_priority(pod: dict) -> int:
         return int(raw)
     except ValueError:
         return PRIORITY_NAMES.get(raw.lower(), 0)
+
+
+def proc_start_time(pid: int) -> Optional[int]:
+    """Kernel start time of ``pid`` in clock ticks since boot (field 22 of /proc/<pid>/stat) -- with the pid it
+    identifies a process across agent restarts (pids are recycled, start times are not)."""
+    try:
+        with open(f"/proc/{pid}/stat", "rb") as f:
+            data = f.read().decode("ascii", "replace")
+        return int(data[data.rindex(")") + 2:].split()[19])
+    except (OSError, ValueError, IndexError):
+        return None
+
+
+def container_id(pid: int) -> str:
+    return f"aitj://{pid}/{proc_start_time(pid) or 0}"
+
+
+def parse_container_id(cid: str) -> Tuple[int, int]:
+    try:
+        pid, start = cid[len("aitj://"):].split("/")
+        return int(pid), int(start)
+    except (ValueError, AttributeError):
+        return 0, 0
 
 
 @dataclass
@@ -369,6 +398,7 @@ class NodeAgent:
         self.register_nodes()
         self._factory.start(stop)
         self._factory.wait_for_cache_sync(stop)
+        self.recover()
         for target, name in ((self._sync_loop, "agent-sync"), (self._reap_loop, "agent-reap"),
                              (self._health_loop, "agent-health"), (self._sweep_loop, "agent-sweep"),
                              (self._probe_loop, "agent-liveness")):
@@ -377,6 +407,62 @@ class NodeAgent:
         threading.Thread(target=lambda: (stop.wait(), self.queue.shutdown(), self._kill_zygotes()),
                          daemon=True).start()
         self._ensure_pool()
+
+    def recover(self) -> Dict[str, int]:
+        """After an agent restart: re-adopt the still-running containers of pods bound to this agent's nodes and fail
+        the ones whose process is gone.  Called from ``start`` before any pod is synced."""
+        out = {"adopted": 0, "lost": 0}
+        for pod in self.pod_lister.list():
+            node = pod.get("spec", {}).get("nodeName") or ""
+            status = pod.get("status", {})
+            if not node or not self._mine(node) or status.get("phase") != C.POD_RUNNING:
+                continue
+            key = M.key_of(pod)
+            with self._lock:
+                if key in self._states:
+                    continue
+            st = _PodState(key=key, uid=M.uid_of(pod), bound_at=time.monotonic())
+            st.started, st.started_at = True, time.monotonic()
+            lost = []
+            for cs in status.get("containerStatuses") or []:
+                if "running" not in (cs.get("state") or {}):
+                    continue
+                pid, start = parse_container_id(cs.get("containerID", ""))
+                sid = f"{key}/{st.uid[:8]}/{cs['name']}"
+                if pid > 0 and start > 0 and proc_start_time(pid) == start:
+                    try:
+                        self.sup.adopt(sid, pid)
+                        st.containers[cs["name"]] = sid
+                        out["adopted"] += 1
+                        continue
+                    except OSError:
+                        pass
+                lost.append(cs["name"])
+            gpus = [int(g) for g in (M.annotations_of(pod).get(C.ANN_GPUS) or "").split(",") if g.strip()]
+            with self._lock:
+                self._states[key] = st
+                for g in gpus:
+                    self._gpu_owner[g] = (st.uid, time.monotonic())
+            if lost:
+                out["lost"] += len(lost)
+                now = M.format_time()
+                statuses = M.deepcopy(status.get("containerStatuses") or [])
+                for cs in statuses:
+                    if cs.get("name") in lost:
+                        cs["ready"] = False
+                        cs["state"] = {"terminated": {"exitCode": 137, "reason": "ContainerStatusUnknown", "finishedAt": now,
+                                                      "message": "process lost across an agent restart"}}
+                self._kill_pod_processes(key, signal.SIGKILL)      # a pod is all-or-nothing: stop its other containers
+                try:
+                    self.cs.core_v1().pods(M.namespace_of(pod)).patch(
+                        M.name_of(pod), {"status": {"phase": C.POD_FAILED, "containerStatuses": statuses}},
+                        subresource="status")
+                except APIError as e:
+                    klog.warning("recover: status update of %s failed: %s", key, e.message)
+                self._release_gpus(st.uid)
+        if out["adopted"] or out["lost"]:
+            klog.info("agent restart recovery: adopted %d running container(s), %d lost", out["adopted"], out["lost"])
+        return out
 
     def run(self, stop: threading.Event) -> None:
         self.start(stop)
@@ -735,6 +821,7 @@ class NodeAgent:
         env["AITJ_NODE_NAME"] = pod.get("spec", {}).get("nodeName", "")
         env["AITJ_WORKDIR"] = self.workdir
         env["AITJ_HEARTBEAT_FILE"] = self.heartbeat_path(pod, c.get("name", ""))
+        env["AITJ_EXIT_FILE"] = self.heartbeat_path(pod, c.get("name", "")) + ".exit"
         env["PYTHONUNBUFFERED"] = "1"
         for e in c.get("env") or []:
             if "name" in e:
@@ -794,6 +881,7 @@ class NodeAgent:
         now = M.format_time()
         for c in mains:
             statuses.append({"name": c["name"], "image": c.get("image", ""), "ready": True, "restartCount": 0,
+                             "containerID": container_id(self.sup.pid_of(st.containers[c["name"]])),
                              "state": {"running": {"startedAt": now}}})
         patch = {"status": {"phase": C.POD_RUNNING, "startTime": pod.get("status", {}).get("startTime") or now,
                             "containerStatuses": statuses,
@@ -814,6 +902,8 @@ class NodeAgent:
                 try:        # a fresh heartbeat: a restarted replica must not inherit its predecessor's stale one
                     with open(env["AITJ_HEARTBEAT_FILE"], "w"):
                         pass
+                    if os.path.exists(env["AITJ_EXIT_FILE"]):
+                        os.unlink(env["AITJ_EXIT_FILE"])
                 except OSError:
                     pass
                 if not self._adopt_zygote(sid, argv, env, cwd, log, cpus):
@@ -862,7 +952,22 @@ class NodeAgent:
             return
         code, sig = int(ev["exit_code"]), int(ev["signal"])
         now = M.format_time()
+        if ev.get("status_unknown"):
+            # adopted after an agent restart: not our child, so no wait status.  A container that recorded its own exit
+            # code in $AITJ_EXIT_FILE (our workers do; any command may) is believed, anything else is "unknown" = 137
+            recorded = None
+            try:
+                with open(self.heartbeat_path(pod, cname) + ".exit") as f:
+                    recorded = int(f.read().strip() or "x")
+            except (OSError, ValueError):
+                pass
+            if recorded is not None:
+                code, sig = recorded, 0
+                ev = dict(ev, status_unknown=False)
         term = {"exitCode": code, "reason": "Completed" if code == 0 else "Error", "finishedAt": now}
+        if ev.get("status_unknown"):
+            term["reason"] = "ContainerStatusUnknown"
+            term["message"] = "the container was adopted after an agent restart; its exit status could not be read"
         if sig:
             term["signal"] = sig
             term["message"] = f"killed by signal {sig}"

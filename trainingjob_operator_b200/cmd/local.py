@@ -40,8 +40,10 @@ class LocalCluster:
         self.http = APIHTTPServer(self.api, port=port).start() if http else None
         self.stop_event = threading.Event()
         self.clientset: Clientset = new_for_config(server=self.api)
-        self.agent = NodeAgent(new_for_config(server=self.api), num_gpus=num_gpus, workdir=self.workdir,
-                               health_prober=health_prober, health_period=health_period, warm_pool=warm_pool)
+        self._agent_kw = dict(num_gpus=num_gpus, workdir=self.workdir, health_prober=health_prober,
+                              health_period=health_period, warm_pool=warm_pool)
+        self.agent = NodeAgent(new_for_config(server=self.api), **self._agent_kw)
+        self._agent_stop = threading.Event()
         self.option = option or options_mod.TrainingJobOperatorOption()
         self.option.master_url = self.http.url if self.http else ""
         if leader_elect:
@@ -56,8 +58,32 @@ class LocalCluster:
     def url(self) -> str:
         return self.http.url if self.http else ""
 
+    def _start_agent(self) -> None:
+        agent_stop = self._agent_stop
+        threading.Thread(target=lambda: (self.stop_event.wait(), agent_stop.set()), daemon=True).start()
+        self.agent.start(agent_stop)
+
+    def restart_agent(self) -> dict:
+        """Simulates an agent crash + restart: the old agent's loops stop without touching its worker processes, a fresh
+        ``NodeAgent`` (new supervisor, empty in-memory state) takes over the same nodes and re-adopts what is still
+        running.  Returns the new agent's recovery summary."""
+        self._agent_stop.set()
+        for t in list(getattr(self.agent, "_threads", [])):
+            t.join(timeout=3)
+        self.agent.queue.shutdown()
+        self.agent._kill_zygotes()
+        kw = dict(self._agent_kw)
+        kw["num_gpus"] = self.agent.num_gpus
+        self.agent = NodeAgent(new_for_config(server=self.api), **kw)
+        self._agent_stop = threading.Event()
+        seen: dict = {}
+        orig = self.agent.recover
+        self.agent.recover = lambda: seen.update(orig()) or seen       # capture what start() recovers
+        self._start_agent()
+        return seen
+
     def start(self) -> "LocalCluster":
-        self.agent.start(self.stop_event)
+        self._start_agent()
         for i in range(self._operators):
             self.start_operator(i)
         return self

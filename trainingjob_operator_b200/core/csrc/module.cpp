@@ -168,6 +168,7 @@ PYBIND11_MODULE(_aitj_core, m) {
       .def("spawn", &Supervisor::spawn, py::arg("id"), py::arg("argv"), py::arg("env"), py::arg("cwd") = "",
            py::arg("stdout_path") = "", py::arg("stderr_path") = "", py::arg("cpus") = std::vector<int>{})
       .def("kill", &Supervisor::kill_proc, py::arg("id"), py::arg("sig") = 15, py::arg("group") = true)
+      .def("adopt", &Supervisor::adopt, py::arg("id"), py::arg("pid"))
       .def("rename", &Supervisor::rename, py::arg("from_id"), py::arg("to_id"))
       .def("alive", &Supervisor::alive)
       .def("pid_of", &Supervisor::pid_of)
@@ -187,6 +188,7 @@ PYBIND11_MODULE(_aitj_core, m) {
                d["exit_code"] = e.exit_code;
                d["signal"] = e.signal;
                d["wall_time_s"] = e.wall_time_s;
+               d["status_unknown"] = e.status_unknown;
                out.append(d);
              }
              return out;

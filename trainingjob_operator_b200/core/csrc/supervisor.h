@@ -47,12 +47,14 @@ struct ExitEvent {
   int exit_code = 0;  // 128+signal when killed by a signal
   int signal = 0;
   double wall_time_s = 0.0;
+  bool status_unknown = false;  // an adopted (non-child) process: its exit is seen through the pidfd, its status is not
 };
 
 struct ProcInfo {
   std::string id;
   int pid = 0;
   int pidfd = -1;
+  bool adopted = false;
   std::chrono::steady_clock::time_point started;
 };
 
@@ -173,6 +175,29 @@ class Supervisor {
     return rc == 0;
   }
 
+  // Take over a process this supervisor did not spawn (the agent was restarted and finds its predecessor's workers
+  // still running).  The caller has verified the pid's identity (start time).  Exit is observed through a pidfd; the
+  // exit status of a non-child cannot be read, so its ExitEvent carries status_unknown.  Throws if the pid is gone.
+  void adopt(const std::string& id, int pid) {
+    int fd = static_cast<int>(syscall(SYS_pidfd_open, pid, 0));
+    if (fd < 0) throw SpawnError(errno, std::string("pidfd_open failed: ") + strerror(errno));
+    ProcInfo info;
+    info.id = id;
+    info.pid = pid;
+    info.pidfd = fd;
+    info.adopted = true;
+    info.started = std::chrono::steady_clock::now();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (procs_.count(id)) {
+        close(fd);
+        throw SpawnError(EEXIST, "process id already supervised: " + id);
+      }
+      procs_[id] = info;
+    }
+    wake();
+  }
+
   // Re-key a supervised process (a pre-warmed worker adopted as a pod's container).  The exit event of the
   // process is reported under the new id.  False if `from` is gone or `to` is taken.
   bool rename(const std::string& from, const std::string& to) {
@@ -267,13 +292,22 @@ class Supervisor {
       info = it->second;
     }
     int st = 0;
-    pid_t r = waitpid(info.pid, &st, nohang ? WNOHANG : 0);
-    if (r == 0) return;
+    pid_t r = waitpid(info.pid, &st, (nohang || info.adopted) ? WNOHANG : 0);
+    if (r == 0 && !info.adopted) return;
     ExitEvent ev;
     ev.id = id;
     ev.pid = info.pid;
-    if (r < 0) {
-      ev.exit_code = 255;
+    if (r <= 0) {
+      if (info.adopted && r < 0 && errno == ECHILD) {
+        // not our child: the readable pidfd (or a vanished pid) is all we get
+        if (::kill(info.pid, 0) == 0 && nohang) return;
+        ev.status_unknown = true;
+        ev.exit_code = 137;
+      } else if (r == 0) {
+        return;
+      } else {
+        ev.exit_code = 255;
+      }
     } else if (WIFSIGNALED(st)) {
       ev.signal = WTERMSIG(st);
       ev.exit_code = 128 + ev.signal;

@@ -570,5 +570,28 @@ def main(argv=None) -> int:
     return 0
 
 
+def _record_exit(code: int) -> None:
+    """``$AITJ_EXIT_FILE``: lets an agent that adopted this process after a restart (and therefore cannot wait() for
+    it) still learn how it ended."""
+    path = os.environ.get("AITJ_EXIT_FILE", "")
+    if not path:
+        return
+    try:
+        with open(path, "w") as f:
+            f.write(str(int(code)))
+    except OSError:
+        pass
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        _code = main()
+    except SystemExit as e:
+        _code = e.code if isinstance(e.code, int) else (0 if e.code is None else 1)
+        _record_exit(_code)
+        raise
+    except BaseException:
+        _record_exit(1)
+        raise
+    _record_exit(_code)
+    sys.exit(_code)
