@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <set>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "store.h"
@@ -171,6 +172,34 @@ static void stress_supervisor() {
   stop = true;
   reaper.join();
   CHECK(exits.load() == 60);
+  // adoption of a process this supervisor did not spawn (agent-restart path)
+  {
+    pid_t pid = fork();
+    if (pid == 0) {
+      execl("/bin/sleep", "sleep", "30", static_cast<char*>(nullptr));
+      _exit(127);
+    }
+    CHECK(pid > 0);
+    setpgid(pid, pid);
+    Supervisor sup2;
+    sup2.adopt("adopted", pid);
+    CHECK(sup2.alive("adopted") && sup2.pid_of("adopted") == pid);
+    bool dup = false;
+    try {
+      sup2.adopt("adopted", pid);
+    } catch (const SpawnError&) {
+      dup = true;
+    }
+    CHECK(dup);
+    sup2.kill_proc("adopted", 9, false);
+    int got = 0;
+    for (int i = 0; i < 100 && !got; ++i)
+      for (auto& ev : sup2.poll_exits(0.05)) {
+        CHECK(ev.id == "adopted" && ev.exit_code == 137);
+        ++got;
+      }
+    CHECK(got == 1 && !sup2.alive("adopted"));
+  }
   bool threw = false;
   try {
     sup.spawn("bad", {"/no/such/binary"}, env, "", "", "", {});
