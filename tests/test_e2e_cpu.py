@@ -482,3 +482,60 @@ def test_agent_restart_readopts_running_workers_and_fails_lost_ones(lc):
     # and their GPU slots were accounted for while adopted, released afterwards
     lc.apply(sh_job("after", "true", replicas=4, gpus=1))
     lc.wait_for_phase("after", "Succeed", timeout=30)
+
+
+@pytest.mark.slow
+def test_agent_process_crash_and_restart_with_live_gloo_workers(tmp_path):
+    """The three daemons as separate processes (README): kill -9 the agent while a 2-rank gloo job trains, start a new
+    agent; it adopts the orphaned workers, learns their exit codes from $AITJ_EXIT_FILE, and the job Succeeds with
+    zero restarts."""
+    import socket
+    import subprocess
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, PYTHONPATH=ROOT, HOME=str(tmp_path))
+    procs = []
+
+    def spawn(mod, *args, log):
+        p = subprocess.Popen([sys.executable, "-m", f"trainingjob_operator_b200.cmd.{mod}", *args], cwd=ROOT, env=env,
+                             stdout=open(tmp_path / log, "w"), stderr=subprocess.STDOUT)
+        procs.append(p)
+        return p
+
+    def ctl(*args):
+        r = subprocess.run([sys.executable, "-m", "trainingjob_operator_b200.cli.kubectl", "--server",
+                            f"http://127.0.0.1:{port}", *args], cwd=ROOT, env=env, capture_output=True, text=True)
+        return r.stdout + r.stderr
+
+    try:
+        spawn("apiserver", "--port", str(port), log="api.log")
+        wait_until(lambda: "No resources" in ctl("get", "aitj") or "NAME" in ctl("get", "aitj"), timeout=30, period=0.3)
+        agent = spawn("agent", "--master", f"127.0.0.1:{port}", "--gpus", "0", "--workdir", str(tmp_path / "agent"),
+                      "--warm-pool", "0", log="agent1.log")
+        spawn("main", "--master", f"127.0.0.1:{port}", "--thread-num", "2", "--logtostderr", log="op.log")
+        worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", "mlp", "--batch", "16",
+                  "--steps", "200", "--cpu", "--step-sleep", "0.05"]
+        job = {"apiVersion": C.API_VERSION, "kind": C.KIND, "metadata": {"name": "survive"},
+               "spec": {"frameworkType": "pytorch", "replicaSpecs": {"trainer": {"replicas": 2, "template": {"spec": {
+                   "containers": [{"name": "aitj-trainer", "command": worker, "workingDir": ROOT,
+                                   "env": [{"name": "PYTHONPATH", "value": ROOT}]}]}}}}}}
+        (tmp_path / "job.yaml").write_text(yaml.safe_dump(job))
+        assert "created" in ctl("apply", "-f", str(tmp_path / "job.yaml"))
+        wait_until(lambda: "Running" in ctl("get", "aitj", "survive", "-o", "wide"), timeout=60, period=0.3)
+        time.sleep(2.0)
+        agent.kill()
+        agent.wait()
+        spawn("agent", "--master", f"127.0.0.1:{port}", "--gpus", "0", "--workdir", str(tmp_path / "agent"),
+              "--warm-pool", "0", log="agent2.log")
+        wait_until(lambda: "adopted 2 running container(s), 0 lost" in (tmp_path / "agent2.log").read_text(),
+                   timeout=30, period=0.3)
+        wait_until(lambda: "Succeed" in ctl("get", "aitj", "survive", "-o", "wide"), timeout=90, period=0.5)
+        wide = ctl("get", "aitj", "survive", "-o", "wide").splitlines()[-1].split()
+        assert wide[1] == "Succeed" and wide[4] == "0"                # PHASE, RESTARTS
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
