@@ -539,3 +539,51 @@ def test_agent_process_crash_and_restart_with_live_gloo_workers(tmp_path):
         for p in procs:
             if p.poll() is None:
                 p.kill()
+
+
+@pytest.mark.slow
+def test_apiserver_process_crash_recovers_from_wal_and_clients_reconnect(tmp_path):
+    """kill -9 the API server under a running job: the restarted one replays its write-ahead log, the operator's and the
+    agent's informers re-list / re-watch, and the job completes."""
+    import socket
+    import subprocess
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, PYTHONPATH=ROOT, HOME=str(tmp_path))
+    procs = []
+
+    def spawn(mod, *args, log):
+        p = subprocess.Popen([sys.executable, "-m", f"trainingjob_operator_b200.cmd.{mod}", *args], cwd=ROOT, env=env,
+                             stdout=open(tmp_path / log, "w"), stderr=subprocess.STDOUT)
+        procs.append(p)
+        return p
+
+    def ctl(*args):
+        r = subprocess.run([sys.executable, "-m", "trainingjob_operator_b200.cli.kubectl", "--server",
+                            f"http://127.0.0.1:{port}", *args], cwd=ROOT, env=env, capture_output=True, text=True)
+        return r.stdout + r.stderr
+
+    try:
+        api = spawn("apiserver", "--port", str(port), log="api1.log")
+        wait_until(lambda: "No resources" in ctl("get", "aitj") or "NAME" in ctl("get", "aitj"), timeout=30, period=0.3)
+        spawn("agent", "--master", f"127.0.0.1:{port}", "--gpus", "0", "--workdir", str(tmp_path / "agent"),
+              "--warm-pool", "0", log="agent.log")
+        spawn("main", "--master", f"127.0.0.1:{port}", "--thread-num", "2", "--logtostderr", log="op.log")
+        (tmp_path / "job.yaml").write_text(yaml.safe_dump(sh_job("apirestart", "sleep 8", replicas=2)))
+        wait_until(lambda: "created" in ctl("apply", "-f", str(tmp_path / "job.yaml")), timeout=30, period=0.5)
+        wait_until(lambda: "Running" in ctl("get", "aitj", "apirestart", "-o", "wide"), timeout=60, period=0.3)
+        api.kill()
+        api.wait()
+        time.sleep(1.0)
+        spawn("apiserver", "--port", str(port), log="api2.log")
+        wait_until(lambda: "apirestart" in ctl("get", "aitj"), timeout=30, period=0.3)       # replayed from the WAL
+        wait_until(lambda: "Succeed" in ctl("get", "aitj", "apirestart", "-o", "wide"), timeout=90, period=0.5)
+        wide = ctl("get", "aitj", "apirestart", "-o", "wide").splitlines()[-1].split()
+        assert wide[1] == "Succeed" and wide[4] == "0"
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
