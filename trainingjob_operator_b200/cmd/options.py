@@ -78,6 +78,11 @@ class TrainingJobOperatorOption:
     scale_down_grace: float = 30.0   # how long an out-of-range replica may drain before deletion
     identity: str = ""               # leader-election identity override (tests)
     metrics_port: int = 0
+    # overall token bucket of the reconcile queue.  The reference inherits client-go's DefaultControllerRateLimiter
+    # (10 qps / burst 100), and because every status write of the controller re-enqueues its job rate-limited, a busy
+    # operator degrades to one reconcile per 100 ms; here the store is in-process, so the bucket is sized for it.
+    queue_qps: float = 2000.0
+    queue_burst: int = 2000
 
 
 def new_training_job_operator_option() -> TrainingJobOperatorOption:
@@ -114,13 +119,16 @@ def add_flags(parser: argparse.ArgumentParser, opt: Optional[TrainingJobOperator
     a("--scale-down-grace", type=parse_duration, default=o.scale_down_grace)
     a("--identity", default=o.identity, help="leader election identity (default <hostname>_<uuid>)")
     a("--metrics-port", type=int, default=o.metrics_port)
+    a("--queue-qps", type=float, default=o.queue_qps,
+      help="overall rate limit of the reconcile work queue (client-go default would be 10)")
+    a("--queue-burst", type=int, default=o.queue_burst, help="burst of that limiter (client-go default would be 100)")
 
 
 def from_args(ns: argparse.Namespace) -> TrainingJobOperatorOption:
     o = TrainingJobOperatorOption()
     for f in ("master_url", "kubeconfig", "run_in_cluster", "thread_num", "creating_restart_time",
               "creating_duration_time", "enable_creating_failed", "namespace", "resync_period", "v", "logtostderr",
-              "gc_interval", "scale_down_grace", "identity", "metrics_port"):
+              "gc_interval", "scale_down_grace", "identity", "metrics_port", "queue_qps", "queue_burst"):
         setattr(o, f, getattr(ns, f))
     o.leader_election = LeaderElectionConfiguration(
         leader_elect=ns.leader_elect, lease_duration=ns.leader_elect_lease_duration,

@@ -73,7 +73,9 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
         self.pod_control = pod_control or RealPodControl(kube_client, self.recorder)
         self.service_control = service_control or RealServiceControl(kube_client, self.recorder)
         self.expectations = core.Expectations(300.0)
-        self.work_queue = core.WorkQueue(C.KIND)
+        # per-item back-off as upstream (5 ms * 2^n <= 1000 s); overall bucket from the options (see cmd/options.py)
+        self.work_queue = core.WorkQueue(C.KIND, 0.005, 1000.0, float(getattr(option, "queue_qps", 10.0)),
+                                         int(getattr(option, "queue_burst", 100)))
 
         job_informer.informer().add_event_handler(
             add=self.add_training_job, update=self.update_training_job, delete=self.delete_training_job,

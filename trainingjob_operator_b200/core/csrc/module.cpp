@@ -163,6 +163,8 @@ PYBIND11_MODULE(_aitj_core, m) {
       .def("count", &Store::count)
       .def("compact", &Store::compact);
 
+  m.def("proc_start_time", &proc_start_time, py::arg("pid"),
+        "kernel start time (clock ticks since boot) of a pid, 0 if it does not exist");
   py::class_<Supervisor>(m, "Supervisor")
       .def(py::init<>())
       .def("spawn", &Supervisor::spawn, py::arg("id"), py::arg("argv"), py::arg("env"), py::arg("cwd") = "",
