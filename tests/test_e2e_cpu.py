@@ -14,6 +14,7 @@ import pytest
 import yaml
 
 from trainingjob_operator_b200.api import constants as C
+from trainingjob_operator_b200.api import meta as M
 from trainingjob_operator_b200.api.types import AITrainingJob
 from trainingjob_operator_b200.cli import kubectl
 from trainingjob_operator_b200.cmd.local import LocalCluster
@@ -485,6 +486,25 @@ def test_agent_restart_readopts_running_workers_and_fails_lost_ones(lc):
 
 
 @pytest.mark.slow
+def test_stale_unbound_view_of_a_finished_pod_is_not_scheduled_again(lc):
+    """Bind + start + exit of an instant command can all finish before the informer cache shows the pod as bound; the
+    queued sync of that stale (unbound, Pending) object must not bind it a second time (the bind patch resets the phase
+    to Pending and nothing would ever start the pod again)."""
+    job = sh_job("quick", "true", replicas=1, gpus=1, restartPolicy="Never")
+    job["spec"]["cleanPodPolicy"] = "None"
+    lc.apply(job)
+    lc.wait_for_phase("quick", "Succeed", timeout=20)
+    pod = lc.pods(selector="TrainingJobName=quick")[0]
+    assert pod["status"]["phase"] == "Succeeded"
+    stale = M.deepcopy(pod)
+    stale["spec"].pop("nodeName", None)
+    stale["status"] = {"phase": "Pending"}
+    lc.agent.schedule(stale)
+    after = lc.pods(selector="TrainingJobName=quick")[0]
+    assert after["status"]["phase"] == "Succeeded"
+    assert after["metadata"]["resourceVersion"] == pod["metadata"]["resourceVersion"]
+
+
 def test_agent_process_crash_and_restart_with_live_gloo_workers(tmp_path):
     """The three daemons as separate processes (README): kill -9 the agent while a 2-rank gloo job trains, start a new
     agent; it adopts the orphaned workers, learns their exit codes from $AITJ_EXIT_FILE, and the job Succeeds with

@@ -670,8 +670,8 @@ class NodeAgent:
             return
         phase = pod.get("status", {}).get("phase") or C.POD_PENDING
         if not node:
-            if phase == C.POD_PENDING:
-                self.schedule(pod)
+            if phase == C.POD_PENDING and not (st is not None and st.started):
+                self.schedule(pod)          # (started: the cache is behind a bind + direct start of this very pod)
             return
         if not self._mine(node):
             return
@@ -767,7 +767,8 @@ class NodeAgent:
         with self._lock:
             for g in [g for g, (u, _t) in self._gpu_owner.items() if u == uid]:
                 del self._gpu_owner[g]
-            self._bound.pop(uid, None)
+            # `_bound` keeps the uid (pruned by age in `schedule`): a pod that ran to completion before the informer cache
+            # even showed it as bound must not be bound a second time by a stale queue entry
         self._kick_pending()
 
     def _mark_unschedulable(self, pod: dict, message: str) -> None:
@@ -790,12 +791,21 @@ class NodeAgent:
         with self._lock:
             self._bound[M.uid_of(pod)] = time.monotonic()
         try:
-            self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch)
+            bound = self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch)
         except APIError:
             with self._lock:
                 self._bound.pop(M.uid_of(pod), None)
             raise
         klog.V(2).info("scheduled %s -> %s gpus=%s", M.key_of(pod), node, gpus)
+        # scheduler and kubelet are one process here: start the containers from the object the bind returned instead of
+        # waiting for it to come back through the informer (one watch round trip per replica on the submit -> Running path)
+        if isinstance(bound, dict) and bound.get("spec", {}).get("nodeName") == node and \
+                not bound.get("metadata", {}).get("deletionTimestamp"):
+            try:
+                self._start_pod(bound, M.key_of(pod))
+                return
+            except APIError as e:
+                klog.V(2).info("agent: direct start of %s failed (%s), retrying through the queue", M.key_of(pod), e.message)
         self.queue.add(M.key_of(pod))
 
     # ------------------------------------------------------------------ kubelet: start

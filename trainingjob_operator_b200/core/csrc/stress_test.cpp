@@ -141,7 +141,8 @@ static void stress_supervisor() {
   std::atomic<int> exits{0};
   std::atomic<bool> stop{false};
   std::thread reaper([&] {
-    while (!stop.load() || exits.load() < 60) {
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(60);
+    while ((!stop.load() || exits.load() < 60) && std::chrono::steady_clock::now() < deadline) {
       for (auto& ev : sup.poll_exits(0.05)) {
         CHECK(ev.exit_code == 0 || ev.exit_code == 3 || ev.exit_code == 137);
         exits++;
@@ -164,7 +165,9 @@ static void stress_supervisor() {
           CHECK(!sup.rename(id, renamed));
           sup.kill_proc(renamed, 9, true);
         } else {
+          // re-keyed while it is already exiting: exactly one event, under whichever id won, and nothing left behind
           sup.spawn(id, {"/bin/true"}, env, "", "", "", {});
+          (void)sup.rename(id, id + "-late");
         }
       }
     });
@@ -172,6 +175,7 @@ static void stress_supervisor() {
   stop = true;
   reaper.join();
   CHECK(exits.load() == 60);
+  CHECK(sup.list().empty());
   // adoption of a process this supervisor did not spawn (agent-restart path)
   {
     pid_t pid = fork();

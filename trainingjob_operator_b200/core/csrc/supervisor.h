@@ -330,14 +330,23 @@ class Supervisor {
     }
     ev.wall_time_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - info.started).count();
     {
-      std::lock_guard<std::mutex> lk(mu_);
-      procs_.erase(id);
-    }
-    if (info.pidfd >= 0) close(info.pidfd);
-    {
-      std::lock_guard<std::mutex> lk(ev_mu_);
+      // One critical section over both tables: an observer never sees the process gone from `list()` while its exit
+      // event is not queued yet.  The entry is looked up again by pid -- `rename` may have re-keyed it while waitpid ran,
+      // and the event must carry the id the owner knows it by now.
+      std::scoped_lock lk(mu_, ev_mu_);
+      auto it = procs_.find(id);
+      if (it == procs_.end() || it->second.pid != info.pid) {
+        it = procs_.end();
+        for (auto jt = procs_.begin(); jt != procs_.end(); ++jt)
+          if (jt->second.pid == info.pid && jt->second.pidfd == info.pidfd) { it = jt; break; }
+      }
+      if (it != procs_.end()) {
+        ev.id = it->first;
+        procs_.erase(it);
+      }
       events_.push_back(ev);
     }
+    if (info.pidfd >= 0) close(info.pidfd);
     ev_cv_.notify_all();
   }
 
