@@ -145,3 +145,16 @@ def test_meta_helpers():
     ref = M.owner_reference(job)
     assert ref["controller"] and ref["blockOwnerDeletion"] and ref["uid"] == "u1" and ref["kind"] == C.KIND
     assert M.get_controller_of({"metadata": {"ownerReferences": [ref]}})["name"] == "j"
+
+
+@pytest.mark.parametrize("path", sorted(os.listdir(os.path.join(ROOT, "examples"))))
+def test_every_example_manifest_validates_and_round_trips(path):
+    d = yaml.safe_load(open(os.path.join(ROOT, "examples", path)))
+    assert validate_dict(d) == []
+    job = AITrainingJob.from_dict(d)
+    set_defaults_aitrainingjob(job)
+    again = AITrainingJob.from_dict(json.loads(json.dumps(job.to_dict())))
+    assert again.to_dict() == job.to_dict()
+    for rt, spec in job.spec.replica_specs.items():
+        names = [c["name"] for c in spec.template["spec"]["containers"]]
+        assert any(n.startswith(C.DEFAULT_CONTAINER_PREFIX) for n in names), (path, rt)   # exit codes only count for aitj-*

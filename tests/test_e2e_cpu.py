@@ -421,6 +421,26 @@ def test_restart_scope_all_resumes_ddp_job_from_checkpoint(tmp_path):
     assert out["kill_to_first_step_s"] < 60
 
 
+def test_fault_tolerant_job_survives_the_loss_of_rank0_in_place(tmp_path):
+    """``faultTolerant: true`` on an elastic job (a field the reference declares and never reads, types.go:47): SIGKILL
+    rank 0 of a gloo DDP job.  Only that replica is re-created; the survivors catch the failed collective, keep their
+    processes and training state, re-rendezvous on the next generation and hand their state to the replacement (the
+    state source is elected, rank 0 being the one that was lost)."""
+    import subprocess
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fault_check.py"), "mlp", "3", "0", "--cpu",
+                        "--fault-tolerant", "--victim", "0", f"AITJ_TEST_TAG={tmp_path.name}"],
+                       cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["restart_counts"] == {"trainer": 1} and out["survivors_kept_their_process"]
+    assert out["recovery"]["recovered_from"] and out["recovery"]["world"] == 3
+    assert out["conditions"][-3:] == ["Terminating", "Restarting", "Running"]
+    joined = out["replacement_joined"][0]
+    assert "joined generation 2 (world 3) at step" in joined and not joined.endswith("at step 0")
+    assert out["kill_to_first_step_s"] < 60
+
+
 def test_hang_detection_and_exec_liveness_probe(lc):
     """A worker that stops heart-beating for AITJ_HANG_TIMEOUT seconds is killed (exit 137) and restarted by the job's
     policy; a failing ``livenessProbe.exec`` does the same (kubelet semantics the reference relies on)."""

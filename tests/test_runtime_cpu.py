@@ -102,6 +102,66 @@ def test_bucket_allreduce_and_flat_ddp_over_gloo():
     assert all("OK" in o for o in outs)
 
 
+def test_state_source_is_elected_not_assumed_to_be_rank0():
+    """After a re-rendezvous the rank with the most optimizer steps hands its state to everybody (ties: lowest rank);
+    a joiner that only has warm-up state never wins -- rank 0 itself may be the replica that was replaced."""
+    script = textwrap.dedent("""
+        import os, sys, torch, torch.distributed as dist
+        sys.path.insert(0, %r)
+        from trainingjob_operator_b200.runtime.worker import sync_state
+        rank = int(os.environ["RANK"]); dist.init_process_group("gloo")
+
+        class A:
+            def __init__(self, steps, fill):
+                self.step_count = steps
+                self.t = torch.full((16,), float(fill))
+            def state_tensors(self): return [self.t]
+            def after_state_load(self): pass
+
+        dev = torch.device("cpu")
+        # rank 0 is a fresh replacement (warm-up steps only, have_state False); ranks 1 and 2 survived at step 40
+        a = A(2 if rank == 0 else 40, rank)
+        loop = sync_state(a, 0 if rank == 0 else 45, dev, have_state=rank != 0)
+        assert loop == 45 and a.step_count == 40 and float(a.t[0]) == 1.0, (rank, loop, a.step_count, a.t[0])
+        # a restarted rank that loaded an older checkpoint loses against the survivors
+        a = A(30 if rank == 1 else 50, rank)
+        loop = sync_state(a, 30 if rank == 1 else 50, dev)
+        assert loop == 50 and a.step_count == 50 and float(a.t[0]) == 0.0
+        # nobody has state (fresh start / restart without checkpoint): rank 0 seeds everybody
+        a = A(2, rank + 5)
+        loop = sync_state(a, 0, dev, have_state=False)
+        assert float(a.t[0]) == 5.0
+        print("OK", rank)
+    """ % ROOT)
+    procs = []
+    for rank in range(3):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="3", MASTER_ADDR="127.0.0.1", MASTER_PORT="29735")
+        procs.append(subprocess.Popen([sys.executable, "-c", script], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_flat_ddp_discards_a_step_that_lost_its_allreduce():
+    from trainingjob_operator_b200.models.mnist_cnn import MLP
+    from trainingjob_operator_b200.parallel.flat_ddp import FlatDDP
+
+    torch.manual_seed(0)
+    m = MLP()
+    ddp = FlatDDP(m, backend="gloo", lr=0.1, optimizer="sgd")
+    x, y = torch.randn(8, 64), torch.randint(0, 10, (8,))
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    assert float(ddp.g32.abs().sum()) > 0
+    before = ddp.p32.clone()
+    ddp.discard_step()
+    assert float(ddp.g32.abs().sum()) == 0.0 and torch.equal(ddp.p32, before)
+    assert all(p.grad is not None and p.grad.data_ptr() >= ddp.g32.data_ptr() for p in m.parameters())
+    torch.nn.functional.cross_entropy(m(x), y).backward()       # the next step accumulates from zero again
+    ddp.finish_backward()
+    ddp.step()
+    assert not torch.equal(ddp.p32, before)
+
+
 def test_staged_join_gates_scale_up_until_joiners_announce(monkeypatch):
     """Survivors adopt a larger world only after every joiner announced readiness for that generation (or the
     timeout passed); scale-down and same-size generations are adopted at once."""

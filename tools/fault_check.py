@@ -2,15 +2,21 @@
 ``restartPolicy: OnFailure`` + ``restartScope: All`` -> every replica is re-created, resumes from rank 0's checkpoint.
 Reports kill -> job Running again -> first training step after the restart.
 
-    python tools/fault_check.py [model] [n] [warm_pool] [--cpu] [--scope Pod|All] [--hang SECONDS]
+    python tools/fault_check.py [model] [n] [warm_pool] [--cpu] [--scope Pod|All] [--hang SECONDS] [--fault-tolerant]
+          [--victim RANK]
 
 ``--scope Pod --hang S``: only the killed replica is re-created by the controller; the survivors, stuck in a collective
 with a dead peer, are caught by the agent's heartbeat-based hang detection after S seconds and restarted too.
+
+``--fault-tolerant``: the job is elastic with ``faultTolerant: true``: only the killed replica is replaced, the survivors
+catch the failed collective, keep their processes (and device state) and re-rendezvous with the replacement; reports
+kill -> first step of the recovered world and checks that the survivors' PIDs did not change.
 """
 import json
 import os
 import signal
 import sys
+import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,11 +31,13 @@ n = int(argv[1]) if len(argv) > 1 else 2
 pool = int(argv[2]) if len(argv) > 2 else 0
 scope = sys.argv[sys.argv.index("--scope") + 1] if "--scope" in sys.argv else "All"
 hang = sys.argv[sys.argv.index("--hang") + 1] if "--hang" in sys.argv else ""
-argv = [a for a in argv if a not in (scope, hang)] if ("--scope" in sys.argv or "--hang" in sys.argv) else argv
-victim = min(3, n - 1)
+ft = "--fault-tolerant" in sys.argv
+victim_arg = sys.argv[sys.argv.index("--victim") + 1] if "--victim" in sys.argv else ""
+victim = int(victim_arg) if victim_arg else min(3, n - 1)
 batch = {"bert": 8, "mlp": 16, "gpt2": 4, "resnet50": 32}.get(model, 8)
 worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", model, "--batch", str(batch),
-          "--steps", "0", "--ckpt-every", "10"] + (["--cpu", "--step-sleep", "0.02"] if cpu else [])
+          "--steps", "0", "--ckpt-every", "10"] + (["--cpu", "--step-sleep", "0.02"] if cpu else []) + \
+         (["--elastic"] if ft else [])
 c = {"name": "aitj-trainer", "command": worker, "workingDir": ROOT, "env": [{"name": "PYTHONPATH", "value": ROOT}]}
 if hang:
     c["env"].append({"name": "AITJ_HANG_TIMEOUT", "value": hang})
@@ -42,6 +50,9 @@ job = {"apiVersion": "elasticdeeplearning.ai/v1", "kind": "AITrainingJob", "meta
        "spec": {"frameworkType": "pytorch", "replicaSpecs": {"trainer": {
            "replicas": n, "restartPolicy": "OnFailure", "restartScope": scope, "restartLimit": 6,
            "template": {"spec": {"terminationGracePeriodSeconds": 1, "containers": [c]}}}}}}
+if ft:
+    job["spec"]["faultTolerant"] = True
+    job["spec"]["replicaSpecs"]["trainer"].update({"minReplicas": n, "maxReplicas": n, "edlPolicy": "Manual"})
 
 
 def wait(fn, timeout=240):
@@ -63,9 +74,9 @@ def first_step_at(lc):
 
 
 out = {"model": model, "replicas": n, "warm_pool": pool, "cpu": cpu, "victim_rank": victim, "restart_scope": scope,
-       "hang_timeout_s": hang or None}
+       "hang_timeout_s": hang or None, "fault_tolerant": ft}
 with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thread_num=2),
-                  workdir=f"/tmp/aitj-fault-{pool}", warm_pool=pool) as lc:
+                  workdir=tempfile.mkdtemp(prefix=f"aitj-fault-{pool}-"), warm_pool=pool) as lc:   # never a stale checkpoint
     if pool:
         wait(lambda: lc.agent.warm_ready() >= pool, 120)
     t_submit = time.time()
@@ -75,9 +86,34 @@ with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thr
     time.sleep(3.0 if not cpu else 1.0)               # let it train and write a checkpoint
     if pool:
         wait(lambda: lc.agent.warm_ready() >= min(pool, n), 120)
-    pid = next(p for sid, p in lc.agent.sup.list() if f"/ft-trainer-{victim}/" in sid)
+    pids = {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/ft-trainer-" in sid}
+    pid = pids[f"ft-trainer-{victim}"]
     t_kill = time.time()
     os.kill(pid, signal.SIGKILL)
+    if ft:
+        rec = wait(lambda: (lambda a: json.loads(a["aitj.b200/rescale-trace"]) if "aitj.b200/rescale-trace" in a
+                            else None)(lc.jobs().get("ft").annotations))
+        out["kill_to_first_step_s"] = round(rec["at"] - t_kill, 3)
+        out["recovery"] = {k: rec.get(k) for k in ("generation", "world", "seconds", "teardown_s", "init_pg_s",
+                                                    "sync_state_s", "first_step_s", "recovered_from")}
+        wait(lambda: (lambda j: j.status.phase == "Running" and
+                      j.status.replica_statuses["trainer"].active == n)(lc.jobs().get("ft")))
+        out["kill_to_running_s"] = round(time.time() - t_kill, 3)
+        now = {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/ft-trainer-" in sid}
+        out["survivors_kept_their_process"] = all(now.get(k) == v for k, v in pids.items()
+                                                  if k != f"ft-trainer-{victim}")
+        j = lc.jobs().get("ft")
+        out["restart_counts"] = j.status.restart_counts
+        out["conditions"] = [c.type for c in j.status.conditions][-6:]
+        logv = open(os.path.join(lc.workdir, "logs", f"default_ft-trainer-{victim}_aitj-trainer.log")).read()
+        out["replacement_joined"] = [ln for ln in logv.splitlines() if "joined generation" in ln][-1:]
+        lc.jobs().delete("ft")
+        time.sleep(0.5)
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_ft.json", "w"), indent=1)
+        print(json.dumps(out))
+        sys.exit(0 if out["restart_counts"].get("trainer", 0) == 1 and out["survivors_kept_their_process"] and
+                 out["recovery"]["recovered_from"] else 1)
     wait(lambda: (lambda j: j.status.phase == "Running" and j.status.restart_counts.get("trainer", 0) >= 1 and
                   j.status.replica_statuses["trainer"].active == n)(lc.jobs().get("ft")))
     out["kill_to_running_s"] = round(time.time() - t_kill, 3)

@@ -96,6 +96,14 @@ class FlatDDP:
             self.reducer.wait()
             self._todo = list(self._pending)
 
+    def discard_step(self) -> None:
+        """Forget a step that died in its gradient all-reduce (a peer was lost): the flat gradient buffer holds local or
+        partly reduced sums that must not leak into the next step; parameters and moments were not touched yet."""
+        if self.reducer is not None:
+            self.reducer._works.clear()
+        self._todo = list(self._pending)
+        self.g32.zero_()
+
     def step(self) -> None:
         """Fused optimizer sweep (+ gradient zeroing); grads are averaged over the world size."""
         self.step_count += 1

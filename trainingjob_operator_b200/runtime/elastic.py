@@ -169,8 +169,8 @@ class ElasticWatcher:
         if rank == 0:
             self._annotate(ANN_WORKER_TRACE, {k: round(v, 4) for k, v in trace.items()})
 
-    def report_rescale(self, rank: int, rec: Dict[str, Any]) -> None:
-        if rank == 0:
+    def report_rescale(self, rank: int, rec: Dict[str, Any], force: bool = False) -> None:
+        if rank == 0 or force:
             rec = dict(rec)
             rec["at"] = round(time.time(), 4)
             self._annotate(ANN_RESCALE, rec)
@@ -178,6 +178,7 @@ class ElasticWatcher:
     def report_result(self, result: Dict[str, Any]) -> None:
         keep = {k: result.get(k) for k in ("samples_per_sec", "ms_per_step", "global_batch", "world", "steps_done",
                                            "loss_first", "loss_last", "gpu_launches", "cuda_graph")}
+        keep["recoveries"] = len(result.get("recoveries") or [])
         self._annotate(ANN_METRICS, keep)
 
     def stop(self) -> None:

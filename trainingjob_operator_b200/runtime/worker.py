@@ -19,6 +19,7 @@ CPU), builds the requested model and runs the measured training loop:
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import signal
@@ -71,6 +72,9 @@ class EngineAdapter:
     def train_step(self) -> float:
         tok, tgt = self.data.next()
         return self.trainer.step(tok, tgt)
+
+    def discard_step(self) -> None:
+        self.engine.params.g32.zero_()
 
     def state_tensors(self) -> List[torch.Tensor]:
         return self.engine.params.state_tensors()
@@ -179,6 +183,10 @@ class TorchAdapter:
             torch.cuda.current_stream().synchronize()
         return float(self.loss_host[0])
 
+    def discard_step(self) -> None:
+        if self.ddp is not None:
+            self.ddp.discard_step()        # .grad are views of the flat buffer it zeroes
+
     def state_tensors(self) -> List[torch.Tensor]:
         return self.ddp.state_tensors()
 
@@ -220,6 +228,10 @@ def init_process_group(rank: int, world: int, port: int, device: torch.device, t
     if device.type == "cuda":
         kw["device_id"] = device
     if attempt_timeout_s > 0:
+        if rank != 0:
+            # TCPStore's own connect loop backs off exponentially (tens of seconds once the master is half a minute
+            # late, e.g. a replacement rank 0 that is still importing torch): probe the port ourselves at a fixed 50 ms
+            _wait_for_listener(port, attempt_timeout_s)
         store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0),
                               timeout=datetime.timedelta(seconds=attempt_timeout_s), wait_for_workers=True)
         store.set_timeout(datetime.timedelta(seconds=timeout_s))
@@ -228,6 +240,19 @@ def init_process_group(rank: int, world: int, port: int, device: torch.device, t
         return
     dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                             timeout=datetime.timedelta(seconds=timeout_s), **kw)
+
+
+def _wait_for_listener(port: int, timeout_s: float) -> bool:
+    import socket
+
+    deadline = time.time() + timeout_s
+    while time.time() < deadline:
+        try:
+            socket.create_connection(("127.0.0.1", port), timeout=1.0).close()
+            return True
+        except OSError:
+            time.sleep(0.05)
+    return False
 
 
 class _KeepBeating:
@@ -261,6 +286,12 @@ def rendezvous(rank: int, rdv: Dict[str, int], device: torch.device, watcher) ->
     longer part of the world."""
     attempt = float(os.environ.get("AITJ_RDV_ATTEMPT_TIMEOUT", "30"))
     deadline = time.time() + float(os.environ.get("AITJ_RDV_TIMEOUT", "600"))
+    # Collective timeout of the group.  gloo does not always fail a receive that is posted on a connection its peer's
+    # death already closed -- the rank then sits out the whole timeout before the faultTolerant recovery can start, and
+    # a blocked gloo collective cannot be aborted from another thread (NCCL can: StallBreaker) -- so a faultTolerant
+    # CPU job gets a short one.
+    coll_timeout = float(os.environ.get("AITJ_COLLECTIVE_TIMEOUT", "0")) or \
+        (15.0 if device.type == "cpu" and os.environ.get("AITJ_FAULT_TOLERANT") == "1" else 120.0)
     cur = dict(rdv)
     while True:
         latest = watcher.fetch_now() if watcher is not None else None
@@ -274,7 +305,7 @@ def rendezvous(rank: int, rdv: Dict[str, int], device: torch.device, watcher) ->
             return cur
         try:
             with _KeepBeating():
-                init_process_group(rank, cur["world"], cur["port"], device,
+                init_process_group(rank, cur["world"], cur["port"], device, timeout_s=coll_timeout,
                                    attempt_timeout_s=attempt if watcher is not None else 0.0)
             return cur
         except Exception as e:  # noqa: BLE001 - peers missing within the attempt window (or a stale port)
@@ -295,20 +326,100 @@ def max_over_ranks(value: float, device: torch.device) -> float:
     return float(t[0])
 
 
-def sync_state(adapter, loop_step: int, device: torch.device) -> int:
-    """Hand-off after every (re-)rendezvous: rank 0 broadcasts {optimizer step, loop step} and then the flat
-    state tensors, so a joiner resumes exactly where the survivors are.  Same call sequence on every rank."""
+def sync_state(adapter, loop_step: int, device: torch.device, have_state: bool = True) -> int:
+    """Hand-off after every (re-)rendezvous.  The source is elected, not assumed to be rank 0: the rank holding the most
+    optimizer steps wins (ties: the lowest rank; ranks that only have a throw-away warm-up state bid -1), so when rank 0
+    itself was the replica that got replaced, its replacement receives the survivors' state instead of overwriting it.
+    The source broadcasts {optimizer step, loop step} and then the flat state tensors.  Same call sequence on every
+    rank."""
     if not dist.is_initialized() or dist.get_world_size() <= 1:
         return loop_step
     from ..parallel.ddp import broadcast_state
 
-    st = torch.tensor([adapter.step_count, loop_step], dtype=torch.int64,
-                      device=device if device.type == "cuda" else "cpu")
-    dist.broadcast(st, 0)
-    broadcast_state(adapter.state_tensors(), 0)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    cdev = device if device.type == "cuda" else "cpu"
+    bid = torch.tensor([int(adapter.step_count) * world + (world - 1 - rank) if have_state else -1],
+                       dtype=torch.int64, device=cdev)
+    dist.all_reduce(bid, op=dist.ReduceOp.MAX)
+    best = int(bid[0])
+    src = 0 if best < 0 else world - 1 - (best % world)
+    st = torch.tensor([adapter.step_count, loop_step], dtype=torch.int64, device=cdev)
+    dist.broadcast(st, src)
+    broadcast_state(adapter.state_tensors(), src)
     adapter.after_state_load()
     adapter.step_count = int(st[0])
     return int(st[1])
+
+
+# ------------------------------------------------------------------------------------ fault tolerance
+def teardown_group(broken: bool = False) -> None:
+    """Leave the current process group.  A group with a dead peer is *aborted* (NCCL: ``ncclCommAbort`` unblocks kernels
+    that wait for the peer; a clean destroy would wait for them), a healthy one is destroyed."""
+    if not dist.is_initialized():
+        return
+    if broken and dist.get_backend() == "nccl":
+        try:
+            from torch.distributed.distributed_c10d import _abort_process_group
+
+            _abort_process_group()
+            return
+        except Exception as e:  # noqa: BLE001
+            print(f"[worker] abort of the process group failed ({type(e).__name__}: {e}); destroying it", flush=True)
+    try:
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001 - sockets of a dead peer
+        print(f"[worker] destroy of the broken process group raised {type(e).__name__}", flush=True)
+
+
+def wait_for_newer_generation(watcher, generation: int, timeout_s: float) -> Optional[Dict[str, int]]:
+    """After a peer was lost: the controller replaces it and publishes the next rendezvous generation; poll for it."""
+    deadline = time.time() + timeout_s
+    while time.time() < deadline:
+        latest = watcher.fetch_now()
+        if latest is not None and latest["generation"] > generation:
+            return latest
+        heartbeat(force=True)
+        time.sleep(0.05)
+    return None
+
+
+class StallBreaker:
+    """NCCL has no error to raise when a peer dies: the surviving ranks' kernels spin on the dead peer's flags until the
+    watchdog gives up (minutes) and takes the process down.  For a ``faultTolerant`` job this side thread aborts the
+    communicator instead, once (a) the controller has published a newer rendezvous generation (= it replaced a replica)
+    and (b) the main thread has not reached a step boundary for ``after_s`` seconds; the blocked step then fails and the
+    main thread takes the same recovery path as an exception from gloo.  Only armed on CUDA (``AITJ_FT_ABORT_AFTER``,
+    default 10 s, 0 disables)."""
+
+    def __init__(self, watcher, after_s: float):
+        import threading
+
+        self.watcher, self.after_s = watcher, after_s
+        self.generation = 0
+        self.last_progress = time.time()
+        self.tripped = False
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, name="stall-breaker", daemon=True)
+        self._t.start()
+
+    def progress(self, generation: int) -> None:
+        self.generation = generation
+        self.last_progress = time.time()
+
+    def _run(self) -> None:
+        while not self._stop.wait(0.5):
+            if self.tripped or time.time() - self.last_progress < self.after_s or not dist.is_initialized():
+                continue
+            latest = self.watcher.fetch_now()
+            if latest is None or latest["generation"] <= self.generation:
+                continue
+            print(f"[worker] no step boundary for {time.time() - self.last_progress:.1f}s while generation "
+                  f"{latest['generation']} is pending: aborting the communicator", flush=True)
+            self.tripped = True
+            teardown_group(broken=True)
+
+    def stop(self) -> None:
+        self._stop.set()
 
 
 # ------------------------------------------------------------------------------------ checkpoint
@@ -373,7 +484,8 @@ def run(args) -> Dict[str, Any]:
     adapter = build_adapter(args, device)
     trace["model_built"] = time.time()
     heartbeat(force=True)
-    if args.elastic and watcher is not None and generation > 1 and world > 1:
+    joiner = bool(args.elastic and watcher is not None and generation > 1 and world > 1)
+    if joiner:
         # Joining a running job: do everything that needs no peer first -- CUDA context, model build, two throw-away
         # steps (kernel loading, cuDNN plans, allocator growth; the state is overwritten by rank 0's broadcast
         # anyway) -- and only then tell the survivors, who keep training until this rank is ready to rendezvous.
@@ -406,7 +518,17 @@ def run(args) -> Dict[str, Any]:
         start_step = load_checkpoint(args, adapter)
         adapter.step_count = start_step
         print(f"[worker {rank}] restart #{restart_count}: resumed from checkpoint at step {start_step}", flush=True)
-    joined_step = sync_state(adapter, start_step, device)
+    # a joiner without a checkpoint only has its throw-away warm-up state: it must never be elected as the source
+    joined_step = sync_state(adapter, start_step, device, have_state=not joiner or start_step > 0)
+    if joiner:
+        print(f"[worker {rank}] joined generation {generation} (world {world}) at step {joined_step}", flush=True)
+    # faultTolerant (types.go:47, never read by the reference): the loss of a peer is survived in place -- see the
+    # except branch of the training loop
+    fault_tolerant = bool(args.elastic and watcher is not None and os.environ.get("AITJ_FAULT_TOLERANT") == "1")
+    breaker = None
+    if fault_tolerant and use_cuda and float(os.environ.get("AITJ_FT_ABORT_AFTER", "10")) > 0:
+        breaker = StallBreaker(watcher, float(os.environ.get("AITJ_FT_ABORT_AFTER", "10")))
+    recoveries: List[Dict[str, Any]] = []
 
     stop = {"flag": False}
     signal.signal(signal.SIGTERM, lambda *_: stop.__setitem__("flag", True))
@@ -424,49 +546,106 @@ def run(args) -> Dict[str, Any]:
 
     launches0 = 0
     while step < total and not stop["flag"]:
-        # ---- elastic: agree on the newest rendezvous generation at the step boundary ------------
-        if watcher is not None and args.elastic:
-            target = watcher.agree(device)
-            if target is not None and target["generation"] != generation:
-                t0 = time.time()
-                new_world = target["world"]
-                print(f"[worker {rank}] rendezvous generation {generation} -> {target['generation']} "
-                      f"(world {world} -> {new_world}) at step {step}", flush=True)
-                if dist.is_initialized():
-                    if use_cuda:
-                        torch.cuda.synchronize()
-                    dist.destroy_process_group()
-                if rank >= new_world:
-                    print(f"[worker {rank}] leaving: world shrinks to {new_world} (generation {target['generation']})",
-                          flush=True)
-                    return {"left": True, "generation": target["generation"], "step": step}
-                generation, world, port = target["generation"], new_world, target["port"]
-                t1 = time.time()
+        if breaker is not None:
+            breaker.progress(generation)
+        failure = None
+        try:
+            # ---- elastic: agree on the newest rendezvous generation at the step boundary ------------
+            if watcher is not None and args.elastic:
+                target = watcher.agree(device)
+                if target is not None and target["generation"] != generation:
+                    t0 = time.time()
+                    new_world = target["world"]
+                    print(f"[worker {rank}] rendezvous generation {generation} -> {target['generation']} "
+                          f"(world {world} -> {new_world}) at step {step}", flush=True)
+                    if dist.is_initialized():
+                        if use_cuda:
+                            torch.cuda.synchronize()
+                        dist.destroy_process_group()
+                    if rank >= new_world:
+                        print(f"[worker {rank}] leaving: world shrinks to {new_world} (generation {target['generation']})",
+                              flush=True)
+                        return {"left": True, "generation": target["generation"], "step": step}
+                    generation, world, port = target["generation"], new_world, target["port"]
+                    t1 = time.time()
+                    if world > 1:
+                        got = rendezvous(rank, {"generation": generation, "world": world, "port": port}, device, watcher)
+                        if got is None:
+                            return {"left": True, "generation": generation, "step": step}
+                        generation, world, port = got["generation"], got["world"], got["port"]
+                    t2 = time.time()
+                    adapter.bind(None)
+                    step = sync_state(adapter, step, device)
+                    heartbeat(force=True)
+                    watcher.adopted(generation, world)
+                    pending_rescale = {"generation": generation, "world": world, "t0": t0,
+                                       "observed_at": target.get("observed_at", t0),
+                                       "teardown_s": t1 - t0, "init_pg_s": t2 - t1, "sync_state_s": time.time() - t2}
+                    continue    # back to the step boundary: every rank (joiners included) runs the same sequence
+            # ---- timed region bookkeeping ----------------------------------------------------------------
+            if step == args.warmup and args.steps > 0:
                 if world > 1:
-                    got = rendezvous(rank, {"generation": generation, "world": world, "port": port}, device, watcher)
-                    if got is None:
-                        return {"left": True, "generation": generation, "step": step}
-                    generation, world, port = got["generation"], got["world"], got["port"]
-                t2 = time.time()
-                adapter.bind(None)
-                step = sync_state(adapter, step, device)
-                heartbeat(force=True)
-                watcher.adopted(generation, world)
-                pending_rescale = {"generation": generation, "world": world, "t0": t0,
-                                   "observed_at": target.get("observed_at", t0),
-                                   "teardown_s": t1 - t0, "init_pg_s": t2 - t1, "sync_state_s": time.time() - t2}
-                continue    # back to the step boundary: every rank (joiners included) runs the same sequence
-        # ---- timed region bookkeeping ----------------------------------------------------------------
-        if step == args.warmup and args.steps > 0:
-            if world > 1:
-                dist.barrier()
-            if use_cuda:
-                torch.cuda.synchronize()
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-            t_wall0 = time.perf_counter()
-            launches0 = oplib.LAUNCHES
-        loss = adapter.train_step()
+                    dist.barrier()
+                if use_cuda:
+                    torch.cuda.synchronize()
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                t_wall0 = time.perf_counter()
+                launches0 = oplib.LAUNCHES
+            loss = adapter.train_step()
+            if breaker is not None and breaker.tripped:
+                raise RuntimeError("the communicator was aborted while this step was in flight")
+        except RuntimeError as e:
+            # ---- faultTolerant: a peer died under a collective -----------------------------------------------------
+            # (gloo raises in the survivors; for NCCL the StallBreaker aborts the communicator.)  The survivors keep
+            # their process, device state and -- on GPUs -- CUDA context: drop the broken group, wait for the
+            # controller to replace the lost replica (restart scope Pod, new rendezvous generation), re-rendezvous and
+            # continue from the survivors' state.  Without faultTolerant the error ends this replica and the job's
+            # restartPolicy / restartScope take over, as in the reference (pod.go:208-250).
+            if not fault_tolerant or world <= 1:
+                raise
+            failure = (type(e).__name__, (str(e).splitlines() or [""])[0][:160])
+        if failure is not None:
+            # (outside the except block: the traceback of the failed step references the work handles of the broken
+            # group, and with them its sockets)
+            t0 = time.time()
+            aborted = breaker is not None and breaker.tripped
+            print(f"[worker {rank}] step {step}: lost a peer ({failure[0]}: {failure[1]}); "
+                  f"keeping state, waiting for the next rendezvous generation", flush=True)
+            # pending work handles keep the group's sockets open; a peer that is blocked on *us* (gloo does not
+            # propagate a failure beyond the dead rank's direct neighbours) only errors out once they really close
+            adapter.discard_step()
+            teardown_group(broken=True)
+            gc.collect()
+            target = wait_for_newer_generation(watcher, generation, float(os.environ.get("AITJ_FT_WAIT", "120")))
+            if target is None:
+                print(f"[worker {rank}] no new rendezvous generation was published: giving up", flush=True)
+                raise RuntimeError(f"collective failed and the job was not repaired: {failure[0]}: {failure[1]}")
+            if rank >= target["world"]:
+                return {"left": True, "generation": target["generation"], "step": step}
+            t1 = time.time()
+            got = rendezvous(rank, {"generation": target["generation"], "world": target["world"],
+                                    "port": target["port"]}, device, watcher)
+            if got is None:
+                return {"left": True, "generation": target["generation"], "step": step}
+            generation, world, port = got["generation"], got["world"], got["port"]
+            t2 = time.time()
+            if aborted and args.ckpt_every > 0 and os.path.exists(ckpt_path(args)):
+                # kernels released by an abort ran on with whatever the dead peer left in the buffers: do not trust
+                # this rank's copy when there is a checkpoint to fall back to
+                step = load_checkpoint(args, adapter)
+                adapter.step_count = step
+            if breaker is not None:
+                breaker.tripped = False
+                breaker.progress(generation)
+            adapter.bind(None)
+            step = sync_state(adapter, step, device)
+            heartbeat(force=True)
+            watcher.adopted(generation, world)
+            pending_rescale = {"generation": generation, "world": world, "t0": t0, "observed_at": t0,
+                               "teardown_s": t1 - t0, "init_pg_s": t2 - t1, "sync_state_s": time.time() - t2,
+                               "recovered_from": failure[0]}
+            continue
         losses.append(loss)
         step += 1
         heartbeat()
@@ -479,11 +658,14 @@ def run(args) -> Dict[str, Any]:
                    "init_pg_s": round(pending_rescale["init_pg_s"], 4),
                    "sync_state_s": round(pending_rescale["sync_state_s"], 4)}
             rec["first_step_s"] = round(rec["seconds"] - rec["teardown_s"] - rec["init_pg_s"] - rec["sync_state_s"], 4)
+            if "recovered_from" in pending_rescale:
+                rec["recovered_from"] = pending_rescale["recovered_from"]
+                recoveries.append(rec)
             rescales.append(rec)
-            print(f"[worker {rank}] rescaled to world={rec['world']} gen={rec['generation']} in "
+            print(f"[worker {rank}] step {step}: rescaled to world={rec['world']} gen={rec['generation']} in "
                   f"{rec['seconds']:.3f}s", flush=True)
             if watcher is not None:
-                watcher.report_rescale(rank, rec)
+                watcher.report_rescale(rank, rec, force="recovered_from" in rec)   # rank 0 may be the replaced one
             pending_rescale = None
         if not first_step_done:
             first_step_done = True
@@ -496,7 +678,10 @@ def run(args) -> Dict[str, Any]:
             time.sleep(args.step_sleep)
 
     result: Dict[str, Any] = {"rank": rank, "world": world, "steps_done": step, "generation": generation,
-                              "final_loss": losses[-1] if losses else None, "rescales": rescales, "trace": trace}
+                              "final_loss": losses[-1] if losses else None, "rescales": rescales,
+                              "recoveries": recoveries, "trace": trace}
+    if breaker is not None:
+        breaker.stop()
     if args.steps > 0 and step >= total:
         if use_cuda:
             ev1.record()
