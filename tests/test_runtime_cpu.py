@@ -231,3 +231,51 @@ def test_zygote_command_parsing():
     assert sp(["python", "-c", "print(1)"]) is None
     assert sp(["/bin/sh", "-c", "true"]) is None
     assert sp(["python"]) is None and sp([]) is None
+
+
+def test_async_checkpoint_is_a_consistent_snapshot_and_never_blocks_on_a_busy_writer(tmp_path, monkeypatch):
+    from trainingjob_operator_b200.runtime import checkpoint as ck
+
+    path = str(tmp_path / "job.pt")
+    w = ck.AsyncCheckpointer(path)
+    a, b = torch.arange(1000, dtype=torch.float32), torch.ones(7, 3)
+    assert ck.load_into(path, [a, b]) is None                    # nothing there yet
+    assert w.save(10, [a, b], extra={"world": 2})
+    a.add_(1.0)                                                  # the step loop moves on while the file is written
+    assert w.wait(30)
+    x, y = torch.zeros(1000), torch.zeros(7, 3)
+    meta = ck.load_into(path, [x, y])
+    assert meta == {"step": 10, "world": 2}
+    assert torch.equal(x, torch.arange(1000, dtype=torch.float32)) and torch.equal(y, b)   # state as of save()
+    assert not os.path.exists(path + ".tmp")
+
+    # a slow disk: the next interval's checkpoint is skipped, not queued, and the old file stays readable
+    gate = __import__("threading").Event()
+    real_save = torch.save
+
+    def slow_save(obj, f):
+        gate.wait(30)
+        real_save(obj, f)
+
+    monkeypatch.setattr(torch, "save", slow_save)
+    assert w.save(20, [a, b])
+    assert w.busy() and w.save(30, [a, b]) is False and w.stats["skipped_busy"] == 1
+    assert ck.load_into(path, [x, y])["step"] == 10              # readers never see a torn / half-written file
+    gate.set()
+    assert w.wait(30) and ck.load_into(path, [x, y])["step"] == 20 and w.stats["saved"] == 2
+
+    # a checkpoint of another architecture is refused, not half-loaded
+    try:
+        ck.load_into(path, [torch.zeros(5)])
+        raise AssertionError("mismatch accepted")
+    except ValueError as e:
+        assert "does not match" in str(e)
+
+    # a failed write surfaces on the next call instead of vanishing in the thread
+    monkeypatch.setattr(torch, "save", lambda obj, f: (_ for _ in ()).throw(OSError("disk full")))
+    assert w.save(40, [a, b])
+    try:
+        w.wait(30)
+        raise AssertionError("write error swallowed")
+    except RuntimeError as e:
+        assert "disk full" in str(e)

@@ -430,21 +430,37 @@ def ckpt_path(args) -> str:
     return os.path.join(d, f"{job}.pt")
 
 
+_CKPT: Dict[str, Any] = {}
+
+
+def checkpointer(args):
+    """The process-wide asynchronous checkpoint writer (``runtime/checkpoint.py``)."""
+    from .checkpoint import AsyncCheckpointer
+
+    path = ckpt_path(args)
+    if _CKPT.get("path") != path:
+        _CKPT["path"], _CKPT["writer"] = path, AsyncCheckpointer(path)
+    return _CKPT["writer"]
+
+
 def save_checkpoint(args, adapter, step: int) -> None:
-    tmp = ckpt_path(args) + ".tmp"
-    torch.save({"step": step, "state": [t.detach().cpu() for t in adapter.state_tensors()]}, tmp)
-    os.replace(tmp, ckpt_path(args))
+    """Snapshot the state in stream order and write it in the background; ``AITJ_CKPT_ASYNC=0`` waits for the file."""
+    w = checkpointer(args)
+    w.save(step, adapter.state_tensors())
+    if os.environ.get("AITJ_CKPT_ASYNC", "1") == "0":
+        w.wait()
 
 
 def load_checkpoint(args, adapter) -> int:
-    p = ckpt_path(args)
-    if not os.path.exists(p):
+    from .checkpoint import load_into
+
+    if _CKPT.get("writer") is not None:
+        _CKPT["writer"].wait()              # our own write in flight (in-place recovery falls back to it)
+    meta = load_into(ckpt_path(args), adapter.state_tensors())
+    if meta is None:
         return 0
-    ck = torch.load(p, map_location="cpu")
-    for dst, src in zip(adapter.state_tensors(), ck["state"]):
-        dst.copy_(src)
     adapter.after_state_load()
-    return int(ck["step"])
+    return int(meta["step"])
 
 
 _HB = {"path": os.environ.get("AITJ_HEARTBEAT_FILE", ""), "last": 0.0}
@@ -682,6 +698,8 @@ def run(args) -> Dict[str, Any]:
                               "recoveries": recoveries, "trace": trace}
     if breaker is not None:
         breaker.stop()
+    if _CKPT.get("writer") is not None:
+        _CKPT["writer"].wait(60.0)
     if args.steps > 0 and step >= total:
         if use_cuda:
             ev1.record()
