@@ -104,6 +104,7 @@ def test_event_recorder_writes_and_aggregates_events():
     rec.eventf(job, "Normal", "SuccessfulCreatePod", "Created pod: %s", "paddle-mnist-trainer-0")
     rec.eventf(job, "Warning", "FailedCreatePod", "Error creating: %s", "x")
     rec.eventf(job, "Warning", "FailedCreatePod", "Error creating: %s", "x")
+    assert rec.flush(5.0)                 # recording is asynchronous (a sink thread writes the Events API)
     evs = events_for(cs, job)
     assert [(e["reason"], e["count"]) for e in evs] == [("SuccessfulCreatePod", 1), ("FailedCreatePod", 2)]
     assert evs[0]["source"]["component"] == "TrainingJobOperator" and evs[0]["involvedObject"]["uid"] == job.uid
@@ -167,3 +168,45 @@ def test_leases_lock_type_also_works():
     e = LeaderElector(cs, cfg, lambda s: None, lambda: None)
     assert e.try_acquire_or_renew() and e.try_acquire_or_renew()
     assert cs.coordination_v1().leases("kube-system").get("trainingjob-operator")
+
+
+def test_indexer_secondary_indices_and_updates_never_hide_an_object_from_lock_free_readers():
+    from trainingjob_operator_b200.client.informers import Indexer
+
+    def mk(ns, name, job, rv):
+        return {"metadata": {"namespace": ns, "name": name, "labels": {"j": job}, "resourceVersion": str(rv)}}
+
+    ix = Indexer({"job": lambda o: [f'{o["metadata"]["namespace"]}/{o["metadata"]["labels"]["j"]}']})
+    for o in (mk("a", "p1", "x", 1), mk("a", "p2", "x", 1), mk("b", "p3", "x", 1)):
+        ix.add(o)
+    assert sorted(o["metadata"]["name"] for o in ix.by_index("job", "a/x")) == ["p1", "p2"]
+    assert [o["metadata"]["name"] for o in ix.list("b")] == ["p3"] and len(ix.list()) == 3
+    ix.add(mk("a", "p1", "y", 2))                                   # label changed: moves between index buckets
+    assert [o["metadata"]["name"] for o in ix.by_index("job", "a/x")] == ["p2"]
+    assert ix.by_index("job", "a/y")[0]["metadata"]["resourceVersion"] == "2"
+    ix.delete(mk("a", "p2", "x", 1))
+    assert ix.by_index("job", "a/x") == [] and ix.get_by_key("a/p2") is None
+    ix.add_indexers({"ns": lambda o: [o["metadata"]["namespace"]]})  # added late: existing objects are indexed
+    assert len(ix.by_index("ns", "a")) == 1 and len(ix.by_index("ns", "b")) == 1
+    ix.replace([mk("c", "q", "z", 1)])
+    assert ix.list("a") == [] and len(ix) == 1 and len(ix.by_index("job", "c/z")) == 1
+
+    # readers take no lock: while a writer keeps updating one object, a reader must see it in every view, every time
+    ix.replace([mk("a", "hot", "x", 0)])
+    stop, missing = threading.Event(), []
+
+    def writer():
+        rv = 0
+        while not stop.is_set():
+            rv += 1
+            ix.add(mk("a", "hot", "x", rv))
+
+    t = threading.Thread(target=writer, daemon=True)
+    t.start()
+    deadline = time.time() + 0.5
+    while time.time() < deadline:
+        if not ix.by_index("job", "a/x") or not ix.list("a") or ix.get_by_key("a/hot") is None:
+            missing.append(1)
+    stop.set()
+    t.join(2)
+    assert not missing

@@ -1,0 +1,72 @@
+"""Control-plane throughput (no GPU needed): J jobs x R replicas of a trivial command submitted at once through the
+public API; time until every job is Succeed, jobs/s and pods/s, API-server write count, reconcile latency.  Run once
+with the default reconcile-queue bucket and once with client-go's 10 qps / burst 100 (what the reference inherits).
+
+    python tools/throughput_bench.py [jobs] [replicas] [thread_num]   -> profiles/control_plane_throughput.json
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from trainingjob_operator_b200.api import constants as C  # noqa: E402
+from trainingjob_operator_b200.cmd.local import LocalCluster  # noqa: E402
+from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption  # noqa: E402
+from trainingjob_operator_b200.utils import klog, metrics  # noqa: E402
+
+
+def job(name, replicas):
+    c = {"name": "aitj-trainer", "command": ["/bin/true"]}
+    return {"apiVersion": C.API_VERSION, "kind": C.KIND, "metadata": {"name": name},
+            "spec": {"cleanPodPolicy": "All",
+                     "replicaSpecs": {"trainer": {"replicas": replicas, "template": {"spec": {"containers": [c]}}}}}}
+
+
+def run(jobs, replicas, threads, **opt_kw):
+    opt = TrainingJobOperatorOption(thread_num=threads, **opt_kw)
+    with LocalCluster(num_gpus=0, option=opt) as lc:
+        klog.set_verbosity(-1)
+        import logging
+        logging.getLogger("aitj").setLevel(logging.ERROR)
+        rv0 = int(lc.clientset.core_v1().pods("default").list()["metadata"]["resourceVersion"] or 0)
+        t0 = time.perf_counter()
+        for i in range(jobs):
+            lc.apply(job(f"tp-{i}", replicas))
+        t_submitted = time.perf_counter() - t0
+        done_at = {}
+        deadline = time.time() + 600
+        while len(done_at) < jobs and time.time() < deadline:
+            for j in lc.jobs().list().items:
+                if j.name not in done_at and j.status.phase == "Succeed":
+                    done_at[j.name] = time.perf_counter() - t0
+            time.sleep(0.01)
+        total = time.perf_counter() - t0
+        rv1 = int(lc.clientset.core_v1().pods("default").list()["metadata"]["resourceVersion"] or 0)
+        lat = sorted(done_at.values())
+        out = {"jobs": jobs, "replicas": replicas, "thread_num": threads, "completed": len(done_at),
+               "submit_all_s": round(t_submitted, 3), "all_succeed_s": round(total, 3),
+               "jobs_per_s": round(len(done_at) / total, 1), "pods_per_s": round(len(done_at) * replicas / total, 1),
+               "store_writes": rv1 - rv0, "writes_per_s": round((rv1 - rv0) / total, 1),
+               "job_latency_p50_s": round(lat[len(lat) // 2], 3) if lat else None,
+               "job_latency_p99_s": round(lat[min(len(lat) - 1, int(0.99 * len(lat)))], 3) if lat else None}
+        return out
+
+
+def main():
+    jobs = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    replicas = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    threads = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    out = {"default_queue": run(jobs, replicas, threads)}
+    print(json.dumps(out["default_queue"]), flush=True)
+    out["client_go_queue_10qps_burst100"] = run(jobs, replicas, threads, queue_qps=10.0, queue_burst=100)
+    print(json.dumps(out["client_go_queue_10qps_burst100"]), flush=True)
+    out["note"] = ("each job: create R pods + R services, bind + start + reap R processes, status writes, delete pods + "
+                   "services (cleanPodPolicy All), final condition.  The reference additionally sits behind client-go's "
+                   "5 qps / burst 10 REST throttle per clientset (SURVEY.md 2.2), which is not modelled here.")
+    os.makedirs("profiles", exist_ok=True)
+    json.dump(out, open("profiles/control_plane_throughput.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

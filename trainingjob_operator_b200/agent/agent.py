@@ -210,6 +210,7 @@ class NodeAgent:
         # binds, so consecutive scheduling decisions must not rely on it alone
         self._gpu_owner: Dict[int, Tuple[str, float]] = {}
         self._bound: Dict[str, float] = {}   # pod uid -> time we bound it (cache may not show nodeName yet)
+        self._unschedulable: set = set()     # keys of pods that did not fit; re-queued when a slot is released
         # warm pool of parked interpreters: supervisor id -> {"fifo": path, "spawned": monotonic}
         self.sync_workers = max(1, int(os.environ.get("AITJ_AGENT_SYNC_WORKERS", "1")))
         self.warm_pool = max(0, int(warm_pool))
@@ -294,10 +295,8 @@ class NodeAgent:
         with self._lock:
             states = [st for st in self._states.values() if st.started and st.containers]
         for st in states:
-            ns, name = M.split_key(st.key)
-            try:
-                pod = self.pod_lister.namespaced(ns).get(name)
-            except APIError:
+            pod = self.pod_lister.peek_key(st.key)          # read-only: no copy per pod per pass
+            if pod is None:
                 continue
             if M.uid_of(pod) != st.uid or pod.get("metadata", {}).get("deletionTimestamp") or \
                     pod.get("status", {}).get("phase") != C.POD_RUNNING:
@@ -387,9 +386,12 @@ class NodeAgent:
         self._release_gpus(M.uid_of(pod))
 
     def _kick_pending(self) -> None:
-        for pod in self.pod_lister.list():
-            if not pod.get("spec", {}).get("nodeName"):
-                self.queue.add(M.key_of(pod))
+        """A slot was freed: retry the pods that were found unschedulable (they also retry on their own once a second;
+        pods that were never looked at yet are in the queue already)."""
+        with self._lock:
+            keys, self._unschedulable = list(self._unschedulable), set()
+        for key in keys:
+            self.queue.add(key)
 
     # ------------------------------------------------------------------ main loops
     def start(self, stop: threading.Event) -> None:
@@ -681,7 +683,7 @@ class NodeAgent:
     # ------------------------------------------------------------------ scheduler
     def _free_gpus(self) -> List[int]:
         ready = set()
-        for n in self.node_lister.list():
+        for n in self.node_lister.peek():
             nm = M.name_of(n)
             if not nm.startswith(f"{self.prefix}gpu-"):
                 continue
@@ -690,7 +692,7 @@ class NodeAgent:
                 ready.add(int(nm.rsplit("-", 1)[1]))
         busy = set()
         live_uids = set()
-        for p in self.pod_lister.list():
+        for p in self.pod_lister.peek():
             done = (p.get("status", {}).get("phase") or C.POD_PENDING) in (C.POD_SUCCEEDED, C.POD_FAILED)
             if not done:
                 live_uids.add(M.uid_of(p))
@@ -724,7 +726,7 @@ class NodeAgent:
             return
         # higher-priority pending pods go first: yield if someone more important is waiting
         mine = (pod_priority(pod), )
-        for other in self.pod_lister.list():
+        for other in self.pod_lister.peek():
             if other.get("spec", {}).get("nodeName") or M.uid_of(other) == M.uid_of(pod):
                 continue
             if other.get("metadata", {}).get("deletionTimestamp") or pod_gpu_request(other) == 0:
@@ -763,16 +765,19 @@ class NodeAgent:
                     self._gpu_owner.pop(g, None)
                 raise
 
-    def _release_gpus(self, uid: str) -> None:
+    def _release_gpus(self, uid: str, kick: bool = True) -> None:
         with self._lock:
             for g in [g for g, (u, _t) in self._gpu_owner.items() if u == uid]:
                 del self._gpu_owner[g]
             # `_bound` keeps the uid (pruned by age in `schedule`): a pod that ran to completion before the informer cache
             # even showed it as bound must not be bound a second time by a stale queue entry
-        self._kick_pending()
+        if kick:
+            self._kick_pending()
 
     def _mark_unschedulable(self, pod: dict, message: str) -> None:
         self.queue.add_after(M.key_of(pod), 1.0)   # safety net: retry even if no event announces a free GPU
+        with self._lock:
+            self._unschedulable.add(M.key_of(pod))
         conds = pod.get("status", {}).get("conditions") or []
         cur = M.condition(conds, "PodScheduled")
         if cur is not None and cur.get("status") == "False" and cur.get("message") == message:
@@ -1013,7 +1018,7 @@ class NodeAgent:
         if all(n in terms for n in want):
             status["phase"] = C.POD_SUCCEEDED if all(terms[n]["exitCode"] == 0 for n in want) else C.POD_FAILED
         if "phase" in status:
-            self._release_gpus(st.uid)
+            self._release_gpus(st.uid, kick=False)      # pending pods are kicked below, after the status write
         klog.V(2).info("pod %s container %s exited code=%d signal=%d", key, cname, code, sig)
         try:
             self.cs.core_v1().pods(ns).patch(name, {"status": status}, subresource="status")

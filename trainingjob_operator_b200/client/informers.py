@@ -44,41 +44,110 @@ def deletion_handling_key(obj) -> str:
 
 
 class Indexer:
-    """Thread-safe ``ns/name`` -> object cache with a namespace index (aitrainingjob.go:79)."""
+    """``ns/name`` -> object cache with a namespace index (aitrainingjob.go:79) and optional secondary indices
+    (client-go ``cache.Indexers``: name -> function returning the index values of an object).
 
-    def __init__(self):
+    Writers (the informer's reflector thread, tests) serialise on a lock.  Readers take none: every read is a single
+    C-level dict operation (``get``, ``list(d.values())``) on a dict that writers only mutate with single operations or
+    replace wholesale, and cached objects are never modified in place -- an update stores a new object.  Under load the
+    read lock was the hottest lock of the process (each blocked acquisition also costs a GIL hand-over)."""
+
+    def __init__(self, indexers: Optional[Dict[str, Callable[[Dict[str, Any]], List[str]]]] = None):
         self._lock = threading.RLock()
         self._items: Dict[str, Dict[str, Any]] = {}
+        self._by_ns: Dict[str, Dict[str, Dict[str, Any]]] = {}
+        self._indexers: Dict[str, Callable[[Dict[str, Any]], List[str]]] = dict(indexers or {})
+        self._indices: Dict[str, Dict[str, Dict[str, Dict[str, Any]]]] = {n: {} for n in self._indexers}
+
+    def add_indexers(self, indexers: Dict[str, Callable[[Dict[str, Any]], List[str]]]) -> None:
+        with self._lock:
+            for name, fn in indexers.items():
+                if name in self._indexers:
+                    continue
+                self._indexers[name] = fn
+                idx: Dict[str, Dict[str, Dict[str, Any]]] = {}
+                for key, o in self._items.items():
+                    for v in fn(o):
+                        idx.setdefault(v, {})[key] = o
+                self._indices[name] = idx
+
+    def _unindex(self, key: str, old: Dict[str, Any]) -> None:
+        ns = self._by_ns.get(M.namespace_of(old))
+        if ns is not None:
+            ns.pop(key, None)
+        for name, fn in self._indexers.items():
+            idx = self._indices[name]
+            for v in fn(old):
+                bucket = idx.get(v)
+                if bucket is not None:
+                    bucket.pop(key, None)
+                    if not bucket:
+                        idx.pop(v, None)
 
     def replace(self, items: List[Dict[str, Any]]) -> None:
         with self._lock:
-            self._items = {M.key_of(o): o for o in items}
+            new_items = {M.key_of(o): o for o in items}
+            by_ns: Dict[str, Dict[str, Dict[str, Any]]] = {}
+            indices: Dict[str, Dict[str, Dict[str, Dict[str, Any]]]] = {n: {} for n in self._indexers}
+            for key, o in new_items.items():
+                by_ns.setdefault(M.namespace_of(o), {})[key] = o
+                for name, fn in self._indexers.items():
+                    for v in fn(o):
+                        indices[name].setdefault(v, {})[key] = o
+            self._items, self._by_ns, self._indices = new_items, by_ns, indices
 
     def add(self, obj) -> None:
+        key = M.key_of(obj)
         with self._lock:
-            self._items[M.key_of(obj)] = obj
+            old = self._items.get(key)
+            self._items[key] = obj
+            # an update must never hide the object from a concurrent (lock-free) reader, not even for a moment: entries
+            # are overwritten in place and only the index values the new version no longer has are removed
+            ns_new = M.namespace_of(obj)
+            self._by_ns.setdefault(ns_new, {})[key] = obj
+            if old is not None and M.namespace_of(old) != ns_new:
+                self._by_ns.get(M.namespace_of(old), {}).pop(key, None)
+            for name, fn in self._indexers.items():
+                idx = self._indices[name]
+                new_vals = fn(obj)
+                for v in new_vals:
+                    idx.setdefault(v, {})[key] = obj
+                if old is not None:
+                    for v in fn(old):
+                        if v not in new_vals:
+                            bucket = idx.get(v)
+                            if bucket is not None:
+                                bucket.pop(key, None)
+                                if not bucket:
+                                    idx.pop(v, None)
 
     def delete(self, obj) -> None:
+        key = M.key_of(obj)
         with self._lock:
-            self._items.pop(M.key_of(obj), None)
+            old = self._items.pop(key, None)
+            if old is not None:
+                self._unindex(key, old)
 
     def get_by_key(self, key: str) -> Optional[Dict[str, Any]]:
-        with self._lock:
-            return self._items.get(key)
+        return self._items.get(key)
 
     def list(self, namespace: str = "") -> List[Dict[str, Any]]:
-        with self._lock:
-            if not namespace:
-                return list(self._items.values())
-            return [o for o in self._items.values() if M.namespace_of(o) == namespace]
+        if not namespace:
+            return list(self._items.values())
+        return list(self._by_ns.get(namespace, _EMPTY).values())
+
+    def by_index(self, name: str, value: str) -> List[Dict[str, Any]]:
+        """Objects whose indexer ``name`` yields ``value`` (uncopied)."""
+        return list(self._indices[name].get(value, _EMPTY).values())
 
     def keys(self) -> List[str]:
-        with self._lock:
-            return list(self._items.keys())
+        return list(self._items.keys())
 
     def __len__(self) -> int:
-        with self._lock:
-            return len(self._items)
+        return len(self._items)
+
+
+_EMPTY: Dict[str, Any] = {}
 
 
 class SharedIndexInformer:
@@ -252,6 +321,10 @@ class NamespaceLister:
         sel = selector or {}
         return [self._conv(o) for o in self._indexer.list(self._ns) if M.selector_matches(sel, M.labels_of(o))]
 
+    def list_where(self, pred: Callable[[Dict[str, Any]], bool]) -> List[Any]:
+        """Copies of the cached objects of this namespace for which ``pred`` holds; ``pred`` reads the uncopied object."""
+        return [self._conv(o) for o in self._indexer.list(self._ns) if pred(o)]
+
     def get(self, name: str) -> Any:
         o = self._indexer.get_by_key(f"{self._ns}/{name}" if self._ns else name)
         if o is None:
@@ -270,6 +343,26 @@ class GenericLister:
     def list(self, selector: Optional[Dict[str, str]] = None) -> List[Any]:
         sel = selector or {}
         return [self._conv(o) for o in self._indexer.list() if M.selector_matches(sel, M.labels_of(o))]
+
+    def by_index(self, name: str, value: str) -> List[Dict[str, Any]]:
+        """The cache's own objects (uncopied, read-only) filed under ``value`` by the informer's indexer ``name``."""
+        return self._indexer.by_index(name, value)
+
+    def copy_of(self, obj: Dict[str, Any]) -> Any:
+        return self._conv(obj)
+
+    def peek_key(self, key: str) -> Optional[Dict[str, Any]]:
+        """The cached object under ``ns/name`` itself (uncopied, read-only), or None."""
+        return self._indexer.get_by_key(key)
+
+    def keys_where(self, pred: Callable[[Dict[str, Any]], bool]) -> List[str]:
+        """``ns/name`` keys of the cached objects for which ``pred`` holds.  ``pred`` sees the cache's own objects (no
+        copy is made -- it must only read): a scan over every pod per event must not cost a deep copy of every pod."""
+        return [M.key_of(o) for o in self._indexer.list() if pred(o)]
+
+    def peek(self) -> List[Dict[str, Any]]:
+        """The cache's own objects, uncopied, for read-only aggregation (free-slot accounting).  Never mutate them."""
+        return list(self._indexer.list())
 
     def namespaced(self, namespace: str) -> NamespaceLister:
         return NamespaceLister(self._indexer, namespace, self._conv, self._what)

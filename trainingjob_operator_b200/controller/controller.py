@@ -50,6 +50,34 @@ metrics.describe("aitj_workqueue_depth", "keys waiting in the AITrainingJob work
 metrics.describe("aitj_job_startup_seconds", "job created -> all replicas Running")
 
 
+INDEX_JOB_LABEL = "jobLabel"              # "<namespace>/<TrainingJobName label>"
+INDEX_CONTROLLER_UID = "controllerUID"    # uid of the controlling owner reference
+
+
+def index_by_job_label(obj: dict) -> list:
+    v = M.labels_of(obj).get(C.LABEL_JOB_NAME)
+    return [f"{M.namespace_of(obj)}/{v}"] if v else []
+
+
+def index_by_controller_uid(obj: dict) -> list:
+    ref = M.get_controller_of(obj)
+    return [ref["uid"]] if ref is not None and ref.get("uid") else []
+
+
+def claim_candidates(lister, job, selector) -> list:
+    """Copies of the objects a ControllerRefManager pass of ``job`` can act on (pod.go:125-150, service.go:99-115 hand it
+    the whole namespace): the ones matching the selector (keep / adopt) -- all of which carry the job-name label -- and
+    the ones the job controls (release when the labels stopped matching)."""
+    seen = {}
+    for o in lister.by_index(INDEX_JOB_LABEL, f"{job.namespace}/{selector.get(C.LABEL_JOB_NAME, '')}"):
+        if M.selector_matches(selector, M.labels_of(o)):
+            seen[M.key_of(o)] = o
+    for o in lister.by_index(INDEX_CONTROLLER_UID, job.uid):
+        if M.namespace_of(o) == job.namespace:
+            seen.setdefault(M.key_of(o), o)
+    return [lister.copy_of(o) for o in seen.values()]
+
+
 class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, TrainingJobHandlers, ElasticMixin):
     kind = C.KIND
     group = C.GROUP_NAME
@@ -83,6 +111,10 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
         self.trainingjob_lister = job_informer.lister()
         self.trainingjob_informer_synced = job_informer.informer().has_synced
 
+        # client-go style secondary indices: a reconcile looks at the pods / services that carry its job label or that it
+        # controls -- not at every object of the namespace
+        for inf in (pod_informer.informer(), service_informer.informer()):
+            inf.indexer.add_indexers({INDEX_JOB_LABEL: index_by_job_label, INDEX_CONTROLLER_UID: index_by_controller_uid})
         pod_informer.informer().add_event_handler(add=self.add_pod, update=self.update_pod, delete=self.delete_pod)
         self.pod_lister = pod_informer.lister()
         self.pod_informer_synced = pod_informer.informer().has_synced

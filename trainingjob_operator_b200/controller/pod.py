@@ -136,8 +136,9 @@ class PodReconciler:
 
     # ---------------------------------------------------------------------------- claim
     def get_pods_by_job_and_selector(self, job: AITrainingJob, selector: Dict[str, str]) -> List[dict]:
-        all_pods = self.pod_lister.namespaced(job.namespace).list()
-        return self.claim_pods(job, selector, all_pods)
+        from .controller import claim_candidates
+
+        return self.claim_pods(job, selector, claim_candidates(self.pod_lister, job, selector))
 
     def claim_pods(self, job: AITrainingJob, selector: Dict[str, str], pods: List[dict]) -> List[dict]:
         def fresh():

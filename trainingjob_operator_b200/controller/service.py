@@ -57,7 +57,9 @@ class ServiceReconciler:
         return
 
     def get_services_by_job_and_selector(self, job: AITrainingJob, selector: Dict[str, str]) -> List[dict]:
-        return self.claim_services(job, selector, self.service_lister.namespaced(job.namespace).list())
+        from .controller import claim_candidates
+
+        return self.claim_services(job, selector, claim_candidates(self.service_lister, job, selector))
 
     def claim_services(self, job: AITrainingJob, selector: Dict[str, str], services: List[dict]) -> List[dict]:
         def fresh():
