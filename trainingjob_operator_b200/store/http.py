@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import json
 import re
+import socket
 import threading
 import urllib.parse
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
@@ -42,6 +43,18 @@ def _resolve(path: str) -> Optional[Tuple[R.ResourceInfo, str, str, str]]:
 class _Handler(BaseHTTPRequestHandler):
     protocol_version = "HTTP/1.1"
     server_version = "aitj-apiserver/1.0"
+    # One segment per response: with the default unbuffered wfile the status line + headers and the body left as two
+    # small writes, and Nagle held the second back until the client's delayed ACK (40 ms) -- every API call of the
+    # separately running agent / operator / CLI paid it.  Buffered writes (flushed once per response, and after every
+    # watch event) plus TCP_NODELAY on both ends.
+    wbufsize = 64 * 1024
+
+    def setup(self):
+        super().setup()
+        try:
+            self.request.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+        except OSError:
+            pass
 
     def log_message(self, fmt, *args):  # silence stderr access log
         pass
@@ -149,6 +162,7 @@ class _Handler(BaseHTTPRequestHandler):
         self.send_header("Content-Type", "application/json")
         self.send_header("Transfer-Encoding", "chunked")
         self.end_headers()
+        self.wfile.flush()
         stopping = self.server.stopping  # type: ignore[attr-defined]
         try:
             while not stream.expired and not stopping.is_set():
@@ -159,6 +173,7 @@ class _Handler(BaseHTTPRequestHandler):
                 self.wfile.write(f"{len(raw):x}\r\n".encode() + raw + b"\r\n")
                 self.wfile.flush()
             self.wfile.write(b"0\r\n\r\n")
+            self.wfile.flush()
         except (BrokenPipeError, ConnectionResetError, OSError):
             pass
         finally:
@@ -232,6 +247,7 @@ class APIHTTPServer:
 
     def __init__(self, api: APIServer, host: str = "127.0.0.1", port: int = 0):
         self.api = api
+        ThreadingHTTPServer.request_queue_size = 128      # listen backlog: --thread-num 1000 operators connect at once
         self._httpd = ThreadingHTTPServer((host, port), _Handler)
         self._httpd.daemon_threads = True
         self._httpd.api = api  # type: ignore[attr-defined]
