@@ -8,7 +8,7 @@ from trainingjob_operator_b200.api import constants as C
 from trainingjob_operator_b200.api.types import AITrainingJob
 from trainingjob_operator_b200.client.clientset import new_for_config
 from trainingjob_operator_b200.client.fake import new_simple_clientset
-from trainingjob_operator_b200.client.informers import DeletedFinalStateUnknown, SharedInformerFactory
+from trainingjob_operator_b200.client.informers import SharedInformerFactory
 from trainingjob_operator_b200.client.leaderelection import LEADER_ANNOTATION, LeaderElectionConfig, LeaderElector
 from trainingjob_operator_b200.client.record import EventRecorder, FakeRecorder, events_for
 from trainingjob_operator_b200.store.apiserver import APIError, APIServer

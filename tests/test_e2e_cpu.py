@@ -7,7 +7,6 @@ import json
 import os
 import signal
 import sys
-import threading
 import time
 
 import pytest

@@ -1,12 +1,10 @@
 """Property tests (hypothesis) of the status engine: whatever pod states are thrown at it, counters never
 exceed what exists, terminal phases are absorbing, and restart counts respect the limit."""
-import random
 
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
 from trainingjob_operator_b200.api import constants as C
-from trainingjob_operator_b200.api.types import AITrainingJob
 from trainingjob_operator_b200.controller import status as S
 
 from test_controller_unit import Harness, job_dict

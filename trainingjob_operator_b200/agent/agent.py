@@ -37,7 +37,6 @@ from __future__ import annotations
 
 import json
 import os
-import shlex
 import shutil
 import signal
 import sys

@@ -10,7 +10,7 @@ core kinds (pods, services, events, nodes, endpoints) and leases that the refere
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Iterator, List, Optional
+from typing import Any, Dict, List, Optional
 
 from ..api import register as R
 from ..api.types import AITrainingJob, AITrainingJobList

@@ -13,11 +13,11 @@ from __future__ import annotations
 
 import threading
 from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Any, Callable, Dict, List, Tuple
 
 from ..api import meta as M
 from ..api import register as R
-from ..store.apiserver import APIError, APIServer
+from ..store.apiserver import APIServer
 from ..store.transport import LocalTransport, Transport
 from .clientset import Clientset
 

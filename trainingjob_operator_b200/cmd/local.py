@@ -14,7 +14,7 @@ import sys
 import tempfile
 import threading
 import time
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 from ..agent.agent import NodeAgent
 from ..api import constants as C

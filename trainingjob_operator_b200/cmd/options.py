@@ -15,7 +15,7 @@ import argparse
 import os
 import re
 from dataclasses import dataclass, field
-from typing import List, Optional
+from typing import Optional
 
 _DUR = re.compile(r"(\d+(?:\.\d+)?)(ns|us|µs|ms|s|m|h)")
 _UNIT = {"ns": 1e-9, "us": 1e-6, "µs": 1e-6, "ms": 1e-3, "s": 1.0, "m": 60.0, "h": 3600.0}

@@ -13,11 +13,11 @@ from __future__ import annotations
 import threading
 from typing import Optional
 
-from ..client.clientset import Clientset, new_for_config
+from ..client.clientset import new_for_config
 from ..client.informers import SharedInformerFactory
 from ..client.leaderelection import LeaderElectionConfig, LeaderElector, default_identity
 from ..client.record import EventRecorder
-from ..controller.controller import TrainingJobController, new_training_job_controller
+from ..controller.controller import new_training_job_controller
 from ..utils import klog
 from .options import TrainingJobOperatorOption, resolve_master
 

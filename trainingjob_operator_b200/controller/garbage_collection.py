@@ -11,7 +11,6 @@ additionally sweeps processes whose pod record vanished (``agent.kubelet``).
 from __future__ import annotations
 
 import threading
-from typing import Optional
 
 from ..api import constants as C
 from ..api import meta as M

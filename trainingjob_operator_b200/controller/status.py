@@ -20,7 +20,7 @@ after a scale-down are not counted (Q1); ``lastReconcileTime`` is written.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 from ..api import constants as C
 from ..api import meta as M

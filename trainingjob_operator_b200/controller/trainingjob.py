@@ -58,8 +58,6 @@ class TrainingJobHandlers:
         self.enqueue_job(obj, False, 0)
 
     def delete_pods_and_services(self, job: AITrainingJob, pods: List[dict], services: List[dict]) -> None:
-        from .pod import gen_expectation_pods_key
-
         live = [p for p in pods if not p.get("metadata", {}).get("deletionTimestamp")]
         if live:
             self.delete_pods_expecting(job, live, None)

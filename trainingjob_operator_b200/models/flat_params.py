@@ -10,7 +10,7 @@ layout makes gradient buckets plain slices (DDP all-reduce without a flatten/unf
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Iterable, List, Optional, Tuple
+from typing import Dict, Iterable, List, Tuple
 
 import torch
 

@@ -7,8 +7,6 @@ Exit code 0 = pass.  ``tests/test_gpu_kernels.py`` drives it under ``@pytest.mar
 from __future__ import annotations
 
 import argparse
-import json
-import math
 import sys
 import time
 

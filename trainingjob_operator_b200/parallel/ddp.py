@@ -14,7 +14,7 @@ multicast alias by the GEMM epilogues that produce them -- lives in ``parallel.s
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 import torch.distributed as dist

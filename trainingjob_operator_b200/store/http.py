@@ -16,7 +16,7 @@ import socket
 import threading
 import urllib.parse
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
-from typing import Any, Dict, Optional, Tuple
+from typing import Any, Optional, Tuple
 
 from ..api import register as R
 from ..utils import metrics as metrics_mod

@@ -13,7 +13,7 @@ import json
 import socket
 import threading
 import urllib.parse
-from typing import Any, Dict, Iterator, Optional
+from typing import Any, Dict, Optional
 
 from ..api import register as R
 from .apiserver import APIError, APIServer
