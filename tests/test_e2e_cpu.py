@@ -154,6 +154,40 @@ def test_gpu_fault_is_node_fail_and_restarts_elsewhere(lc):
     kubectl.main(["inject", "gpu-heal", node], clientset=lc.clientset, out=buf)
 
 
+def test_auto_elastic_job_shrinks_around_a_lost_gpu_and_grows_back(lc):
+    """``edlPolicy: Auto`` (declared, never read by the reference: replica.go:19): a GPU drops out under a 4-replica job.
+    The replica that lived there cannot be placed again, so the role shrinks by exactly one (no overshoot while the
+    surplus replica drains), the indices are re-packed onto the healthy GPUs and the job runs at 3; when the GPU heals the
+    job grows back to 4 without anybody touching it."""
+    job = sh_job("auto", "sleep 60", replicas=4, gpus=1, restartPolicy="OnNodeFail", minReplicas=2, maxReplicas=4,
+                 edlPolicy="Auto")
+    job["spec"]["faultTolerant"] = True
+    lc.apply(job)
+    wait_until(lambda: lc.jobs().get("auto").status.phase == "Running")
+    buf = io.StringIO()
+    assert kubectl.main(["inject", "gpu-fault", "gpu-1", "--message", "Xid 79"], clientset=lc.clientset, out=buf) == 0
+    sizes = set()
+
+    def settled():
+        j = lc.jobs().get("auto")
+        sizes.add(j.spec.replica_specs["trainer"].replicas)
+        pods = lc.pods(selector="TrainingJobName=auto")
+        return j if (j.status.phase == "Running" and j.spec.replica_specs["trainer"].replicas == 3 and
+                     len(pods) == 3 and all(p["status"].get("phase") == "Running" for p in pods)) else None
+
+    j = wait_until(settled, timeout=30)
+    assert sizes <= {4, 3}                                             # never shrank below what was needed
+    assert j.status.rendezvous.world_sizes == {"trainer": 3} and j.status.restart_counts.get("trainer") == 1
+    pods = lc.pods(selector="TrainingJobName=auto")
+    assert sorted(p["metadata"]["name"] for p in pods) == ["auto-trainer-0", "auto-trainer-1", "auto-trainer-2"]
+    assert "gpu-1" not in {p["spec"]["nodeName"] for p in pods}
+    kubectl.main(["inject", "gpu-heal", "gpu-1"], clientset=lc.clientset, out=buf)
+    j = wait_until(lambda: (lambda x: x if x.status.phase == "Running" and
+                            x.status.replica_statuses["trainer"].active == 4 else None)(lc.jobs().get("auto")),
+                   timeout=30)
+    assert j.spec.replica_specs["trainer"].replicas == 4 and j.status.rendezvous.world_sizes == {"trainer": 4}
+
+
 def test_unschedulable_message_and_priority(lc):
     lc.apply(sh_job("big", "sleep 30", replicas=6, gpus=1))       # only 4 GPU slots
     job = wait_until(lambda: (lambda j: j if j.status.replica_statuses.get("trainer") and

@@ -363,6 +363,8 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
         if ready(old) == ready(cur):
             return
         self._enqueue_jobs_on_node(M.name_of(cur))
+        if ready(cur):
+            self._enqueue_autoscaled_jobs()      # a slot came back: edlPolicy Auto roles may grow into it
 
     def _node_changed_del(self, obj) -> None:
         node = obj.obj if isinstance(obj, DeletedFinalStateUnknown) else obj
@@ -377,6 +379,13 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
                 continue
             job = self.resolve_controller_ref(M.namespace_of(pod), ref)
             if job is not None:
+                self.enqueue_job(job, False, 0)
+
+    def _enqueue_autoscaled_jobs(self) -> None:
+        for job in self.trainingjob_lister.list():
+            if job.status.phase in C.ENDING_PHASES:
+                continue
+            if any(r.edl_policy == C.EDL_POLICY_AUTO for r in job.spec.replica_specs.values()):
                 self.enqueue_job(job, False, 0)
 
     # ------------------------------------------------------------------ lifecycle trace

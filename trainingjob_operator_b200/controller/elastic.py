@@ -31,6 +31,8 @@ from ..utils import klog, metrics
 
 metrics.describe("aitj_rendezvous_generations_total", "rendezvous generation bumps (scale up/down, restart)")
 
+AUTO_RECHECK_SECONDS = 2.0
+
 _PORT_LOCK = threading.Lock()
 _RECENT_PORTS: List[int] = []
 
@@ -50,6 +52,13 @@ def allocate_port() -> int:
                 del _RECENT_PORTS[:-64]
                 return port
         return port
+
+
+def _index_of(pod: dict) -> int:
+    try:
+        return int(M.labels_of(pod).get(C.LABEL_REPLICA_INDEX, "0"))
+    except ValueError:
+        return 0
 
 
 def desired_world_sizes(job: AITrainingJob) -> Dict[str, int]:
@@ -125,7 +134,10 @@ class ElasticMixin:
     def reconcile_elastic(self, job: AITrainingJob, pods: List[dict]) -> bool:
         """For ``edlPolicy: Auto`` roles choose replicas in [min,max] from free healthy GPU slots.
         Returns True when the job spec was patched (the caller stops; the update event re-queues)."""
-        if job.status.phase in (C.PHASE_TERMINATING, C.PHASE_RESTARTING) or job.status.restart_replica_name:
+        # not while replicas are being torn down for a restart (barrier pending).  Once they are re-created the job sits in
+        # Restarting until all of them run again -- if one cannot be placed because its GPU is gone, shrinking to what
+        # fits is exactly what gets the job out of that state (growth needs every replica Running, so it cannot fire)
+        if job.status.phase == C.PHASE_TERMINATING or job.status.restart_replica_name:
             return False
         patch: Dict[str, dict] = {}
         ready = None
@@ -141,6 +153,9 @@ class ElasticMixin:
             unschedulable = [p for p in mine if not p.get("spec", {}).get("nodeName")
                              and self.get_pod_scheduling_message(p)]
             target = cur
+            surplus = [p for p in mine if _index_of(p) >= cur]
+            if unschedulable and surplus:
+                continue      # a previous shrink is still draining: its slots may be all the waiting replicas need
             if unschedulable:
                 target = cur - len(unschedulable)          # shrink to what fits
             elif ready > 0 and all(p.get("status", {}).get("phase") == C.POD_RUNNING for p in mine) \
@@ -153,6 +168,10 @@ class ElasticMixin:
                 patch[rt] = {"replicas": target}
                 ready = max(0, ready - max(0, target - cur))
         if not patch:
+            if any(s.edl_policy == C.EDL_POLICY_AUTO and s.max_replicas is not None and
+                   int(s.replicas or 0) < s.max_replicas for s in job.spec.replica_specs.values()):
+                # slots freed by *other* jobs raise no event on this one: look again in a while
+                self.work_queue.add_after(job.key(), AUTO_RECHECK_SECONDS)
             return False
         try:
             self.trainingjob_client.elasticdeeplearning_v1().aitrainingjobs(job.namespace).patch(
