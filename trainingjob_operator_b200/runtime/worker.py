@@ -638,6 +638,8 @@ def run(args) -> Dict[str, Any]:
                 print(f"[worker {rank}] no new rendezvous generation was published: giving up", flush=True)
                 raise RuntimeError(f"collective failed and the job was not repaired: {failure[0]}: {failure[1]}")
             if rank >= target["world"]:
+                print(f"[worker {rank}] leaving: world shrinks to {target['world']} (generation {target['generation']})",
+                      flush=True)
                 return {"left": True, "generation": target["generation"], "step": step}
             t1 = time.time()
             got = rendezvous(rank, {"generation": target["generation"], "world": target["world"],
