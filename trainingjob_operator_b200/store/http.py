@@ -242,13 +242,24 @@ class _Handler(BaseHTTPRequestHandler):
             self._error(e)
 
 
+class _QuietServer(ThreadingHTTPServer):
+    request_queue_size = 128          # listen backlog: --thread-num 1000 operators connect at once
+
+    def handle_error(self, request, client_address):
+        import sys
+
+        exc = sys.exc_info()[1]
+        if isinstance(exc, (ConnectionResetError, BrokenPipeError, TimeoutError)):
+            return                    # a client went away mid-request (a killed worker): not worth a traceback
+        super().handle_error(request, client_address)
+
+
 class APIHTTPServer:
     """Threaded HTTP server bound to loopback; ``start()`` returns once it is listening."""
 
     def __init__(self, api: APIServer, host: str = "127.0.0.1", port: int = 0):
         self.api = api
-        ThreadingHTTPServer.request_queue_size = 128      # listen backlog: --thread-num 1000 operators connect at once
-        self._httpd = ThreadingHTTPServer((host, port), _Handler)
+        self._httpd = _QuietServer((host, port), _Handler)
         self._httpd.daemon_threads = True
         self._httpd.api = api  # type: ignore[attr-defined]
         self._httpd.stopping = threading.Event()  # type: ignore[attr-defined]
