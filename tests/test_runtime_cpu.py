@@ -279,3 +279,58 @@ def test_async_checkpoint_is_a_consistent_snapshot_and_never_blocks_on_a_busy_wr
         raise AssertionError("write error swallowed")
     except RuntimeError as e:
         assert "disk full" in str(e)
+
+
+def test_gathering_ranks_is_bounded_and_ends_early_on_a_newer_generation(tmp_path):
+    """Two of three ranks wait on a generation's store.  (a) The moment a newer generation is published they stop
+    waiting (StaleGeneration) instead of sitting out the attempt; (b) without one they give up at the attempt deadline;
+    (c) with all ranks present the group forms and works."""
+    script = textwrap.dedent("""
+        import os, sys, time, torch, torch.distributed as dist
+        sys.path.insert(0, %r)
+        from trainingjob_operator_b200.runtime import worker as W
+        rank, world, port = int(os.environ["RANK"]), int(os.environ["WORLD"]), int(os.environ["PORT"])
+        flag = os.environ["FLAG"]
+        dev = torch.device("cpu")
+        t0 = time.time()
+        try:
+            W.init_process_group(rank, world, port, dev, timeout_s=20, attempt_timeout_s=float(os.environ["ATTEMPT"]),
+                                 stale=lambda: os.path.exists(flag))
+        except W.StaleGeneration:
+            print("STALE %%.2f" %% (time.time() - t0)); sys.exit(0)
+        except TimeoutError:
+            print("TIMEOUT %%.2f" %% (time.time() - t0)); sys.exit(0)
+        except Exception as e:            # the store's host saw the newer generation first and closed the store
+            print("LOST %%.2f %%s" %% (time.time() - t0, type(e).__name__)); sys.exit(0)
+        t = torch.ones(1) * (rank + 1)
+        dist.all_reduce(t)
+        print("SUM %%d" %% int(t[0]))
+        dist.destroy_process_group()
+    """ % ROOT)
+
+    def launch(ranks, world, port, attempt, flag):
+        procs = []
+        for r in ranks:
+            env = dict(os.environ, RANK=str(r), WORLD=str(world), PORT=str(port), ATTEMPT=str(attempt), FLAG=flag)
+            procs.append(subprocess.Popen([sys.executable, "-c", script], env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True))
+        return procs
+
+    import time
+    flag = str(tmp_path / "newer-generation")
+    # (a) rank 2 never comes; the newer generation appears after ~2 s of a 60 s attempt
+    procs = launch([0, 1], 3, 29741, 60, flag)
+    time.sleep(6.0)                       # interpreter start + torch import, then they wait on the store
+    open(flag, "w").close()
+    t_flag = time.time()
+    outs = [p.communicate(timeout=60)[0] for p in procs]
+    assert time.time() - t_flag < 10, outs                       # not the 60 s attempt
+    assert "STALE" in outs[0] and ("STALE" in outs[1] or "LOST" in outs[1]), outs
+    os.unlink(flag)
+    # (b) bounded by the attempt when nothing else happens
+    outs = [p.communicate(timeout=90)[0] for p in launch([0, 1], 3, 29742, 3, flag)]
+    assert "TIMEOUT" in outs[0] and ("TIMEOUT" in outs[1] or "LOST" in outs[1]), outs     # (host gone first: LOST)
+    assert float(outs[0].split("TIMEOUT")[1].split()[0]) < 10, outs
+    # (c) everybody present
+    outs = [p.communicate(timeout=90)[0] for p in launch([0, 1, 2], 3, 29743, 30, flag)]
+    assert all("SUM 6" in o for o in outs), outs

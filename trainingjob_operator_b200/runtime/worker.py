@@ -216,11 +216,17 @@ def build_adapter(args, device: torch.device):
 
 
 # ------------------------------------------------------------------------------------ process group
+class StaleGeneration(RuntimeError):
+    """The job moved on to a newer rendezvous generation while this rank was waiting for its peers."""
+
+
 def init_process_group(rank: int, world: int, port: int, device: torch.device, timeout_s: float = 120.0,
-                       attempt_timeout_s: float = 0.0):
-    """Rendezvous on the generation's loopback port.  With ``attempt_timeout_s`` the TCP-store phase (all ranks
+                       attempt_timeout_s: float = 0.0, stale=None):
+    """Rendezvous on the generation's loopback port.  With ``attempt_timeout_s`` the gathering phase (all ranks
     present) is bounded separately and raises on expiry, so the caller can re-read the job's current rendezvous
-    generation and try again; ``timeout_s`` stays the collective timeout of the process group."""
+    generation and try again; ``timeout_s`` stays the collective timeout of the process group.  ``stale()`` is polled
+    while gathering: when it turns true (the controller published a newer generation) the wait ends at once with
+    ``StaleGeneration`` instead of sitting out the attempt."""
     import datetime
 
     backend = "nccl" if device.type == "cuda" else "gloo"
@@ -228,30 +234,62 @@ def init_process_group(rank: int, world: int, port: int, device: torch.device, t
     if device.type == "cuda":
         kw["device_id"] = device
     if attempt_timeout_s > 0:
+        deadline = time.time() + attempt_timeout_s
         if rank != 0:
             # TCPStore's own connect loop backs off exponentially (tens of seconds once the master is half a minute
             # late, e.g. a replacement rank 0 that is still importing torch): probe the port ourselves at a fixed 50 ms
-            _wait_for_listener(port, attempt_timeout_s)
+            _wait_for_listener(port, attempt_timeout_s, stale)
+        # the store does not wait for the workers itself (that wait cannot be interrupted): every rank files a key and
+        # polls for the others', so the gathering is bounded by *our* deadline and ends early on a newer generation
         store = dist.TCPStore("127.0.0.1", port, world, is_master=(rank == 0),
-                              timeout=datetime.timedelta(seconds=attempt_timeout_s), wait_for_workers=True)
-        store.set_timeout(datetime.timedelta(seconds=timeout_s))
-        dist.init_process_group(backend, store=store, rank=rank, world_size=world,
-                                timeout=datetime.timedelta(seconds=timeout_s), **kw)
+                              timeout=datetime.timedelta(seconds=max(1.0, deadline - time.time())),
+                              wait_for_workers=False)
+        try:
+            _gather_ranks(store, rank, world, deadline, stale)
+            store.set_timeout(datetime.timedelta(seconds=timeout_s))
+            dist.init_process_group(backend, store=store, rank=rank, world_size=world,
+                                    timeout=datetime.timedelta(seconds=timeout_s), **kw)
+        except BaseException:
+            if dist.is_initialized():
+                dist.destroy_process_group()
+            del store                     # closes the listening socket: the next attempt may use the same port
+            gc.collect()
+            raise
         return
     dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                             timeout=datetime.timedelta(seconds=timeout_s), **kw)
 
 
-def _wait_for_listener(port: int, timeout_s: float) -> bool:
+def _gather_ranks(store, rank: int, world: int, deadline: float, stale) -> None:
+    keys = [f"aitj/arrived/{r}" for r in range(world)]
+    store.set(keys[rank], "1")            # idempotent: a rank that retries on the same store does not count twice
+    next_stale_check = 0.0
+    while not store.check(keys):
+        now = time.time()
+        if now > deadline:
+            raise TimeoutError(f"only some of the {world} ranks arrived on the rendezvous store")
+        if stale is not None and now >= next_stale_check:
+            next_stale_check = now + 0.25
+            if stale():
+                raise StaleGeneration("a newer rendezvous generation was published")
+        time.sleep(0.01)
+
+
+def _wait_for_listener(port: int, timeout_s: float, stale=None) -> bool:
     import socket
 
     deadline = time.time() + timeout_s
+    next_stale_check = time.time() + 0.25
     while time.time() < deadline:
         try:
             socket.create_connection(("127.0.0.1", port), timeout=1.0).close()
             return True
         except OSError:
             time.sleep(0.05)
+        if stale is not None and time.time() >= next_stale_check:
+            next_stale_check = time.time() + 0.25
+            if stale():
+                raise StaleGeneration("a newer rendezvous generation was published")
     return False
 
 
@@ -305,8 +343,15 @@ def rendezvous(rank: int, rdv: Dict[str, int], device: torch.device, watcher) ->
             return cur
         try:
             with _KeepBeating():
+                gen_now = cur["generation"]
+
+                def stale() -> bool:
+                    r = watcher.fetch_now()
+                    return r is not None and r["generation"] > gen_now
+
                 init_process_group(rank, cur["world"], cur["port"], device, timeout_s=coll_timeout,
-                                   attempt_timeout_s=attempt if watcher is not None else 0.0)
+                                   attempt_timeout_s=attempt if watcher is not None else 0.0,
+                                   stale=stale if watcher is not None else None)
             return cur
         except Exception as e:  # noqa: BLE001 - peers missing within the attempt window (or a stale port)
             if dist.is_initialized():
