@@ -693,3 +693,31 @@ def test_trace_annotation_records_latency_markers(h):
     job = h.sync()
     tr = json.loads(job.annotations[C.ANN_TRACE])
     assert {"submitted", "firstReconcile", "running"} <= set(tr) and tr["running"] >= tr["submitted"]
+
+
+def test_worker_reports_on_the_job_become_metrics():
+    import json
+
+    from trainingjob_operator_b200.controller.trainingjob import observe_worker_reports
+    from trainingjob_operator_b200.utils import metrics
+
+    metrics.reset()
+    base = {"metadata": {"namespace": "default", "name": "j", "annotations": {}}}
+
+    r1 = {"metadata": {"namespace": "default", "name": "j", "annotations": {
+        "aitj.b200/rescale-trace": json.dumps({"generation": 2, "world": 8, "seconds": 3.5})}}}
+    observe_worker_reports(base, r1)
+    observe_worker_reports(r1, r1)                                   # unchanged annotation: not observed twice
+    r2 = {"metadata": {"namespace": "default", "name": "j", "annotations": {
+        "aitj.b200/rescale-trace": json.dumps({"generation": 3, "world": 8, "seconds": 1.7, "recovered_from": "RuntimeError"}),
+        "aitj.b200/metrics": json.dumps({"samples_per_sec": 6414.0, "world": 8}),
+        "aitj.b200/worker-trace": "not json at all"}}}
+    observe_worker_reports(r1, r2)
+    text = metrics.render()
+    assert 'aitj_rescale_seconds_count{kind="rescale"} 1' in text and 'aitj_rescale_seconds_count{kind="recovery"} 1' in text
+    assert 'aitj_job_recoveries_total{job="j",namespace="default"} 1.0' in text
+    assert 'aitj_job_samples_per_second{job="j",namespace="default"} 6414.0' in text
+    bad = {"metadata": {"namespace": "default", "name": "j", "annotations": {"aitj.b200/rescale-trace": "{broken",
+                                                                            "aitj.b200/metrics": "[1]"}}}
+    observe_worker_reports(r2, bad)                                  # malformed reports are ignored, not fatal
+    metrics.reset()

@@ -16,7 +16,43 @@ from ..api import meta as M
 from ..api.types import AITrainingJob
 from ..api.validation import validate_dict
 from ..store.apiserver import APIError
-from ..utils import klog
+from ..utils import klog, metrics
+
+# what the workers report back onto the job (runtime/elastic.py) becomes scrapeable (rescale latency and
+# per-job samples/sec belong on /metrics; the reference has no metrics at all)
+ANN_WORKER_METRICS = "aitj.b200/metrics"
+ANN_WORKER_RESCALE = "aitj.b200/rescale-trace"
+metrics.describe("aitj_rescale_seconds", "membership change observed by the workers -> first step at the new world "
+                                         "(kind=rescale|recovery)")
+metrics.describe("aitj_job_samples_per_second", "whole-job training throughput reported by rank 0")
+metrics.describe("aitj_job_recoveries_total", "in-place recoveries of faultTolerant jobs (a rank was lost, the others kept "
+                                              "their state)")
+
+
+def observe_worker_reports(old: dict, cur: dict) -> None:
+    """Turn changed worker-report annotations into metrics (called from the job update handler)."""
+    import json
+
+    a_old, a_cur = M.annotations_of(old), M.annotations_of(cur)
+    labels = {"namespace": M.namespace_of(cur) or "default", "job": M.name_of(cur)}
+    raw = a_cur.get(ANN_WORKER_RESCALE)
+    if raw and raw != a_old.get(ANN_WORKER_RESCALE):
+        try:
+            rec = json.loads(raw)
+            kind = "recovery" if rec.get("recovered_from") else "rescale"
+            metrics.observe("aitj_rescale_seconds", float(rec["seconds"]), labels={"kind": kind})
+            if kind == "recovery":
+                metrics.inc("aitj_job_recoveries_total", labels=labels)
+        except (ValueError, KeyError, TypeError):
+            pass
+    raw = a_cur.get(ANN_WORKER_METRICS)
+    if raw and raw != a_old.get(ANN_WORKER_METRICS):
+        try:
+            v = json.loads(raw).get("samples_per_sec")
+            if v is not None:
+                metrics.set_gauge("aitj_job_samples_per_second", float(v), labels=labels)
+        except (ValueError, TypeError, AttributeError):
+            pass
 
 
 class TrainingJobHandlers:
@@ -42,6 +78,7 @@ class TrainingJobHandlers:
                          "; ".join(errs))
             return
         klog.V(2).info("Informer: Update TrainingJob %s/%s.", M.namespace_of(old), M.name_of(old))
+        observe_worker_reports(old, cur)
         spec_changed = old.get("spec") != cur.get("spec") or \
             M.annotations_of(old) != M.annotations_of(cur)
         # a spec/annotation edit by the user is acted on immediately; our own status writes are rate limited
