@@ -321,10 +321,6 @@ class NamespaceLister:
         sel = selector or {}
         return [self._conv(o) for o in self._indexer.list(self._ns) if M.selector_matches(sel, M.labels_of(o))]
 
-    def list_where(self, pred: Callable[[Dict[str, Any]], bool]) -> List[Any]:
-        """Copies of the cached objects of this namespace for which ``pred`` holds; ``pred`` reads the uncopied object."""
-        return [self._conv(o) for o in self._indexer.list(self._ns) if pred(o)]
-
     def get(self, name: str) -> Any:
         o = self._indexer.get_by_key(f"{self._ns}/{name}" if self._ns else name)
         if o is None:
@@ -354,11 +350,6 @@ class GenericLister:
     def peek_key(self, key: str) -> Optional[Dict[str, Any]]:
         """The cached object under ``ns/name`` itself (uncopied, read-only), or None."""
         return self._indexer.get_by_key(key)
-
-    def keys_where(self, pred: Callable[[Dict[str, Any]], bool]) -> List[str]:
-        """``ns/name`` keys of the cached objects for which ``pred`` holds.  ``pred`` sees the cache's own objects (no
-        copy is made -- it must only read): a scan over every pod per event must not cost a deep copy of every pod."""
-        return [M.key_of(o) for o in self._indexer.list() if pred(o)]
 
     def peek(self) -> List[Dict[str, Any]]:
         """The cache's own objects, uncopied, for read-only aggregation (free-slot accounting).  Never mutate them."""

@@ -167,6 +167,9 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
             stop.wait()
         finally:
             self.work_queue.shutdown()
+            flush = getattr(self.recorder, "flush", None)
+            if flush is not None:
+                flush(2.0)                    # events are written by a sink thread: do not drop the tail on a clean stop
             klog.info("Shutting down training-job controller")
 
     def create_crd(self) -> None:
