@@ -311,6 +311,33 @@ def test_cli_workflow_matches_readme(lc, tmp_path):
     assert kubectl.humanize_key("RestartReplicaName") == "Restart Replica Name"
 
 
+def test_cli_create_and_wait_for_scripting(lc, tmp_path):
+    """``kubectl create -f`` / ``kubectl wait --for=...``: what a script around the reference's README workflow uses."""
+    path = str(tmp_path / "job.yaml")
+    yaml.safe_dump(sh_job("w", "sleep 1", replicas=2), open(path, "w"))
+
+    def run(*argv):
+        buf = io.StringIO()
+        rc = kubectl.main(list(argv), clientset=lc.clientset, out=buf)
+        return rc, buf.getvalue()
+
+    rc, out = run("create", "-f", path)
+    assert rc == 0 and out.strip() == "aitrainingjob.elasticdeeplearning.ai/w created"
+    assert run("create", "-f", path)[0] == 1                                  # AlreadyExists, unlike apply
+    rc, out = run("wait", "aitj/w", "--for=condition=Running", "--timeout=20s")
+    assert rc == 0 and "condition met" in out
+    assert run("wait", "aitj", "w", "--for=phase=Failed", "--timeout=0.3")[0] == 1      # times out, exit 1
+    rc, out = run("wait", "aitj", "w", "--for=jsonpath={.status.phase}=Succeed", "--timeout=30s")
+    assert rc == 0
+    assert run("wait", "aitj/w", "--for=condition=Running=False", "--timeout=5s")[0] == 0   # history: flipped to False
+    assert run("wait", "aitj/w", "--for=nonsense", "--timeout=1s")[0] == 1
+    run("delete", "aitj", "w")
+    rc, out = run("wait", "aitj/w", "--for=delete", "--timeout=20s")
+    assert rc == 0 and out.strip().endswith("deleted")
+    assert kubectl.parse_timeout("2m") == 120.0 and kubectl.parse_timeout("1.5") == 1.5 and \
+        kubectl.parse_timeout("-1s") > 3600
+
+
 def test_leader_failover_keeps_the_job_running(tmp_path):
     """BASELINE config 5 shape: two operators, kill the leader, the standby takes over, workers never notice."""
     opt = TrainingJobOperatorOption(thread_num=1)

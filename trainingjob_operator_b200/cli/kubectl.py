@@ -260,6 +260,50 @@ def load_manifests(path: str) -> List[Dict[str, Any]]:
     return out
 
 
+def parse_timeout(text: str) -> float:
+    """``30s`` / ``2m`` / ``1h`` / bare seconds (kubectl's --timeout syntax); negative = a week."""
+    t = text.strip()
+    mult = {"s": 1.0, "m": 60.0, "h": 3600.0}.get(t[-1:], None)
+    v = float(t[:-1]) if mult else float(t)
+    v *= mult or 1.0
+    return v if v >= 0 else 7 * 24 * 3600.0
+
+
+def _wait_predicate(cond: str):
+    """Predicate over the fetched object (None = not found) for ``wait --for=...``."""
+    if cond == "delete":
+        return lambda obj: obj is None
+    kind, _, rest = cond.partition("=")
+    if kind == "phase":
+        return lambda obj: obj is not None and (obj.get("status") or {}).get("phase") == rest
+    if kind == "condition":
+        ctype, _, want = rest.partition("=")
+        want = (want or "True").lower()
+
+        def has_condition(obj) -> bool:
+            if obj is None:
+                return False
+            last = None
+            for c in (obj.get("status") or {}).get("conditions") or []:
+                if str(c.get("type", "")).lower() == ctype.lower():
+                    last = c                                      # the condition list is a history: the newest entry counts
+            return last is not None and str(last.get("status", "")).lower() == want
+        return has_condition
+    if kind == "jsonpath":
+        expr, _, want = rest.partition("=")
+        path = [p for p in expr.strip("'\"{} ").split(".") if p]
+
+        def at_path(obj) -> bool:
+            cur: Any = obj
+            for p in path:
+                if not isinstance(cur, dict) or p not in cur:
+                    return False
+                cur = cur[p]
+            return str(cur) == want.strip("'\"")
+        return at_path
+    raise RuntimeError(f"unrecognized condition: {cond!r} (use delete, phase=..., condition=..., jsonpath=...)")
+
+
 # ------------------------------------------------------------------------------------ commands
 class CLI:
     def __init__(self, cs: Clientset, out=sys.stdout):
@@ -311,6 +355,54 @@ class CLI:
                     rc.update(new)
                     self.p(f"{self._qualified(info)}/{name} configured")
         return 0
+
+    def create(self, files: List[str], namespace: str) -> int:
+        """``kubectl create -f``: like apply, but an existing object is an error (AlreadyExists)."""
+        for f in files:
+            for obj in load_manifests(f):
+                info = R.by_kind(obj["kind"])
+                ns = obj.get("metadata", {}).get("namespace") or namespace
+                if info.kind == C.KIND:
+                    obj.setdefault("metadata", {}).setdefault("annotations", {}).setdefault(
+                        C.ANN_TRACE, json.dumps({"submitted": round(time.time(), 4)}))
+                self.cs.resource(info, ns).create(obj)
+                self.p(f"{self._qualified(info)}/{M.name_of(obj)} created")
+        return 0
+
+    def wait(self, resource: str, names: List[str], namespace: str, cond: str, timeout: float) -> int:
+        """``kubectl wait --for=delete | --for=condition=<Type>[=True|False] | --for=jsonpath='{.a.b}'=value``, plus the
+        shorthand ``--for=phase=<Phase>`` (``.status.phase``).  Exit 0 once every named object satisfies it, 1 on timeout."""
+        if "/" in resource and not names:
+            resource, n = resource.split("/", 1)
+            names = [n]
+        if not names:
+            raise RuntimeError("wait needs a resource name (TYPE NAME or TYPE/NAME)")
+        info = self._info(resource)
+        rc = self.cs.resource(info, namespace)
+        check = _wait_predicate(cond)
+        deadline = time.monotonic() + timeout
+        pending = list(names)
+        while True:
+            still = []
+            for n in pending:
+                try:
+                    obj: Optional[Dict[str, Any]] = rc.get(n)
+                except APIError as e:
+                    if e.reason != "NotFound":
+                        raise
+                    obj = None
+                if check(obj):
+                    self.p(f"{self._qualified(info)}/{n} " + ("deleted" if obj is None else "condition met"))
+                else:
+                    still.append(n)
+            pending = still
+            if not pending:
+                return 0
+            if time.monotonic() > deadline:
+                for n in pending:
+                    print(f"error: timed out waiting for the condition on {info.plural}/{n}", file=sys.stderr)
+                return 1
+            time.sleep(0.05)
 
     def get(self, resource: str, names: List[str], namespace: str, all_ns: bool, output: str, watch: bool,
             selector: str) -> int:
@@ -515,6 +607,9 @@ def build_parser() -> argparse.ArgumentParser:
         p.add_argument("--namespace", "-n", dest="ns2", default=None)
 
     a = sub.add_parser("apply"); a.add_argument("-f", "--filename", action="append", required=True); common(a)
+    cr = sub.add_parser("create"); cr.add_argument("-f", "--filename", action="append", required=True); common(cr)
+    wt = sub.add_parser("wait"); wt.add_argument("resource"); wt.add_argument("names", nargs="*")
+    wt.add_argument("--for", dest="cond", required=True); wt.add_argument("--timeout", default="30s"); common(wt)
     g = sub.add_parser("get"); g.add_argument("resource"); g.add_argument("names", nargs="*")
     g.add_argument("-o", "--output", default=""); g.add_argument("-w", "--watch", action="store_true")
     g.add_argument("-A", "--all-namespaces", action="store_true"); g.add_argument("-l", "--selector", default="")
@@ -552,6 +647,10 @@ def main(argv=None, clientset: Optional[Clientset] = None, out=sys.stdout) -> in
         cli = CLI(clientset, out)
         if args.cmd == "apply":
             return cli.apply(args.filename, ns)
+        if args.cmd == "create":
+            return cli.create(args.filename, ns)
+        if args.cmd == "wait":
+            return cli.wait(args.resource, args.names, ns, args.cond, parse_timeout(args.timeout))
         if args.cmd == "get":
             return cli.get(args.resource, args.names, ns, args.all_namespaces, args.output, args.watch, args.selector)
         if args.cmd == "describe":
@@ -585,7 +684,7 @@ def main(argv=None, clientset: Optional[Clientset] = None, out=sys.stdout) -> in
     except APIError as e:
         print(f"Error from server ({e.reason}): {e.message}", file=sys.stderr)
         return 1
-    except (RuntimeError, FileNotFoundError) as e:
+    except (RuntimeError, FileNotFoundError, ValueError) as e:
         print(f"error: {e}", file=sys.stderr)
         return 1
     return 0
