@@ -163,6 +163,20 @@ class WatchStream:
             return None
         return {"type": etype, "object": obj}
 
+    def poll_raw(self, timeout: float = 0.2) -> Optional[bytes]:
+        """One event already serialised as a JSON line, or None.  The store keeps objects as JSON bytes: the HTTP watch
+        forwards them with the resourceVersion spliced in instead of decoding and re-encoding every event once per
+        watcher (the label selector is evaluated on the labels the store keeps next to the bytes)."""
+        if self._closed.is_set():
+            return None
+        ev = self._server._store.watch_next(self._wid, timeout)
+        if ev is None:
+            return None
+        etype, rec = ev
+        if self._selector and not M.selector_matches(self._selector, rec.get("labels") or {}):
+            return None
+        return b'{"type":"' + etype.encode() + b'","object":' + self._server._raw_with_rv(rec) + b'}\n'
+
     @property
     def expired(self) -> bool:
         return self._closed.is_set() or (self._deadline is not None and time.monotonic() > self._deadline)
@@ -181,13 +195,26 @@ class APIServer:
         self.request_count = 0
 
     # ------------------------------------------------------------------ encoding helpers
+    _MD_PREFIX = b'{"metadata":{'
+
     @staticmethod
     def _encode(obj: Dict[str, Any]) -> bytes:
-        o = dict(obj)
-        md = dict(o.get("metadata") or {})
+        md = dict(obj.get("metadata") or {})
         md.pop("resourceVersion", None)
-        o["metadata"] = md
+        o = {"metadata": md}                 # metadata first: `_raw_with_rv` splices the resourceVersion in after it
+        for k, v in obj.items():
+            if k != "metadata":
+                o[k] = v
         return json.dumps(o, separators=(",", ":")).encode()
+
+    @classmethod
+    def _raw_with_rv(cls, rec: Dict[str, Any]) -> bytes:
+        """The stored JSON with ``metadata.resourceVersion`` set, without a decode / encode round trip."""
+        data: bytes = rec["data"]
+        n = len(cls._MD_PREFIX)
+        if data.startswith(cls._MD_PREFIX) and data[n:n + 1] == b'"':
+            return cls._MD_PREFIX + b'"resourceVersion":"' + str(rec["rv"]).encode() + b'",' + data[n:]
+        return json.dumps(cls._decode(rec), separators=(",", ":")).encode()     # written by an older layout (WAL)
 
     @staticmethod
     def _decode(rec: Dict[str, Any]) -> Dict[str, Any]:
@@ -260,9 +287,16 @@ class APIServer:
         return self._decode(rec)
 
     def get(self, info: R.ResourceInfo, namespace: str, name: str) -> Dict[str, Any]:
+        return self._decode(self._get_record(info, namespace, name))
+
+    def get_raw(self, info: R.ResourceInfo, namespace: str, name: str) -> bytes:
+        """``get`` as the JSON bytes the HTTP façade sends (no decode / encode round trip)."""
+        return self._raw_with_rv(self._get_record(info, namespace, name))
+
+    def _get_record(self, info: R.ResourceInfo, namespace: str, name: str) -> Dict[str, Any]:
         self.request_count += 1
         try:
-            return self._decode(self._store.get(info.kind, self._ns(info, namespace, True), name))
+            return self._store.get(info.kind, self._ns(info, namespace, True), name)
         except core.StoreError as e:
             err = _wrap(e)
             if err.reason == "NotFound":

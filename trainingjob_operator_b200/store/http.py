@@ -72,6 +72,13 @@ class _Handler(BaseHTTPRequestHandler):
         self.end_headers()
         self.wfile.write(raw)
 
+    def _send_raw_json(self, code: int, raw: bytes) -> None:
+        self.send_response(code)
+        self.send_header("Content-Type", "application/json")
+        self.send_header("Content-Length", str(len(raw)))
+        self.end_headers()
+        self.wfile.write(raw)
+
     def _send_text(self, code: int, text: str, ctype: str = "text/plain; charset=utf-8") -> None:
         raw = text.encode()
         self.send_response(code)
@@ -145,7 +152,7 @@ class _Handler(BaseHTTPRequestHandler):
                 raise APIError(404, "NotFound", f"the server could not find the requested resource ({u.path})")
             info, ns, name, _sub = r
             if name:
-                self._send_json(200, self.api.get(info, ns, name))
+                self._send_raw_json(200, self.api.get_raw(info, ns, name))
             elif q.get("watch") in ("true", "1"):
                 self._watch(info, ns, q)
             else:
@@ -166,10 +173,9 @@ class _Handler(BaseHTTPRequestHandler):
         stopping = self.server.stopping  # type: ignore[attr-defined]
         try:
             while not stream.expired and not stopping.is_set():
-                ev = stream.poll(0.25)
-                if ev is None:
+                raw = stream.poll_raw(0.25)
+                if raw is None:
                     continue
-                raw = json.dumps(ev).encode() + b"\n"
                 self.wfile.write(f"{len(raw):x}\r\n".encode() + raw + b"\r\n")
                 self.wfile.flush()
             self.wfile.write(b"0\r\n\r\n")
