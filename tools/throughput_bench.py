@@ -104,6 +104,15 @@ def run_daemons(jobs, replicas, threads):
             time.sleep(0.05)
         total = time.perf_counter() - t0
         lat = sorted(done_at.values())
+        cpu = {}
+        try:
+            import psutil
+
+            for name, p in zip(("apiserver", "agent", "operator"), procs):
+                t = psutil.Process(p.pid).cpu_times()
+                cpu[name] = round(t.user + t.system, 2)
+        except Exception:  # noqa: BLE001
+            pass
         # single-job latency in the same topology: submit -> phase Running, 8 replicas of /bin/sleep
         single = []
         for i in range(10):
@@ -119,7 +128,7 @@ def run_daemons(jobs, replicas, threads):
         single.sort()
         return {"topology": "3 processes over loopback HTTP",
                 "submit_to_running_p50_s": round(single[len(single) // 2], 4),
-                "submit_to_running_max_s": round(single[-1], 4), "jobs": jobs, "replicas": replicas, "thread_num": threads,
+                "submit_to_running_max_s": round(single[-1], 4), "cpu_seconds_until_all_succeed": cpu, "jobs": jobs, "replicas": replicas, "thread_num": threads,
                 "completed": len(done_at), "submit_all_s": round(t_submitted, 3), "all_succeed_s": round(total, 3),
                 "jobs_per_s": round(len(done_at) / total, 1), "pods_per_s": round(len(done_at) * replicas / total, 1),
                 "job_latency_p50_s": round(lat[len(lat) // 2], 3) if lat else None,
