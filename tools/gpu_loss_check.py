@@ -4,7 +4,7 @@ replacement, shrinks the role to 3; the survivors catch the broken collective, k
 the replacement joins on the freed slot and training continues at world 3.  Prints the job's state changes with
 timestamps relative to the fault, then the workers' own log lines.
 
-    python tools/gpu_loss_check.py [seconds_to_watch]
+    python tools/gpu_loss_check.py [seconds_to_watch] [--gpu MODEL]     # MODEL: resnet50 | mnist | bert | gpt2 (4 GPUs)
 """
 import io
 import json
@@ -35,18 +35,24 @@ from trainingjob_operator_b200.cmd.local import LocalCluster
 from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption
 opt = TrainingJobOperatorOption(thread_num=2, gc_interval=0.5, scale_down_grace=10.0)
 wd = tempfile.mkdtemp()
-worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", "mlp", "--batch", "16",
-          "--steps", "0", "--cpu", "--elastic", "--step-sleep", "0.02"]
+GPU_MODEL = sys.argv[sys.argv.index("--gpu") + 1] if "--gpu" in sys.argv else ""
+if GPU_MODEL:
+    sys.argv = [a for a in sys.argv if a not in ("--gpu", GPU_MODEL)]
+    worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", GPU_MODEL, "--batch",
+              {"resnet50": "64", "mnist": "512"}.get(GPU_MODEL, "8"), "--steps", "0", "--elastic"]
+else:
+    worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", "mlp", "--batch", "16",
+              "--steps", "0", "--cpu", "--elastic", "--step-sleep", "0.02"]
 job = {"apiVersion": "elasticdeeplearning.ai/v1", "kind": "AITrainingJob", "metadata": {"name": "af"},
        "spec": {"frameworkType": "pytorch", "faultTolerant": True, "replicaSpecs": {"trainer": {
            "replicas": 4, "minReplicas": 2, "maxReplicas": 4, "edlPolicy": "Auto", "restartPolicy": "OnNodeFail", "restartLimit": 3,
            "template": {"spec": {"terminationGracePeriodSeconds": 1, "containers": [
                {"name": "aitj-trainer", "command": worker, "workingDir": ROOT, "resources": {"limits": {"nvidia.com/gpu": 1}},
                 "env": [{"name": "PYTHONPATH", "value": ROOT}]}]}}}}}}
-with LocalCluster(num_gpus=4, workdir=wd, option=opt, health_prober=lambda i: (True, ""), health_period=0.1) as lc:
+with LocalCluster(num_gpus=4, workdir=wd, option=opt, health_prober=lambda i: (True, ""), health_period=0.1) as lc:   # faults are injected, not probed
     lc.apply(job)
     wait_until(lambda: "aitj.b200/worker-trace" in lc.jobs().get("af").annotations, timeout=60)
-    time.sleep(1.0)
+    time.sleep(3.0 if GPU_MODEL else 1.0)
     buf = io.StringIO()
     t0 = time.time()
     kubectl.main(["inject", "gpu-fault", "gpu-1", "--message", "Xid 79"], clientset=lc.clientset, out=buf)
