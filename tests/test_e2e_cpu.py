@@ -188,6 +188,31 @@ def test_auto_elastic_job_shrinks_around_a_lost_gpu_and_grows_back(lc):
     assert j.spec.replica_specs["trainer"].replicas == 4 and j.status.rendezvous.world_sizes == {"trainer": 4}
 
 
+def test_auto_elastic_job_yields_gpus_to_more_important_work_and_takes_them_back(lc):
+    """An ``edlPolicy: Auto`` role occupies every GPU; a job with a higher ``spec.priority`` arrives and cannot be placed.
+    The elastic job gives back exactly what is missing (never below ``minReplicas``), the important job runs, and when it
+    is done the elastic job grows into the free slots again."""
+    lc.apply(sh_job("bg", "sleep 120", replicas=4, gpus=1, minReplicas=1, maxReplicas=4, edlPolicy="Auto"))
+    wait_until(lambda: lc.jobs().get("bg").status.phase == "Running")
+    vip = sh_job("vip", "sleep 3", replicas=2, gpus=1)
+    vip["spec"]["priority"] = "high"
+    lc.apply(vip)
+    seen = set()
+
+    def vip_running():
+        seen.add(lc.jobs().get("bg").spec.replica_specs["trainer"].replicas)
+        return lc.jobs().get("vip").status.phase in ("Running", "Succeed")
+
+    wait_until(vip_running, timeout=30)
+    assert min(seen) == 2                                         # gave back two slots, not more
+    assert lc.jobs().get("bg").status.restart_counts.get("trainer", 0) == 0
+    lc.wait_for_phase("vip", "Succeed", timeout=30)
+    j = wait_until(lambda: (lambda x: x if x.spec.replica_specs["trainer"].replicas == 4 and x.status.phase == "Running"
+                            and x.status.replica_statuses["trainer"].active == 4 else None)(lc.jobs().get("bg")),
+                   timeout=30)
+    assert j.status.rendezvous.world_sizes == {"trainer": 4}
+
+
 def test_unschedulable_message_and_priority(lc):
     lc.apply(sh_job("big", "sleep 30", replicas=6, gpus=1))       # only 4 GPU slots
     job = wait_until(lambda: (lambda j: j if j.status.replica_statuses.get("trainer") and

@@ -53,9 +53,8 @@ from ..core import _aitj_core as core
 from ..store.apiserver import APIError
 from ..utils import klog, lifecycle, metrics
 
-GPU_RESOURCE = "nvidia.com/gpu"
+GPU_RESOURCE = M.GPU_RESOURCE
 OWN_SCHEDULERS = ("", "default-scheduler", "aitj-scheduler")
-PRIORITY_NAMES = {"critical": 1000, "high": 100, "medium": 50, "normal": 50, "low": 10}
 _PASS_ENV = ("PATH", "HOME", "USER", "LANG", "LC_ALL", "LD_LIBRARY_PATH", "VIRTUAL_ENV", "PYTHONPATH", "TMPDIR",
              "CUDA_HOME", "NCCL_DEBUG", "NCCL_SOCKET_IFNAME", "NCCL_IB_DISABLE", "TORCH_NCCL_ASYNC_ERROR_HANDLING",
              "GRAFT_REPO_ROOT", "HF_HOME", "TORCH_HOME", "XDG_CACHE_HOME")
@@ -112,26 +111,11 @@ def nvml_health_prober() -> Callable[[int], Tuple[bool, str]]:
     return probe
 
 
-def pod_gpu_request(pod: dict) -> int:
-    n = 0
-    for c in pod.get("spec", {}).get("containers") or []:
-        res = c.get("resources") or {}
-        v = (res.get("limits") or {}).get(GPU_RESOURCE, (res.get("requests") or {}).get(GPU_RESOURCE, 0))
-        try:
-            n += int(v)
-        except (TypeError, ValueError):
-            pass
-    return n
+pod_gpu_request = M.pod_gpu_request
 
 
 def pod_priority(pod: dict) -> int:
-    raw = M.labels_of(pod).get(C.LABEL_PRIORITY, "")
-    if not raw:
-        return 0
-    try:
-        return int(raw)
-    except ValueError:
-        return PRIORITY_NAMES.get(raw.lower(), 0)
+    return M.priority_value(M.labels_of(pod).get(C.LABEL_PRIORITY, ""))
 
 
 def proc_start_time(pid: int) -> Optional[int]:

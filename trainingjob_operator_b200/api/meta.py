@@ -155,3 +155,31 @@ def condition(conds: Iterable[Dict[str, Any]], ctype: str) -> Optional[Dict[str,
         if c.get("type") == ctype:
             return c
     return None
+
+
+# ------------------------------------------------------------------------------ pod resources / priority
+GPU_RESOURCE = "nvidia.com/gpu"
+PRIORITY_NAMES = {"critical": 1000, "high": 100, "medium": 50, "normal": 50, "low": 10}
+
+
+def pod_gpu_request(pod: Dict[str, Any]) -> int:
+    """GPUs a pod asks for: the sum of its containers' ``nvidia.com/gpu`` limits (requests as fallback)."""
+    n = 0
+    for c in pod.get("spec", {}).get("containers") or []:
+        res = c.get("resources") or {}
+        v = (res.get("limits") or {}).get(GPU_RESOURCE, (res.get("requests") or {}).get(GPU_RESOURCE, 0))
+        try:
+            n += int(v)
+        except (TypeError, ValueError):
+            pass
+    return n
+
+
+def priority_value(raw: Any) -> int:
+    """``spec.priority`` / the pod label ``priority`` (pod.go:503-505): an integer or one of the well-known names."""
+    if raw in (None, ""):
+        return 0
+    try:
+        return int(raw)
+    except (TypeError, ValueError):
+        return PRIORITY_NAMES.get(str(raw).lower(), 0)

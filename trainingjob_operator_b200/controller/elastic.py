@@ -156,11 +156,14 @@ class ElasticMixin:
             surplus = [p for p in mine if _index_of(p) >= cur]
             if unschedulable and surplus:
                 continue      # a previous shrink is still draining: its slots may be all the waiting replicas need
+            higher, at_least = self._waiting_gpu_demand(job)
             if unschedulable:
                 target = cur - len(unschedulable)          # shrink to what fits
-            elif ready > 0 and all(p.get("status", {}).get("phase") == C.POD_RUNNING for p in mine) \
-                    and len(mine) == cur:
-                target = cur + ready                       # grow into free slots
+            elif higher > ready and not surplus:
+                target = cur - (higher - ready)            # yield to more important work that cannot be placed
+            elif ready > 0 and at_least == 0 and len(mine) == cur and \
+                    all(p.get("status", {}).get("phase") == C.POD_RUNNING for p in mine):
+                target = cur + ready                       # grow into free slots nobody at our priority or above waits for
             target = clamp_replicas(spec, target)
             if target != cur:
                 klog.info("job %s role %s: edlPolicy Auto: replicas %d -> %d (free slots %d, unschedulable %d)",
@@ -168,9 +171,10 @@ class ElasticMixin:
                 patch[rt] = {"replicas": target}
                 ready = max(0, ready - max(0, target - cur))
         if not patch:
-            if any(s.edl_policy == C.EDL_POLICY_AUTO and s.max_replicas is not None and
-                   int(s.replicas or 0) < s.max_replicas for s in job.spec.replica_specs.values()):
-                # slots freed by *other* jobs raise no event on this one: look again in a while
+            if any(s.edl_policy == C.EDL_POLICY_AUTO and (s.min_replicas is not None or s.max_replicas is not None)
+                   for s in job.spec.replica_specs.values()):
+                # slots freed by other jobs, or more important pods that cannot be placed, raise no event on this job:
+                # look again in a while
                 self.work_queue.add_after(job.key(), AUTO_RECHECK_SECONDS)
             return False
         try:
@@ -181,6 +185,30 @@ class ElasticMixin:
             return False
         metrics.inc("aitj_autoscale_total")
         return True
+
+    def _waiting_gpu_demand(self, job: AITrainingJob) -> tuple:
+        """GPUs asked for by other jobs' pods that the scheduler could not place: (by strictly more important pods, by pods
+        at least as important as this job).  ``spec.priority`` is copied onto every pod as the ``priority`` label
+        (pod.go:503-505) and the node agent's scheduler already orders by it; an ``edlPolicy: Auto`` role additionally
+        gives slots back (down to ``minReplicas``) when that ordering alone cannot help."""
+        mine = M.priority_value(job.spec.priority)
+        higher = at_least = 0
+        for pod in self.pod_lister.peek():
+            if pod.get("spec", {}).get("nodeName") or pod.get("metadata", {}).get("deletionTimestamp"):
+                continue
+            if M.labels_of(pod).get(C.LABEL_JOB_NAME) == job.name and M.namespace_of(pod) == job.namespace:
+                continue
+            if not self.get_pod_scheduling_message(pod):
+                continue                    # not (yet) found unschedulable
+            want = M.pod_gpu_request(pod)
+            if want <= 0:
+                continue
+            prio = M.priority_value(M.labels_of(pod).get(C.LABEL_PRIORITY, ""))
+            if prio > mine:
+                higher += want
+            if prio >= mine:
+                at_least += want
+        return higher, at_least
 
     def _free_gpu_slots(self, job: AITrainingJob) -> int:
         ready_nodes = {n for n in self.get_node_status() if n.startswith("gpu-")}
