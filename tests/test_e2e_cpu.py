@@ -351,7 +351,7 @@ def test_cli_create_and_wait_for_scripting(lc, tmp_path):
     assert run("create", "-f", path)[0] == 1                                  # AlreadyExists, unlike apply
     rc, out = run("wait", "aitj/w", "--for=condition=Running", "--timeout=20s")
     assert rc == 0 and "condition met" in out
-    assert run("wait", "aitj", "w", "--for=phase=Failed", "--timeout=0.3")[0] == 1      # times out, exit 1
+    assert run("wait", "aitj", "--for=phase=Failed", "--timeout=0.3", "w")[0] == 1      # times out; name after the flags
     rc, out = run("wait", "aitj", "w", "--for=jsonpath={.status.phase}=Succeed", "--timeout=30s")
     assert rc == 0
     assert run("wait", "aitj/w", "--for=condition=Running=False", "--timeout=5s")[0] == 0   # history: flipped to False

@@ -638,7 +638,14 @@ def build_parser() -> argparse.ArgumentParser:
 
 
 def main(argv=None, clientset: Optional[Clientset] = None, out=sys.stdout) -> int:
-    args = build_parser().parse_args(argv)
+    parser = build_parser()
+    args, extra = parser.parse_known_args(argv)
+    if extra:
+        # kubectl accepts flags anywhere (`wait aitj --for=delete NAME`); argparse stops collecting a `nargs="*"` positional at
+        # the first flag, so names that follow flags arrive here
+        if any(e.startswith("-") for e in extra) or not hasattr(args, "names"):
+            parser.error("unrecognized arguments: " + " ".join(extra))
+        args.names = list(args.names) + extra
     ns = getattr(args, "ns2", None) or args.namespace
     try:
         if clientset is None:
