@@ -721,3 +721,55 @@ def test_worker_reports_on_the_job_become_metrics():
                                                                             "aitj.b200/metrics": "[1]"}}}
     observe_worker_reports(r2, bad)                                  # malformed reports are ignored, not fatal
     metrics.reset()
+
+
+def _replicas(h):
+    return h.cs.tracker.get(R.AITRAININGJOB, "default", "job")["spec"]["replicaSpecs"]["trainer"]["replicas"]
+
+
+def _foreign_pending(h, name, gpus, priority, job_name="vip"):
+    p = {"apiVersion": "v1", "kind": "Pod",
+         "metadata": {"name": name, "namespace": "default", "uid": f"uid-{name}",
+                      "labels": {C.LABEL_GROUP_NAME: C.GROUP_NAME, C.LABEL_JOB_NAME: job_name, C.LABEL_PRIORITY: priority}},
+         "spec": {"containers": [{"name": "aitj-x", "resources": {"limits": {"nvidia.com/gpu": gpus}}}]},
+         "status": {"phase": "Pending", "conditions": [{"type": "PodScheduled", "status": "False",
+                                                        "message": "0/4 nodes are available"}]}}
+    h.pods_idx.add(p)
+    return p
+
+
+def test_edl_policy_auto_does_not_repeat_a_shrink_that_is_still_draining(h):
+    job = h.add_job(job_dict(roles={"trainer": {"replicas": 3, "minReplicas": 1, "maxReplicas": 4,
+                                                "edlPolicy": "Auto"}}))
+    h.set_nodes(["gpu-0", "gpu-2", "gpu-3", "cpu-0"])                     # gpu-1 is gone
+    h.pod(job, "trainer", 0, node="gpu-0")
+    h.pod(job, "trainer", 1, phase="Pending", node="", unschedulable="0/3 nodes are available")
+    h.pod(job, "trainer", 2, node="gpu-2")
+    h.pod(job, "trainer", 3, node="gpu-3")                                # surplus of the 4 -> 3 shrink, still draining
+    h.sync()
+    assert _replicas(h) == 3                                              # its slot is all rank 1 needs: no 3 -> 2
+
+
+def test_edl_policy_auto_yields_to_higher_priority_only_and_never_below_min(h):
+    job = h.add_job(job_dict(roles={"trainer": {"replicas": 4, "minReplicas": 3, "maxReplicas": 4,
+                                                "edlPolicy": "Auto"}}))
+    for i in range(4):
+        h.pod(job, "trainer", i, node=f"gpu-{i}")
+    _foreign_pending(h, "peer-0", 1, "")                                   # same priority: no reason to yield
+    h.sync()
+    assert _replicas(h) == 4
+    _foreign_pending(h, "vip-0", 2, "high")                                # wants 2, none free
+    h.sync()
+    assert _replicas(h) == 3                                               # clamped by minReplicas
+
+
+def test_edl_policy_auto_does_not_grow_into_slots_that_equals_or_betters_wait_for(h):
+    job = h.add_job(job_dict(roles={"trainer": {"replicas": 2, "minReplicas": 1, "maxReplicas": 4,
+                                                "edlPolicy": "Auto"}}))
+    h.pod(job, "trainer", 0, node="gpu-0"); h.pod(job, "trainer", 1, node="gpu-1")
+    _foreign_pending(h, "peer-0", 1, "")                                   # found unschedulable a moment ago
+    h.sync()
+    assert _replicas(h) == 2                                               # gpu-2 / gpu-3 are free, but not for us
+    h.pods_idx.delete({"metadata": {"name": "peer-0", "namespace": "default"}})
+    h.sync()
+    assert _replicas(h) == 4
