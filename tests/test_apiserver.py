@@ -206,3 +206,35 @@ def test_wal_survives_restart(tmp_path):
     cs2 = new_for_config(server=APIServer(wal))
     again = cs2.elasticdeeplearning_v1().aitrainingjobs("default").get("paddle-mnist")
     assert again.uid == j.uid and again.resource_version == j.resource_version
+
+
+def test_housekeeping_expires_old_events_and_compacts_the_wal(tmp_path):
+    """Events have a TTL (kube-apiserver --event-ttl) and the write-ahead log is rewritten as a snapshot once it has
+    outgrown its budget; both survive a restart of the server."""
+    import os
+
+    from trainingjob_operator_b200.api import meta as M
+    from trainingjob_operator_b200.api import register as R
+    from trainingjob_operator_b200.store.apiserver import APIServer
+
+    wal = str(tmp_path / "store.wal")
+    api = APIServer(wal)
+    ev = R.by_kind("Event")
+    pod = R.by_kind("Pod")
+    old = M.format_time(M.now() - __import__("datetime").timedelta(hours=2))
+    api.create(ev, "default", {"metadata": {"name": "old"}, "reason": "R", "lastTimestamp": old})
+    api.create(ev, "default", {"metadata": {"name": "fresh"}, "reason": "R", "lastTimestamp": M.format_time()})
+    p = api.create(pod, "default", {"metadata": {"name": "p"}, "spec": {}})
+    for i in range(300):                                         # churn: every update is one more WAL record
+        p["metadata"]["annotations"] = {"i": str(i), "pad": "x" * 200}
+        p = api.update(pod, "default", "p", p)
+    before = os.path.getsize(wal)
+    done = api.housekeeping_once(event_ttl_s=3600, wal_max_bytes=16 << 10)
+    assert done == {"events_expired": 1, "wal_compacted": 1}
+    assert [e["metadata"]["name"] for e in api.list(ev)["items"]] == ["fresh"]
+    assert os.path.getsize(wal) < before / 10
+    assert api.housekeeping_once(event_ttl_s=3600, wal_max_bytes=16 << 10) == {"events_expired": 0, "wal_compacted": 0}
+    again = APIServer(wal)                                        # the compacted log replays to the same state
+    assert again.get(pod, "default", "p")["metadata"]["annotations"]["i"] == "299"
+    assert [e["metadata"]["name"] for e in again.list(ev)["items"]] == ["fresh"]
+    assert int(again.get(pod, "default", "p")["metadata"]["resourceVersion"]) == int(p["metadata"]["resourceVersion"])

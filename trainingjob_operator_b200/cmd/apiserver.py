@@ -17,6 +17,9 @@ def main(argv=None) -> int:
     ap.add_argument("--host", default="127.0.0.1")
     ap.add_argument("--data-dir", default=os.path.expanduser("~/.aitj"))
     ap.add_argument("--no-wal", action="store_true")
+    ap.add_argument("--event-ttl", type=float, default=3600.0, help="seconds an Event is kept (kube-apiserver: 1h)")
+    ap.add_argument("--wal-compact-mb", type=float, default=64.0,
+                    help="rewrite the write-ahead log as a snapshot once it is larger than this")
     ap.add_argument("--v", type=int, default=0)
     args = ap.parse_args(argv)
     klog.configure(args.v, True)
@@ -25,6 +28,7 @@ def main(argv=None) -> int:
     srv = APIHTTPServer(api, args.host, args.port).start()
     print(f"aitj-apiserver listening on {srv.url}", flush=True)
     stop = setup_signal_handler()
+    api.start_housekeeping(stop, event_ttl_s=args.event_ttl, wal_max_bytes=int(args.wal_compact_mb * (1 << 20)))
     stop.wait()
     srv.stop()
     return 0

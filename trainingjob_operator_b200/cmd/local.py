@@ -83,6 +83,7 @@ class LocalCluster:
         return seen
 
     def start(self) -> "LocalCluster":
+        self.api.start_housekeeping(self.stop_event)       # event TTL + WAL compaction, as the stand-alone daemon does
         self._start_agent()
         for i in range(self._operators):
             self.start_operator(i)

@@ -13,6 +13,7 @@ and graceful pod deletion (the kubelet analogue confirms the kill, then removes 
 from __future__ import annotations
 
 import json
+import os
 import threading
 import time
 from typing import Any, Dict, Iterator, List, Optional
@@ -189,6 +190,7 @@ class WatchStream:
 
 class APIServer:
     def __init__(self, wal_path: str = "", admission: bool = True, history: int = 16384):
+        self._wal_path = wal_path
         self._store = core.Store(wal_path, history)
         self._admission = admission
         self.started_at = time.time()
@@ -450,6 +452,44 @@ class APIServer:
 
     def compact(self) -> None:
         self._store.compact()
+
+    # ------------------------------------------------------------------ housekeeping
+    def housekeeping_once(self, event_ttl_s: float = 3600.0, wal_max_bytes: int = 64 << 20) -> Dict[str, int]:
+        """What etcd / kube-apiserver do in the background: Events expire (``--event-ttl``, 1 h upstream) and the
+        write-ahead log -- which records every write, ~2 KB each -- is rewritten as a snapshot of the live objects once it
+        has outgrown ``wal_max_bytes``.  Returns what was done."""
+        done = {"events_expired": 0, "wal_compacted": 0}
+        if event_ttl_s > 0:
+            ev = R.by_kind("Event")
+            for rec in self.list(ev).get("items", []):
+                stamp = rec.get("lastTimestamp") or rec.get("metadata", {}).get("creationTimestamp")
+                if stamp and M.seconds_since(stamp) > event_ttl_s:
+                    try:
+                        self.delete(ev, M.namespace_of(rec), M.name_of(rec), grace_period_seconds=0)
+                        done["events_expired"] += 1
+                    except APIError:
+                        pass
+        if self._wal_path and wal_max_bytes > 0:
+            try:
+                if os.path.getsize(self._wal_path) > wal_max_bytes:
+                    self.compact()
+                    done["wal_compacted"] = 1
+            except OSError:
+                pass
+        return done
+
+    def start_housekeeping(self, stop: threading.Event, period_s: float = 60.0, event_ttl_s: float = 3600.0,
+                           wal_max_bytes: int = 64 << 20) -> threading.Thread:
+        def loop():
+            while not stop.wait(period_s):
+                try:
+                    self.housekeeping_once(event_ttl_s, wal_max_bytes)
+                except Exception:  # noqa: BLE001 - never take the API server down for housekeeping
+                    pass
+
+        t = threading.Thread(target=loop, name="apiserver-housekeeping", daemon=True)
+        t.start()
+        return t
 
     def stats(self) -> Dict[str, Any]:
         return {"resourceVersion": self._store.current_rv(), "watchers": self._store.num_watchers(),
