@@ -287,6 +287,21 @@ def test_delete_job_kills_processes_and_gc_sweeps_orphans(lc):
     wait_until(lambda: not [p for p in lc.pods() if p["metadata"]["name"] == "ghost-trainer-0"], timeout=15)
 
 
+def test_agent_removes_files_of_vanished_pods_after_the_retention(lc):
+    lc.apply(sh_job("once", "echo hello", replicas=1))
+    lc.wait_for_phase("once", "Succeed", timeout=20)
+    wait_until(lambda: lc.pods(selector="TrainingJobName=once") == [])          # cleanPodPolicy All
+    log = os.path.join(lc.workdir, "logs", "default_once-trainer-0_aitj-trainer.log")
+    assert "hello" in open(log).read()                                           # kept for post-mortems ...
+    lc.apply(sh_job("stays", "sleep 30", replicas=1))
+    wait_until(lambda: lc.jobs().get("stays").status.phase == "Running")
+    wait_until(lambda: os.path.exists(os.path.join(lc.workdir, "logs", "default_stays-trainer-0_aitj-trainer.log")))
+    assert lc.agent.sweep_files(retention_s=3600) == 0                           # ... for the retention period
+    assert lc.agent.sweep_files(retention_s=0) >= 1
+    assert not os.path.exists(log)
+    assert os.path.exists(os.path.join(lc.workdir, "logs", "default_stays-trainer-0_aitj-trainer.log"))   # pod alive
+
+
 def test_cli_workflow_matches_readme(lc, tmp_path):
     """README.md:14-19 of the reference: apply -f / get aitj / describe aitj / delete -f."""
     spec = yaml.safe_load(open(os.path.join(ROOT, "examples", "paddle-mnist.yaml")))

@@ -623,8 +623,37 @@ class NodeAgent:
         return ok
 
     def _sweep_loop(self, stop: threading.Event) -> None:
+        n = 0
         while not stop.wait(5.0):
             self.sweep_orphans()
+            n += 1
+            if n % 120 == 0:                  # every ten minutes
+                self.sweep_files()
+
+    def sweep_files(self, retention_s: Optional[float] = None) -> int:
+        """Container logs, heartbeat and exit-code files outlive their pod on purpose (``aitjctl logs`` of a finished
+        replica, post-mortems; kubelet would delete them with the pod) -- but not forever: files of pods that no longer
+        exist are removed once they have not been written for ``AITJ_LOG_RETENTION`` seconds (default one day)."""
+        if retention_s is None:
+            retention_s = float(os.environ.get("AITJ_LOG_RETENTION", "86400"))
+        live = {f"{M.namespace_of(p)}_{M.name_of(p)}_" for p in self.pod_lister.peek()}
+        now, removed = time.time(), 0
+        for d in (self.log_dir, self.heartbeat_dir):
+            try:
+                names = os.listdir(d)
+            except OSError:
+                continue
+            for fn in names:
+                if any(fn.startswith(prefix) for prefix in live):
+                    continue
+                path = os.path.join(d, fn)
+                try:
+                    if now - os.stat(path).st_mtime > retention_s:
+                        os.unlink(path)
+                        removed += 1
+                except OSError:
+                    pass
+        return removed
 
     # ------------------------------------------------------------------ per-pod sync
     def _mine(self, node_name: str) -> bool:
