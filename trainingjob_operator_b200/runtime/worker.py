@@ -224,7 +224,10 @@ def ckpt_path(args) -> str:
     d = args.ckpt_dir or os.path.join(os.environ.get("AITJ_WORKDIR", "/tmp"), "ckpt")
     os.makedirs(d, exist_ok=True)
     job = os.environ.get("TRAININGJOB_NAME", "job")
-    return os.path.join(d, f"{job}.pt")
+    # per job *object*, not per name: a job submitted again under the same name must never resume from its predecessor's
+    # state (the uid survives every restart of the job's replicas, which is what a checkpoint is for)
+    uid = os.environ.get("AITJ_JOB_UID", "")[:8]
+    return os.path.join(d, f"{job}-{uid}.pt" if uid else f"{job}.pt")
 
 
 _CKPT: Dict[str, Any] = {}
