@@ -274,6 +274,10 @@ def run(args) -> Dict[str, Any]:
         if use_cuda else torch.device("cpu")
     if use_cuda:
         torch.cuda.set_device(device)
+    if args.elastic and os.environ.get("AITJ_FAULT_TOLERANT") == "1":
+        # NCCL's watchdog would take the process down on an asynchronous communicator error or a collective timeout
+        # (TearDown / SkipCleanUp); a faultTolerant job handles the loss of a peer itself (StallBreaker + recovery below)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
     trace = {"process_start": t_proc, "torch_imported": time.time()}
     heartbeat(force=True)
     watcher = ElasticWatcher.from_env(generation)
