@@ -29,15 +29,16 @@ agent, which keeps the exact object contract the controller logic reads
   the container) is treated the same way: event ``Unhealthy`` + ``Killing``, SIGKILL => exit 137 => the job's restart
   policy takes over.  This is the hang detection the reference leaves to kubelet probes; a DDP rank
   stuck in a collective because a peer died is the case it exists for.
+(The scheduler, the liveness probes and the warm pool live in ``scheduler.py``, ``liveness.py`` and ``warmpool.py`` and are
+mixed into ``NodeAgent``.)
+
 * **warm pool** (``warm_pool=N``): N parked interpreters with torch already imported (``runtime/zygote.py``);
   a container whose command is ``python -m mod`` / ``python script`` adopts one instead of paying the
   interpreter start + ``import torch`` (seconds) on the spawn -> Running path.
 """
 from __future__ import annotations
 
-import json
 import os
-import shutil
 import signal
 import sys
 import threading
@@ -52,17 +53,12 @@ from ..client.record import EventRecorder
 from ..core import _aitj_core as core
 from ..store.apiserver import APIError
 from ..utils import klog, lifecycle, metrics
-
-GPU_RESOURCE = M.GPU_RESOURCE
-OWN_SCHEDULERS = ("", "default-scheduler", "aitj-scheduler")
-_PASS_ENV = ("PATH", "HOME", "USER", "LANG", "LC_ALL", "LD_LIBRARY_PATH", "VIRTUAL_ENV", "PYTHONPATH", "TMPDIR",
-             "CUDA_HOME", "NCCL_DEBUG", "NCCL_SOCKET_IFNAME", "NCCL_IB_DISABLE", "TORCH_NCCL_ASYNC_ERROR_HANDLING",
-             "GRAFT_REPO_ROOT", "HF_HOME", "TORCH_HOME", "XDG_CACHE_HOME")
+from .liveness import LivenessMixin
+from .scheduler import GPU_RESOURCE, OWN_SCHEDULERS, SchedulerMixin, pod_gpu_request, pod_priority  # noqa: F401
+from .warmpool import PASS_ENV as _PASS_ENV
+from .warmpool import ZYGOTE_PREFIX, WarmPoolMixin
 
 metrics.describe("aitj_spawn_seconds", "pod bound -> all containers started")
-metrics.describe("aitj_warm_adoptions_total", "containers started by adopting a pre-warmed interpreter")
-metrics.describe("aitj_liveness_kills_total", "containers killed by a failed liveness probe / missing heartbeat")
-ZYGOTE_PREFIX = "~zygote/"     # supervisor ids of parked interpreters ('~' cannot start a namespace name)
 
 
 def detect_gpu_count() -> int:
@@ -111,13 +107,6 @@ def nvml_health_prober() -> Callable[[int], Tuple[bool, str]]:
     return probe
 
 
-pod_gpu_request = M.pod_gpu_request
-
-
-def pod_priority(pod: dict) -> int:
-    return M.priority_value(M.labels_of(pod).get(C.LABEL_PRIORITY, ""))
-
-
 def proc_start_time(pid: int) -> Optional[int]:
     """Kernel start time of ``pid`` in clock ticks since boot (field 22 of /proc/<pid>/stat) -- with the pid it
     identifies a process across agent restarts (pids are recycled, start times are not).  Read by the native core
@@ -157,7 +146,7 @@ class _PodState:
     probe_failures: Dict[str, int] = field(default_factory=dict)
 
 
-class NodeAgent:
+class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
     def __init__(self, clientset, num_gpus: Optional[int] = None, workdir: str = "/tmp/aitj-agent",
                  health_prober: Optional[Callable[[int], Tuple[bool, str]]] = None, health_period: float = 2.0,
                  cpu_slots: int = 64, image_map: Optional[Dict[str, List[str]]] = None,
@@ -265,82 +254,6 @@ class NodeAgent:
         while not stop.wait(self.health_period):
             self.check_health_once()
 
-    # ------------------------------------------------------------------ liveness probes / hang detection
-    def _probe_loop(self, stop: threading.Event) -> None:
-        while not stop.wait(0.25):
-            try:
-                self.check_liveness_once()
-            except Exception as e:  # noqa: BLE001
-                klog.V(2).info("agent: liveness pass failed: %r", e)
-
-    def check_liveness_once(self) -> None:
-        now = time.monotonic()
-        with self._lock:
-            states = [st for st in self._states.values() if st.started and st.containers]
-        for st in states:
-            pod = self.pod_lister.peek_key(st.key)          # read-only: no copy per pod per pass
-            if pod is None:
-                continue
-            if M.uid_of(pod) != st.uid or pod.get("metadata", {}).get("deletionTimestamp") or \
-                    pod.get("status", {}).get("phase") != C.POD_RUNNING:
-                continue
-            for c in pod.get("spec", {}).get("containers") or []:
-                sid = st.containers.get(c["name"])
-                if not sid or not self.sup.alive(sid):
-                    continue
-                verdict = self._probe_container(pod, st, c, now)
-                if verdict:
-                    self.recorder.event(pod, "Warning", "Unhealthy", f"Liveness probe failed: {verdict}")
-                    self.recorder.event(pod, "Normal", "Killing",
-                                        f"Container {c['name']} failed liveness probe, will be restarted")
-                    klog.warning("pod %s container %s: liveness failed (%s), killing", st.key, c["name"], verdict)
-                    metrics.inc("aitj_liveness_kills_total")
-                    st.probe_failures.pop(c["name"], None)
-                    self.sup.kill(sid, signal.SIGKILL, True)
-
-    def _probe_container(self, pod: dict, st: _PodState, c: dict, now: float) -> str:
-        """'' while the container is considered alive, else the reason to kill it."""
-        cname = c["name"]
-        env = {str(e.get("name")): str(e.get("value", "")) for e in c.get("env") or [] if "name" in e}
-        # built-in hang detection: the worker touches its heartbeat file every step
-        try:
-            hang = float(env.get("AITJ_HANG_TIMEOUT", "0") or 0)
-        except ValueError:
-            hang = 0.0
-        if hang > 0:
-            try:
-                age = time.time() - os.stat(self.heartbeat_path(pod, cname)).st_mtime
-            except OSError:
-                age = now - st.started_at            # never written: count from container start
-            if age > hang:
-                return f"no heartbeat for {age:.1f}s (AITJ_HANG_TIMEOUT={hang:g}s)"
-        probe = (c.get("livenessProbe") or {})
-        cmd = (probe.get("exec") or {}).get("command")
-        if not cmd:
-            return ""
-        period = float(probe.get("periodSeconds", 10))
-        if now - st.started_at < float(probe.get("initialDelaySeconds", 0)) or now < st.probe_next.get(cname, 0.0):
-            return ""
-        st.probe_next[cname] = now + period
-        import subprocess
-
-        gpus = [int(g) for g in (M.annotations_of(pod).get(C.ANN_GPUS) or "").split(",") if g.strip()]
-        try:
-            r = subprocess.run([str(x) for x in cmd], env=self._container_env(pod, c, gpus), capture_output=True,
-                               timeout=float(probe.get("timeoutSeconds", 1)), cwd=c.get("workingDir") or None)
-            ok, why = r.returncode == 0, f"exit code {r.returncode}"
-        except subprocess.TimeoutExpired:
-            ok, why = False, "timed out"
-        except OSError as e:
-            ok, why = False, str(e)
-        if ok:
-            st.probe_failures[cname] = 0
-            return ""
-        st.probe_failures[cname] = st.probe_failures.get(cname, 0) + 1
-        if st.probe_failures[cname] >= int(probe.get("failureThreshold", 3)):
-            return f"exec {cmd!r}: {why} ({st.probe_failures[cname]} consecutive failures)"
-        return ""
-
     def check_health_once(self) -> None:
         for i in range(self.num_gpus):
             name = self.gpu_node(i)
@@ -367,14 +280,6 @@ class NodeAgent:
         pod = obj.obj if isinstance(obj, DeletedFinalStateUnknown) else obj
         self.queue.add(M.key_of(pod))
         self._release_gpus(M.uid_of(pod))
-
-    def _kick_pending(self) -> None:
-        """A slot was freed: retry the pods that were found unschedulable (they also retry on their own once a second;
-        pods that were never looked at yet are in the queue already)."""
-        with self._lock:
-            keys, self._unschedulable = list(self._unschedulable), set()
-        for key in keys:
-            self.queue.add(key)
 
     # ------------------------------------------------------------------ main loops
     def start(self, stop: threading.Event) -> None:
@@ -490,138 +395,6 @@ class NodeAgent:
                 else:
                     self._on_exit(ev)
 
-    # ------------------------------------------------------------------ warm pool
-    def _zygote_env(self) -> Dict[str, str]:
-        env = {k: os.environ[k] for k in _PASS_ENV if k in os.environ}
-        env["PYTHONUNBUFFERED"] = "1"
-        return env
-
-    def _ensure_pool(self) -> None:
-        """Top the pool up to ``warm_pool`` parked interpreters (no-op when disabled or shutting down)."""
-        if self.warm_pool <= 0 or self._stopping or self._zy_failures >= 3:
-            return
-        os.makedirs(self._zy_dir, exist_ok=True)
-        with self._lock:
-            while len(self._zygotes) < self.warm_pool:
-                # GPU box: one parked interpreter per GPU slot, CUDA context included; CPU-only box: generic ones
-                gpu = None
-                if self.num_gpus > 0:
-                    taken = {z["gpu"] for z in self._zygotes.values()}
-                    gpu = next((g for g in range(min(self.num_gpus, self.warm_pool)) if g not in taken), None)
-                    if gpu is None:
-                        return
-                self._zy_seq += 1
-                zid = f"{ZYGOTE_PREFIX}{os.getpid()}-{self._zy_seq}"
-                fifo = os.path.join(self._zy_dir, f"z{os.getpid()}-{self._zy_seq}.fifo")
-                for path in (fifo, fifo + ".ready"):
-                    try:
-                        os.unlink(path)
-                    except OSError:
-                        pass
-                try:
-                    os.mkfifo(fifo, 0o600)
-                    env = self._zygote_env()
-                    cmd = [sys.executable, "-m", "trainingjob_operator_b200.runtime.zygote", fifo]
-                    if gpu is not None:
-                        env["CUDA_VISIBLE_DEVICES"] = str(gpu)
-                        env["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
-                        cmd.append("--cuda")
-                    self.sup.spawn(zid, cmd, env, "", os.path.join(self.log_dir, "zygotes.log"), "",
-                                   self._cpus_for([gpu]) if gpu is not None else [])
-                except OSError as e:
-                    klog.warning("warm pool: cannot start an interpreter: %s", e)
-                    self._zy_failures += 1
-                    return
-                self._zygotes[zid] = {"fifo": fifo, "spawned": time.monotonic(), "gpu": gpu}
-
-    def warm_ready(self) -> int:
-        """Number of parked interpreters that finished their imports."""
-        with self._lock:
-            return sum(1 for z in self._zygotes.values() if os.path.exists(z["fifo"] + ".ready"))
-
-    def _on_zygote_exit(self, ev: Dict[str, Any]) -> None:
-        with self._lock:
-            z = self._zygotes.pop(ev["id"], None)
-        if z is None:
-            return
-        for path in (z["fifo"], z["fifo"] + ".ready"):
-            try:
-                os.unlink(path)
-            except OSError:
-                pass
-        if self._stopping:
-            return
-        if time.monotonic() - z["spawned"] < 5.0:
-            self._zy_failures += 1
-            klog.warning("warm pool: parked interpreter exited early (code %s)", ev.get("exit_code"))
-        self._ensure_pool()
-
-    def _kill_zygotes(self) -> None:
-        self._stopping = True
-        with self._lock:
-            ids = list(self._zygotes)
-        for zid in ids:
-            self.sup.kill(zid, signal.SIGKILL, True)
-
-    def _adopt_zygote(self, sid: str, argv: List[str], env: Dict[str, str], cwd: str, log: str,
-                      cpus: List[int]) -> bool:
-        """Start the container by handing it to a parked interpreter.  False => caller spawns it cold."""
-        if self.warm_pool <= 0 or self._stopping:
-            return False
-        from ..runtime.zygote import split_python_command
-
-        if split_python_command(argv) is None:
-            return False
-        exe = shutil.which(argv[0], path=env.get("PATH")) or argv[0]
-        try:
-            if os.path.realpath(exe) != os.path.realpath(sys.executable):
-                return False
-        except OSError:
-            return False
-        want_gpu: Optional[int] = None
-        if self.num_gpus > 0:
-            vis = env.get("CUDA_VISIBLE_DEVICES", "")
-            if not vis.isdigit():
-                return False          # CPU-only or multi-GPU container: parked interpreters are pinned to one slot each
-            want_gpu = int(vis)
-        with self._lock:
-            zid = next((z for z, info in self._zygotes.items()
-                        if info["gpu"] == want_gpu and os.path.exists(info["fifo"] + ".ready")), None)
-            info = self._zygotes.pop(zid) if zid else None
-        if info is None:
-            return False
-        fd = -1
-        deadline = time.monotonic() + 0.25
-        while fd < 0:
-            try:
-                fd = os.open(info["fifo"], os.O_WRONLY | os.O_NONBLOCK)
-            except OSError:          # ENXIO: the reader has not reached open() yet
-                if time.monotonic() > deadline:
-                    break
-                time.sleep(0.002)
-        ok = fd >= 0 and self.sup.rename(zid, sid)
-        if ok:
-            msg = json.dumps({"argv": argv, "env": env, "cwd": cwd, "log": log, "cpus": cpus}) + "\n"
-            try:
-                os.write(fd, msg.encode())
-            except OSError:
-                ok = False
-                self.sup.kill(sid, signal.SIGKILL, True)
-        if fd >= 0:
-            os.close(fd)
-        if not ok:
-            self.sup.kill(zid, signal.SIGKILL, True)
-            for path in (info["fifo"], info["fifo"] + ".ready"):
-                try:
-                    os.unlink(path)
-                except OSError:
-                    pass
-        else:
-            metrics.inc("aitj_warm_adoptions_total")
-            klog.V(2).info("container %s adopted parked interpreter %s", sid, zid)
-        threading.Thread(target=self._ensure_pool, daemon=True).start()
-        return ok
-
     def _sweep_loop(self, stop: threading.Event) -> None:
         n = 0
         while not stop.wait(5.0):
@@ -691,139 +464,6 @@ class NodeAgent:
             return
         if phase == C.POD_PENDING:
             self._start_pod(pod, key)
-
-    # ------------------------------------------------------------------ scheduler
-    def _free_gpus(self) -> List[int]:
-        ready = set()
-        for n in self.node_lister.peek():
-            nm = M.name_of(n)
-            if not nm.startswith(f"{self.prefix}gpu-"):
-                continue
-            if any(c.get("type") == "Ready" and c.get("status") == "True"
-                   for c in n.get("status", {}).get("conditions") or []):
-                ready.add(int(nm.rsplit("-", 1)[1]))
-        busy = set()
-        live_uids = set()
-        for p in self.pod_lister.peek():
-            done = (p.get("status", {}).get("phase") or C.POD_PENDING) in (C.POD_SUCCEEDED, C.POD_FAILED)
-            if not done:
-                live_uids.add(M.uid_of(p))
-            if not p.get("spec", {}).get("nodeName") or done:
-                continue
-            for g in (M.annotations_of(p).get(C.ANN_GPUS) or "").split(","):
-                if g.strip():
-                    busy.add(int(g))
-        with self._lock:
-            # drop allocations whose pod is finished or gone (seen by the cache); keep binds the cache has not
-            # caught up with yet (younger than 1 s)
-            for g, (uid, at) in list(self._gpu_owner.items()):
-                if uid not in live_uids and time.monotonic() - at > 1.0:
-                    del self._gpu_owner[g]
-            busy |= set(self._gpu_owner)
-        return sorted(ready - busy)
-
-    def schedule(self, pod: dict) -> None:
-        if (pod.get("spec", {}).get("schedulerName") or "") not in OWN_SCHEDULERS:
-            return
-        want = pod_gpu_request(pod)
-        ns, name = M.namespace_of(pod), M.name_of(pod)
-        with self._lock:
-            if M.uid_of(pod) in self._bound:
-                return                      # already bound by us; the informer just has not caught up
-            if len(self._bound) > 4096:
-                cutoff = time.monotonic() - 60.0
-                self._bound = {u: t for u, t in self._bound.items() if t > cutoff}
-        if want == 0:
-            self._bind(pod, self.cpu_node, [])
-            return
-        # higher-priority pending pods go first: yield if someone more important is waiting
-        mine = (pod_priority(pod), )
-        for other in self.pod_lister.peek():
-            if other.get("spec", {}).get("nodeName") or M.uid_of(other) == M.uid_of(pod):
-                continue
-            if other.get("metadata", {}).get("deletionTimestamp") or pod_gpu_request(other) == 0:
-                continue
-            if (pod_priority(other),) > mine:
-                self.queue.add_after(M.key_of(pod), 0.05)
-                free = self._free_gpus()
-                if len(free) < pod_gpu_request(other) + want:
-                    self._mark_unschedulable(pod, f"0/{self.num_gpus} nodes are available: waiting for "
-                                             f"higher-priority pod {M.name_of(other)}.")
-                    return
-        with self._lock:
-            free = self._free_gpus()
-            if len(free) < want:
-                total = self.num_gpus
-                self._mark_unschedulable(pod, f"0/{total} nodes are available: {total - len(free)} Insufficient "
-                                         f"{GPU_RESOURCE}, {len(free)} free but {want} requested.")
-                return
-            gpus = free[:want]
-            if want == 1:
-                # rank i prefers GPU slot i when it is free: replicas are created in parallel, so arrival order is not
-                # rank order, and a stable rank -> GPU mapping is what the pinned warm pool and a human reading
-                # nvidia-smi both expect
-                try:
-                    pref = int(M.labels_of(pod).get(C.LABEL_REPLICA_INDEX, "")) % max(1, self.num_gpus)
-                    if pref in free:
-                        gpus = [pref]
-                except ValueError:
-                    pass
-            for g in gpus:
-                self._gpu_owner[g] = (M.uid_of(pod), time.monotonic())
-            try:
-                self._bind(pod, self.gpu_node(gpus[0]), gpus)
-            except APIError:
-                for g in gpus:
-                    self._gpu_owner.pop(g, None)
-                raise
-
-    def _release_gpus(self, uid: str, kick: bool = True) -> None:
-        with self._lock:
-            for g in [g for g, (u, _t) in self._gpu_owner.items() if u == uid]:
-                del self._gpu_owner[g]
-            # `_bound` keeps the uid (pruned by age in `schedule`): a pod that ran to completion before the informer cache
-            # even showed it as bound must not be bound a second time by a stale queue entry
-        if kick:
-            self._kick_pending()
-
-    def _mark_unschedulable(self, pod: dict, message: str) -> None:
-        self.queue.add_after(M.key_of(pod), 1.0)   # safety net: retry even if no event announces a free GPU
-        with self._lock:
-            self._unschedulable.add(M.key_of(pod))
-        conds = pod.get("status", {}).get("conditions") or []
-        cur = M.condition(conds, "PodScheduled")
-        if cur is not None and cur.get("status") == "False" and cur.get("message") == message:
-            return
-        patch = {"status": {"phase": C.POD_PENDING, "conditions": [
-            {"type": "PodScheduled", "status": "False", "reason": "Unschedulable", "message": message,
-             "lastTransitionTime": M.format_time()}]}}
-        self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch, subresource="status")
-
-    def _bind(self, pod: dict, node: str, gpus: List[int]) -> None:
-        patch = {"spec": {"nodeName": node},
-                 "metadata": {"annotations": {C.ANN_GPUS: ",".join(str(g) for g in gpus)}},
-                 "status": {"phase": C.POD_PENDING, "hostIP": "127.0.0.1", "podIP": "127.0.0.1",
-                            "conditions": [{"type": "PodScheduled", "status": "True",
-                                            "lastTransitionTime": M.format_time()}]}}
-        with self._lock:
-            self._bound[M.uid_of(pod)] = time.monotonic()
-        try:
-            bound = self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch)
-        except APIError:
-            with self._lock:
-                self._bound.pop(M.uid_of(pod), None)
-            raise
-        klog.V(2).info("scheduled %s -> %s gpus=%s", M.key_of(pod), node, gpus)
-        # scheduler and kubelet are one process here: start the containers from the object the bind returned instead of
-        # waiting for it to come back through the informer (one watch round trip per replica on the submit -> Running path)
-        if isinstance(bound, dict) and bound.get("spec", {}).get("nodeName") == node and \
-                not bound.get("metadata", {}).get("deletionTimestamp"):
-            try:
-                self._start_pod(bound, M.key_of(pod))
-                return
-            except APIError as e:
-                klog.V(2).info("agent: direct start of %s failed (%s), retrying through the queue", M.key_of(pod), e.message)
-        self.queue.add(M.key_of(pod))
 
     # ------------------------------------------------------------------ kubelet: start
     def _container_argv(self, c: dict) -> Tuple[Optional[List[str]], str]:
