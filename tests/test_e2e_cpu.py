@@ -378,6 +378,18 @@ def test_cli_create_and_wait_for_scripting(lc, tmp_path):
         kubectl.parse_timeout("-1s") > 3600
 
 
+def test_control_plane_throughput_does_not_collapse_with_the_number_of_jobs():
+    """Guards the scaling fixes of DESIGN.md §2 (the same run took 12 s for 20 jobs before them): 30 jobs x 4 replicas of
+    /bin/true submitted at once all reach Succeed, and they do so at a rate that a per-job cost growing with the number of
+    jobs could not sustain.  Generous bound: CI boxes are slow, the regression was 10x."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import throughput_bench
+
+    out = throughput_bench.run(30, 4, 4)
+    assert out["completed"] == 30
+    assert out["all_succeed_s"] < 20.0, out
+
+
 def test_leader_failover_keeps_the_job_running(tmp_path):
     """BASELINE config 5 shape: two operators, kill the leader, the standby takes over, workers never notice."""
     opt = TrainingJobOperatorOption(thread_num=1)
