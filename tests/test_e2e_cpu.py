@@ -553,6 +553,22 @@ def test_fault_tolerant_job_survives_the_loss_of_rank0_in_place(tmp_path):
     assert out["kill_to_first_step_s"] < 60
 
 
+def test_fault_tolerant_job_survives_a_second_loss_during_the_recovery(tmp_path):
+    """Rank 2 dies while the survivors are still waiting to rendezvous with rank 1's replacement: the controller publishes
+    another generation, the waiting ranks abandon the stale rendezvous at once (no 30 s attempt) and everybody meets on
+    the newest one; the two survivors keep their processes and their state throughout."""
+    import subprocess
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fault_check.py"), "mlp", "4", "0", "--cpu",
+                        "--fault-tolerant", "--victim", "1", "--second-victim", "2", "--second-after", "0.7"],
+                       cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["restart_counts"] == {"trainer": 2} and out["survivors_kept_their_process"]
+    assert out["recovery"]["generation"] >= 3 and out["recovery"]["world"] == 4
+    assert out["kill_to_first_step_s"] < 25                       # far below one rendezvous attempt (30 s)
+
+
 def test_hang_detection_and_exec_liveness_probe(lc):
     """A worker that stops heart-beating for AITJ_HANG_TIMEOUT seconds is killed (exit 137) and restarted by the job's
     policy; a failing ``livenessProbe.exec`` does the same (kubelet semantics the reference relies on)."""

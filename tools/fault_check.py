@@ -3,7 +3,7 @@
 Reports kill -> job Running again -> first training step after the restart.
 
     python tools/fault_check.py [model] [n] [warm_pool] [--cpu] [--scope Pod|All] [--hang SECONDS] [--fault-tolerant]
-          [--victim RANK]
+          [--victim RANK] [--second-victim RANK --second-after SECONDS]
 
 ``--scope Pod --hang S``: only the killed replica is re-created by the controller; the survivors, stuck in a collective
 with a dead peer, are caught by the agent's heartbeat-based hang detection after S seconds and restarted too.
@@ -34,6 +34,8 @@ hang = sys.argv[sys.argv.index("--hang") + 1] if "--hang" in sys.argv else ""
 ft = "--fault-tolerant" in sys.argv
 victim_arg = sys.argv[sys.argv.index("--victim") + 1] if "--victim" in sys.argv else ""
 victim = int(victim_arg) if victim_arg else min(3, n - 1)
+second = int(sys.argv[sys.argv.index("--second-victim") + 1]) if "--second-victim" in sys.argv else None
+second_after = float(sys.argv[sys.argv.index("--second-after") + 1]) if "--second-after" in sys.argv else 0.0
 batch = {"bert": 8, "mlp": 16, "gpt2": 4, "resnet50": 32}.get(model, 8)
 worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", model, "--batch", str(batch),
           "--steps", "0", "--ckpt-every", "10"] + (["--cpu", "--step-sleep", "0.02"] if cpu else []) + \
@@ -91,8 +93,14 @@ with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thr
     t_kill = time.time()
     os.kill(pid, signal.SIGKILL)
     if ft:
-        rec = wait(lambda: (lambda a: json.loads(a["aitj.b200/rescale-trace"]) if "aitj.b200/rescale-trace" in a
-                            else None)(lc.jobs().get("ft").annotations))
+        want_gen = 2
+        if second is not None:             # a second rank dies while the first loss is still being repaired
+            time.sleep(second_after)
+            os.kill(pids[f"ft-trainer-{second}"], signal.SIGKILL)
+            want_gen = 3
+            out["second_victim_rank"], out["second_after_s"] = second, second_after
+        rec = wait(lambda: (lambda r: r if r and r.get("generation", 0) >= want_gen and r.get("recovered_from") else None)(
+            json.loads(lc.jobs().get("ft").annotations.get("aitj.b200/rescale-trace", "null"))))
         out["kill_to_first_step_s"] = round(rec["at"] - t_kill, 3)
         out["recovery"] = {k: rec.get(k) for k in ("generation", "world", "seconds", "teardown_s", "init_pg_s",
                                                     "sync_state_s", "first_step_s", "recovered_from")}
@@ -101,7 +109,7 @@ with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thr
         out["kill_to_running_s"] = round(time.time() - t_kill, 3)
         now = {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/ft-trainer-" in sid}
         out["survivors_kept_their_process"] = all(now.get(k) == v for k, v in pids.items()
-                                                  if k != f"ft-trainer-{victim}")
+                                                  if k not in (f"ft-trainer-{victim}", f"ft-trainer-{second}"))
         j = lc.jobs().get("ft")
         out["restart_counts"] = j.status.restart_counts
         out["conditions"] = [c.type for c in j.status.conditions][-6:]
@@ -112,8 +120,8 @@ with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thr
         os.makedirs("gpurun_out", exist_ok=True)
         json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_ft.json", "w"), indent=1)
         print(json.dumps(out))
-        sys.exit(0 if out["restart_counts"].get("trainer", 0) == 1 and out["survivors_kept_their_process"] and
-                 out["recovery"]["recovered_from"] else 1)
+        sys.exit(0 if out["restart_counts"].get("trainer", 0) == (1 if second is None else 2) and
+                 out["survivors_kept_their_process"] and out["recovery"]["recovered_from"] else 1)
     wait(lambda: (lambda j: j.status.phase == "Running" and j.status.restart_counts.get("trainer", 0) >= 1 and
                   j.status.replica_statuses["trainer"].active == n)(lc.jobs().get("ft")))
     out["kill_to_running_s"] = round(time.time() - t_kill, 3)
