@@ -233,10 +233,11 @@ def teardown_group(broken: bool = False) -> None:
         print(f"[worker] destroy of the broken process group raised {type(e).__name__}", flush=True)
 
 
-def wait_for_newer_generation(watcher, generation: int, timeout_s: float) -> Optional[Dict[str, int]]:
-    """After a peer was lost: the controller replaces it and publishes the next rendezvous generation; poll for it."""
+def wait_for_newer_generation(watcher, generation: int, timeout_s: float, should_stop=None) -> Optional[Dict[str, int]]:
+    """After a peer was lost: the controller replaces it and publishes the next rendezvous generation; poll for it.
+    ``should_stop()`` (SIGTERM received: the job is being torn down instead of repaired) ends the wait."""
     deadline = time.time() + timeout_s
-    while time.time() < deadline:
+    while time.time() < deadline and not (should_stop is not None and should_stop()):
         latest = watcher.fetch_now()
         if latest is not None and latest["generation"] > generation:
             return latest

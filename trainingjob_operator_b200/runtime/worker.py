@@ -419,7 +419,11 @@ def run(args) -> Dict[str, Any]:
             adapter.discard_step()
             teardown_group(broken=True)
             gc.collect()
-            target = wait_for_newer_generation(watcher, generation, float(os.environ.get("AITJ_FT_WAIT", "120")))
+            target = wait_for_newer_generation(watcher, generation, float(os.environ.get("AITJ_FT_WAIT", "120")),
+                                               should_stop=lambda: stop["flag"])
+            if target is None and stop["flag"]:
+                print(f"[worker {rank}] terminated while waiting for the job to be repaired", flush=True)
+                break
             if target is None:
                 print(f"[worker {rank}] no new rendezvous generation was published: giving up", flush=True)
                 raise RuntimeError(f"collective failed and the job was not repaired: {failure[0]}: {failure[1]}")
