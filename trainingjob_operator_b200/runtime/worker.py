@@ -578,15 +578,21 @@ def _record_exit(code: int) -> None:
         pass
 
 
-if __name__ == "__main__":
+def cli() -> None:
+    """Process entry point (``python -m ...runtime.worker`` and the ``aitj-worker`` script): runs ``main`` and records the
+    exit code in ``$AITJ_EXIT_FILE`` however it ends."""
     try:
-        _code = main()
+        code = main()
     except SystemExit as e:
-        _code = e.code if isinstance(e.code, int) else (0 if e.code is None else 1)
-        _record_exit(_code)
+        code = e.code if isinstance(e.code, int) else (0 if e.code is None else 1)
+        _record_exit(code)
         raise
     except BaseException:
         _record_exit(1)
         raise
-    _record_exit(_code)
-    sys.exit(_code)
+    _record_exit(code)
+    sys.exit(code)
+
+
+if __name__ == "__main__":
+    cli()
