@@ -341,6 +341,8 @@ def test_cli_workflow_matches_readme(lc, tmp_path):
     assert lc.jobs().get("paddle-mnist").annotations["note"] == "hello"
     rc, out = run("api-resources")
     assert "aitrainingjobs" in out and "aitj" in out
+    rc, out = run("top")
+    assert rc == 0 and out.splitlines()[0].split()[:4] == ["NAME", "PHASE", "WORLD", "SAMPLES/S"] and "paddle-mnist" in out
     rc, out = run("delete", "-f", path)
     assert rc == 0 and 'aitrainingjob.elasticdeeplearning.ai "paddle-mnist" deleted' in out
     wait_until(lambda: lc.pods() == [])

@@ -579,6 +579,29 @@ class CLI:
         self.p(table(rows))
         return 0
 
+    def top(self, namespace: str, all_ns: bool) -> int:
+        """``kubectl top``'s place in this world: what the jobs' rank-0 workers last reported (``aitj.b200/metrics``,
+        ``aitj.b200/rescale-trace``) -- throughput, step time, world size, in-place recoveries."""
+        jobs = self.cs.elasticdeeplearning_v1().aitrainingjobs("" if all_ns else namespace).list().items
+        rows = [["NAME", "PHASE", "WORLD", "SAMPLES/S", "MS/STEP", "STEPS", "RECOVERIES", "LAST RESCALE"]]
+        for j in jobs:
+            try:
+                m = json.loads(j.annotations.get("aitj.b200/metrics", "{}")) or {}
+                r = json.loads(j.annotations.get("aitj.b200/rescale-trace", "{}")) or {}
+            except ValueError:
+                m, r = {}, {}
+            world = sum((j.status.rendezvous.world_sizes or {}).values()) if j.status.rendezvous else ""
+            rows.append([j.name, j.status.phase or "<none>", str(world or "<none>"),
+                         f"{m['samples_per_sec']:.1f}" if m.get("samples_per_sec") else "<none>",
+                         f"{m['ms_per_step']:.2f}" if m.get("ms_per_step") else "<none>",
+                         str(m.get("steps_done", "<none>")), str(m.get("recoveries", 0)),
+                         f"{r['seconds']:.2f}s -> world {r.get('world')}" if r.get("seconds") else "<none>"])
+        if len(rows) == 1:
+            self.p("No resources found.")
+            return 0
+        self.p(table(rows))
+        return 0
+
     def inject(self, what: str, target: str, namespace: str, value: str) -> int:
         """Fault injection: ``gpu-fault gpu-3`` / ``gpu-heal gpu-3`` mark a GPU slot NotReady / Ready;
         ``preempt <job>`` / ``fail <job>`` write the external control annotations (pod.go:160-165)."""
@@ -629,6 +652,8 @@ def build_parser() -> argparse.ArgumentParser:
     lg = sub.add_parser("logs"); lg.add_argument("pod"); lg.add_argument("-c", "--container")
     lg.add_argument("--workdir", default=os.path.expanduser("~/.aitj")); lg.add_argument("--tail", type=int)
     lg.add_argument("-f", "--follow", action="store_true"); common(lg)
+    tp = sub.add_parser("top"); tp.add_argument("resource", nargs="?", default="aitj")
+    tp.add_argument("-A", "--all-namespaces", action="store_true"); common(tp)
     sub.add_parser("api-resources")
     sub.add_parser("version")
     sub.add_parser("cluster-info")
@@ -678,6 +703,8 @@ def main(argv=None, clientset: Optional[Clientset] = None, out=sys.stdout) -> in
             return cli.edit(args.resource, args.name, ns)
         if args.cmd == "logs":
             return cli.logs(args.pod, ns, args.container, args.workdir, args.tail, args.follow)
+        if args.cmd == "top":
+            return cli.top(ns, args.all_namespaces)
         if args.cmd == "api-resources":
             return cli.api_resources()
         if args.cmd == "version":
