@@ -431,10 +431,13 @@ def test_elastic_rescale_with_gloo_workers(tmp_path):
                    "replicas": 2, "minReplicas": 2, "maxReplicas": 4, "edlPolicy": "Manual",
                    "template": {"spec": {"containers": [{"name": "aitj-trainer", "command": worker,
                                                          "workingDir": ROOT,
-                                                         "env": [{"name": "PYTHONPATH", "value": ROOT}]}]}}}}}}
+                                                         "env": [{"name": "PYTHONPATH", "value": ROOT},
+                                                                 {"name": "AITJ_REPORT_EVERY", "value": "0.5"}]}]}}}}}}
         lc2.apply(job)
         wait_until(lambda: lc2.jobs().get("el").status.phase == "Running", timeout=60)
         wait_until(lambda: "aitj.b200/worker-trace" in lc2.jobs().get("el").annotations, timeout=90)
+        live = wait_until(lambda: json.loads(lc2.jobs().get("el").annotations.get("aitj.b200/metrics", "null")), timeout=30)
+        assert live["live"] and live["world"] == 2 and live["samples_per_sec"] > 0      # interim report of a running job
         pids = pod_pids(lc2, "el")
         # ---- scale up 2 -> 3
         lc2.jobs().patch("el", {"spec": {"replicaSpecs": {"trainer": {"replicas": 3}}}})

@@ -181,5 +181,11 @@ class ElasticWatcher:
         keep["recoveries"] = len(result.get("recoveries") or [])
         self._annotate(ANN_METRICS, keep)
 
+    def report_live(self, rank: int, rec: Dict[str, Any]) -> None:
+        """Interim throughput of a running job (``aitjctl top``, ``aitj_job_samples_per_second``): written from a
+        short-lived side thread so the step loop never waits for the API server."""
+        if rank == 0:
+            threading.Thread(target=self._annotate, args=(ANN_METRICS, dict(rec, live=True)), daemon=True).start()
+
     def stop(self) -> None:
         self._stop.set()

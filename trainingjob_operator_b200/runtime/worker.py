@@ -347,6 +347,9 @@ def run(args) -> Dict[str, Any]:
     from ..ops import lib as oplib
 
     launches0 = 0
+    # rank 0 publishes its wall-clock throughput every AITJ_REPORT_EVERY seconds (0 = only the final, device-timed result)
+    report_every = float(os.environ.get("AITJ_REPORT_EVERY", "10"))
+    live_t0, live_step0 = time.time(), step
     while step < total and not stop["flag"]:
         if breaker is not None:
             breaker.progress(generation)
@@ -480,6 +483,13 @@ def run(args) -> Dict[str, Any]:
             trace["first_step_done"] = time.time()
             if watcher is not None:
                 watcher.report_trace(rank, trace)
+        if rank == 0 and watcher is not None and report_every > 0 and time.time() - live_t0 >= report_every:
+            dt, n = time.time() - live_t0, step - live_step0
+            if n > 0:
+                watcher.report_live(rank, {"samples_per_sec": round(args.batch * world * n / dt, 2),
+                                           "ms_per_step": round(dt * 1e3 / n, 3), "world": world, "steps_done": step,
+                                           "global_batch": args.batch * world, "recoveries": len(recoveries)})
+            live_t0, live_step0 = time.time(), step
         if args.ckpt_every > 0 and rank == 0 and step % args.ckpt_every == 0:
             save_checkpoint(args, adapter, adapter.step_count)
         if args.step_sleep > 0:
