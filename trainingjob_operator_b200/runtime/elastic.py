@@ -179,13 +179,22 @@ class ElasticWatcher:
         keep = {k: result.get(k) for k in ("samples_per_sec", "ms_per_step", "global_batch", "world", "steps_done",
                                            "loss_first", "loss_last", "gpu_launches", "cuda_graph")}
         keep["recoveries"] = len(result.get("recoveries") or [])
+        t = getattr(self, "_live_thread", None)
+        if t is not None:
+            t.join(5.0)                     # an interim report in flight must not land after (and over) the final one
         self._annotate(ANN_METRICS, keep)
 
     def report_live(self, rank: int, rec: Dict[str, Any]) -> None:
         """Interim throughput of a running job (``aitjctl top``, ``aitj_job_samples_per_second``): written from a
         short-lived side thread so the step loop never waits for the API server."""
-        if rank == 0:
-            threading.Thread(target=self._annotate, args=(ANN_METRICS, dict(rec, live=True)), daemon=True).start()
+        if rank != 0:
+            return
+        t = getattr(self, "_live_thread", None)
+        if t is not None and t.is_alive():
+            return                          # the previous report is still on its way: skip this one
+        self._live_thread = threading.Thread(target=self._annotate, args=(ANN_METRICS, dict(rec, live=True)),
+                                             daemon=True)
+        self._live_thread.start()
 
     def stop(self) -> None:
         self._stop.set()
