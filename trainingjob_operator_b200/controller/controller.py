@@ -249,7 +249,6 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
         return True
 
     def _forget_job(self, key: str) -> None:
-        self.forget_rendezvous(key)
         with self._written_lock:
             self._written_rv.pop(key, None)
 

@@ -127,9 +127,6 @@ class ElasticMixin:
         tr["rescales"] = tr["rescales"][-16:]
         job.set_annotation(C.ANN_TRACE, json.dumps(tr, sort_keys=True))
 
-    def forget_rendezvous(self, key: str) -> None:
-        return
-
     # ------------------------------------------------------------------ edlPolicy: Auto
     def reconcile_elastic(self, job: AITrainingJob, pods: List[dict]) -> bool:
         """For ``edlPolicy: Auto`` roles choose replicas in [min,max] from free healthy GPU slots.
