@@ -35,10 +35,3 @@ def set_defaults_aitrainingjob(job: AITrainingJob) -> AITrainingJob:
     for spec in job.spec.replica_specs.values():
         set_defaults_replica_spec(spec)
     return job
-
-
-def set_defaults_dict(obj: dict) -> dict:
-    """Default a JSON dict in place-free fashion; returns a new dict."""
-    job = AITrainingJob.from_dict(obj)
-    set_defaults_aitrainingjob(job)
-    return job.to_dict()

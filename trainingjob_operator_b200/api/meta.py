@@ -142,10 +142,6 @@ def parse_selector(sel: Optional[str]) -> Dict[str, str]:
     return out
 
 
-def format_selector(sel: Dict[str, str]) -> str:
-    return ",".join(f"{k}={v}" for k, v in sorted(sel.items()))
-
-
 def selector_matches(selector: Dict[str, str], labels: Dict[str, str]) -> bool:
     return all(labels.get(k) == v for k, v in selector.items())
 

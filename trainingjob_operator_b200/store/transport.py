@@ -221,14 +221,3 @@ class HTTPTransport(Transport):
             except ValueError:
                 raise APIError(resp.status, "InternalError", raw.decode(errors="replace")[:300]) from None
         return _HTTPWatch(conn, resp)
-
-    def raw_get(self, path: str) -> Any:
-        return self._request("GET", path)
-
-
-def transport_for(master: Optional[str] = None, server: Optional[APIServer] = None) -> Transport:
-    if server is not None:
-        return LocalTransport(server)
-    if not master:
-        raise ValueError("either an in-process APIServer or --master URL is required")
-    return HTTPTransport(master)
