@@ -356,16 +356,10 @@ class PodReconciler:
                     return cond.get("message", "")
         return ""
 
-    def force_delete_pod(self, namespace: str, name: str, job) -> None:
-        """pod.go:469-481: grace period 0."""
-        try:
-            self.pod_control.delete_pod(namespace, name, job, grace_period_seconds=0)
-        except APIError as e:
-            klog.error("Delete job pod %s/%s failed, reason: %s", namespace, name, e.message)
-
     def delete_pods_expecting(self, job: AITrainingJob, victims: List[dict], grace: Optional[int]) -> None:
         """Delete pods and record the expected deletions (the reference observes deletions without ever
-        expecting them)."""
+        expecting them).  ``grace=0`` is the reference's ``forceDeletePod`` (pod.go:469-481), used for
+        replicas on a failed node; ``None`` is the pod's own termination grace period."""
         per_role: Dict[str, int] = {}
         for p in victims:
             rt = M.labels_of(p).get(C.LABEL_REPLICA_NAME, "")
