@@ -422,13 +422,22 @@ class PodReconciler:
                 errors.append(e)
             metrics.observe("aitj_pod_create_seconds", time.perf_counter() - t0)
 
-        if len(templates) == 1:
-            one(templates[0])
+        # Concurrency only pays when a create is a network round trip (separate API server process); against the
+        # in-process store the creates are sub-millisecond and pure CPU, so threads would just queue on the GIL.
+        remote = getattr(getattr(self.kube_client, "transport", None), "master", None) is not None
+        if len(templates) == 1 or not remote:
+            for item in templates:
+                one(item)
         else:
-            with cf.ThreadPoolExecutor(max_workers=min(16, len(templates))) as ex:
-                list(ex.map(one, templates))
+            list(self._create_pool().map(one, templates))
         if errors:
             raise errors[0]
+
+    def _create_pool(self) -> cf.ThreadPoolExecutor:
+        pool = getattr(self, "_pod_create_pool", None)
+        if pool is None:                    # one long-lived pool per controller, not one per reconcile pass
+            pool = self._pod_create_pool = cf.ThreadPoolExecutor(max_workers=16, thread_name_prefix="pod-create")
+        return pool
 
     def build_pod_template(self, job: AITrainingJob, rt: str, index: str, restart_count: str,
                            spec: ReplicaSpec) -> dict:
