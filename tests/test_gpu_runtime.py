@@ -37,3 +37,22 @@ def test_async_checkpoint_snapshots_in_stream_order_on_the_device(tmp_path):
     """ % (ROOT, str(tmp_path / "s.pt"), str(tmp_path / "s.pt")))
     r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_fault_tolerant_recovery_keeps_the_survivor_on_its_gpu(tmp_path):
+    """In-place recovery over NCCL (needs two GPUs): SIGKILL rank 1 of a faultTolerant BERT-shaped job; rank 0 keeps its
+    process, CUDA context and state (the StallBreaker aborts the communicator it is stuck in), the replacement joins."""
+    import json
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fault_check.py"), "bert", "2", "0",
+                        "--fault-tolerant", "--victim", "1"], cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=420)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["survivors_kept_their_process"] and out["restart_counts"] == {"trainer": 1}
+    assert out["recovery"]["world"] == 2 and out["recovery"]["recovered_from"]
