@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 echo "== async checkpoint, CUDA path"
-timeout 300 python -m pytest tests/test_gpu_runtime.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/followup_ckpt.txt
+AITJ_GPU_FT_TEST=1 timeout 700 python -m pytest tests/test_gpu_runtime.py -q -m gpu 2>&1 | tail -3 | tee gpurun_out/followup_ckpt.txt
 echo "== in-place recovery (faultTolerant), BERT-shaped, 4 ranks, rank 0 and rank 3 killed"
 for v in 0 3; do
   timeout 420 python tools/fault_check.py bert 4 0 --fault-tolerant --victim $v 2>&1 | grep '^{' | tee -a gpurun_out/followup_fault_tolerant.jsonl
