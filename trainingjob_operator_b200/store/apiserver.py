@@ -286,7 +286,8 @@ class APIServer:
                                      M.owner_uids(obj))
         except core.StoreError as e:
             raise _wrap(e) from None
-        return self._decode(rec)
+        md["resourceVersion"] = str(rec["rv"])      # `obj` is our own copy and exactly what was stored: no re-parse
+        return obj
 
     def get(self, info: R.ResourceInfo, namespace: str, name: str) -> Dict[str, Any]:
         return self._decode(self._get_record(info, namespace, name))
@@ -320,14 +321,18 @@ class APIServer:
                 "metadata": {"resourceVersion": str(rv)}, "items": items}
 
     def update(self, info: R.ResourceInfo, namespace: str, name: str, obj: Dict[str, Any],
-               subresource: str = "") -> Dict[str, Any]:
+               subresource: str = "", _cur: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        """``_cur``: the live object the caller has just read and built ``obj`` from (``patch``); saves reading and
+        parsing it a second time -- if it is stale the store's optimistic-concurrency check says so (Conflict)."""
         self.request_count += 1
         ns = self._ns(info, namespace or M.namespace_of(obj), True)
-        try:
-            cur_rec = self._store.get(info.kind, ns, name)
-        except core.StoreError as e:
-            raise _wrap(e) from None
-        cur = self._decode(cur_rec)
+        if _cur is not None and obj.get("metadata", {}).get("resourceVersion"):
+            cur = _cur
+        else:
+            try:
+                cur = self._decode(self._store.get(info.kind, ns, name))
+            except core.StoreError as e:
+                raise _wrap(e) from None
         new = M.deepcopy(obj)
         md = new.setdefault("metadata", {})
         if md.get("name") and md["name"] != name:
@@ -366,7 +371,8 @@ class APIServer:
                                      M.owner_uids(new), expected)
         except core.StoreError as e:
             raise _wrap(e) from None
-        return self._decode(rec)
+        md["resourceVersion"] = str(rec["rv"])
+        return new
 
     def patch(self, info: R.ResourceInfo, namespace: str, name: str, patch: Any,
               patch_type: str = "application/merge-patch+json", subresource: str = "") -> Dict[str, Any]:
@@ -379,7 +385,7 @@ class APIServer:
                 new = merge_patch(cur, patch)
             new["metadata"]["resourceVersion"] = cur["metadata"]["resourceVersion"]
             try:
-                return self.update(info, namespace, name, new, subresource=subresource)
+                return self.update(info, namespace, name, new, subresource=subresource, _cur=cur)
             except APIError as e:
                 if e.reason != "Conflict":
                     raise
