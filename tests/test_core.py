@@ -195,3 +195,26 @@ def test_supervisor_spawn_errors_are_synchronous(tmp_path):
     with pytest.raises(OSError):
         sup.spawn("dup", ["/bin/sleep", "5"], ENV)
     sup.kill("dup", signal.SIGKILL, True)
+
+
+def test_store_wal_survives_a_torn_tail_and_a_second_crash(tmp_path):
+    """kill -9 in the middle of an append leaves half a record at the end of the log.  Replay stops there -- and cuts the
+    file back, so that what is written afterwards is still found by the *next* replay."""
+    from trainingjob_operator_b200.core import _aitj_core as core
+
+    wal = str(tmp_path / "store.wal")
+    s = core.Store(wal)
+    s.create("Pod", "default", "a", "uid-a", b'{"metadata":{"name":"a"}}', {"k": "v"}, [])
+    s.create("Pod", "default", "b", "uid-b", b'{"metadata":{"name":"b"}}', {}, [])
+    del s
+    size = os.path.getsize(wal)
+    with open(wal, "ab") as f:
+        f.write(b'P 3 3 Pod7 default1 c5 uid-c400 {"metadata":{"na')           # torn: 400 bytes promised, 17 written
+    s2 = core.Store(wal)
+    assert s2.count("Pod") == 2 and s2.current_rv() == 2
+    assert os.path.getsize(wal) == size                                         # torn bytes removed
+    s2.create("Pod", "default", "c", "uid-c", b'{"metadata":{"name":"c"}}', {}, [])
+    del s2
+    s3 = core.Store(wal)                                                        # second start: nothing hidden
+    assert s3.count("Pod") == 3 and s3.get("Pod", "default", "c")["uid"] == "uid-c"
+    assert s3.get("Pod", "default", "a")["labels"] == {"k": "v"}

@@ -81,9 +81,9 @@ def test_success_path_env_contract_and_cleanup(lc):
     assert lc.clientset.core_v1().services("default").list()["items"] == []       # cleanPodPolicy All
     log = open(os.path.join(lc.workdir, "logs", "default_ok-trainer-1_aitj-trainer.log")).read()
     assert "r=1 n=2 h=ok-trainer-0.default:2222,ok-trainer-1.default:2222 w=2 g=1 p=2222" in log
-    evs = [e["reason"] for e in lc.clientset.core_v1().events("default").list()["items"]]
-    for r in ("SuccessfulCreatePod", "SuccessfulCreateService", "SuccessfulDeletePod", "SuccessfulDeleteService"):
-        assert r in evs
+    want = {"SuccessfulCreatePod", "SuccessfulCreateService", "SuccessfulDeletePod", "SuccessfulDeleteService"}
+    # (events are written by the recorder's sink thread, a moment after the action they describe)
+    wait_until(lambda: want <= {e["reason"] for e in lc.clientset.core_v1().events("default").list()["items"]})
     tr = json.loads(job.annotations[C.ANN_TRACE])
     assert 0 <= tr["running"] - tr["submitted"] < 5.0              # reconcile -> all-running latency is recorded
 
@@ -415,8 +415,8 @@ def test_leader_failover_keeps_the_job_running(tmp_path):
         final = lc2.wait_for_phase("ha", "Succeed", timeout=30)     # the new leader finishes the job
         assert final.status.restart_counts.get("trainer", 0) == 0
         assert failover < 6.0
-        evs = [e["message"] for e in lc2.clientset.core_v1().events("kube-system").list()["items"]]
-        assert any("became leader" in m for m in evs)
+        wait_until(lambda: any("became leader" in e["message"]
+                               for e in lc2.clientset.core_v1().events("kube-system").list()["items"]), timeout=5)
 
 
 @pytest.mark.slow
@@ -584,9 +584,11 @@ def test_hang_detection_and_exec_liveness_probe(lc):
         {"name": "AITJ_HANG_TIMEOUT", "value": "1"}]
     lc.apply(j)
     wait_until(lambda: lc.jobs().get("hang").status.restart_counts.get("trainer", 0) >= 1, timeout=30)
-    evs = [(e["reason"], e["message"]) for e in lc.clientset.core_v1().events("default").list()["items"]]
-    assert any(r == "Unhealthy" and "no heartbeat" in m for r, m in evs), evs
-    assert any(r == "Killing" for r, _ in evs)
+    def events():
+        return [(e["reason"], e["message"]) for e in lc.clientset.core_v1().events("default").list()["items"]]
+
+    wait_until(lambda: any(r == "Killing" for r, _ in events()), timeout=5)        # written by the recorder's sink thread
+    assert any(r == "Unhealthy" and "no heartbeat" in m for r, m in events()), events()
     job = lc.jobs().get("hang")
     assert job.status.phase in ("Running", "Terminating", "Restarting", "Creating", "Pending")   # being restarted, not failed
     lc.jobs().delete("hang")
@@ -603,6 +605,32 @@ def test_hang_detection_and_exec_liveness_probe(lc):
     os.remove(marker)
     final = lc.wait_for_phase("probe", "Failed", timeout=20)
     assert "137" in final.status.conditions[-1].message
+
+
+def test_container_exit_is_reported_once_the_api_server_is_reachable_again(lc):
+    """The worker exits while the API server cannot be reached (it is being restarted): the agent keeps the termination
+    and records it as soon as the server answers again -- the pod must not stay Running forever (kubelet semantics)."""
+    lc.apply(sh_job("blip", "sleep 1", replicas=1))
+    wait_until(lambda: lc.jobs().get("blip").status.phase == "Running")
+    t = lc.agent.cs.transport
+    real_get, real_patch = t.get, t.patch
+    down = {"on": True}
+
+    def flaky(real):
+        def call(*a, **kw):
+            if down["on"]:
+                raise APIError(503, "ServiceUnavailable", "cannot reach API server")
+            return real(*a, **kw)
+        return call
+
+    t.get, t.patch = flaky(real_get), flaky(real_patch)
+    try:
+        time.sleep(2.5)                                   # the container exits at ~1 s, well inside the outage
+        assert lc.pods(selector="TrainingJobName=blip")[0]["status"]["phase"] == "Running"     # nobody could be told
+    finally:
+        down["on"] = False
+    lc.wait_for_phase("blip", "Succeed", timeout=15)
+    t.get, t.patch = real_get, real_patch
 
 
 def test_agent_restart_readopts_running_workers_and_fails_lost_ones(lc):

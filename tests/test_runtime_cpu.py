@@ -91,6 +91,7 @@ def test_bucket_allreduce_and_flat_ddp_over_gloo():
         assert torch.allclose(pl[0], pl[1]) and not torch.allclose(pl[0], before)
         assert float(ddp.g32.abs().sum()) == 0.0            # grads zeroed by the optimizer sweep
         print("OK", rank)
+        dist.destroy_process_group()        # else gloo's threads can still be joinable at exit ("terminate called ...")
     """ % ROOT)
     procs = []
     for rank in range(2):
@@ -132,6 +133,7 @@ def test_state_source_is_elected_not_assumed_to_be_rank0():
         loop = sync_state(a, 0, dev, have_state=False)
         assert float(a.t[0]) == 5.0
         print("OK", rank)
+        dist.destroy_process_group()
     """ % ROOT)
     procs = []
     for rank in range(3):

@@ -127,6 +127,10 @@ def parse_container_id(cid: str) -> Tuple[int, int]:
         return 0, 0
 
 
+class _RetryExit(Exception):
+    """The API server could not be reached while a container exit was being recorded; the reaper tries again."""
+
+
 @dataclass
 class _PodState:
     key: str
@@ -388,12 +392,21 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
                 self.queue.done(key)
 
     def _reap_loop(self, stop: threading.Event) -> None:
+        retry: List[Dict[str, Any]] = []       # exits whose status write did not reach the API server yet
         while not stop.is_set():
-            for ev in self.sup.poll_exits(0.5):
+            events = self.sup.poll_exits(0.5)
+            again, retry = retry, []
+            for ev in again + list(events):
                 if ev["id"].startswith(ZYGOTE_PREFIX):
                     self._on_zygote_exit(ev)
-                else:
+                    continue
+                try:
                     self._on_exit(ev)
+                except _RetryExit as e:
+                    # kubelet semantics: a container's termination is reported until the API server has it -- an exit that
+                    # happens while the server is restarting must not leave the pod Running forever
+                    klog.V(2).info("agent: exit of %s not recorded yet (%s), will retry", ev["id"], e)
+                    retry.append(ev)
 
     def _sweep_loop(self, stop: threading.Event) -> None:
         n = 0
@@ -618,8 +631,10 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
         ns, name = M.split_key(key)
         try:
             pod = self.cs.core_v1().pods(ns).get(name)
-        except APIError:
-            return
+        except APIError as e:
+            if e.reason == "NotFound":
+                return
+            raise _RetryExit(e.message) from None
         if M.uid_of(pod) != st.uid:
             return
         code, sig = int(ev["exit_code"]), int(ev["signal"])
@@ -653,7 +668,11 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
             patch = {"status": {"phase": C.POD_FAILED, "reason": "InitContainerFailed",
                                 "message": f"init container {cname} exited with {code}",
                                 "initContainerStatuses": [{"name": cname, "state": {"terminated": term}}]}}
-            self.cs.core_v1().pods(ns).patch(name, patch, subresource="status")
+            try:
+                self.cs.core_v1().pods(ns).patch(name, patch, subresource="status")
+            except APIError as e:
+                if e.reason != "NotFound":
+                    raise _RetryExit(e.message) from None
             return
         statuses = M.deepcopy(pod.get("status", {}).get("containerStatuses") or [])
         found = False
@@ -675,7 +694,8 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
         try:
             self.cs.core_v1().pods(ns).patch(name, {"status": status}, subresource="status")
         except APIError as e:
-            klog.warning("status update of %s failed: %s", key, e.message)
+            if e.reason != "NotFound":
+                raise _RetryExit(e.message) from None
         self._kick_pending()
 
     # ------------------------------------------------------------------ kubelet: terminate

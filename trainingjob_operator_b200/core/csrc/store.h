@@ -22,6 +22,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <unistd.h>
 #include <unordered_map>
 #include <vector>
 
@@ -306,10 +307,23 @@ class Store {
     wal_ << '\n';
     wal_.flush();
   }
+  // Replays the log; a record torn by a crash in the middle of an append ends the replay, and the file is cut back to
+  // the last complete record so that what is appended from now on is not hidden behind the torn bytes at the next start.
   void replay() {
     std::ifstream f(wal_path_, std::ios::binary);
     if (!f.good()) return;
     std::string op;
+    std::streamoff good = 0;
+    struct Trunc {
+      const std::string& path; std::ifstream& f; std::streamoff& good;
+      ~Trunc() {
+        f.clear();
+        f.seekg(0, std::ios::end);
+        const std::streamoff size = f.tellg();
+        f.close();
+        if (size > good && good >= 0) { int rc = ::truncate(path.c_str(), good); (void)rc; }
+      }
+    } trunc{wal_path_, f, good};
     while (f >> op) {
       uint64_t rv;
       if (!(f >> rv)) break;
@@ -347,6 +361,8 @@ class Store {
         break;
       }
       if (rv > rv_) rv_ = rv;
+      if (f.peek() == '\n') f.get();
+      good = f.tellg();
     }
   }
 
