@@ -633,6 +633,31 @@ def test_container_exit_is_reported_once_the_api_server_is_reachable_again(lc):
     t.get, t.patch = real_get, real_patch
 
 
+def test_running_status_is_reported_after_an_api_outage_at_container_start(lc):
+    """The containers start while the status write fails (API server restarting): the pod must not stay Pending with a
+    live process -- the agent repeats the Running report, and does not start the containers a second time."""
+    t = lc.agent.cs.transport
+    real_patch = t.patch
+    fails = {"n": 0}
+
+    def flaky(info, ns, name, patch, *a, **kw):
+        if info.kind == "Pod" and isinstance(patch, dict) and (patch.get("status") or {}).get("phase") == "Running" \
+                and fails["n"] < 2:
+            fails["n"] += 1
+            raise APIError(503, "ServiceUnavailable", "cannot reach API server")
+        return real_patch(info, ns, name, patch, *a, **kw)
+
+    t.patch = flaky
+    try:
+        lc.apply(sh_job("late", "sleep 3", replicas=1))
+        wait_until(lambda: lc.jobs().get("late").status.phase == "Running", timeout=15)
+        assert fails["n"] == 2
+        assert len([sid for sid, _ in lc.agent.sup.list() if "/late-trainer-0/" in sid]) == 1     # one process, not two
+        lc.wait_for_phase("late", "Succeed", timeout=20)
+    finally:
+        t.patch = real_patch
+
+
 def test_agent_restart_readopts_running_workers_and_fails_lost_ones(lc):
     """a restarted agent re-adopts its predecessor's live workers (pid + start time from
     ``containerID``), keeps supervising them to completion, and marks a pod whose process vanished as failed instead

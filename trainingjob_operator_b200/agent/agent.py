@@ -137,6 +137,7 @@ class _PodState:
     uid: str
     containers: Dict[str, str] = field(default_factory=dict)   # container name -> supervisor id
     started: bool = False
+    running_unreported: bool = False      # containers are up but the Running status write did not reach the API server
     init_index: int = 0
     term_sent_at: float = 0.0
     bound_at: float = 0.0
@@ -531,7 +532,7 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
             st = self._states.get(key)
             if st is None:
                 st = self._states[key] = _PodState(key=key, uid=M.uid_of(pod), bound_at=time.monotonic())
-            if st.started or time.monotonic() < st.next_retry:
+            if (st.started and not st.running_unreported) or time.monotonic() < st.next_retry:
                 return
         with st.status_lock:
             self._start_pod_locked(pod, st)
@@ -549,6 +550,10 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
             return
         statuses = []
         ok = True
+        if st.started and st.running_unreported and not all(
+                self.sup.alive(st.containers.get(c["name"], "")) for c in mains):
+            st.running_unreported = False      # a container has exited meanwhile: the exit path reports from here on
+            return
         for c in mains:
             if c["name"] in st.containers:
                 continue
@@ -569,7 +574,12 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
                             "containerStatuses": statuses,
                             "conditions": [{"type": "PodScheduled", "status": "True"},
                                            {"type": "Ready", "status": "True", "lastTransitionTime": now}]}}
-        self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch, subresource="status")
+        try:
+            self.cs.core_v1().pods(M.namespace_of(pod)).patch(M.name_of(pod), patch, subresource="status")
+        except APIError:
+            st.running_unreported = True       # the sync loop re-queues the pod; only the status write is repeated
+            raise
+        st.running_unreported = False
         metrics.observe("aitj_spawn_seconds", time.monotonic() - st.bound_at)
 
     def _spawn_container(self, pod: dict, st: _PodState, c: dict, gpus: List[int], init: bool) -> str:
