@@ -44,7 +44,7 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self):
         self.proc = None
@@ -54,11 +54,13 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 
-    def stop(self):
+    def stop(self, window=None):
+        """``window`` = (t0, t1) epoch seconds of the timed region: only samples taken inside it are summarised (the
+        process spends most of its life importing / initialising at idle clocks, which used to drown the median)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -67,11 +69,24 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         self.f.close()
+        import datetime
+
         sm, mx, reasons, power = [], [], set(), []
+        rows = []
         for line in open(self.path):
             p = [x.strip() for x in line.split(",")]
             if len(p) < 9:
                 continue
+            ts = None
+            if len(p) >= 10:
+                try:
+                    ts = datetime.datetime.strptime(p[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    ts = None
+            rows.append((ts, p))
+        inside = [r for r in rows if window and r[0] is not None and window[0] - 0.1 <= r[0] <= window[1] + 0.1]
+        scope = "timed region" if inside else "whole process (no sample fell inside the timed region)"
+        for ts, p in (inside or rows):
             try:
                 sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
             except ValueError:
@@ -82,7 +97,8 @@ class ClockSampler:
         sm.sort()
         busy = [x for x in sm if x > 0]
         return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm),
+                "scope": scope}
 
 
 def worker_args(a, result_path=""):
@@ -113,7 +129,7 @@ def run_device_timed(a):
     if sampler:
         sampler.start()
     res = worker.run(wa)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(res.get("timed_region_epoch")) if sampler else None
     return res, clocks
 
 
@@ -165,12 +181,53 @@ def run_e2e(a, n_gpus):
     return out
 
 
+def run_torch_stock(a, rank):
+    """Comparator arm (baseline/torch_stock.py): stock nn.Module + DDP + fused AdamW + SDPA under bf16 autocast, eager
+    or torch.compile-d -- what a user container launched by the reference operator would run.  No repo code on its path."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("aitj_torch_stock", os.path.join(ROOT, "baseline", "torch_stock.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    d = MODEL_DEFAULTS["gpt2"]
+    sampler = ClockSampler() if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t0 = time.time()
+    r = mod.run(a.batch or d["batch"], a.seq or d["seq"], a.steps, a.warmup, compiled=a.impl.endswith("compiled"))
+    t1 = time.time()
+    clocks = sampler.stop((t1 - r["ms_per_step"] * a.steps / 1e3 - 0.05, t1)) if sampler else None
+    if rank != 0:
+        return 0
+    line = {
+        "metric": "samples/sec (whole job, device-timed CUDA events, max over ranks) of the launched DDP training job",
+        "value": r["samples_per_sec"], "unit": "samples/sec", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 autocast (fp32 master weights)", "data": "synthetic tokens / random-init weights (no network)",
+        "impl": a.impl,
+        "config": {"model": d["name"], "global_batch": r["global_batch"], "per_gpu_batch": r["batch_per_gpu"],
+                   "seq_len": r["seq_len"], "parallelism": f"dp{a.gpus}", "params": r["params"],
+                   "stack": "nn.Module + DistributedDataParallel + torch.optim.AdamW(fused=True) + SDPA"
+                            + (" + torch.compile" if r["compiled"] else " (eager)") + ", grad-clip 1.0",
+                   "torch": r["torch"], "warmup_wall_s": r["warmup_wall_s"],
+                   "loss_first": r["loss_first"], "loss_last": r["loss_last"],
+                   "repo_native_code_mapped": r["repo_native_code_mapped"]},
+        "clocks": clocks,
+        "e2e": {"value": r["samples_per_sec"], "unit": "samples/sec", "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": r["d2h_bytes_per_step"],
+                "note": "the timed loop itself copies tokens from pinned memory and reads the loss back every step"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_stock", "torch_stock_compiled"])
     ap.add_argument("--model", default="gpt2", choices=sorted(MODEL_DEFAULTS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default per model)")
     ap.add_argument("--seq", type=int, default=0)
@@ -189,6 +246,8 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if a.impl.startswith("torch_stock") and (a.gpus == world or a.gpus == 1):
+        return run_torch_stock(a, rank)
     if a.gpus != world and world == 1 and a.gpus > 1:
         # launched without torchrun: spawn the ranks ourselves so `python bench.py --gpus N` also works
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",

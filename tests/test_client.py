@@ -210,3 +210,48 @@ def test_indexer_secondary_indices_and_updates_never_hide_an_object_from_lock_fr
     stop.set()
     t.join(2)
     assert not missing
+
+
+def test_http_transport_does_not_repeat_a_write_that_may_have_been_applied():
+    """A read time-out after the request was sent: GET is retried, POST / PUT / PATCH / DELETE surface the failure (a
+    create that landed would otherwise come back as AlreadyExists, a guarded PUT as Conflict)."""
+    import http.server
+    import threading
+    import time as _time
+
+    import pytest as _pytest
+
+    from trainingjob_operator_b200.api import register as R
+    from trainingjob_operator_b200.store.apiserver import APIError
+    from trainingjob_operator_b200.store.transport import HTTPTransport
+
+    seen = []
+
+    class Slow(http.server.BaseHTTPRequestHandler):
+        def _serve(self):
+            n = int(self.headers.get("Content-Length") or 0)
+            if n:
+                self.rfile.read(n)
+            seen.append(self.command)
+            _time.sleep(0.6)                       # "applied", but the answer comes too late
+
+        do_GET = do_POST = do_PUT = do_DELETE = do_PATCH = _serve
+
+        def log_message(self, *a):
+            pass
+
+    srv = http.server.ThreadingHTTPServer(("127.0.0.1", 0), Slow)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    try:
+        tr = HTTPTransport(f"http://127.0.0.1:{srv.server_address[1]}", timeout=0.2)
+        with _pytest.raises(APIError) as ei:
+            tr.create(R.POD, "default", {"metadata": {"name": "p"}})
+        assert ei.value.reason == "Timeout" and seen == ["POST"]           # sent once, not twice
+        with _pytest.raises(APIError) as ei:
+            tr.get(R.POD, "default", "p")
+        assert ei.value.reason == "ServiceUnavailable" and seen.count("GET") == 2
+        with _pytest.raises(APIError):
+            tr.delete(R.POD, "default", "p")
+        assert seen.count("DELETE") == 1
+    finally:
+        srv.shutdown()

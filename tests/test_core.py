@@ -218,3 +218,49 @@ def test_store_wal_survives_a_torn_tail_and_a_second_crash(tmp_path):
     s3 = core.Store(wal)                                                        # second start: nothing hidden
     assert s3.count("Pod") == 3 and s3.get("Pod", "default", "c")["uid"] == "uid-c"
     assert s3.get("Pod", "default", "a")["labels"] == {"k": "v"}
+
+
+def test_store_restart_makes_older_watches_gone_and_keeps_the_version_counter(tmp_path):
+    """After a restart the event history is empty: a watch from a resourceVersion older than the log's end must be told
+    to re-list (Gone) instead of silently missing what happened in between; and a compaction whose newest operations were
+    deletes must not let resourceVersions be handed out twice."""
+    wal = str(tmp_path / "store.wal")
+    s = core.Store(wal)
+    s.create("Pod", "ns", "a", "u1", b"{}", {}, [])          # rv 1
+    s.create("Pod", "ns", "b", "u2", b"{}", {}, [])          # rv 2
+    s.remove("Pod", "ns", "b")                               # rv 3
+    del s
+    s2 = core.Store(wal)
+    assert s2.current_rv() == 3
+    with pytest.raises(core.StoreError) as ei:
+        s2.watch_open("Pod", "ns", 1)                        # events 2, 3 are not replayable any more
+    assert ei.value.reason == "Gone"
+    w = s2.watch_open("Pod", "ns", 3)                        # from "now": fine
+    s2.create("Pod", "ns", "c", "u3", b"{}", {}, [])         # rv 4
+    assert s2.watch_next(w, 0.2)[1]["name"] == "c"
+    w2 = s2.watch_open("Pod", "ns", 3)                       # history of this incarnation replays
+    assert s2.watch_next(w2, 0.2)[1]["name"] == "c"
+    s2.remove("Pod", "ns", "c")                              # rv 5: the newest operation is a delete
+    s2.compact()
+    del s2
+    s3 = core.Store(wal)
+    assert s3.current_rv() == 5                              # not 1 (the highest rv among the live objects)
+    assert s3.create("Pod", "ns", "d", "u4", b"{}", {}, [])["rv"] == 6
+
+
+def test_store_wal_cut_right_after_a_records_last_digit(tmp_path):
+    """A crash can end the log on the final count digit of a record (its separator and newline missing): the record is
+    complete, and whatever is appended next must not be glued onto it."""
+    wal = str(tmp_path / "store.wal")
+    s = core.Store(wal)
+    s.create("Pod", "default", "a", "uid-a", b"{}", {}, [])
+    del s
+    raw = open(wal, "rb").read()
+    assert raw.endswith(b" 0 \n")
+    open(wal, "wb").write(raw[:-2])                          # "... 0" -- cut after the owner count
+    s2 = core.Store(wal)
+    assert s2.count("Pod") == 1
+    s2.create("Pod", "default", "b", "uid-b", b"{}", {}, [])
+    del s2
+    s3 = core.Store(wal)
+    assert s3.count("Pod") == 2 and s3.current_rv() == 2

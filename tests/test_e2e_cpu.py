@@ -538,6 +538,21 @@ def test_restart_scope_all_resumes_ddp_job_from_checkpoint(tmp_path):
     assert out["kill_to_first_step_s"] < 60
 
 
+@pytest.mark.slow
+def test_finite_job_resumed_past_its_warmup_still_finishes_with_a_throughput_record(tmp_path):
+    """BASELINE config 4 as written (--steps > 0, --ckpt-every): the replicas re-created after the SIGKILL resume from a
+    checkpoint that lies past the warm-up, so the timed region has to be armed at the first step they run -- they used
+    to crash on an unarmed timer at the end, restart until restartLimit and leave the job Failed."""
+    import subprocess
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fault_check.py"), "mlp", "2", "0", "--cpu",
+                        "--steps", "150"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["final_phase"] == "Succeed" and out["final_restart_counts"] == {"trainer": 1} and out["resumed"]
+    assert out["metrics"]["samples_per_sec"] > 0 and out["metrics"]["steps_done"] == 155
+
+
 def test_fault_tolerant_job_survives_the_loss_of_rank0_in_place(tmp_path):
     """``faultTolerant: true`` on an elastic job (a field the reference declares and never reads, types.go:47): SIGKILL
     rank 0 of a gloo DDP job.  Only that replica is re-created; the survivors catch the failed collective, keep their

@@ -3,7 +3,7 @@
 Reports kill -> job Running again -> first training step after the restart.
 
     python tools/fault_check.py [model] [n] [warm_pool] [--cpu] [--scope Pod|All] [--hang SECONDS] [--fault-tolerant]
-          [--victim RANK] [--second-victim RANK --second-after SECONDS]
+          [--victim RANK] [--second-victim RANK --second-after SECONDS] [--steps K]
 
 ``--scope Pod --hang S``: only the killed replica is re-created by the controller; the survivors, stuck in a collective
 with a dead peer, are caught by the agent's heartbeat-based hang detection after S seconds and restarted too.
@@ -36,9 +36,12 @@ victim_arg = sys.argv[sys.argv.index("--victim") + 1] if "--victim" in sys.argv 
 victim = int(victim_arg) if victim_arg else min(3, n - 1)
 second = int(sys.argv[sys.argv.index("--second-victim") + 1]) if "--second-victim" in sys.argv else None
 second_after = float(sys.argv[sys.argv.index("--second-after") + 1]) if "--second-after" in sys.argv else 0.0
+# --steps K: a finite job (K timed steps after 5 warm-up steps); the check then also waits for it to end Succeed after the
+# restart -- a replica resumed from a checkpoint past the warm-up must still produce its throughput record and exit 0
+steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 0
 batch = {"bert": 8, "mlp": 16, "gpt2": 4, "resnet50": 32}.get(model, 8)
 worker = [sys.executable, "-m", "trainingjob_operator_b200.runtime.worker", "--model", model, "--batch", str(batch),
-          "--steps", "0", "--ckpt-every", "10"] + (["--cpu", "--step-sleep", "0.02"] if cpu else []) + \
+          "--steps", str(steps), "--warmup", "5", "--ckpt-every", "10"] + (["--cpu", "--step-sleep", "0.02"] if cpu else []) + \
          (["--elastic"] if ft else [])
 c = {"name": "aitj-trainer", "command": worker, "workingDir": ROOT, "env": [{"name": "PYTHONPATH", "value": ROOT}]}
 if hang:
@@ -132,9 +135,16 @@ with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thr
     out["conditions"] = [c.type for c in j.status.conditions][-6:]
     log0 = open(os.path.join(lc.workdir, "logs", "default_ft-trainer-0_aitj-trainer.log")).read()
     out["resumed"] = [ln for ln in log0.splitlines() if "resumed from checkpoint" in ln][-1:]
+    if steps:
+        done = wait(lambda: (lambda j: j if j.status.phase in ("Succeed", "Failed", "Timeout", "NodeFail") else None)(
+            lc.jobs().get("ft")), 300)
+        out["final_phase"] = done.status.phase
+        out["final_restart_counts"] = done.status.restart_counts
+        out["metrics"] = json.loads(done.annotations.get("aitj.b200/metrics", "null"))
     lc.jobs().delete("ft")
     time.sleep(0.5)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_{scope.lower()}.json", "w"), indent=1)
 print(json.dumps(out))
-sys.exit(0 if out["restart_counts"].get("trainer", 0) >= 1 and out["resumed"] else 1)
+sys.exit(0 if out["restart_counts"].get("trainer", 0) >= 1 and out["resumed"] and
+         (not steps or out.get("final_phase") == "Succeed") else 1)

@@ -1,29 +1,25 @@
-"""Controller core: wiring, work queue, sync handler, reconcile loop.
+"""The controller shell: informers -> rate-limited work queue -> observe -> ``engine.reconcile`` -> ``Executor``.
 
-Parity: /root/reference/pkg/controller/controller.go:37-462:
+The capability set is the reference controller's (/root/reference/pkg/controller/controller.go:37-462, SURVEY.md
+§2.8, §3.1-3.2): three informers (jobs, pods, services; here also nodes, instead of a live node LIST per pass) feed a
+de-duplicating rate-limited queue of ``namespace/name`` keys, N workers pop keys, terminal / deleting jobs are skipped,
+the ``AITrainingJob`` kind registers itself on start-up (``AlreadyExists`` tolerated), errors re-queue with per-item
+back-off, orphans are swept on a timer.  The shape is not the reference's: a pass is
 
-* struct + constructor (controller.go:37-159): three informers (jobs, pods, services) with event
-  handlers, event recorder, pod/service control, expectations, a named rate-limited work queue;
-* ``Run`` (controller.go:182-208): self-register the CRD, wait for cache sync, N workers, GC, block;
-* ``createCRD`` (controller.go:210-234; AlreadyExists tolerated);
-* worker / processNextWorkItem (controller.go:236-268): Forget on success, AddRateLimited on error;
-* ``syncHandler`` (controller.go:270-312): lister Get, NotFound => done, expectations gate, defaults,
-  reconcile only non-deleted jobs in a reconcilable phase;
-* ``reconcileTrainingJobs`` (controller.go:314-388): claim pods + services, per-role pods then services,
-  ``Restarting`` => condition Terminating + RestartReplicaName + break, ending phases collected,
-  aggregate messages, ``updateStatus``, write back only if the status changed;
-* expectations check (controller.go:390-404), ``enqueueJob`` (controller.go:406-421), owner-ref
-  resolution (controller.go:424-440), labels / owner reference (controller.go:161-180).
+    observe(key)  -- read-only snapshot of the job and what it owns (claiming adopts / releases by selector + owner uid)
+    engine.reconcile(observation) -> decision          -- pure (``controller.engine``)
+    executor.apply(decision)                           -- all writes, expectations bookkeeping (``controller.executor``)
 
-New behind the reference's unused fields: the rendezvous generation (elastic rescale, ``elastic.py``)
-and the lifecycle trace annotation used to measure reconcile -> all-ranks-running latency.
+plus the two gates that protect a pass from its own past: the expectations gate (creations / deletions of the previous
+pass must have been seen by the informers) and the staleness gate (a cached job older than this controller's own last
+status write is not acted on -- pods vanish within milliseconds on one box, so a stale ``Running`` phase could re-create
+the replicas of a job that just finished).
 """
 from __future__ import annotations
 
-import json
 import threading
 import time
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 from ..api import constants as C
 from ..api import meta as M
@@ -37,18 +33,18 @@ from ..cmd.options import TrainingJobOperatorOption
 from ..core import _aitj_core as core
 from ..store.apiserver import APIError
 from ..utils import klog, lifecycle, metrics
-from .control import RealPodControl, RealServiceControl
-from .elastic import ElasticMixin
+from . import elastic as E
+from . import engine
+from .control import ControllerRefManager, RealPodControl, RealServiceControl, recheck_deletion_timestamp
+from .executor import Executor
 from .garbage_collection import GarbageCollector
-from .pod import PodReconciler, gen_expectation_pods_key
-from .service import ServiceReconciler, gen_expectation_services_key
-from .status import StatusEngine, update_conditions
+from .pod import gen_expectation_pods_key, job_labels, owner_reference_of
+from .service import gen_expectation_services_key
 from .trainingjob import TrainingJobHandlers
 
-metrics.describe("aitj_reconcile_seconds", "duration of one syncHandler pass")
+metrics.describe("aitj_reconcile_seconds", "duration of one pass over a job key")
 metrics.describe("aitj_workqueue_depth", "keys waiting in the AITrainingJob work queue")
 metrics.describe("aitj_job_startup_seconds", "job created -> all replicas Running")
-
 
 INDEX_JOB_LABEL = "jobLabel"              # "<namespace>/<TrainingJobName label>"
 INDEX_CONTROLLER_UID = "controllerUID"    # uid of the controlling owner reference
@@ -65,9 +61,9 @@ def index_by_controller_uid(obj: dict) -> list:
 
 
 def claim_candidates(lister, job, selector) -> list:
-    """Copies of the objects a ControllerRefManager pass of ``job`` can act on (pod.go:125-150, service.go:99-115 hand it
-    the whole namespace): the ones matching the selector (keep / adopt) -- all of which carry the job-name label -- and
-    the ones the job controls (release when the labels stopped matching)."""
+    """Private copies of the objects a claim pass of ``job`` can act on: the ones matching the selector (keep / adopt)
+    -- found through the job-label index -- and the ones the job controls (release when their labels stopped
+    matching) -- found through the controller-uid index.  The reference hands the whole namespace to the ref manager."""
     seen = {}
     for o in lister.by_index(INDEX_JOB_LABEL, f"{job.namespace}/{selector.get(C.LABEL_JOB_NAME, '')}"):
         if M.selector_matches(selector, M.labels_of(o)):
@@ -78,7 +74,12 @@ def claim_candidates(lister, job, selector) -> list:
     return [lister.copy_of(o) for o in seen.values()]
 
 
-class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, TrainingJobHandlers, ElasticMixin):
+def _node_is_ready(node: dict) -> bool:
+    return any(c.get("type") == "Ready" and c.get("status") == "True"
+               for c in node.get("status", {}).get("conditions") or [])
+
+
+class TrainingJobController(TrainingJobHandlers):
     kind = C.KIND
     group = C.GROUP_NAME
 
@@ -91,73 +92,60 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
         self.option = option
         self.master_url = getattr(option, "master_url", "")
 
-        job_informer = trainingjob_informer_factory.elasticdeeplearning().v1().aitrainingjobs()
-        pod_informer = kube_informer_factory.core().v1().pods()
-        service_informer = kube_informer_factory.core().v1().services()
-        node_informer = kube_informer_factory.core().v1().nodes()
-
-        klog.V(2).info("Creating event broadcaster")
         self.recorder = recorder or EventRecorder(kube_client, C.CONTROLLER_NAME)
         self.pod_control = pod_control or RealPodControl(kube_client, self.recorder)
         self.service_control = service_control or RealServiceControl(kube_client, self.recorder)
         self.expectations = core.Expectations(300.0)
-        # per-item back-off as upstream (5 ms * 2^n <= 1000 s); overall bucket from the options (see cmd/options.py)
+        # per-item back-off 5 ms * 2^n <= 1000 s as upstream; the overall bucket comes from the options
         self.work_queue = core.WorkQueue(C.KIND, 0.005, 1000.0, float(getattr(option, "queue_qps", 10.0)),
                                          int(getattr(option, "queue_burst", 100)))
+        self.executor = Executor(kube_client, trainingjob_client, self.pod_control, self.service_control,
+                                 self.expectations, self.work_queue)
 
-        job_informer.informer().add_event_handler(
-            add=self.add_training_job, update=self.update_training_job, delete=self.delete_training_job,
-            filter_func=lambda o: o.get("kind", C.KIND) == C.KIND)
-        self.trainingjob_lister = job_informer.lister()
-        self.trainingjob_informer_synced = job_informer.informer().has_synced
-
-        # client-go style secondary indices: a reconcile looks at the pods / services that carry its job label or that it
-        # controls -- not at every object of the namespace
-        for inf in (pod_informer.informer(), service_informer.informer()):
+        jobs = trainingjob_informer_factory.elasticdeeplearning().v1().aitrainingjobs()
+        pods = kube_informer_factory.core().v1().pods()
+        services = kube_informer_factory.core().v1().services()
+        nodes = kube_informer_factory.core().v1().nodes()
+        for inf in (pods.informer(), services.informer()):
             inf.indexer.add_indexers({INDEX_JOB_LABEL: index_by_job_label, INDEX_CONTROLLER_UID: index_by_controller_uid})
-        pod_informer.informer().add_event_handler(add=self.add_pod, update=self.update_pod, delete=self.delete_pod)
-        self.pod_lister = pod_informer.lister()
-        self.pod_informer_synced = pod_informer.informer().has_synced
-
-        service_informer.informer().add_event_handler(add=self.add_service, update=self.update_service,
-                                                      delete=self.delete_service)
-        self.service_lister = service_informer.lister()
-        self.service_informer_synced = service_informer.informer().has_synced
-
-        # a node going NotReady must wake the jobs that have replicas on it (the reference polls the node
-        # list on every pass instead, pod.go:441)
-        node_informer.informer().add_event_handler(update=self._node_changed, delete=self._node_changed_del)
-        self.node_lister = node_informer.lister()
-        self.node_informer_synced = node_informer.informer().has_synced
+        jobs.informer().add_event_handler(add=self.add_training_job, update=self.update_training_job,
+                                          delete=self.delete_training_job,
+                                          filter_func=lambda o: o.get("kind", C.KIND) == C.KIND)
+        pods.informer().add_event_handler(add=self.add_pod, update=self.update_pod, delete=self.delete_pod)
+        services.informer().add_event_handler(add=self.add_service)
+        # a GPU dropping out must wake the jobs with replicas on it (the reference polls the node list every pass)
+        nodes.informer().add_event_handler(update=self._node_changed, delete=self._node_removed)
+        self.trainingjob_lister, self.pod_lister = jobs.lister(), pods.lister()
+        self.service_lister, self.node_lister = services.lister(), nodes.lister()
+        self._synced = (jobs.informer().has_synced, pods.informer().has_synced, services.informer().has_synced,
+                        nodes.informer().has_synced)
 
         self._workers: List[threading.Thread] = []
         self.gc: Optional[GarbageCollector] = None
         self.sync_count = 0
-        # resourceVersion of our own last write per job: a cached copy older than that must not be acted on
-        self._written_rv: Dict[str, int] = {}
+        self._written_rv: Dict[str, Tuple[str, int]] = {}   # job key -> (uid, resourceVersion of our own last write)
         self._written_lock = threading.Lock()
+        # AITJ_RECORD_DIR: every pass is written down as (observation, decision) JSON and can be replayed offline
+        import os
 
-    # ------------------------------------------------------------------ identity helpers
-    def gen_owner_reference(self, job: AITrainingJob) -> dict:
-        """controller.go:161-173."""
-        return {"apiVersion": C.API_VERSION, "kind": C.KIND, "name": job.name, "uid": job.uid,
-                "blockOwnerDeletion": True, "controller": True}
+        self._recorder = None
+        if os.environ.get("AITJ_RECORD_DIR"):
+            from .replay import Recorder
 
-    def gen_labels(self, job_name: str) -> Dict[str, str]:
-        """controller.go:175-180."""
-        return {C.LABEL_GROUP_NAME: C.GROUP_NAME, C.LABEL_JOB_NAME: job_name.replace("/", "-")}
+            self._recorder = Recorder(os.environ["AITJ_RECORD_DIR"])
+
+    # ------------------------------------------------------------------ identity (used by tools / tests)
+    gen_owner_reference = staticmethod(owner_reference_of)
+    gen_labels = staticmethod(job_labels)
 
     # ------------------------------------------------------------------ run
     def run(self, workers: int, stop: threading.Event) -> None:
         klog.info("Starting training-job controller")
         try:
-            klog.info("Starting to create TrainingJob CRD")
             self.create_crd()
             klog.info("Waiting for informer caches to sync")
-            if not wait_for_cache_sync(stop, self.trainingjob_informer_synced, self.pod_informer_synced,
-                                       self.service_informer_synced, self.node_informer_synced):
+            if not wait_for_cache_sync(stop, *self._synced):
                 raise RuntimeError("failed to wait for caches for sync")
-            klog.info("Starting workers")
             lifecycle.register_stop(lambda: (stop.set(), self.work_queue.shutdown()))
             for i in range(max(1, workers)):
                 self._workers.append(lifecycle.spawn(self._worker_loop, f"aitj-worker-{i}", (stop,)))
@@ -169,10 +157,11 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
             self.work_queue.shutdown()
             flush = getattr(self.recorder, "flush", None)
             if flush is not None:
-                flush(2.0)                    # events are written by a sink thread: do not drop the tail on a clean stop
+                flush(2.0)        # events are written by a sink thread: do not drop the tail on a clean stop
             klog.info("Shutting down training-job controller")
 
     def create_crd(self) -> None:
+        """The kind registers itself (controller.go:210-234); somebody else having done so is fine."""
         try:
             self.api_extensions_client.apiextensions_v1beta1().customresourcedefinitions().create(R.crd_object())
         except APIError as e:
@@ -181,8 +170,7 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
                 raise
 
     def _worker_loop(self, stop: threading.Event) -> None:
-        # wait.Until(tc.worker, time.Second, stopCh): restart the worker 1 s after it returns
-        while not stop.is_set():
+        while not stop.is_set():       # a worker that returns is restarted after a second, as wait.Until does
             self.worker(stop)
             if self.work_queue.shutting_down():
                 return
@@ -200,68 +188,121 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
         metrics.set_gauge("aitj_workqueue_depth", len(self.work_queue))
         t0 = time.perf_counter()
         try:
-            forget = self.sync_handler(key)
-            if forget:
+            if self.sync_handler(key):
                 self.work_queue.forget(key)
-        except APIError as e:
-            if e.reason == "NotFound":
-                # the job (or the owner of something we tried to create) vanished mid-pass: nothing left to do
+        except Exception as e:  # noqa: BLE001
+            if isinstance(e, APIError) and e.reason == "NotFound":
+                # the job (or the owner of something a pass tried to create) vanished mid-pass: nothing left to do
                 klog.V(2).info("Sync %r: %s", key, e.message)
                 self.work_queue.forget(key)
             else:
                 klog.error("Sync %r failed with %r", key, e)
                 metrics.inc("aitj_reconcile_errors_total")
                 self.work_queue.add_rate_limited(key)
-        except Exception as e:  # noqa: BLE001 - utilruntime.HandleError + AddRateLimited
-            klog.error("Sync %r failed with %r", key, e)
-            metrics.inc("aitj_reconcile_errors_total")
-            self.work_queue.add_rate_limited(key)
         finally:
             self.work_queue.done(key)
             metrics.observe("aitj_reconcile_seconds", time.perf_counter() - t0)
         return True
 
-    # ------------------------------------------------------------------ sync
+    # ------------------------------------------------------------------ one pass
     def sync_handler(self, key: str) -> bool:
-        t0 = time.perf_counter()
         namespace, name = M.split_key(key)
         if not namespace or not name:
             raise ValueError(f"invalid trainingjob key {key!r}")
         try:
-            job = self.trainingjob_lister.aitrainingjobs(namespace).get(name)
+            job = self.trainingjob_lister.aitrainingjobs(namespace).get(name)      # a private copy
         except APIError as e:
-            if e.reason == "NotFound":
-                klog.V(4).info("%s %s has been deleted", self.kind, key)
-                self._forget_job(key)
-                return True
-            raise
+            if e.reason != "NotFound":
+                raise
+            with self._written_lock:
+                self._written_rv.pop(key, None)
+            return True
         if self._cache_is_stale(key, job):
-            # our own status write has not reached the informer cache yet: acting on the old phase could e.g.
-            # re-create pods of a job we just terminated (pods vanish faster here than under a kubelet)
             self.work_queue.add_after(key, 0.005)
             return True
-        need_sync = self.satisfied_expectations(job)
-        set_defaults_aitrainingjob(job)  # on our private copy (lister returns copies)
+        gate_open = self.satisfied_expectations(job)
+        set_defaults_aitrainingjob(job)
         self.sync_count += 1
-        if need_sync and job.deletion_timestamp is None and job.status.phase in C.RECONCILABLE_PHASES:
+        if gate_open and job.deletion_timestamp is None and job.status.phase in C.RECONCILABLE_PHASES:
             self.reconcile_training_jobs(job)
-        klog.V(4).info("Finished syncing %s %r (%.3f ms)", self.kind, key, (time.perf_counter() - t0) * 1e3)
         return True
 
-    def _forget_job(self, key: str) -> None:
-        with self._written_lock:
-            self._written_rv.pop(key, None)
+    def reconcile_training_jobs(self, job: AITrainingJob) -> None:
+        spare: Tuple[int, ...] = ()
+        for _ in range(3):
+            obs = self.observe(job, spare)
+            before = self._recorder.snapshot(obs) if self._recorder is not None else None
+            decision = engine.reconcile(obs)
+            if before is not None:
+                self._recorder.write(before, obs, decision)
+            if not decision.ports_wanted:
+                break
+            # the pass needs free loopback ports (a new MASTER_PORT, per-replica host ports): allocate, decide again
+            spare = tuple(E.allocate_port() for _ in range(decision.ports_wanted))
+            job = self.trainingjob_lister.aitrainingjobs(job.namespace).get(job.name)
+            set_defaults_aitrainingjob(job)
+        else:
+            raise RuntimeError(f"job {job.key()}: the engine keeps asking for ports")
+        written = self.executor.apply(obs.job, decision)
+        if written is not None:
+            self._remember_write(obs.job.key(), written)
+
+    def observe(self, job: AITrainingJob, spare_ports: Tuple[int, ...] = ()) -> engine.Observation:
+        selector = {C.LABEL_GROUP_NAME: self.group, C.LABEL_JOB_NAME: job.name}
+        pods = self.claim_pods(job, selector, claim_candidates(self.pod_lister, job, selector))
+        services = self.claim_services(job, selector, claim_candidates(self.service_lister, job, selector))
+        nodes = self._nodes()
+        cluster = E.observe_cluster(job, nodes, self.pod_lister.peek()) if E.auto_roles(job) else None
+        return engine.Observation(job=job, pods=pods, services=services,
+                                  ready_nodes=frozenset(M.name_of(n) for n in nodes if _node_is_ready(n)),
+                                  now=M.now(), now_epoch=time.time(),
+                                  options=engine.EngineOptions.from_operator_option(self.option),
+                                  cluster=cluster, spare_ports=spare_ports)
+
+    def _nodes(self) -> List[dict]:
+        try:
+            return self.node_lister.list() if self.node_lister is not None else \
+                self.kube_client.core_v1().nodes().list().get("items", [])
+        except APIError as e:
+            klog.error("cannot list nodes: %s", e.message)
+            return []
+
+    def get_node_status(self) -> Dict[str, bool]:
+        return {M.name_of(n): True for n in self._nodes() if _node_is_ready(n)}
+
+    # ------------------------------------------------------------------ claiming (adopt / release)
+    def _claim(self, patch_fn, job: AITrainingJob, selector: Dict[str, str], objs: List[dict]) -> List[dict]:
+        def live_owner():
+            f = self.trainingjob_client.elasticdeeplearning_v1().aitrainingjobs(job.namespace).get(job.name)
+            if f.uid != job.uid:
+                raise RuntimeError(f"original {C.KIND} {job.namespace}/{job.name} is gone: got uid {f.uid}, "
+                                   f"wanted {job.uid}")
+            return f
+
+        return ControllerRefManager(patch_fn, job, selector, recheck_deletion_timestamp(live_owner)).claim(objs)
+
+    def claim_pods(self, job, selector, pods):
+        return self._claim(self.pod_control.patch_pod, job, selector, pods)
+
+    def claim_services(self, job, selector, services):
+        return self._claim(self.service_control.patch_service, job, selector, services)
+
+    # ------------------------------------------------------------------ gates
+    def satisfied_expectations(self, job: AITrainingJob) -> bool:
+        """Every pod / service key of the job must be satisfied (the reference ORs them, controller.go:390-404, lets a
+        pass run while another create is still in flight and then trips over AlreadyExists)."""
+        key = job.key()
+        return all(self.expectations.satisfied(gen_expectation_pods_key(key, rt)) and
+                   self.expectations.satisfied(gen_expectation_services_key(key, rt))
+                   for rt in job.spec.replica_specs)
 
     def _cache_is_stale(self, key: str, job: AITrainingJob) -> bool:
         with self._written_lock:
             rec = self._written_rv.get(key)
-        if rec is None:
-            return False
-        uid, rv = rec
-        if uid != job.uid:
+        if rec is None or rec[0] != job.uid:
             return False
         try:
-            return int(job.resource_version or 0) < rv
+            return int(job.resource_version or 0) < rec[1]
         except ValueError:
             return False
 
@@ -273,70 +314,9 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
         with self._written_lock:
             self._written_rv[key] = (updated.uid, rv)
 
-    def reconcile_training_jobs(self, job: AITrainingJob) -> None:
-        klog.V(4).info("Reconcile training job: %s/%s", job.namespace, job.name)
-        old_status = job.status.to_dict()
-        old_annotations = dict(job.annotations)
-        old_spec = job.spec.to_dict()
-        selector = {C.LABEL_GROUP_NAME: self.group, C.LABEL_JOB_NAME: job.name}
-        pods = self.get_pods_by_job_and_selector(job, selector)
-        services = self.get_services_by_job_and_selector(job, selector)
-
-        self.trace(job, "firstReconcile")
-        if self.reconcile_elastic(job, pods):
-            return  # spec was patched (auto-scale); the update event re-queues the job
-
-        ending_phases: Dict[str, str] = {}
-        aggregation: List[str] = []
-        if not job.status.restart_replica_name:
-            self.reconcile_rendezvous(job, pods)
-            for rtype in list(job.spec.replica_specs):
-                ending_phase, msg = self.reconcile_pods(job, pods, rtype)
-                if msg and msg not in aggregation:
-                    aggregation.append(msg)
-                if ending_phase == C.PHASE_RESTARTING:
-                    update_conditions(job, C.PHASE_TERMINATING, C.TRAINING_JOB_REASON[C.PHASE_TERMINATING], msg)
-                    job.status.restart_replica_name = rtype
-                    self.bump_rendezvous(job, "restart")
-                    break
-                if ending_phase:
-                    ending_phases[rtype] = ending_phase
-                    continue
-                self.reconcile_services(job, services, rtype)
-        message = "; ".join(aggregation)
-        prev_phase = job.status.phase
-        self.update_status(job, pods, services, ending_phases, message)
-        if job.status.phase == C.PHASE_RUNNING and prev_phase != C.PHASE_RUNNING:
-            self.trace(job, "running")
-            self._observe_startup(job)
-        if job.status.phase in C.ENDING_PHASES:
-            self.trace(job, "ended")
-
-        changed = job.status.to_dict() != old_status or dict(job.annotations) != old_annotations \
-            or job.spec.to_dict() != old_spec
-        if changed:
-            job.status.last_reconcile_time = M.format_time()
-            updated = self.update_training_job_phase(job)
-            if updated is not None:
-                self._remember_write(job.key(), updated)
-
-    def satisfied_expectations(self, job: AITrainingJob) -> bool:
-        """Expectations gate (controller.go:390-404).  The reference ORs over every role's pod and service
-        keys, so one satisfied key lets a pass run while another create is still in flight (it then trips over
-        AlreadyExists); here every key must be satisfied before the next pass, which is what the expectations
-        cache is for."""
-        key = job.key()
-        for rtype in job.spec.replica_specs:
-            if not self.expectations.satisfied(gen_expectation_pods_key(key, rtype)):
-                return False
-            if not self.expectations.satisfied(gen_expectation_services_key(key, rtype)):
-                return False
-        return True
-
+    # ------------------------------------------------------------------ queue feeding
     def enqueue_job(self, job, is_limited: bool, delay: float) -> None:
-        """controller.go:406-421."""
         key = deletion_handling_key(job)
-        klog.V(4).info("Enqueue key: %s", key)
         if is_limited:
             self.work_queue.add_rate_limited(key)
         elif delay and delay > 0:
@@ -345,76 +325,108 @@ class TrainingJobController(PodReconciler, ServiceReconciler, StatusEngine, Trai
             self.work_queue.add(key)
 
     def resolve_controller_ref(self, namespace: str, ref: dict) -> Optional[AITrainingJob]:
-        """controller.go:424-440: kind must match, uid must match."""
+        """The job a controller reference points at -- kind, name and uid must all match."""
         if ref.get("kind") != self.kind:
             return None
         try:
             job = self.trainingjob_lister.aitrainingjobs(namespace).get(ref.get("name", ""))
         except APIError:
             return None
-        if job.uid != ref.get("uid"):
-            return None
-        return job
+        return job if job.uid == ref.get("uid") else None
 
-    # ------------------------------------------------------------------ node events
+    def _owner_of(self, obj: dict) -> Tuple[Optional[AITrainingJob], Optional[str]]:
+        ref = M.get_controller_of(obj)
+        if ref is None:
+            return None, None
+        job = self.resolve_controller_ref(M.namespace_of(obj), ref)
+        return job, (M.labels_of(obj).get(C.LABEL_REPLICA_NAME) if job is not None else None)
+
+    def add_pod(self, pod: dict) -> None:
+        if pod.get("metadata", {}).get("deletionTimestamp"):
+            return
+        job, rt = self._owner_of(pod)
+        if job is None or rt is None:
+            return
+        self.expectations.creation_observed(gen_expectation_pods_key(job.key(), rt))
+        self.work_queue.add(job.key())
+
+    def update_pod(self, old: dict, cur: dict) -> None:
+        if M.resource_version(cur) == M.resource_version(old):
+            return            # a resync re-delivery, nothing changed
+        cur_ref, old_ref = M.get_controller_of(cur), M.get_controller_of(old)
+        owners = [(M.namespace_of(old), old_ref)] if (old_ref is not None and old_ref != cur_ref) else []
+        if cur_ref is not None:
+            owners.append((M.namespace_of(cur), cur_ref))
+        for ns, ref in owners:
+            job = self.resolve_controller_ref(ns, ref)
+            if job is not None:
+                self.enqueue_job(job, False, 0)
+
+    def delete_pod(self, obj) -> None:
+        pod = obj.obj if isinstance(obj, DeletedFinalStateUnknown) else obj
+        job, rt = self._owner_of(pod)
+        if job is None or rt is None:
+            return
+        self.expectations.deletion_observed(gen_expectation_pods_key(job.key(), rt))
+        self.work_queue.add(job.key())
+
+    def add_service(self, svc: dict) -> None:
+        if svc.get("metadata", {}).get("deletionTimestamp"):
+            return
+        job, rt = self._owner_of(svc)
+        if job is None or rt is None:
+            return
+        self.expectations.creation_observed(gen_expectation_services_key(job.key(), rt))
+        self.work_queue.add(job.key())
+
     def _node_changed(self, old: dict, cur: dict) -> None:
-        def ready(n):
-            return any(c.get("type") == "Ready" and c.get("status") == "True"
-                       for c in n.get("status", {}).get("conditions") or [])
-
-        if ready(old) == ready(cur):
+        if _node_is_ready(old) == _node_is_ready(cur):
             return
         self._enqueue_jobs_on_node(M.name_of(cur))
-        if ready(cur):
-            self._enqueue_autoscaled_jobs()      # a slot came back: edlPolicy Auto roles may grow into it
+        if _node_is_ready(cur):           # a slot came back: edlPolicy Auto roles may grow into it
+            for job in self.trainingjob_lister.list():
+                if job.status.phase not in C.ENDING_PHASES and E.auto_roles(job):
+                    self.enqueue_job(job, False, 0)
 
-    def _node_changed_del(self, obj) -> None:
+    def _node_removed(self, obj) -> None:
         node = obj.obj if isinstance(obj, DeletedFinalStateUnknown) else obj
         self._enqueue_jobs_on_node(M.name_of(node))
 
     def _enqueue_jobs_on_node(self, node_name: str) -> None:
         for pod in self.pod_lister.list():
-            if pod.get("spec", {}).get("nodeName") != node_name:
-                continue
-            ref = M.get_controller_of(pod)
-            if ref is None:
-                continue
-            job = self.resolve_controller_ref(M.namespace_of(pod), ref)
-            if job is not None:
-                self.enqueue_job(job, False, 0)
+            if pod.get("spec", {}).get("nodeName") == node_name:
+                job, _ = self._owner_of(pod)
+                if job is not None:
+                    self.enqueue_job(job, False, 0)
 
-    def _enqueue_autoscaled_jobs(self) -> None:
-        for job in self.trainingjob_lister.list():
-            if job.status.phase in C.ENDING_PHASES:
-                continue
-            if any(r.edl_policy == C.EDL_POLICY_AUTO for r in job.spec.replica_specs.values()):
-                self.enqueue_job(job, False, 0)
+    # ------------------------------------------------------------------ unit-test seams into the pure engine
+    def _obs_for(self, job: AITrainingJob, pods: List[dict], services: List[dict], ready=None) -> engine.Observation:
+        ready = frozenset(ready) if ready is not None else frozenset(self.get_node_status())
+        return engine.Observation(job=job, pods=pods, services=services, ready_nodes=ready, now=M.now(),
+                                  now_epoch=time.time(), options=engine.EngineOptions.from_operator_option(self.option))
 
-    # ------------------------------------------------------------------ lifecycle trace
-    def trace(self, job: AITrainingJob, event: str) -> None:
-        """Sub-second lifecycle timestamps kept in an annotation (metav1.Time has 1 s resolution)."""
-        raw = job.annotations.get(C.ANN_TRACE)
-        try:
-            tr = json.loads(raw) if raw else {}
-        except ValueError:
-            tr = {}
-        if event in tr and event != "ended":
-            return
-        tr[event] = round(time.time(), 4)
-        job.set_annotation(C.ANN_TRACE, json.dumps(tr, sort_keys=True))
+    def reconcile_containers(self, job, pod, rtype, node_status):
+        """(phase, restart?, message) of one replica, as ``pod.classify_replica`` + ``RESTART_MATRIX`` see it."""
+        from .pod import classify_replica
 
-    def _observe_startup(self, job: AITrainingJob) -> None:
-        try:
-            tr = json.loads(job.annotations.get(C.ANN_TRACE, "{}"))
-            t0 = tr.get("submitted") or tr.get("firstReconcile")
-            if t0 and "running" in tr:
-                metrics.observe("aitj_job_startup_seconds", tr["running"] - t0)
-        except ValueError:
-            pass
+        v = classify_replica(job, pod, node_status, engine.EngineOptions.from_operator_option(self.option).window,
+                             M.now())
+        return v.phase, v.wants_restart(job.spec.replica_specs[rtype].restart_policy), v.message
+
+    def reconcile_pods(self, job, pods, rtype):
+        """(ending phase, message) of one role; the role's actions are applied."""
+        d = engine.Decision()
+        out = engine.plan_role(self._obs_for(job, pods, []), d, rtype)
+        self.executor.apply(job, d)
+        return out.phase, out.message
+
+    def update_status(self, job, pods, services, role_phases, message):
+        d = engine.Decision()
+        engine.derive_status(self._obs_for(job, pods, services), d, role_phases, message)
+        self.executor.apply(job, d)
 
 
 def new_training_job_controller(kube_client, trainingjob_client, ext_api_client, kube_informer_factory,
                                 trainingjob_informer_factory, option, **kw) -> TrainingJobController:
-    """``NewTrainingJobController`` (controller.go:73-159)."""
     return TrainingJobController(kube_client, trainingjob_client, ext_api_client, kube_informer_factory,
                                  trainingjob_informer_factory, option, **kw)

@@ -1,21 +1,16 @@
-"""Job event handlers, naming and teardown.
+"""Job event handlers and worker-report metrics.
 
-Parity: /root/reference/pkg/controller/trainingjob.go:12-73 -- ``<job>-<role>-<index>`` naming
-(:12-15, implemented in ``pod.gen_general_name``), add -> enqueue now (:17-24), update with a new
-resourceVersion -> enqueue rate-limited + delayed enqueue when ``timeLimit`` changed (:26-47), delete
--> enqueue (:49-51), delete pods then services (:53-73).  The reference's two
-``// FIXME: need to validate trainingjob`` (:21,:33) are resolved: invalid objects are rejected at
-admission and, defensively, skipped here with a warning.  Quirk Q9 (services leak when there are no
-pods) is fixed: services are deleted regardless.
+What the reference does on job events (/root/reference/pkg/controller/trainingjob.go:17-51): add -> enqueue now,
+update with a new resourceVersion -> enqueue rate-limited plus a delayed enqueue when ``timeLimit`` changed, delete ->
+enqueue.  Its two ``// FIXME: need to validate trainingjob`` (:21,:33) are resolved: invalid objects are rejected at
+admission and, defensively, skipped here with a warning.  Naming (:12-15) lives in ``pod.gen_general_name``; the
+teardown of a finished job (:53-73, and quirk Q9: services leaked when there were no pods) is part of the engine's
+``terminate`` decision.
 """
 from __future__ import annotations
 
-from typing import List
-
 from ..api import meta as M
-from ..api.types import AITrainingJob
 from ..api.validation import validate_dict
-from ..store.apiserver import APIError
 from ..utils import klog, metrics
 
 # what the workers report back onto the job (runtime/elastic.py) becomes scrapeable (rescale latency and
@@ -93,13 +88,3 @@ class TrainingJobHandlers:
 
     def delete_training_job(self, obj) -> None:
         self.enqueue_job(obj, False, 0)
-
-    def delete_pods_and_services(self, job: AITrainingJob, pods: List[dict], services: List[dict]) -> None:
-        live = [p for p in pods if not p.get("metadata", {}).get("deletionTimestamp")]
-        if live:
-            self.delete_pods_expecting(job, live, None)
-        for svc in services:
-            try:
-                self.service_control.delete_service(M.namespace_of(svc), M.name_of(svc), job)
-            except APIError as e:
-                klog.warning("delete service %s failed: %s", M.name_of(svc), e.message)

@@ -53,7 +53,20 @@ class Store {
     if (!wal_path.empty()) {
       wal_path_ = wal_path;
       replay();
+      // what was logged before this start cannot be replayed to a watcher: a watch from an older resourceVersion must
+      // be told to re-list (Gone) instead of silently missing the events in between
+      history_floor_ = rv_;
+      bool need_nl = false;
+      {
+        std::ifstream f(wal_path_, std::ios::binary | std::ios::ate);
+        if (f.good() && f.tellg() > 0) {
+          f.seekg(-1, std::ios::end);
+          need_nl = f.get() != '\n';
+        }
+      }
       wal_.open(wal_path_, std::ios::app | std::ios::binary);
+      // a crash can cut the log right after a record's last digit; without a separator the next record would be glued to it
+      if (need_nl) { wal_ << '\n'; wal_.flush(); }
     }
   }
 
@@ -170,7 +183,8 @@ class Store {
     w->kind = kind;
     w->ns = ns;
     if (since_rv != 0 && since_rv < rv_) {
-      if (!history_.empty() && history_.front().obj.rv > since_rv + 1 && trimmed_)
+      // history_floor_: newest resourceVersion whose event is no longer (or was never) in history_
+      if (since_rv < history_floor_)
         throw StoreError("Gone", "too old resource version: " + std::to_string(since_rv));
       for (auto& ev : history_) {
         if (ev.obj.rv <= since_rv) continue;
@@ -235,6 +249,9 @@ class Store {
     const std::string tmp = wal_path_ + ".tmp";
     {
       std::ofstream f(tmp, std::ios::trunc | std::ios::binary);
+      // the snapshot only holds live objects: when the newest operations were deletes the highest rv in it is below
+      // rv_, and resourceVersions would be handed out twice after a restart -- so the counter itself is recorded
+      f << "V " << rv_ << '\n';
       for (auto& kk : objs_)
         for (auto& kv : kk.second) write_put(f, kv.second);
     }
@@ -263,8 +280,8 @@ class Store {
     WatchEvent ev{type, o};
     history_.push_back(ev);
     if (history_.size() > history_cap_) {
+      history_floor_ = history_.front().obj.rv;
       history_.pop_front();
-      trimmed_ = true;
     }
     for (auto& kv : watchers_) {
       Watcher& w = *kv.second;
@@ -352,6 +369,8 @@ class Store {
         }
         if (bad) break;
         objs_[o.kind][o.ns + "/" + o.name] = o;
+      } else if (op == "V") {
+        // resourceVersion counter at the time of a compaction (no object)
       } else if (op == "D") {
         std::string kind, ns, name;
         if (!read_str(f, kind) || !read_str(f, ns) || !read_str(f, name)) break;
@@ -371,7 +390,7 @@ class Store {
   std::map<std::string, std::map<std::string, StoredObject>> objs_;
   std::deque<WatchEvent> history_;
   size_t history_cap_;
-  bool trimmed_ = false;
+  uint64_t history_floor_ = 0;
   std::unordered_map<int64_t, std::shared_ptr<Watcher>> watchers_;
   int64_t watch_id_ = 0;
   std::string wal_path_;

@@ -341,6 +341,8 @@ def run(args) -> Dict[str, Any]:
     timing: Dict[str, Any] = {}
     ev0 = ev1 = None
     t_wall0 = 0.0
+    t_epoch0 = 0.0
+    timed_from = -1          # first step inside the timed region (-1: not armed yet)
     step = joined_step
     first_step_done = False
     pending_rescale = None
@@ -388,7 +390,9 @@ def run(args) -> Dict[str, Any]:
                                        "teardown_s": t1 - t0, "init_pg_s": t2 - t1, "sync_state_s": time.time() - t2}
                     continue    # back to the step boundary: every rank (joiners included) runs the same sequence
             # ---- timed region bookkeeping ----------------------------------------------------------------
-            if step == args.warmup and args.steps > 0:
+            # armed at the first step boundary at or past the warm-up: a replica resumed from a checkpoint (or an
+            # elastic joiner) starts past `--warmup` and still gets a timed region (and counts the steps it timed)
+            if timed_from < 0 and step >= args.warmup and args.steps > 0:
                 if world > 1:
                     dist.barrier()
                 if use_cuda:
@@ -396,6 +400,8 @@ def run(args) -> Dict[str, Any]:
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     ev0.record()
                 t_wall0 = time.perf_counter()
+                t_epoch0 = time.time()
+                timed_from = step
                 launches0 = oplib.LAUNCHES
             loss = adapter.train_step()
             if breaker is not None and breaker.tripped:
@@ -502,26 +508,30 @@ def run(args) -> Dict[str, Any]:
         breaker.stop()
     if _CKPT.get("writer") is not None:
         _CKPT["writer"].wait(60.0)
-    if args.steps > 0 and step >= total:
+    n_timed = step - timed_from if timed_from >= 0 else 0
+    if args.steps > 0 and step >= total and n_timed > 0:
         if use_cuda:
             ev1.record()
             torch.cuda.synchronize()
+        t_epoch1 = time.time()
         if world > 1:
             dist.barrier()
         wall = time.perf_counter() - t_wall0
         dev_ms = ev0.elapsed_time(ev1) if use_cuda else wall * 1e3
         dev_ms = max_over_ranks(dev_ms, device)
         global_batch = args.batch * world
+        result.update({"timed_steps": n_timed, "timed_from_step": timed_from,
+                       "timed_region_epoch": [t_epoch0, t_epoch1]})
         graph_launches = adapter.launches_per_step()
         eager_launches = (oplib.LAUNCHES - launches0)
         result.update({
-            "ms_per_step": dev_ms / args.steps,
-            "samples_per_sec": global_batch * args.steps / (dev_ms / 1e3),
-            "wall_ms_per_step": wall * 1e3 / args.steps,
+            "ms_per_step": dev_ms / n_timed,
+            "samples_per_sec": global_batch * n_timed / (dev_ms / 1e3),
+            "wall_ms_per_step": wall * 1e3 / n_timed,
             "global_batch": global_batch, "batch_per_gpu": args.batch,
             "h2d_bytes_per_step": adapter.h2d_bytes, "d2h_bytes_per_step": adapter.d2h_bytes,
-            "gpu_launches": graph_launches * args.steps if graph_launches else eager_launches,
-            "launches_per_step": graph_launches or (eager_launches // max(1, args.steps)),
+            "gpu_launches": graph_launches * n_timed if graph_launches else eager_launches,
+            "launches_per_step": graph_launches or (eager_launches // max(1, n_timed)),
             "loss_first": losses[0] if losses else None, "loss_last": losses[-1] if losses else None,
             "flops_per_step": getattr(adapter, "flops_per_step", 0.0),
             "describe": adapter.describe,

@@ -144,11 +144,18 @@ class HTTPTransport(Transport):
         headers = {"Accept": "application/json", "User-Agent": self._ua}
         if data is not None:
             headers["Content-Type"] = content_type
+        # One retry -- but never of a write the server may already have applied: a create reported as AlreadyExists or a
+        # guarded PUT reported as Conflict would make callers (leader election, expectation bookkeeping) see a failure
+        # for a write that landed.  Safe to repeat: any GET; a failure while the request was still being written; and a
+        # kept-alive connection the server had already closed (it never saw the request).
         last: Optional[Exception] = None
         for attempt in range(2):
             conn = self._conn()
+            reused = conn.sock is not None
+            sent = False
             try:
                 conn.request(method, url, body=data, headers=headers)
+                sent = True
                 resp = conn.getresponse()
                 raw = resp.read()
                 break
@@ -156,6 +163,13 @@ class HTTPTransport(Transport):
                 last = e
                 conn.close()
                 self._local.conn = None
+                stale_keepalive = reused and isinstance(e, (http.client.RemoteDisconnected, ConnectionResetError,
+                                                            BrokenPipeError))
+                if method != "GET" and sent and not stale_keepalive:
+                    timed_out = isinstance(e, (socket.timeout, TimeoutError))
+                    raise APIError(504 if timed_out else 503, "Timeout" if timed_out else "ServiceUnavailable",
+                                   f"{method} {path}: no answer from API server {self.master} ({e}); the request may "
+                                   f"have been applied") from None
         else:
             raise APIError(503, "ServiceUnavailable", f"cannot reach API server {self.master}: {last}")
         out = json.loads(raw) if raw else {}
