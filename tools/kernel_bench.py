@@ -69,7 +69,7 @@ def main():
         b = (torch.randn(k, n, device="cuda") if b_mn else torch.randn(n, k, device="cuda")).bfloat16()
         out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
         flops = 2.0 * m * n * k
-        for bn in (512, 256):
+        for bn in (1024, 512, 256):
             med, best = timeit(lambda: F.gemm(a, b, out, a_mn=a_mn, b_mn=b_mn, block_n=bn))
             rows.append({"kernel": f"tcgen05 {name} bn={bn}", "M": m, "N": n, "K": k, "ms_med": med, "ms_best": best,
                          "tflops": flops / med / 1e9, "frac_of_measured_peak": flops / med / 1e9 / PEAK_TF})
@@ -85,8 +85,8 @@ def main():
         dw = torch.zeros(nout, kin, device="cuda")
         sk = F.auto_split_k(nout, kin, M)
         flops = 2.0 * M * nout * kin
-        for bn, tag in ((512, "2cta"), (0, "1cta")):
-            skk = F.auto_split_k(nout, kin, M, 256) * (2 if bn == 512 else 1)
+        for bn, tag in ((1024, "quad"), (512, "2cta"), (0, "1cta")):
+            skk = F.auto_split_k(nout, kin, M, 256) * (2 if bn >= 512 else 1)
             med, best = timeit(lambda: F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=skk, block_n=bn))
             rows.append({"kernel": f"tcgen05 {name} {tag} sk={skk}", "M": nout, "N": kin, "K": M, "ms_med": med,
                          "ms_best": best, "tflops": flops / med / 1e9,

@@ -60,6 +60,7 @@ class FlatParams:
         self.mc_base = 0
         self.small_range = None
         self.g_small = None
+        self.shard = None          # parallel.symm.ShardedGradState when gradients are owner-sharded over NVLink
         self.init_parameters(seed)
 
     def init_parameters(self, seed: int = 0) -> None:
@@ -92,6 +93,14 @@ class FlatParams:
     def grad(self, name: str):
         """Where gradient-producing kernels accumulate ``name``'s gradient: the local fp32 slice, or -- when a
         symmetric buffer with an NVSwitch multicast alias is attached -- that alias (reduce-to-all-peers)."""
+        if self.shard is not None:
+            s = self.by_name[name]
+            if len(s.shape) == 1 and self.small_range is not None:
+                a = s.offset - self.small_range[0]
+                return self.g_small[a:a + s.numel]
+            from ..ops.functional import PeerView
+
+            return PeerView(self._view(self.g32, name))
         if self.mc_base:
             from ..ops.functional import RawView
 
@@ -123,8 +132,51 @@ class FlatParams:
                     self.small_range = (lo, hi)
                     self.g_small = torch.zeros(hi - lo, dtype=torch.float32, device=self.device)
 
+    def _small_region(self) -> None:
+        """1-D parameters (biases, LayerNorm) are accumulated locally with scalar atomics and sent once per step; only
+        possible when they form one contiguous tail region of the layout."""
+        self.small_range = None
+        one_d = [s for s in self.specs if len(s.shape) == 1]
+        if one_d:
+            lo = min(s.offset for s in one_d)
+            hi = max(s.offset + s.padded for s in one_d)
+            if all(len(s.shape) == 1 for s in self.specs if lo <= s.offset < hi):
+                self.small_range = (lo, hi)
+                self.g_small = torch.zeros(hi - lo, dtype=torch.float32, device=self.device)
+
+    def attach_shard(self, shard) -> None:
+        """Owner-sharded mode: gradients and the bf16 parameter copy move into ``shard``'s symmetric buffers."""
+        self.g32 = shard.g[: self.total]
+        self.g32.zero_()
+        shard.w.copy_(self.p16)
+        self.p16 = shard.w
+        self.mc_base = 0
+        self.shard = shard
+        self._small_region()
+        if self.small_range is None:
+            raise RuntimeError("owner-sharded gradients need the 1-D parameters in one tail region of the layout")
+
+    def detach_shard(self) -> None:
+        """Back to private buffers (the world shrank to one rank, or another gradient path was selected)."""
+        if self.shard is None:
+            return
+        p16 = torch.empty(self.total, dtype=torch.bfloat16, device=self.device)
+        p16.copy_(self.p16)
+        self.p16 = p16
+        self.g32 = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.shard = None
+        self.small_range = None
+        self.g_small = None
+
     def push_small_grads(self) -> None:
-        """Multicast mode: send the locally accumulated 1-D parameter gradients to every peer (one kernel)."""
+        """Multicast mode: send the locally accumulated 1-D parameter gradients to every peer (one kernel); owner-sharded
+        mode: to the ranks that own them."""
+        if self.shard is not None:
+            from ..ops import functional as F
+
+            lo, hi = self.small_range
+            F.peer_push(self.g32[lo:hi], self.g_small)
+            return
         if self.mc_base and self.small_range is not None:
             from ..ops import functional as F
 

@@ -24,6 +24,9 @@ import torch.nn.functional as TF
 from .flat_params import FlatParams, ParamSpec
 
 
+# measured per-shape kernel choices (kind:NxK -> (block_n, split_k)); empty = CTA pair wherever a 256x256 tile fits
+_DEFAULT_GEMM_CFG: Dict[str, Tuple[int, int]] = {}
+
 _QKV_GATHER = os.environ.get("AITJ_QKV_GATHER", "1") != "0"
 _FUSE_COLSUM = os.environ.get("AITJ_FUSE_COLSUM", "1") != "0" and os.environ.get("AITJ_GEMM_EPI_WARPS", "16") != "8" \
     and os.environ.get("AITJ_GEMM_GROUP_STORE", "0") == "0"
@@ -120,6 +123,13 @@ class GPT2Engine:
         self.attn_impl = os.environ.get("AITJ_ATTN", "cudnn")
         if self.attn_impl == "tcgen05" and (seq_len % 128 or cfg.n_embd // cfg.n_head != 64 or gemm_backend != "tcgen05"):
             self.attn_impl = "cudnn"
+        # attention backward: "tcgen05" (ops/csrc/attention_bwd_tcgen05.cu: dq/dk/dv written straight into the packed d_qkv)
+        # needs our forward's log-sum-exp, so it implies the tcgen05 forward; "cudnn" = library kernel + gather
+        self.attn_bwd_impl = os.environ.get("AITJ_ATTN_BWD", "cudnn")
+        if self.attn_impl != "tcgen05":
+            self.attn_bwd_impl = "cudnn"
+        self._attn_delta = None
+        self._dq_acc = None
         self._philox = torch.zeros((), dtype=torch.int64, device=device)
         # backward GEMMs may leave a few SMs to the gradient all-reduce kernels that run next to them (DDP): a
         # persistent grid of exactly #SMs CTAs needs a second wave as soon as a collective holds some SMs
@@ -156,6 +166,13 @@ class GPT2Engine:
 
         # CTA-pair (cta_group::2) GEMM: 256x256 tile per 2-CTA cluster (AITJ_GEMM_PAIR=0 falls back to 1-CTA)
         self.pair = _os.environ.get("AITJ_GEMM_PAIR", "1") != "0"
+        # per-GEMM kernel choice measured in the step (tools/gemm_cfg_sweep.py): "kind:NxK=block_n[/split_k]" entries,
+        # block_n 512 = CTA pair, 256 / 128 = 1-CTA tiles; AITJ_GEMM_CFG overrides / extends the table
+        self.gemm_cfg: Dict[str, Tuple[int, int]] = dict(_DEFAULT_GEMM_CFG)
+        for item in filter(None, _os.environ.get("AITJ_GEMM_CFG", "").split(",")):
+            k, v = item.split("=")
+            bn, _, sk = v.partition("/")
+            self.gemm_cfg[k.strip()] = (int(bn), int(sk or 0))
         self.grad_hook = None  # called as hook(name_of_bucket) when a gradient bucket is complete
         self._graph = None
         self.split_k: Dict[Tuple[int, int], int] = {}
@@ -165,7 +182,7 @@ class GPT2Engine:
         F = self.F
         if self.backend == "tcgen05":
             F.gemm(x, w, out, bias=bias, residual=residual, gelu=gelu, save_pre=gelu, aux=aux,
-                   block_n=self._bn(x.shape[0], w.shape[0]))
+                   block_n=self._bn(x.shape[0], w.shape[0], f"fwd:{w.shape[0]}x{w.shape[1]}"))
             return out
         # library path (cuBLAS) + standalone elementwise kernels; numerics cross-check / fallback bench arm
         y = torch.addmm(bias, x, w.t()) if bias is not None else x @ w.t()
@@ -178,15 +195,18 @@ class GPT2Engine:
             out.copy_(y)
         return out
 
-    def _bn(self, m: int, n: int) -> int:
-        """512 = CTA-pair kernel when the problem has at least one full 256x256 tile, else auto 1-CTA."""
+    def _bn(self, m: int, n: int, key: str = "") -> int:
+        """512 = CTA-pair kernel when the problem has at least one full 256x256 tile, else auto 1-CTA; a measured
+        per-shape choice in ``gemm_cfg`` wins."""
+        if key in self.gemm_cfg:
+            return self.gemm_cfg[key][0]
         return 512 if self.pair and m >= 256 and n >= 256 else 0
 
     def _dgrad(self, dy, w, out, dgelu_aux=None, colsum=None):
         """out[M,K] = dy[M,N] @ w[N,K]  (* gelu'(aux)); colsum (fp32[K], optional) += column sums of out."""
         F = self.F
         if self.backend == "tcgen05":
-            bn = self._bn(dy.shape[0], w.shape[1])
+            bn = self._bn(dy.shape[0], w.shape[1], f"dgrad:{w.shape[1]}x{w.shape[0]}")
             fused = colsum is not None and bn == 512 and _FUSE_COLSUM
             F.gemm(dy, w, out, b_mn=True, dgelu=dgelu_aux is not None, aux=dgelu_aux,
                    block_n=bn, max_ctas=self.bwd_max_ctas, colsum=colsum if fused else None)
@@ -214,10 +234,12 @@ class GPT2Engine:
                 F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=1,
                        block_n=256 if tiles256 >= F.num_sms() else 128)
                 return
-            bn = self._bn(dw.shape[0], dw.shape[1])
+            ck = f"wgrad:{dw.shape[0]}x{dw.shape[1]}"
+            bn = self._bn(dw.shape[0], dw.shape[1], ck)
             sk = self.split_k.get(key)
             if sk is None:
-                sk = F.auto_split_k(dw.shape[0], dw.shape[1], dy.shape[0], pair=(bn == 512))
+                sk = self.gemm_cfg.get(ck, (0, 0))[1] or \
+                    F.auto_split_k(dw.shape[0], dw.shape[1], dy.shape[0], block_n=bn if bn != 512 else 0, pair=(bn == 512))
                 self.split_k[key] = sk
             F.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=sk, block_n=bn,
                    max_ctas=self.bwd_max_ctas)
@@ -254,6 +276,14 @@ class GPT2Engine:
         """d_qkv <- SDPA backward; d_bias (the qkv bias gradient) += colsum(d_qkv), fused into the gather."""
         B, T, H = self.B, self.T, self.cfg.n_head
         D = self.cfg.n_embd // H
+        if self.attn_bwd_impl == "tcgen05":
+            if self._dq_acc is None:
+                self._attn_delta = torch.empty(B, H, T, device=self.dev, dtype=torch.float32)
+                self._dq_acc = torch.zeros(B * T, H * D, device=self.dev, dtype=torch.float32)
+            self.F.attention_bwd(lb.qkv, lb.att, d_att, lb.lse, self._attn_delta, self._dq_acc, d_qkv, B, T, H,
+                                 causal=self.causal)
+            self.F.colsum(d_qkv, d_bias)
+            return
         do = d_att.view(B, T, H, D).transpose(1, 2)
         if self.attn_impl == "tcgen05":
             # cuDNN's SDPA backward accepts our forward's output and log-sum-exp ([B,H,T,1], natural log)
@@ -379,6 +409,22 @@ class GPT2Engine:
     def optimizer_step(self, lr: float = 3e-4, step: int = 1, weight_decay: float = 0.1, max_norm: float = 1.0,
                        grad_div: float = 1.0, beta1: float = 0.9, beta2: float = 0.95, use_dyn: bool = False) -> None:
         F, P = self.F, self.params
+        sh = P.shard
+        if sh is not None:
+            # owner-sharded: this rank holds the summed gradient of [lo, hi) only.  Clip on the global norm (partial
+            # square sums exchanged by multicast store), AdamW on the shard, bf16 parameters stored into every rank's copy.
+            lo, hi = sh.lo, sh.hi
+            self.sumsq.zero_()
+            if max_norm > 0 and hi > lo:
+                F.sumsq(P.g32[lo:hi], self.sumsq)
+            F.norm_share(sh.parts_mc, self.sumsq, sh.rank)
+            sh.barrier()
+            if hi > lo:
+                F.adamw(P.p32[lo:hi], P.g32[lo:hi], P.m[lo:hi], P.v[lo:hi], sh.w_mc + 2 * lo, P.wd_mask[lo // 256:],
+                        lr=lr, beta1=beta1, beta2=beta2, eps=1e-8, weight_decay=weight_decay, step=step,
+                        sumsq_buf=sh.parts if max_norm > 0 else None, max_norm=max_norm, grad_div=grad_div,
+                        zero_grad=True, dyn=self.dyn if use_dyn else None, sumsq_n=sh.world, p16_multicast=True)
+            return
         if max_norm > 0:
             self.sumsq.zero_()
             F.sumsq(P.g32, self.sumsq)

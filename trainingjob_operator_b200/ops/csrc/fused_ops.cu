@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "ptx.cuh"
+#include <string.h>
 
 namespace aitj {
 
@@ -121,7 +122,7 @@ __device__ __forceinline__ void ln_bwd_block_reduce(const float (&acc)[V * 8], f
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < H; ++w) t += red[w][c];
-    grad_add_f32(dst + c, t, mc != 0);
+    grad_add_f32(dst + c, t, mc);
   }
 }
 
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __res
     const int m = static_cast<int>(i / vec_per_row), c = static_cast<int>(i % vec_per_row) * 4;
     uint2 u = *reinterpret_cast<const uint2*>(dx + static_cast<size_t>(m) * C + c);
     float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
-    grad_add_v4_f32(dwte + tok[m] * C + c, f0.x, f0.y, f1.x, f1.y, mc != 0);
-    if (dwpe) grad_add_v4_f32(dwpe + static_cast<size_t>(m % T) * C + c, f0.x, f0.y, f1.x, f1.y, mc != 0);
+    grad_add_v4_f32(dwte + tok[m] * C + c, f0.x, f0.y, f1.x, f1.y, mc);
+    if (dwpe) grad_add_v4_f32(dwpe + static_cast<size_t>(m % T) * C + c, f0.x, f0.y, f1.x, f1.y, mc);
   }
 }
 
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][c];
-    grad_add_f32(db + blockIdx.x * 256 + c, s, mc != 0);
+    grad_add_f32(db + blockIdx.x * 256 + c, s, mc);
   }
 }
 
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(256) qkv_gather_colsum_kernel(QkvSrc src, __nv
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][c];
-    grad_add_f32(db + blockIdx.x * 256 + c, s, mc != 0);
+    grad_add_f32(db + blockIdx.x * 256 + c, s, mc);
   }
 }
 
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g,
 // sumsq (device scalar, may be null) drives global-norm clipping without a host sync.
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2, max_norm, grad_div;
-  int zero_grad;
+  int zero_grad, sumsq_n, p16_mc;
 };
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v,
@@ -486,12 +487,17 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                     const uint8_t* __restrict__ wd_mask,
                                                     const float* __restrict__ sumsq,
                                                     const float* __restrict__ dyn, size_t n, AdamArgs a) {
+  // a.sumsq_n partial sums of squares (one per rank's shard in the owner-sharded mode; summed in rank order, so every
+  // rank computes the identical clip factor); a.p16_mc: `p16` is an NVSwitch multicast address -- the refreshed bf16
+  // parameters of this shard are stored into every rank's copy (sharded optimizer + all-gather in one sweep)
   // dyn (device, optional) = {lr, bias_correction1, bias_correction2}: lets a captured CUDA graph replay
   // with a per-step learning rate / step count without re-capturing.
   if (dyn != nullptr) { a.lr = dyn[0]; a.bc1 = dyn[1]; a.bc2 = dyn[2]; }
   float clip = 1.0f;
   if (sumsq != nullptr && a.max_norm > 0.f) {
-    const float norm = sqrtf(*sumsq) / a.grad_div;
+    float total = 0.f;
+    for (int i = 0; i < a.sumsq_n; ++i) total += sumsq[i];
+    const float norm = sqrtf(total) / a.grad_div;
     if (norm > a.max_norm) clip = a.max_norm / (norm + 1e-6f);
   }
   const float gmul = clip / a.grad_div;
@@ -522,8 +528,27 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
     uint2 o;
     o.x = pack_bf16x2(pp[0], pp[1]);
     o.y = pack_bf16x2(pp[2], pp[3]);
-    reinterpret_cast<uint2*>(p16)[i] = o;
+    if (a.p16_mc) mc_store_v2_b32(reinterpret_cast<uint2*>(p16) + i, o.x, o.y);
+    else reinterpret_cast<uint2*>(p16)[i] = o;
   }
+}
+
+// Owner-sharded mode: the locally accumulated 1-D gradients (biases, LayerNorm; built from many scalar atomics) go to
+// their owners in one sweep -- dst is the LOCAL address of the segment in the symmetric gradient buffer, each 16-byte
+// piece is added into the copy of the rank that owns it; src is cleared.
+__global__ void __launch_bounds__(256) peer_push_kernel(float* __restrict__ dst, float* __restrict__ src, size_t n) {
+  const size_t nvec = n / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(src)[i];
+    red_add_v4_f32(peer_ptr(dst + i * 4), v.x, v.y, v.z, v.w);
+    reinterpret_cast<float4*>(src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// This rank's partial sum of squared gradients goes into slot `rank` of every rank's `parts` array (multicast store).
+__global__ void norm_share_kernel(float* __restrict__ parts_mc, const float* __restrict__ mine, int rank) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) mc_store_f32(parts_mc + rank, *mine);
 }
 
 // Push a locally accumulated fp32 gradient segment into every peer's buffer through the switch and clear it:
@@ -709,11 +734,40 @@ int aitj_sumsq(const void* g, long long n, void* out, void* stream) {
   return LAUNCH_OK();
 }
 
+static int g_adam_sumsq_n = 1, g_adam_p16_mc = 0;   // consumed by the next aitj_adamw call
+int aitj_adamw_set_shard(int sumsq_n, int p16_mc) { g_adam_sumsq_n = sumsq_n; g_adam_p16_mc = p16_mc; return 0; }
+
+int aitj_fused_set_peers(const void* base, const long long* delta, const long long* bound, int n) {
+  if (n < 1 || n > 8) return -1;
+  PeerTable t;
+  memset(&t, 0, sizeof(t));
+  t.base = reinterpret_cast<const float*>(base);
+  for (int i = 0; i < n; ++i) t.delta[i] = delta[i];
+  for (int i = 0; i <= n; ++i) t.bound[i] = bound[i];
+  t.n = n;
+  return cudaMemcpyToSymbol(c_peers, &t, sizeof(t)) == cudaSuccess ? 0 : -2;
+}
+
+int aitj_peer_push(void* dst_local, void* src, long long n, void* stream) {
+  if (n % 4) return -1;
+  peer_push_kernel<<<grid_for(static_cast<size_t>(n) / 4, 256, 148 * 2), 256, 0, S(stream)>>>(
+      reinterpret_cast<float*>(dst_local), reinterpret_cast<float*>(src), static_cast<size_t>(n));
+  return LAUNCH_OK();
+}
+
+int aitj_norm_share(void* parts_mc, const void* mine, int rank, void* stream) {
+  norm_share_kernel<<<1, 32, 0, S(stream)>>>(reinterpret_cast<float*>(parts_mc), reinterpret_cast<const float*>(mine),
+                                             rank);
+  return LAUNCH_OK();
+}
+
 int aitj_adamw(void* p, void* g, void* m, void* v, void* p16, const void* wd_mask, const void* sumsq,
                const void* dyn, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float max_norm,
                float grad_div, int zero_grad, void* stream) {
   if (n % 256) return -1;
   AdamArgs a;
+  a.sumsq_n = g_adam_sumsq_n; a.p16_mc = g_adam_p16_mc;
+  g_adam_sumsq_n = 1; g_adam_p16_mc = 0;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   a.bc2 = 1.0f - powf(beta2, static_cast<float>(step));

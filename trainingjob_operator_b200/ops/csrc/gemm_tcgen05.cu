@@ -21,6 +21,7 @@
 // The reference operator has no GPU code; this kernel belongs to the launched
 // workers' training step that BASELINE.json measures (samples/sec).
 #include "ptx.cuh"
+#include <string.h>
 
 namespace aitj {
 
@@ -43,7 +44,10 @@ enum : int {
   EPI_DEBUG_NOTMA = 1024,  // profiling only: stage the tile in shared memory but do not issue the TMA store
   EPI_DEBUG_LDONLY = 2048, // profiling only: read the accumulators (tcgen05.ld) and drop them
   EPI_NO_SIDE_TMA = 8192,  // A/B switch: fetch the residual / pre-GELU tile with per-thread global loads again
-  EPI_GROUP_STORE = 4096   // CTA-pair kernel, bf16 outputs: one 128x64 TMA store per column quarter instead of four 32x64
+  EPI_GROUP_STORE = 4096,  // CTA-pair kernel, bf16 outputs: one 128x64 TMA store per column quarter instead of four 32x64
+  EPI_PEER = 16384         // with EPI_ACCUM: `out` lies in the symmetric, owner-sharded gradient buffer; every 32-row group of the
+                           // tile is added into the copy of the rank that owns it (red.global.add over NVLink peer memory):
+                           // weight-gradient GEMM + reduce-scatter in one kernel, split-K partials included
 };
 
 struct GemmArgs {
@@ -62,6 +66,13 @@ struct GemmArgs {
   float* colsum;
   // optional per-CTA role timeline (8 x u64 per CTA, see aitj_gemm_set_trace): where each warp role waits
   unsigned long long* trace;
+  // EPI_PEER with TMA: one fp32 tensor map of `out` per rank (device memory, 128 B each), indexed by the owner of a
+  // 32-row group; null = add from registers (red.global.add.v4.f32 on the peer mapping)
+  const CUtensorMap* peer_maps;
+  // EPI_PEER with split_k > 1: arrival counters, one per 32x32-aligned sub-block start (self-resetting).  The splits
+  // accumulate into the LOCAL copy; the last one to finish a sub-block moves it to its owner and clears the local copy,
+  // so a gradient crosses NVLink once instead of split_k times
+  unsigned int* peer_counters;
 };
 
 // trace slots
@@ -130,11 +141,69 @@ template <int kCols>
 __device__ __forceinline__ void epilogue_f32(const GemmArgs& a, const CUtensorMap* tm_out, uint32_t tmem_acc, int row0,
                                              int n0, int c_begin, uint8_t* sbuf, int lane) {
   const int flags = a.flags;
-  if (flags & EPI_MC) {
-    // fused GEMM -> all-reduce: the accumulators are reduced into ALL peers' gradient buffers through the
-    // NVSwitch (multimem.red).  The 32x32 fp32 chunk is transposed through the staging buffer so that each warp
-    // instruction covers 4 rows x 128 contiguous bytes (full lines on NVLink) instead of 32 rows x 16 bytes.
+  if ((flags & EPI_PEER) && a.split_k > 1 && a.peer_counters != nullptr) {
+    if (row0 >= a.M || n0 + c_begin >= a.N) return;
     float* obase = reinterpret_cast<float*>(a.out);
+    float* first = obase + static_cast<size_t>(row0) * a.ldc;
+    const long long delta = c_peers.delta[peer_owner(first)];
+    // (1) split-K partial -> local copy, exactly like the single-GPU path
+#pragma unroll 1
+    for (int c = 0; c < kCols / 32; ++c) {
+      const int col0 = n0 + c_begin + c * 32;
+      if (col0 >= a.N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + c_begin + c * 32, r);
+      tmem_ld_wait();
+      stage_acquire(lane);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) stage_write16(sbuf, lane, q, make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]));
+      stage_commit(tm_out, sbuf, col0, row0, lane, true);
+    }
+    if (delta == 0) return;                 // this rank owns these rows: they are where they belong
+    // (2) my reduce-adds have landed -> count this split in; the last arrival owns the move
+    unsigned int* ctr = a.peer_counters + static_cast<size_t>(row0 >> 5) * ((a.N + 31) >> 5) + ((n0 + c_begin) >> 5);
+    unsigned int seen = 0;
+    if (lane == 0) {
+      tma_store_wait<0>();
+      __threadfence();
+      seen = atomicAdd(ctr, 1u);
+    }
+    seen = __shfl_sync(0xffffffffu, seen, 0);
+    if (seen != static_cast<unsigned int>(a.split_k - 1)) return;
+    __threadfence();
+    // (3) the finished 32 x kCols block goes to its owner over NVLink; the local copy is cleared for the next step
+    constexpr int kVecPerRow = kCols / 4;
+#pragma unroll 4
+    for (int i = lane; i < 32 * kVecPerRow; i += 32) {
+      const int r = i / kVecPerRow, c4 = i - r * kVecPerRow;
+      const int grow = row0 + r, gcol = n0 + c_begin + c4 * 4;
+      if (grow < a.M && gcol < a.N) {
+        float* p = obase + static_cast<size_t>(grow) * a.ldc + gcol;
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+        red_add_v4_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(p) + delta), v.x, v.y, v.z, v.w);
+        __stcg(reinterpret_cast<float4*>(p), make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+    if (lane == 0) *ctr = 0u;
+    return;
+  }
+  if ((flags & EPI_PEER) && a.peer_maps != nullptr) {
+    // fused GEMM -> reduce-scatter through the TMA unit: the same staged 32x32 fp32 chunks as the local split-K path,
+    // but the bulk reduce-add targets the OWNER's copy of the gradient (its tensor map covers the peer mapping)
+    if (row0 >= a.M) return;
+    tm_out = a.peer_maps + peer_owner(reinterpret_cast<const float*>(a.out) + static_cast<size_t>(row0) * a.ldc);
+  } else if (flags & (EPI_MC | EPI_PEER)) {
+    // fused GEMM -> all-reduce (EPI_MC): the accumulators are reduced into ALL peers' gradient buffers through the
+    // NVSwitch (multimem.red).  Fused GEMM -> reduce-scatter (EPI_PEER): they are added into the OWNER's buffer only
+    // (ownership is by flat offset with 32-row granularity, so this warp's 32 rows have one owner).  The 32x32 fp32
+    // chunk is transposed through the staging buffer so that each warp instruction covers 4 rows x 128 contiguous
+    // bytes (full lines on NVLink) instead of 32 rows x 16 bytes.
+    float* obase = reinterpret_cast<float*>(a.out);
+    const bool mc = (flags & EPI_MC) != 0;
+    if (!mc && row0 < a.M) {
+      float* first = obase + static_cast<size_t>(row0) * a.ldc;
+      obase += peer_ptr(first) - first;
+    }
 #pragma unroll 1
     for (int c = 0; c < kCols / 32; ++c) {
       const int col0 = n0 + c_begin + c * 32;
@@ -154,8 +223,11 @@ __device__ __forceinline__ void epilogue_f32(const GemmArgs& a, const CUtensorMa
           const int grow = row0 + rr;
           if (grow < a.M) {
             const uint4 v = *reinterpret_cast<const uint4*>(sbuf + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-            mc_red_add_v4_f32(obase + static_cast<size_t>(grow) * a.ldc + col0 + chunk * 4, __uint_as_float(v.x),
-                              __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+            float* dst = obase + static_cast<size_t>(grow) * a.ldc + col0 + chunk * 4;
+            if (mc) mc_red_add_v4_f32(dst, __uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
+                                      __uint_as_float(v.w));
+            else red_add_v4_f32(dst, __uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
+                                __uint_as_float(v.w));
           }
         }
       }
@@ -187,7 +259,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorM
   const int flags = a.flags;
   const int row = row0 + lane;
   const bool row_ok = row < a.M;
-  if (flags & (EPI_MC | EPI_OUT_F32 | EPI_ACCUM)) {
+  if (flags & (EPI_MC | EPI_PEER | EPI_OUT_F32 | EPI_ACCUM)) {
     epilogue_f32<kCols>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane);
     return;
   }
@@ -802,6 +874,217 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == 1) tmem_dealloc_2cta<kTmemCols>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------ 4-CTA cluster: two CTA pairs sharing B by TMA multicast
+// The CTA-pair kernel above moves 64 B/clk into each SM's shared memory at full MMA rate, and all of it is read from
+// L2 -- whose slices together deliver ~6300 B/clk (B300_MICROARCH.md: LTS throughput cap), i.e. ~43 B/clk per SM: the
+// K=768 GEMMs of the step are L2-output bound at about two thirds of the tensor peak.  Here two pairs of one cluster
+// work on vertically adjacent 256x256 tiles (same n_blk, m_blk = 2i and 2i+1), so they need the same B tile: each of
+// the four CTAs fetches only HALF of the B half it needs (64 of 128 rows) and multicasts it to the CTA with the same
+// role in the other pair.  L2 reads per CTA and k-block drop from 32 KB to 24 KB.
+//
+// Protocol differences to the pair kernel:
+//  * full_bar is per CTA (its own A, its own 8 KB of B, the partner's 8 KB of B all signal it); the non-leader's warp 1
+//    forwards "my stage landed" to the leader's peer_full barrier, and the MMA issuer waits for both;
+//  * empty_bar collects the commits of BOTH pairs' leaders (a producer's multicast also writes the other pair's smem).
+template <bool kAMN, bool kBMN>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(64 + 32 * 16, 1)
+gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
+                      const __grid_constant__ CUtensorMap tmap_side, const GemmArgs args) {
+  constexpr int kEpiW = 16;
+  constexpr int kPairM = 256, kPairN = 256;
+  constexpr int kStageA = BLOCK_M * BLOCK_K * 2;
+  constexpr int kStageB = (kPairN / 2) * BLOCK_K * 2;
+  constexpr int kStageBytes = kStageA + kStageB;
+  constexpr int kStages = 5;
+  constexpr uint32_t kTmemCols = 2 * kPairN;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kPairM, kPairN, kAMN ? 1u : 0u, kBMN ? 1u : 0u);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr int kStagingBytes = kEpiW * 4096;
+  uint8_t* staging = smem + kStages * kStageBytes;
+  __nv_bfloat16* sbias = reinterpret_cast<__nv_bfloat16*>(staging + kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes + 1024);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* peer_full = empty_bar + kStages;     // leader's copy: the pair's other CTA has its stage
+  uint64_t* tmem_full = peer_full + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* side_bar = tmem_empty + 3;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();      // 0..3
+  const uint32_t pair = crank >> 1;              // which of the two tiles of the cluster
+  const uint32_t rank = crank & 1u;              // role inside the pair
+  const uint32_t leader_rank = pair << 1;
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (args.flags & EPI_SAVE_PRE) tma_prefetch_desc(&tmap_aux);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);    // own producer's arrive(expect_tx); bytes from own loads + the partner's multicast
+      mbar_init(&empty_bar[i], 2);   // both pairs' leaders commit to every CTA of the cluster
+      mbar_init(&peer_full[i], 1);   // (leader) arrive of the other CTA's relay
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiW);
+    }
+    for (int i = 0; i < kEpiW; ++i) mbar_init(&side_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m2 = (args.tiles_m + 1) >> 1;                 // super-rows of two 256-row tiles
+  const int num_work = tiles_m2 * args.tiles_n * args.split_k;
+  const int cluster_id = blockIdx.x >> 2;
+  const int num_clusters = gridDim.x >> 2;
+  GemmArgs sched = args;
+  sched.tiles_m = tiles_m2;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (all four CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint16_t mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));   // same role, both pairs
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const WorkItem wi = decode_work(sched, w);
+        const int m0 = (wi.m_blk * 2 + static_cast<int>(pair)) * kPairM + static_cast<int>(rank) * BLOCK_M;
+        const int n0 = wi.n_blk * kPairN + static_cast<int>(rank) * (kPairN / 2) + static_cast<int>(pair) * 64;
+        for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+          mbar_wait_cluster(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kStageA + pair * 8192;            // my 64 rows of this role's 128-row B half
+          if constexpr (!kAMN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + j * 64, kb * BLOCK_K);
+          }
+          if constexpr (!kBMN) {
+            tma_load_2d_mcast(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0, mask);      // box 64 (k) x 64 (n rows)
+          } else {
+            tma_load_2d_mcast(sb, &tmap_b, &full_bar[stage], n0, kb * BLOCK_K, mask);      // box 64 (n) x 64 (k rows)
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      if (leader) {
+        // -------------------------------------------------------- MMA issuer (leader of each pair)
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const uint16_t pair_mask = static_cast<uint16_t>(3u << leader_rank);
+        for (int w = cluster_id; w < num_work; w += num_clusters) {
+          const WorkItem wi = decode_work(sched, w);
+          mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kPairN;
+          for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+            mbar_wait_cluster(&full_bar[stage], phase);
+            mbar_wait_cluster(&peer_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+            const uint32_t b_addr = a_addr + kStageA;
+#pragma unroll
+            for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+              const uint64_t da = kAMN ? make_sw128_desc(a_addr + ks * 2048, BLOCK_K * 128, 1024)
+                                       : make_sw128_desc(a_addr + ks * UMMA_K * 2, 16, 1024);
+              const uint64_t db = kBMN ? make_sw128_desc(b_addr + ks * 2048, BLOCK_K * 128, 1024)
+                                       : make_sw128_desc(b_addr + ks * UMMA_K * 2, 16, 1024);
+              umma_bf16_2cta(d_tmem, da, db, kIdesc, (kb > wi.kb0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty_bar[stage], 0xF);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit_2cta(&tmem_full[acc], pair_mask);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      } else {
+        // -------------------------------------------------------- relay: "this CTA's stage has landed" -> leader
+        for (int w = cluster_id; w < num_work; w += num_clusters) {
+          const WorkItem wi = decode_work(sched, w);
+          for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+            mbar_wait_cluster(&full_bar[stage], phase);
+            mbar_arrive_remote(&peer_full[stage], leader_rank);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..17, all four CTAs)
+    const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int epi_tid = threadIdx.x - 64;
+    uint8_t* sbuf = staging + (half * 4 + lg) * 4096;
+    StoreGroup sg;
+    sg.buf = staging + half * 16384;
+    sg.bar_id = 2 + half;
+    sg.issuer = lg == 0 && lane == 0;
+    sg.grouped = false;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int side_kind = args.flags & (EPI_DGELU | EPI_RESIDUAL);
+    const bool side_tma = !(args.flags & (EPI_SAVE_PRE | EPI_MC | EPI_OUT_F32 | EPI_ACCUM | EPI_NO_SIDE_TMA)) &&
+                          (side_kind == EPI_DGELU || side_kind == EPI_RESIDUAL);
+    uint64_t* my_side_bar = &side_bar[warp - 2];
+    uint32_t side_phase = 0;
+    for (int w = cluster_id; w < num_work; w += num_clusters) {
+      const WorkItem wi = decode_work(sched, w);
+      const int m_blk = wi.m_blk * 2 + static_cast<int>(pair);
+      bool side_now = false;
+      if (side_tma && wi.kb1 > wi.kb0 && wi.n_blk * kPairN + half * 64 < args.N) {
+        side_now = true;
+        stage_acquire(lane);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(my_side_bar, 4096);
+          tma_load_2d(sbuf, &tmap_side, my_side_bar, wi.n_blk * kPairN + half * 64,
+                      m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32);
+        }
+      }
+      stage_bias<kPairN, 32 * kEpiW>(args, sbias + acc * 256, wi.n_blk * kPairN, epi_tid);
+      mbar_wait_cluster(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (wi.kb1 > wi.kb0 && !(args.flags & EPI_DEBUG_SKIP)) {
+        const uint32_t t_acc = tmem_base + acc * kPairN + (static_cast<uint32_t>(lg * 32) << 16);
+        const int row0 = m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32;
+        sg.row0_cta = m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
+        epilogue_cols64(args, &tmap_out, &tmap_aux, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * 64,
+                        sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase);
+        if (side_now) side_phase ^= 1u;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], leader_rank);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta<kTmemCols>(tmem_base);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -896,7 +1179,70 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
 }
 
+
+static int g_quad_clusters = 0;
+
+template <bool kAMN, bool kBMN>
+static int launch_gemm_quad(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
+                            const CUtensorMap& tside, const GemmArgs& args, int max_ctas, cudaStream_t stream) {
+  constexpr int kSmem = 5 * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + 16 * 4096 + 1024 + 1024 + 256;
+  static int max_clusters = 0;
+  auto kern = gemm_bf16_quad_kernel<kAMN, kBMN>;
+  if (!max_clusters) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return -20;
+    // how many 4-CTA clusters the GPU can hold at once (GPCs whose SM count is not a multiple of 4 strand a few SMs)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() / 4 * 4);
+    cfg.blockDim = dim3(64 + 32 * 16);
+    cfg.dynamicSmemBytes = kSmem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms() / 4; }
+    max_clusters = n;
+    g_quad_clusters = n;
+    if (getenv("AITJ_GEMM_QUAD_CLUSTERS")) max_clusters = atoi(getenv("AITJ_GEMM_QUAD_CLUSTERS"));
+  }
+  const int num_work = ((args.tiles_m + 1) / 2) * args.tiles_n * args.split_k;
+  int clusters = max_clusters;
+  if (num_work < clusters) clusters = num_work;
+  if (max_ctas > 3 && clusters > max_ctas / 4) clusters = max_ctas / 4;
+  if (clusters < 1) clusters = 1;
+  kern<<<clusters * 4, 64 + 32 * 16, kSmem, stream>>>(ta, tb, to, tx, tside, args);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
+}
+
+
+
 }  // namespace aitj
+
+// ---- EPI_PEER: per-rank tensor maps of a gradient tensor, built once per (tensor, shape) and kept in device memory
+#include <map>
+#include <tuple>
+static aitj::PeerTable g_peer_host;          // host copy of the table installed by aitj_gemm_set_peers
+static unsigned int* g_peer_counters = nullptr;      // arrival counters of the split-K "last one moves it" protocol
+constexpr long long kPeerCounterSlots = 1 << 16;
+static bool g_peer_tma = false;
+static std::map<std::tuple<const void*, int, int, int>, CUtensorMap*> g_peer_map_cache;
+
+static const CUtensorMap* peer_maps_for(const void* out, int M, int N, int ldc) {
+  auto key = std::make_tuple(out, M, N, ldc);
+  auto it = g_peer_map_cache.find(key);
+  if (it != g_peer_map_cache.end()) return it->second;
+  // first use of this tensor: must happen outside stream capture (the warm-up steps before a graph is captured do it)
+  CUtensorMap host[8];
+  for (int r = 0; r < g_peer_host.n; ++r) {
+    const char* base = reinterpret_cast<const char*>(out) + g_peer_host.delta[r];
+    if (aitj::encode_2d(&host[r], base, N, M, ldc, 32, 32, true)) return nullptr;
+  }
+  CUtensorMap* dev = nullptr;
+  if (cudaMalloc(&dev, sizeof(CUtensorMap) * 8) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(dev, host, sizeof(CUtensorMap) * g_peer_host.n, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  g_peer_map_cache[key] = dev;
+  return dev;
+}
 
 static unsigned long long* g_gemm_trace = nullptr;
 static float* g_gemm_colsum = nullptr;   // consumed by the next aitj_gemm_bf16 call
@@ -922,8 +1268,10 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   if ((N & 7) || (ldc & 7) || (lda & 7) || (ldb & 7)) return -1;
   if ((reinterpret_cast<uintptr_t>(out) & 15) || ((flags & EPI_SAVE_PRE) && (reinterpret_cast<uintptr_t>(aux) & 15))) return -4;
   if (split_k > 1 && !(flags & EPI_ACCUM)) return -2;
-  if ((flags & EPI_MC) && !(flags & EPI_ACCUM)) return -5;
-  const bool pair = block_n == 512;
+  if ((flags & (EPI_MC | EPI_PEER)) && !(flags & EPI_ACCUM)) return -5;
+  // block_n == 1024: two CTA pairs per 4-CTA cluster sharing B by TMA multicast (needs the 16-warp epilogue)
+  const bool quad = block_n == 1024 && pair_epilogue_warps() == 16 && !(flags & EPI_GROUP_STORE);
+  const bool pair = block_n == 512 || block_n == 1024;
   if (pair) block_n = 256;
   if (block_n == 0) block_n = (N > 128) ? 256 : 128;
   if (block_n != 128 && block_n != 256) return -3;
@@ -947,6 +1295,8 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   if (args.colsum && !(pair && pair_epilogue_warps() == 16 && !(flags & (EPI_OUT_F32 | EPI_ACCUM | EPI_GROUP_STORE))))
     return -6;   // only the 16-warp CTA-pair bf16 epilogue implements it
   args.trace = g_gemm_trace;
+  args.peer_maps = nullptr;
+  args.peer_counters = nullptr;
   args.tiles_m = pair ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;
   args.tiles_n = (N + block_n - 1) / block_n;
   args.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
@@ -960,13 +1310,24 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   if (!a_mn) rc = encode_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
   else       rc = encode_2d(&ta, A, M, K, lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b_mn) rc = encode_2d(&tb, B, K, N, ldb, BLOCK_K, pair ? 128 : block_n);
+  if (!b_mn) rc = encode_2d(&tb, B, K, N, ldb, BLOCK_K, quad ? 64 : (pair ? 128 : block_n));
   else       rc = encode_2d(&tb, B, N, K, ldb, 64, BLOCK_K);
   if (rc) return rc - 1000;
   CUtensorMap to, tx;
   const bool out_f32 = (flags & (EPI_OUT_F32 | EPI_ACCUM)) != 0;
-  if (flags & EPI_MC) {
-    to = ta;   // the multicast path stores from registers; the tensor map is never dereferenced
+  const bool peer_move = (flags & EPI_PEER) && args.split_k > 1 && g_peer_counters != nullptr &&
+                         static_cast<long long>((M + 31) / 32) * ((N + 31) / 32) <= kPeerCounterSlots;
+  if ((flags & EPI_PEER) && !peer_move && g_peer_tma) {
+    const CUtensorMap* pm = peer_maps_for(out, M, N, ldc);
+    if (!pm) return -7;
+    args.peer_maps = pm;
+  }
+  if (peer_move) {
+    args.peer_counters = g_peer_counters;
+    rc = encode_2d(&to, out, N, M, ldc, 32, 32, true);
+    if (rc) return rc - 2000;
+  } else if (flags & (EPI_MC | EPI_PEER)) {
+    to = ta;   // the multicast / direct peer paths never dereference the local output map
   } else {
     rc = encode_2d(&to, out, N, M, ldc, out_f32 ? 32 : 64, 32, out_f32);
     if (rc) return rc - 2000;
@@ -994,6 +1355,12 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
       rc = encode_2d(&tside, side_ptr, N, M, ldc, 64, 32, false);
       if (rc) return rc - 6000;
     }
+    if (quad) {
+      if (!a_mn && !b_mn) return launch_gemm_quad<false, false>(ta, tb, to, tx, tside, args, max_ctas, stream);
+      if (!a_mn && b_mn) return launch_gemm_quad<false, true>(ta, tb, to, tx, tside, args, max_ctas, stream);
+      if (a_mn && !b_mn) return launch_gemm_quad<true, false>(ta, tb, to, tx, tside, args, max_ctas, stream);
+      return launch_gemm_quad<true, true>(ta, tb, to, tx, tside, args, max_ctas, stream);
+    }
 #define AITJ_PAIR(W)                                                                                  \
     if (!a_mn && !b_mn) return launch_gemm_2cta<false, false, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream); \
     if (!a_mn && b_mn) return launch_gemm_2cta<false, true, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream);   \
@@ -1013,6 +1380,36 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
 #undef AITJ_DISPATCH
 }
 
+// Ownership table of the symmetric gradient buffer for EPI_PEER (see ptx.cuh: PeerTable); one copy per translation unit.
+int aitj_gemm_set_peers(const void* base, const long long* delta, const long long* bound, int n) {
+  if (n < 1 || n > 8) return -1;
+  aitj::PeerTable t;
+  memset(&t, 0, sizeof(t));
+  t.base = reinterpret_cast<const float*>(base);
+  for (int i = 0; i < n; ++i) t.delta[i] = delta[i];
+  for (int i = 0; i <= n; ++i) t.bound[i] = bound[i];
+  t.n = n;
+  g_peer_host = t;
+  if (!g_peer_counters) {
+    if (cudaMalloc(&g_peer_counters, sizeof(unsigned int) * kPeerCounterSlots) != cudaSuccess) return -3;
+    cudaMemset(g_peer_counters, 0, sizeof(unsigned int) * kPeerCounterSlots);
+  }
+  {
+    const char* e = getenv("AITJ_RS_MOVE");            // 0: every split-K partial crosses NVLink (A/B arm)
+    if (e && atoi(e) == 0) { cudaFree(g_peer_counters); g_peer_counters = nullptr; }
+  }
+  for (auto& kv : g_peer_map_cache) cudaFree(kv.second);     // maps of a previous symmetric allocation
+  g_peer_map_cache.clear();
+  {
+    // AITJ_RS_TMA=0: add from registers instead of bulk reduce-adds through the TMA unit
+    const char* e = getenv("AITJ_RS_TMA");
+    g_peer_tma = !(e && atoi(e) == 0);
+  }
+  return cudaMemcpyToSymbol(aitj::c_peers, &t, sizeof(t)) == cudaSuccess ? 0 : -2;
+}
+
 int aitj_num_sms() { return aitj::num_sms(); }
+// what cudaOccupancyMaxActiveClusters reported for the 4-CTA cluster kernel (0 until it has been launched once)
+int aitj_gemm_quad_clusters() { return aitj::g_quad_clusters; }
 
 }  // extern "C"

@@ -228,6 +228,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA load whose tile lands at the same shared-memory offset of every CTA in `mask` (cluster multicast); each
+// destination CTA's mbarrier at the same offset as `bar` receives complete_tx for the bytes delivered to it.
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
@@ -267,13 +277,55 @@ __device__ __forceinline__ void mc_red_add_v4_f32(float* p, float a, float b, fl
                "f"(d)
                : "memory");
 }
-__device__ __forceinline__ void grad_add_f32(float* p, float v, bool mc) {
-  if (mc) mc_red_add_f32(p, v);
+// ---------------------------------------------------------------- owner-sharded gradients over NVLink peer memory
+// Reduce-scatter without a collective: the flat fp32 gradient buffer is a symmetric allocation (same layout on every
+// rank, every peer's copy mapped into this process), rank r *owns* the flat range [bound[r], bound[r+1]) and runs the
+// optimizer on it, and every gradient-producing kernel adds its contribution straight into the owner's copy with
+// `red.global.add` on the peer mapping -- (N-1)/N of the bytes cross NVLink once, nothing is received that the rank
+// does not own (multimem.red above delivers every contribution to all N ranks).  One table per translation unit
+// (no -rdc): set through aitj_*_set_peers before the first launch, never changed while a CUDA graph that uses it lives.
+struct PeerTable {
+  const float* base;          // this rank's gradient buffer
+  long long delta[8];         // bytes from a local address to the same offset in rank r's buffer (0 for this rank)
+  long long bound[9];         // ownership bounds in elements, bound[0] = 0, bound[n] = total
+  int n;
+};
+static __constant__ PeerTable c_peers;
+
+__device__ __forceinline__ int peer_owner(const float* p) {
+  const long long e = p - c_peers.base;
+  int o = 0;
+#pragma unroll
+  for (int r = 1; r < 8; ++r) o += (r < c_peers.n && e >= c_peers.bound[r]) ? 1 : 0;
+  return o;
+}
+__device__ __forceinline__ float* peer_ptr(float* p) {
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(p) + c_peers.delta[peer_owner(p)]);
+}
+
+// gradient accumulation modes of the kernels that produce gradients
+enum : int { GRAD_LOCAL = 0, GRAD_MULTICAST = 1, GRAD_PEER = 2 };
+
+__device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void grad_add_f32(float* p, float v, int mode) {
+  if (mode == GRAD_MULTICAST) mc_red_add_f32(p, v);
+  else if (mode == GRAD_PEER) atomicAdd(peer_ptr(p), v);
   else atomicAdd(p, v);
 }
-__device__ __forceinline__ void grad_add_v4_f32(float* p, float a, float b, float c, float d, bool mc) {
-  if (mc) mc_red_add_v4_f32(p, a, b, c, d);
-  else asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void grad_add_v4_f32(float* p, float a, float b, float c, float d, int mode) {
+  if (mode == GRAD_MULTICAST) mc_red_add_v4_f32(p, a, b, c, d);
+  else red_add_v4_f32(mode == GRAD_PEER ? peer_ptr(p) : p, a, b, c, d);
+}
+// bf16 parameters leave the sharded optimizer through the NVSwitch multicast alias: one store, every rank's copy
+__device__ __forceinline__ void mc_store_v2_b32(void* p, uint32_t a, uint32_t b) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(__uint_as_float(a)),
+               "f"(__uint_as_float(b))
+               : "memory");
+}
+__device__ __forceinline__ void mc_store_f32(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 // ---------------------------------------------------------------- misc math / packing

@@ -18,6 +18,7 @@ EPI_DGELU = 16
 EPI_OUT_F32 = 32
 EPI_ACCUM = 64
 EPI_MC = 128
+EPI_PEER = 16384
 
 
 class RawView:
@@ -42,7 +43,31 @@ class RawView:
         return len(self.shape)
 
 
+class PeerView:
+    """A gradient tensor inside the symmetric, owner-sharded buffer (``parallel.symm.ShardedGradState``): kernels are
+    given its LOCAL address and add into the copy of the rank that owns each piece."""
+
+    is_peer = True
+
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+        self.shape = tuple(t.shape)
+        self.dtype = t.dtype
+
+    def data_ptr(self) -> int:
+        return self.t.data_ptr()
+
+    def stride(self, i: int) -> int:
+        return self.t.stride(i)
+
+    def dim(self) -> int:
+        return self.t.dim()
+
+
 def _is_mc(t) -> int:
+    """Gradient accumulation mode of a destination: 0 local atomics, 1 NVSwitch multicast, 2 owner's copy (peer)."""
+    if getattr(t, "is_peer", False):
+        return 2
     return 1 if getattr(t, "is_multicast", False) else 0
 
 _NUM_SMS = None
@@ -102,9 +127,12 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
         assert aux is not None and aux.stride(0) == out.stride(0)
     if out.dtype == torch.float32:
         flags |= EPI_ACCUM if accumulate else EPI_OUT_F32
-        if _is_mc(out):
+        if _is_mc(out) == 1:
             assert accumulate, "multicast outputs are reduce-only"
             flags |= EPI_MC
+        elif _is_mc(out) == 2:
+            assert accumulate, "owner-sharded outputs are reduce-only"
+            flags |= EPI_PEER
     else:
         assert out.dtype == torch.bfloat16 and not accumulate
     if colsum is not None:
@@ -194,6 +222,20 @@ def attention_fwd(qkv, out, lse, B, T, H, causal=True, scale=0.0):
     return out
 
 
+def attention_bwd(qkv, out, d_out, lse, delta, dq_acc, d_qkv, B, T, H, causal=True, scale=0.0):
+    """Flash attention backward on tcgen05 (head dim 64).  qkv / d_qkv bf16 [B*T, 3*H*64] (d_qkv receives dq | dk | dv in
+    place), out / d_out bf16 [B*T, H*64], lse fp32 [B,H,T] from ``attention_fwd``; delta fp32 [B,H,T] and dq_acc fp32
+    [B*T, H*64] are scratch -- dq_acc must be zero on entry and is zero again on exit."""
+    assert qkv.dtype == torch.bfloat16 and d_qkv.dtype == torch.bfloat16 and dq_acc.dtype == torch.float32
+    assert qkv.is_contiguous() and out.is_contiguous() and d_out.is_contiguous() and d_qkv.is_contiguous()
+    assert qkv.shape == (B * T, 3 * H * 64) and d_qkv.shape == qkv.shape and out.shape == (B * T, H * 64)
+    assert d_out.shape == out.shape and dq_acc.shape == out.shape and lse.numel() == B * H * T == delta.numel()
+    lib.call("aitj_attn_bwd", qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+             dq_acc.data_ptr(), d_qkv.data_ptr(), B, T, H, int(causal), float(scale), _stream())
+    lib.LAUNCHES += 2          # delta + dq_finish ride along with the main kernel
+    return d_qkv
+
+
 def qkv_gather_colsum(dq, dk, dv, d_qkv, db):
     """d_qkv[B*T, 3*H*D] <- (dq, dk, dv), each logically [B,H,T,D] with any B/H/T strides; db[3*H*D] += colsum."""
     import ctypes
@@ -214,10 +256,15 @@ def sumsq(g, out):
 
 
 def adamw(p, g, m, v, p16, wd_mask, *, lr, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.1, step=1, sumsq_buf=None,
-          max_norm=0.0, grad_div=1.0, zero_grad=True, dyn=None):
+          max_norm=0.0, grad_div=1.0, zero_grad=True, dyn=None, sumsq_n=1, p16_multicast=False):
     """One sweep: AdamW on fp32 master state + bf16 compute copy refresh + grad zeroing.
-    ``dyn`` (device float[3] = lr, 1-beta1^t, 1-beta2^t) overrides lr/step for CUDA-graph replay."""
-    lib.call("aitj_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p16.data_ptr(), wd_mask.data_ptr(),
+    ``dyn`` (device float[3] = lr, 1-beta1^t, 1-beta2^t) overrides lr/step for CUDA-graph replay.
+    ``sumsq_n`` > 1: ``sumsq_buf`` holds that many partial square sums (one per rank).  ``p16_multicast``: ``p16`` is an
+    int -- the NVSwitch multicast address of this range of the bf16 copy -- and the sweep stores into every rank's copy."""
+    if sumsq_n != 1 or p16_multicast:
+        lib.load().aitj_adamw_set_shard(int(sumsq_n), int(bool(p16_multicast)))
+    p16_ptr = int(p16) if p16_multicast else p16.data_ptr()
+    lib.call("aitj_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p16_ptr, wd_mask.data_ptr(),
              _ptr(sumsq_buf), _ptr(dyn), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
              int(step), float(max_norm), float(grad_div), int(bool(zero_grad)), _stream())
 
@@ -225,6 +272,16 @@ def adamw(p, g, m, v, p16, wd_mask, *, lr, beta1=0.9, beta2=0.95, eps=1e-8, weig
 def mc_push(dst_mc_ptr: int, src, n: int):
     """dst_mc[0:n] (+)= src[0:n] through the NVSwitch multicast alias; src is cleared."""
     lib.call("aitj_mc_push", int(dst_mc_ptr), src.data_ptr(), int(n), _stream())
+
+
+def peer_push(dst_local, src):
+    """Owner-sharded mode: dst_local[i] (in the owner's copy) += src[i]; src is cleared."""
+    lib.call("aitj_peer_push", dst_local.data_ptr(), src.data_ptr(), int(src.numel()), _stream())
+
+
+def norm_share(parts_mc_ptr: int, mine, rank: int):
+    """parts[rank] <- mine[0] in every rank's copy (multicast store)."""
+    lib.call("aitj_norm_share", int(parts_mc_ptr), mine.data_ptr(), int(rank), _stream())
 
 
 def cast_f32_bf16(src, dst):

@@ -63,6 +63,7 @@ _SIGS = {
     "aitj_num_sms": [],
     "aitj_attn_set_trace": [_P],
     "aitj_attn_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "aitj_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "aitj_gemm_set_trace": [_P],
     "aitj_gemm_set_colsum": [_P],
     "aitj_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
@@ -76,6 +77,11 @@ _SIGS = {
     "aitj_adamw": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _F, _I, _P],
     "aitj_cast_f32_bf16": [_P, _P, _L, _P],
     "aitj_mc_push": [_P, _P, _L, _P],
+    "aitj_peer_push": [_P, _P, _L, _P],
+    "aitj_norm_share": [_P, _P, _I, _P],
+    "aitj_adamw_set_shard": [_I, _I],
+    "aitj_gemm_set_peers": [_P, _P, _P, _I],
+    "aitj_fused_set_peers": [_P, _P, _P, _I],
     "aitj_gelu_fwd": [_P, _P, _L, _P],
     "aitj_gelu_bwd": [_P, _P, _P, _L, _P],
 }

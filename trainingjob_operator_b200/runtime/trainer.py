@@ -59,10 +59,29 @@ class EngineTrainer:
         self.group = group
         self.step_count = 0
         self.cuda = engine.dev.type == "cuda"
-        backend = allreduce or os.environ.get("AITJ_ALLREDUCE", "nccl")
+        # rs (default): gradients are reduce-scattered to their owner rank by the kernels that produce them, over NVLink
+        # peer memory; sharded AdamW; bf16 parameters all-gathered by multicast stores (parallel/symm.ShardedGradState).
+        # mc: every contribution multicast to all ranks (round-1 path).  nccl: bucketed library all-reduce.
+        backend = allreduce or os.environ.get("AITJ_ALLREDUCE", "rs")
         self.allreduce_backend = backend if self.world > 1 else "none"
         self.symm = None
+        self.shard = None
         self.reducer = None
+        if getattr(engine.params, "shard", None) is not None:
+            engine.params.detach_shard()      # re-bound after a re-rendezvous: the old group's symmetric buffers go
+        if self.world > 1 and backend == "rs" and self.cuda:
+            from ..parallel.symm import ShardedGradState
+
+            sh = ShardedGradState(engine.params, engine.dev, group)
+            if sh.available:
+                engine.params.attach_shard(sh)
+                self.shard = sh
+                self.allreduce_backend = "rs (wgrad GEMM epilogue red.add to the owner over NVLink peer memory, sharded " \
+                                         "AdamW, multicast all-gather of bf16 parameters)"
+                sh.barrier()
+            else:
+                self.allreduce_backend = f"nccl (rs unavailable: {sh.reason})"
+                backend = "nccl"
         if self.world > 1 and backend == "mc" and self.cuda:
             # fused GEMM -> all-reduce: gradients are reduced through the NVSwitch multicast alias by the kernels
             # that produce them (parallel/symm.py); no gradient collective is launched at all
@@ -75,7 +94,7 @@ class EngineTrainer:
                 self.allreduce_backend = f"nccl (mc unavailable: {self.symm.reason})"
                 self.symm = None
                 backend = "nccl"
-        if self.world > 1 and self.symm is None:
+        if self.world > 1 and self.symm is None and self.shard is None:
             self.reducer = BucketAllReducer(engine.params.g32, engine.grad_buckets(), group, backend)
         engine.grad_hook = self.reducer.hook if self.reducer else None
         if self.reducer is not None and hasattr(engine, "bwd_max_ctas"):
@@ -108,9 +127,14 @@ class EngineTrainer:
         e.backward()
         if self.symm is not None:
             self.symm.barrier()   # every peer's multimem reductions of this step have landed
+        if self.shard is not None:
+            self.shard.barrier()  # every contribution to this rank's shard has landed
         if self.reducer:
             self.reducer.wait()
         self._optimizer()
+        if self.shard is not None:
+            # every rank's bf16 parameters have arrived (next forward) and every shard is zeroed (next backward)
+            self.shard.barrier()
 
     def _optimizer(self) -> None:
         self.engine.optimizer_step(lr=self.lr, step=max(1, self.step_count), weight_decay=self.weight_decay,

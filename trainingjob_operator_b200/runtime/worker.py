@@ -69,7 +69,11 @@ class EngineAdapter:
 
     def bind(self, group=None) -> None:
         old = self.trainer
-        self.trainer = EngineTrainer(self.engine, lr=self.args.lr, use_graph=not self.args.no_graph, group=group)
+        # a faultTolerant job survives the loss of a peer in place, which needs every rank to hold the whole optimizer
+        # state and a collective that can be aborted: library all-reduce instead of the owner-sharded peer-memory path
+        allreduce = "nccl" if os.environ.get("AITJ_FAULT_TOLERANT") == "1" and "AITJ_ALLREDUCE" not in os.environ else None
+        self.trainer = EngineTrainer(self.engine, lr=self.args.lr, use_graph=not self.args.no_graph, group=group,
+                                     allreduce=allreduce)
         if old is not None:
             self.trainer.step_count = old.step_count
 
@@ -79,6 +83,22 @@ class EngineAdapter:
 
     def discard_step(self) -> None:
         self.engine.params.g32.zero_()
+        if self.engine.params.g_small is not None:
+            self.engine.params.g_small.zero_()
+
+    def prepare_state(self) -> None:
+        """Collective.  With the owner-sharded optimizer every rank only keeps its own range of the fp32 master weights
+        and moments current: gather them so that ``state_tensors`` is the whole state on every rank (before a
+        checkpoint, before the process group is re-formed)."""
+        sh = self.engine.params.shard
+        if sh is None or not dist.is_initialized():
+            return
+        P = self.engine.params
+        for r in range(sh.world):
+            a, b = sh.bounds[r], sh.bounds[r + 1]
+            if b > a:
+                for t in (P.p32, P.m, P.v):
+                    dist.broadcast(t[a:b], src=r)
 
     def state_tensors(self) -> List[torch.Tensor]:
         return self.engine.params.state_tensors()
@@ -190,6 +210,9 @@ class TorchAdapter:
     def discard_step(self) -> None:
         if self.ddp is not None:
             self.ddp.discard_step()        # .grad are views of the flat buffer it zeroes
+
+    def prepare_state(self) -> None:
+        return                             # every rank holds the whole state
 
     def state_tensors(self) -> List[torch.Tensor]:
         return self.ddp.state_tensors()
@@ -366,6 +389,7 @@ def run(args) -> Dict[str, Any]:
                     print(f"[worker {rank}] rendezvous generation {generation} -> {target['generation']} "
                           f"(world {world} -> {new_world}) at step {step}", flush=True)
                     if dist.is_initialized():
+                        adapter.prepare_state()       # sharded optimizer state -> whole state on every survivor
                         if use_cuda:
                             torch.cuda.synchronize()
                         dist.destroy_process_group()
@@ -496,8 +520,10 @@ def run(args) -> Dict[str, Any]:
                                            "ms_per_step": round(dt * 1e3 / n, 3), "world": world, "steps_done": step,
                                            "global_batch": args.batch * world, "recoveries": len(recoveries)})
             live_t0, live_step0 = time.time(), step
-        if args.ckpt_every > 0 and rank == 0 and step % args.ckpt_every == 0:
-            save_checkpoint(args, adapter, adapter.step_count)
+        if args.ckpt_every > 0 and step % args.ckpt_every == 0:
+            adapter.prepare_state()
+            if rank == 0:
+                save_checkpoint(args, adapter, adapter.step_count)
         if args.step_sleep > 0:
             time.sleep(args.step_sleep)
 
