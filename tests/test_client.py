@@ -255,3 +255,55 @@ def test_http_transport_does_not_repeat_a_write_that_may_have_been_applied():
         assert seen.count("DELETE") == 1
     finally:
         srv.shutdown()
+
+
+def test_client_side_throttle_is_a_token_bucket_and_never_touches_watches():
+    """--kube-api-qps / --kube-api-burst (client-go's default 5 / 10 is what the reference runs with): the first `burst`
+    requests pass immediately, the rest are spaced 1/qps apart; watches are long-lived streams and are not throttled."""
+    import time as _time
+
+    from trainingjob_operator_b200.api import register as R
+    from trainingjob_operator_b200.store.transport import ThrottledTransport, Transport
+
+    calls = []
+
+    class Null(Transport):
+        def get(self, info, namespace, name):
+            calls.append(("get", _time.monotonic()))
+            return {}
+
+        def watch(self, *a, **kw):
+            calls.append(("watch", _time.monotonic()))
+            return iter(())
+
+    t = ThrottledTransport(Null(), qps=50.0, burst=5)
+    t0 = _time.monotonic()
+    for _ in range(10):
+        t.get(R.POD, "default", "x")
+    spent = _time.monotonic() - t0
+    assert 0.08 <= spent < 0.5                      # 5 free, then 5 x 20 ms
+    assert t.requests == 10 and t.waited_s > 0.05
+    t1 = _time.monotonic()
+    for _ in range(20):
+        t.watch(R.POD)
+    assert _time.monotonic() - t1 < 0.05 and t.requests == 10
+
+
+def test_reference_throttle_flags_parse_and_reach_the_clientsets():
+    import argparse
+
+    from trainingjob_operator_b200.cmd import options as O
+    from trainingjob_operator_b200.cmd.server import create_client_sets
+    from trainingjob_operator_b200.store.apiserver import APIServer
+    from trainingjob_operator_b200.store.transport import ThrottledTransport
+
+    p = argparse.ArgumentParser()
+    O.add_flags(p)
+    ns = p.parse_args(["--kube-api-qps", "5", "--kube-api-burst", "10", "--live-node-list", "--queue-qps", "10",
+                       "--queue-burst", "100"])
+    assert (ns.kube_api_qps, ns.kube_api_burst, ns.live_node_list) == (5.0, 10, True)
+    opt = O.TrainingJobOperatorOption(kube_api_qps=5.0, kube_api_burst=10)
+    kube, *_ = create_client_sets(opt, server=APIServer(""))
+    assert isinstance(kube.transport, ThrottledTransport) and kube.transport.burst == 10
+    plain, *_ = create_client_sets(O.TrainingJobOperatorOption(), server=APIServer(""))
+    assert not isinstance(plain.transport, ThrottledTransport)

@@ -22,7 +22,7 @@ def _run_case(name: str, timeout: int = 420):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["gemm_tn", "gemm_nn", "gemm_tt", "gemm_epilogue", "gemm_2cta", "gemm_quad", "graph_step", "fused_ops", "attention", "attention_bwd",
-                                  "gpt2_engine"])
+                                  "gpt2_engine", "bert_engine"])
 def test_kernel_numerics(case):
     _run_case(case)
 

@@ -54,7 +54,25 @@ for _ in range(STEPS):
     torch.cuda.synchronize()
     for i, n in enumerate(names):
         acc[n] += ev[i].elapsed_time(ev[i + 1])
-out = {"rank": rank, "world": world, "allreduce": tr.allreduce_backend[:40],
+# per-kernel device time of one more step (events around every launch of the kernel library)
+from trainingjob_operator_b200.ops import lib as _lib  # noqa: E402
+
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+_lib.profile_start()
+tok, tgt = data.next()
+eng.tok.copy_(tok, non_blocking=True); eng.tgt.copy_(tgt, non_blocking=True)
+tr._device_step()
+prof = _lib.profile_stop()
+groups = {}
+for label, (n, ms) in prof.items():
+    key = label.split(" ")[0] if label.startswith("gemm:") else label
+    g = groups.setdefault(key, [0, 0.0])
+    g[0] += n; g[1] += ms
+out = {"rank": rank, "world": world, "kernels_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(groups.items())},
+       "wgrad_detail_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(prof.items()) if k.startswith("gemm:wgrad")},
+       "allreduce": tr.allreduce_backend[:40],
        "ms": {n: round(v / STEPS, 3) for n, v in acc.items()}, "total_ms": round(sum(acc.values()) / STEPS, 3)}
 if world > 1:
     allo = [None] * world

@@ -83,6 +83,12 @@ class TrainingJobOperatorOption:
     # operator degrades to one reconcile per 100 ms; here the store is in-process, so the bucket is sized for it.
     queue_qps: float = 2000.0
     queue_burst: int = 2000
+    # client-side API throttle per clientset (client-go: 5 qps / burst 10, which the reference runs with); 0 = none
+    kube_api_qps: float = 0.0
+    kube_api_burst: int = 0
+    # reproduce the reference's per-pass API behaviour: one live Node LIST per role per reconcile (pod.go:181,441)
+    # instead of the node informer
+    live_node_list: bool = False
 
 
 def new_training_job_operator_option() -> TrainingJobOperatorOption:
@@ -122,13 +128,19 @@ def add_flags(parser: argparse.ArgumentParser, opt: Optional[TrainingJobOperator
     a("--queue-qps", type=float, default=o.queue_qps,
       help="overall rate limit of the reconcile work queue (client-go default would be 10)")
     a("--queue-burst", type=int, default=o.queue_burst, help="burst of that limiter (client-go default would be 100)")
+    a("--kube-api-qps", type=float, default=o.kube_api_qps,
+      help="client-side request throttle per clientset (client-go / the reference: 5); 0 = unthrottled")
+    a("--kube-api-burst", type=int, default=o.kube_api_burst, help="burst of that throttle (client-go / the reference: 10)")
+    a("--live-node-list", type=_bool, nargs="?", const=True, default=o.live_node_list,
+      help="LIST nodes from the API server once per role per reconcile, as the reference does, instead of using the informer")
 
 
 def from_args(ns: argparse.Namespace) -> TrainingJobOperatorOption:
     o = TrainingJobOperatorOption()
     for f in ("master_url", "kubeconfig", "run_in_cluster", "thread_num", "creating_restart_time",
               "creating_duration_time", "enable_creating_failed", "namespace", "resync_period", "v", "logtostderr",
-              "gc_interval", "scale_down_grace", "identity", "metrics_port", "queue_qps", "queue_burst"):
+              "gc_interval", "scale_down_grace", "identity", "metrics_port", "queue_qps", "queue_burst",
+              "kube_api_qps", "kube_api_burst", "live_node_list"):
         setattr(o, f, getattr(ns, f))
     o.leader_election = LeaderElectionConfiguration(
         leader_elect=ns.leader_elect, lease_duration=ns.leader_elect_lease_duration,

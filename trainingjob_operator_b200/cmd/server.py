@@ -29,10 +29,19 @@ class LeaseLost(RuntimeError):
 def create_client_sets(opt: TrainingJobOperatorOption, server=None):
     """server.go:111-151: kube, leader-election, trainingjob and apiextensions clients."""
     if server is not None:
-        mk = lambda: new_for_config(server=server)  # noqa: E731
+        base = lambda: new_for_config(server=server)  # noqa: E731
     else:
         master = resolve_master(opt)
-        mk = lambda: new_for_config(master=master)  # noqa: E731
+        base = lambda: new_for_config(master=master)  # noqa: E731
+
+    def mk():
+        cs = base()
+        if getattr(opt, "kube_api_qps", 0) and opt.kube_api_qps > 0:
+            from ..store.transport import ThrottledTransport
+
+            cs.transport = ThrottledTransport(cs.transport, opt.kube_api_qps, opt.kube_api_burst or 2 * int(opt.kube_api_qps))
+        return cs
+
     return mk(), mk(), mk(), mk()
 
 

@@ -252,6 +252,13 @@ class TrainingJobController(TrainingJobHandlers):
         pods = self.claim_pods(job, selector, claim_candidates(self.pod_lister, job, selector))
         services = self.claim_services(job, selector, claim_candidates(self.service_lister, job, selector))
         nodes = self._nodes()
+        if getattr(self.option, "live_node_list", False):
+            # the reference's behaviour, for the control-plane comparison: one live (throttled) LIST per role per pass
+            for _ in job.spec.replica_specs:
+                try:
+                    nodes = self.kube_client.core_v1().nodes().list().get("items", [])
+                except APIError as e:
+                    klog.error("cannot list nodes: %s", e.message)
         cluster = E.observe_cluster(job, nodes, self.pod_lister.peek()) if E.auto_roles(job) else None
         return engine.Observation(job=job, pods=pods, services=services,
                                   ready_nodes=frozenset(M.name_of(n) for n in nodes if _node_is_ready(n)),

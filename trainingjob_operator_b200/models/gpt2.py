@@ -177,6 +177,10 @@ class GPT2Engine:
         self._graph = None
         self.split_k: Dict[Tuple[int, int], int] = {}
 
+    def input_tensors(self) -> List[torch.Tensor]:
+        """Device tensors a step reads its inputs from, in the order the data source yields them."""
+        return [self.tok, self.tgt]
+
     # ------------------------------------------------------------------ GEMM front-ends
     def _linear(self, x, w, out, bias=None, residual=None, gelu=False, aux=None):
         F = self.F
@@ -202,13 +206,14 @@ class GPT2Engine:
             return self.gemm_cfg[key][0]
         return 512 if self.pair and m >= 256 and n >= 256 else 0
 
-    def _dgrad(self, dy, w, out, dgelu_aux=None, colsum=None):
-        """out[M,K] = dy[M,N] @ w[N,K]  (* gelu'(aux)); colsum (fp32[K], optional) += column sums of out."""
+    def _dgrad(self, dy, w, out, dgelu_aux=None, colsum=None, residual=None):
+        """out[M,K] = dy[M,N] @ w[N,K]  (* gelu'(aux)) (+ residual: the gradient arriving over a skip connection);
+        colsum (fp32[K], optional) += column sums of out."""
         F = self.F
         if self.backend == "tcgen05":
             bn = self._bn(dy.shape[0], w.shape[1], f"dgrad:{w.shape[1]}x{w.shape[0]}")
             fused = colsum is not None and bn == 512 and _FUSE_COLSUM
-            F.gemm(dy, w, out, b_mn=True, dgelu=dgelu_aux is not None, aux=dgelu_aux,
+            F.gemm(dy, w, out, b_mn=True, dgelu=dgelu_aux is not None, aux=dgelu_aux, residual=residual,
                    block_n=bn, max_ctas=self.bwd_max_ctas, colsum=colsum if fused else None)
             if colsum is not None and not fused:
                 F.colsum(out, colsum)
@@ -216,6 +221,8 @@ class GPT2Engine:
         y = dy @ w
         if dgelu_aux is not None:
             F.gelu_bwd(dgelu_aux, y, out)
+        elif residual is not None:
+            torch.add(y, residual, out=out)
         else:
             out.copy_(y)
         if colsum is not None:

@@ -221,7 +221,9 @@ __global__ void __launch_bounds__(kLnBwdWarps * 32, 1) layernorm_bwd_kernel(cons
 __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __restrict__ tok,
                                                             const __nv_bfloat16* __restrict__ wte,
                                                             const __nv_bfloat16* __restrict__ wpe,
-                                                            __nv_bfloat16* __restrict__ out, int M, int T, int C) {
+                                                            __nv_bfloat16* __restrict__ out, int M, int T, int C,
+                                                            const int64_t* __restrict__ typ = nullptr,
+                                                            const __nv_bfloat16* __restrict__ wtt = nullptr) {
   const int vec_per_row = C / 8;
   const size_t total = static_cast<size_t>(M) * vec_per_row;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -230,13 +232,15 @@ __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __res
     const int64_t t = tok[m];
     uint4 a = *reinterpret_cast<const uint4*>(wte + t * C + c);
     uint4 b = wpe ? *reinterpret_cast<const uint4*>(wpe + static_cast<size_t>(m % T) * C + c) : make_uint4(0, 0, 0, 0);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    // optional third table (BERT's token-type / segment embeddings)
+    uint4 d = wtt ? *reinterpret_cast<const uint4*>(wtt + typ[m] * C + c) : make_uint4(0, 0, 0, 0);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, dw[4] = {d.x, d.y, d.z, d.w};
     uint4 o;
     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float2 fa = unpack_bf16x2(aw[j]), fb = unpack_bf16x2(bw[j]);
-      ow[j] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+      float2 fa = unpack_bf16x2(aw[j]), fb = unpack_bf16x2(bw[j]), fd = unpack_bf16x2(dw[j]);
+      ow[j] = pack_bf16x2(fa.x + fb.x + fd.x, fa.y + fb.y + fd.y);
     }
     *reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * C + c) = o;
   }
@@ -245,7 +249,9 @@ __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __res
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __restrict__ tok,
                                                             const __nv_bfloat16* __restrict__ dx,
                                                             float* __restrict__ dwte, float* __restrict__ dwpe, int M,
-                                                            int T, int C, int mc) {
+                                                            int T, int C, int mc,
+                                                            const int64_t* __restrict__ typ = nullptr,
+                                                            float* __restrict__ dwtt = nullptr) {
   const int vec_per_row = C / 4;
   const size_t total = static_cast<size_t>(M) * vec_per_row;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -255,6 +261,7 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __res
     float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
     grad_add_v4_f32(dwte + tok[m] * C + c, f0.x, f0.y, f1.x, f1.y, mc);
     if (dwpe) grad_add_v4_f32(dwpe + static_cast<size_t>(m % T) * C + c, f0.x, f0.y, f1.x, f1.y, mc);
+    if (dwtt) grad_add_v4_f32(dwtt + typ[m] * C + c, f0.x, f0.y, f1.x, f1.y, mc);
   }
 }
 
@@ -677,6 +684,27 @@ int aitj_embedding_bwd(const void* tok, const void* dx, void* dwte, void* dwpe, 
   embedding_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, S(stream)>>>(
       reinterpret_cast<const int64_t*>(tok), CBF(dx), reinterpret_cast<float*>(dwte), reinterpret_cast<float*>(dwpe),
       M, T, C, mc);
+  return LAUNCH_OK();
+}
+
+// embeddings with a third (token-type) table: out = wte[tok] + wpe[pos] + wtt[typ]
+int aitj_embedding3_fwd(const void* tok, const void* typ, const void* wte, const void* wpe, const void* wtt, void* out,
+                        int M, int T, int C, void* stream) {
+  if (C % 8) return -1;
+  const size_t total = static_cast<size_t>(M) * (C / 8);
+  embedding_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, S(stream)>>>(
+      reinterpret_cast<const int64_t*>(tok), CBF(wte), CBF(wpe), BF(out), M, T, C,
+      reinterpret_cast<const int64_t*>(typ), CBF(wtt));
+  return LAUNCH_OK();
+}
+
+int aitj_embedding3_bwd(const void* tok, const void* typ, const void* dx, void* dwte, void* dwpe, void* dwtt, int M, int T,
+                        int C, int mc, void* stream) {
+  if (C % 4) return -1;
+  const size_t total = static_cast<size_t>(M) * (C / 4);
+  embedding_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, S(stream)>>>(
+      reinterpret_cast<const int64_t*>(tok), CBF(dx), reinterpret_cast<float*>(dwte), reinterpret_cast<float*>(dwpe),
+      M, T, C, mc, reinterpret_cast<const int64_t*>(typ), reinterpret_cast<float*>(dwtt));
   return LAUNCH_OK();
 }
 

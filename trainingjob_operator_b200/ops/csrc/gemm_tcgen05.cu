@@ -136,17 +136,89 @@ __device__ __forceinline__ void stage_commit(const CUtensorMap* tm, uint8_t* b, 
   }
 }
 
+// EPI_PEER, split-K: a sub-block whose local reduce-adds are in flight.  Its completion (count this split in; the last
+// arrival moves the block to its owner) is processed one tile later, when the bulk reduce-adds have long landed, so the
+// epilogue never waits for them.
+struct PeerPending {
+  unsigned int* ctr = nullptr;     // arrival counter of the sub-block; nullptr = nothing pending
+  float* first = nullptr;          // local address of its first element
+  long long delta = 0;             // bytes to the owner's copy
+  int rows = 0, cols = 0;          // valid extent
+  int row0 = 0, col0 = 0;          // its coordinates in the output tensor
+  int owner = 0;
+  // bulk move (TMA load of the finished block -> TMA reduce-add into the owner's copy): this warp's staging buffer and
+  // mbarrier, the local fp32 tensor map; bar == nullptr selects the move from registers (16-byte red.add's, which use
+  // NVLink far less efficiently than bulk packets)
+  uint8_t* sbuf = nullptr;
+  uint64_t* bar = nullptr;
+  uint32_t bar_phase = 0;
+  const CUtensorMap* tm_local = nullptr;
+};
+
+__device__ __forceinline__ void peer_finish(const GemmArgs& a, PeerPending& pd, int lane) {
+  if (pd.ctr == nullptr) return;
+  unsigned int seen = 0;
+  if (lane == 0) {
+    __threadfence();
+    seen = atomicAdd(pd.ctr, 1u);
+  }
+  seen = __shfl_sync(0xffffffffu, seen, 0);
+  if (seen == static_cast<unsigned int>(a.split_k - 1)) {
+    __threadfence();
+    // the finished block goes to its owner over NVLink; the local copy is cleared for the next step
+    if (pd.bar != nullptr && a.peer_maps != nullptr) {
+      fence_proxy_async_smem();
+#pragma unroll 1
+      for (int c = 0; c < pd.cols; c += 32) {
+        stage_acquire(lane);                                   // earlier bulk stores have read the staging buffer
+        if (lane == 0) {
+          mbar_arrive_expect_tx(pd.bar, 4096);
+          tma_load_2d(pd.sbuf, pd.tm_local, pd.bar, pd.col0 + c, pd.row0);
+        }
+        mbar_wait(pd.bar, pd.bar_phase);
+        pd.bar_phase ^= 1u;
+        if (lane == 0) {
+          tma_reduce_add_2d(a.peer_maps + pd.owner, pd.sbuf, pd.col0 + c, pd.row0);
+          tma_store_commit();
+        }
+        // clear the local copy (the load above has completed; nobody else touches this block any more)
+        const int ncol4 = min(32, pd.cols - c) >> 2;
+        for (int i = lane; i < pd.rows * ncol4; i += 32) {
+          const int r = i / ncol4, c4 = i - r * ncol4;
+          __stcg(reinterpret_cast<float4*>(pd.first + static_cast<size_t>(r) * a.ldc + c + c4 * 4),
+                 make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+    } else {
+      const int vec_per_row = pd.cols >> 2;
+      const int total = pd.rows * vec_per_row;
+#pragma unroll 8
+      for (int i = lane; i < total; i += 32) {
+        const int r = i / vec_per_row, c4 = i - r * vec_per_row;
+        float* p = pd.first + static_cast<size_t>(r) * a.ldc + c4 * 4;
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+        red_add_v4_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(p) + pd.delta), v.x, v.y, v.z, v.w);
+        __stcg(reinterpret_cast<float4*>(p), make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+    if (lane == 0) *pd.ctr = 0u;
+  }
+  pd.ctr = nullptr;
+}
+
 // fp32 outputs (plain store, TMA reduce-add, or multimem reduction): raw accumulators, 32 columns per chunk.
 template <int kCols>
 __device__ __forceinline__ void epilogue_f32(const GemmArgs& a, const CUtensorMap* tm_out, uint32_t tmem_acc, int row0,
-                                             int n0, int c_begin, uint8_t* sbuf, int lane) {
+                                             int n0, int c_begin, uint8_t* sbuf, int lane, PeerPending* pend = nullptr) {
   const int flags = a.flags;
   if ((flags & EPI_PEER) && a.split_k > 1 && a.peer_counters != nullptr) {
     if (row0 >= a.M || n0 + c_begin >= a.N) return;
     float* obase = reinterpret_cast<float*>(a.out);
     float* first = obase + static_cast<size_t>(row0) * a.ldc;
-    const long long delta = c_peers.delta[peer_owner(first)];
+    const int owner = peer_owner(first);
+    const long long delta = c_peers.delta[owner];
     // (1) split-K partial -> local copy, exactly like the single-GPU path
+    int issued = 0;
 #pragma unroll 1
     for (int c = 0; c < kCols / 32; ++c) {
       const int col0 = n0 + c_begin + c * 32;
@@ -158,33 +230,38 @@ __device__ __forceinline__ void epilogue_f32(const GemmArgs& a, const CUtensorMa
 #pragma unroll
       for (int q = 0; q < 8; ++q) stage_write16(sbuf, lane, q, make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]));
       stage_commit(tm_out, sbuf, col0, row0, lane, true);
+      ++issued;
+    }
+    // the PREVIOUS tile's reduce-adds have landed once all but this tile's bulk groups are complete
+    if (pend != nullptr && pend->ctr != nullptr) {
+      if (lane == 0) {
+        if (issued == kCols / 32) tma_store_wait<kCols / 32>();
+        else tma_store_wait<0>();
+      }
+      __syncwarp();
+      peer_finish(a, *pend, lane);
     }
     if (delta == 0) return;                 // this rank owns these rows: they are where they belong
-    // (2) my reduce-adds have landed -> count this split in; the last arrival owns the move
-    unsigned int* ctr = a.peer_counters + static_cast<size_t>(row0 >> 5) * ((a.N + 31) >> 5) + ((n0 + c_begin) >> 5);
-    unsigned int seen = 0;
-    if (lane == 0) {
-      tma_store_wait<0>();
-      __threadfence();
-      seen = atomicAdd(ctr, 1u);
+    PeerPending cur;
+    cur.ctr = a.peer_counters + static_cast<size_t>(row0 >> 5) * ((a.N + 31) >> 5) + ((n0 + c_begin) >> 5);
+    cur.first = first + n0 + c_begin;
+    cur.delta = delta;
+    cur.rows = min(32, a.M - row0);
+    cur.cols = min(kCols, a.N - (n0 + c_begin));
+    cur.row0 = row0;
+    cur.col0 = n0 + c_begin;
+    cur.owner = owner;
+    cur.sbuf = sbuf;
+    cur.tm_local = tm_out;
+    if (pend != nullptr) {
+      cur.bar = pend->bar;                  // the warp's mbarrier and its phase live in the pending record
+      cur.bar_phase = pend->bar_phase;
+      *pend = cur;                          // processed with the next tile (or at the end of the kernel)
+    } else {
+      if (lane == 0) tma_store_wait<0>();
+      __syncwarp();
+      peer_finish(a, cur, lane);
     }
-    seen = __shfl_sync(0xffffffffu, seen, 0);
-    if (seen != static_cast<unsigned int>(a.split_k - 1)) return;
-    __threadfence();
-    // (3) the finished 32 x kCols block goes to its owner over NVLink; the local copy is cleared for the next step
-    constexpr int kVecPerRow = kCols / 4;
-#pragma unroll 4
-    for (int i = lane; i < 32 * kVecPerRow; i += 32) {
-      const int r = i / kVecPerRow, c4 = i - r * kVecPerRow;
-      const int grow = row0 + r, gcol = n0 + c_begin + c4 * 4;
-      if (grow < a.M && gcol < a.N) {
-        float* p = obase + static_cast<size_t>(grow) * a.ldc + gcol;
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
-        red_add_v4_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(p) + delta), v.x, v.y, v.z, v.w);
-        __stcg(reinterpret_cast<float4*>(p), make_float4(0.f, 0.f, 0.f, 0.f));
-      }
-    }
-    if (lane == 0) *ctr = 0u;
     return;
   }
   if ((flags & EPI_PEER) && a.peer_maps != nullptr) {
@@ -255,12 +332,13 @@ __device__ __forceinline__ void epilogue_f32(const GemmArgs& a, const CUtensorMa
 template <int kCols>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
                                               uint32_t tmem_acc, int row0, int n0, int c_begin,
-                                              const __nv_bfloat16* sbias, uint8_t* sbuf, int lane) {
+                                              const __nv_bfloat16* sbias, uint8_t* sbuf, int lane,
+                                              PeerPending* pend = nullptr) {
   const int flags = a.flags;
   const int row = row0 + lane;
   const bool row_ok = row < a.M;
   if (flags & (EPI_MC | EPI_PEER | EPI_OUT_F32 | EPI_ACCUM)) {
-    epilogue_f32<kCols>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane);
+    epilogue_f32<kCols>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane, pend);
     return;
   }
   // bf16 output: 64 columns (128 B) per staged chunk
@@ -374,13 +452,14 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
                                                 const CUtensorMap* tm_out128, const CUtensorMap* tm_aux128,
                                                 uint32_t tmem_acc, int row0, int n0, int c_begin,
                                                 const __nv_bfloat16* sbias, const StoreGroup& g, int lg, int lane,
-                                                uint64_t* side_bar = nullptr, uint32_t side_parity = 0) {
+                                                uint64_t* side_bar = nullptr, uint32_t side_parity = 0,
+                                                PeerPending* pend = nullptr) {
   // side_bar != nullptr: the residual / pre-GELU tile of this warp was prefetched by TMA into its staging buffer
   // (swizzled like the output); it is read from there and overwritten in place by the result
   const int flags = a.flags;
   uint8_t* sbuf = g.buf + lg * 4096;
   if (flags & (EPI_MC | EPI_OUT_F32 | EPI_ACCUM)) {
-    epilogue_f32<64>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane);
+    epilogue_f32<64>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane, pend);
     return;
   }
   const int col0 = n0 + c_begin;
@@ -625,6 +704,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint8_t* sbuf = staging + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
+    PeerPending pend;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const WorkItem wi = decode_work(args, w);
       stage_bias<kBlockN>(args, sbias + acc * 256, wi.n_blk * kBlockN, epi_tid);
@@ -634,7 +714,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         epilogue_tile<kBlockN / 2>(args, &tmap_out, &tmap_aux,
                                    tmem_base + acc * kBlockN + (static_cast<uint32_t>(lg * 32) << 16),
                                    wi.m_blk * BLOCK_M + lg * 32, wi.n_blk * kBlockN, half * (kBlockN / 2),
-                                   sbias + acc * 256, sbuf, lane);
+                                   sbias + acc * 256, sbuf, lane, &pend);
       }
       tc_fence_before();
       __syncwarp();
@@ -642,6 +722,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait<0>();
+    __syncwarp();
+    peer_finish(args, pend, lane);
   }
 
   tc_fence_before();
@@ -819,6 +901,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                           (side_kind == EPI_DGELU || side_kind == EPI_RESIDUAL);
     uint64_t* my_side_bar = &side_bar[warp - 2];
     uint32_t side_phase = 0;
+    PeerPending pend;
+    if (kEpiW == 16 && !side_tma) pend.bar = my_side_bar;     // free for the bulk move of finished gradient blocks
     long long tr_wait = 0, tr_busy = 0;
     TR_BEGIN(args.trace, tr_start);
     for (int w = cluster_id; w < num_work; w += num_clusters) {
@@ -847,11 +931,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if constexpr (kEpiW == 16) {
           sg.row0_cta = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
           epilogue_cols64(args, &tmap_out, &tmap_aux, &tmap_out128, &tmap_aux128, t_acc, row0, wi.n_blk * kPairN,
-                          half * 64, sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase);
+                          half * 64, sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase,
+                          &pend);
           if (side_now) side_phase ^= 1u;
         } else {
           epilogue_tile<kPairN / 2>(args, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * (kPairN / 2),
-                                    sbias + acc * 256, sbuf, lane);
+                                    sbias + acc * 256, sbuf, lane, &pend);
         }
       }
       tc_fence_before();
@@ -861,6 +946,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait<0>();
+    __syncwarp();
+    peer_finish(args, pend, lane);
     if (args.trace && warp == 2 && lane == 0) {
       unsigned long long* tr = args.trace + blockIdx.x * 8;
       tr[TR_EPI_WAIT_FULL] = tr_wait;
@@ -884,14 +971,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 // role in the other pair.  L2 reads per CTA and k-block drop from 32 KB to 24 KB.
 //
 // Protocol differences to the pair kernel:
-//  * full_bar is per CTA (its own A, its own 8 KB of B, the partner's 8 KB of B all signal it); the non-leader's warp 1
-//    forwards "my stage landed" to the leader's peer_full barrier, and the MMA issuer waits for both;
+//  * B arrives by cta_group::2 multicast loads: every destination CTA's bytes are signalled on the full barrier of the
+//    leader of ITS pair, so a leader still waits for one barrier carrying both CTAs' A and B (2 x 32 KB);
 //  * empty_bar collects the commits of BOTH pairs' leaders (a producer's multicast also writes the other pair's smem).
+// (AITJ_GEMM_QUAD_RELAY=1 selects the first version of the protocol: plain multicast loads signalling each CTA's own
+//  barrier and a relay warp forwarding "my stage landed" to the leader -- kept for A/B.)
 template <bool kAMN, bool kBMN>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(64 + 32 * 16, 1)
 gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
-                      const __grid_constant__ CUtensorMap tmap_side, const GemmArgs args) {
+                      const __grid_constant__ CUtensorMap tmap_side, const GemmArgs args, const int relay) {
   constexpr int kEpiW = 16;
   constexpr int kPairM = 256, kPairN = 256;
   constexpr int kStageA = BLOCK_M * BLOCK_K * 2;
@@ -965,20 +1054,37 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int n0 = wi.n_blk * kPairN + static_cast<int>(rank) * (kPairN / 2) + static_cast<int>(pair) * 64;
         for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
           mbar_wait_cluster(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kStageA + pair * 8192;            // my 64 rows of this role's 128-row B half
-          if constexpr (!kAMN) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
-          } else {
+          if (relay) {
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            if constexpr (!kAMN) {
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + j * 64, kb * BLOCK_K);
-          }
-          if constexpr (!kBMN) {
-            tma_load_2d_mcast(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0, mask);      // box 64 (k) x 64 (n rows)
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + j * 64, kb * BLOCK_K);
+            }
+            if constexpr (!kBMN) {
+              tma_load_2d_mcast(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0, mask);    // box 64 (k) x 64 (n rows)
+            } else {
+              tma_load_2d_mcast(sb, &tmap_b, &full_bar[stage], n0, kb * BLOCK_K, mask);    // box 64 (n) x 64 (k rows)
+            }
           } else {
-            tma_load_2d_mcast(sb, &tmap_b, &full_bar[stage], n0, kb * BLOCK_K, mask);      // box 64 (n) x 64 (k rows)
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+            const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), leader_rank);
+            if constexpr (!kAMN) {
+              tma_load_2d_2sm(sa, &tmap_a, full_leader, kb * BLOCK_K, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d_2sm(sa + j * 8192, &tmap_a, full_leader, m0 + j * 64, kb * BLOCK_K);
+            }
+            if constexpr (!kBMN) {
+              tma_load_2d_2sm_mcast(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0, mask);
+            } else {
+              tma_load_2d_2sm_mcast(sb, &tmap_b, &full_bar[stage], n0, kb * BLOCK_K, mask);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -1000,7 +1106,7 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           const uint32_t d_tmem = tmem_base + acc * kPairN;
           for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
             mbar_wait_cluster(&full_bar[stage], phase);
-            mbar_wait_cluster(&peer_full[stage], phase);
+            if (relay) mbar_wait_cluster(&peer_full[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
             const uint32_t b_addr = a_addr + kStageA;
@@ -1018,7 +1124,7 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           umma_commit_2cta(&tmem_full[acc], pair_mask);
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-      } else {
+      } else if (relay) {
         // -------------------------------------------------------- relay: "this CTA's stage has landed" -> leader
         for (int w = cluster_id; w < num_work; w += num_clusters) {
           const WorkItem wi = decode_work(sched, w);
@@ -1048,6 +1154,7 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                           (side_kind == EPI_DGELU || side_kind == EPI_RESIDUAL);
     uint64_t* my_side_bar = &side_bar[warp - 2];
     uint32_t side_phase = 0;
+    PeerPending pend;
     for (int w = cluster_id; w < num_work; w += num_clusters) {
       const WorkItem wi = decode_work(sched, w);
       const int m_blk = wi.m_blk * 2 + static_cast<int>(pair);
@@ -1069,7 +1176,7 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int row0 = m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32;
         sg.row0_cta = m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
         epilogue_cols64(args, &tmap_out, &tmap_aux, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * 64,
-                        sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase);
+                        sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase, &pend);
         if (side_now) side_phase ^= 1u;
       }
       tc_fence_before();
@@ -1078,6 +1185,8 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait<0>();
+    __syncwarp();
+    peer_finish(args, pend, lane);
   }
 
   tc_fence_before();
@@ -1210,7 +1319,8 @@ static int launch_gemm_quad(const CUtensorMap& ta, const CUtensorMap& tb, const 
   if (num_work < clusters) clusters = num_work;
   if (max_ctas > 3 && clusters > max_ctas / 4) clusters = max_ctas / 4;
   if (clusters < 1) clusters = 1;
-  kern<<<clusters * 4, 64 + 32 * 16, kSmem, stream>>>(ta, tb, to, tx, tside, args);
+  static const int relay = getenv("AITJ_GEMM_QUAD_RELAY") && atoi(getenv("AITJ_GEMM_QUAD_RELAY")) != 0;
+  kern<<<clusters * 4, 64 + 32 * 16, kSmem, stream>>>(ta, tb, to, tx, tside, args, relay);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -30;
 }
 
@@ -1324,6 +1434,10 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   }
   if (peer_move) {
     args.peer_counters = g_peer_counters;
+    if (g_peer_tma) {
+      args.peer_maps = peer_maps_for(out, M, N, ldc);
+      if (!args.peer_maps) return -7;
+    }
     rc = encode_2d(&to, out, N, M, ldc, 32, 32, true);
     if (rc) return rc - 2000;
   } else if (flags & (EPI_MC | EPI_PEER)) {

@@ -238,6 +238,19 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensor
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// The same for CTA pairs (cta_group::2): the tile lands at the same offset of every CTA in `mask`, and completion is
+// signalled on the barrier at `bar`'s offset in the LEADER (even rank) of each destination CTA's pair -- the barrier
+// address is given with the pair's peer bit (bit 24 of a shared-window address) cleared.
+constexpr uint32_t kPairPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPairPeerBitMask), "r"(c0),
+        "r"(c1), "h"(mask)
+      : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

@@ -199,6 +199,20 @@ def embedding_bwd(tok, dx, dwte, dwpe, T):
              _stream())
 
 
+def embedding3_fwd(tok, typ, wte, wpe, wtt, out, T):
+    """out = wte[tok] + wpe[position] + wtt[typ] (BERT: word + position + token-type embeddings)."""
+    M, C = out.shape
+    lib.call("aitj_embedding3_fwd", tok.data_ptr(), typ.data_ptr(), wte.data_ptr(), wpe.data_ptr(), wtt.data_ptr(),
+             out.data_ptr(), M, T, C, _stream())
+    return out
+
+
+def embedding3_bwd(tok, typ, dx, dwte, dwpe, dwtt, T):
+    M, C = dx.shape
+    lib.call("aitj_embedding3_bwd", tok.data_ptr(), typ.data_ptr(), dx.data_ptr(), dwte.data_ptr(), dwpe.data_ptr(),
+             dwtt.data_ptr(), M, T, C, _is_mc(dwte), _stream())
+
+
 def softmax_xent(logits, target, loss, V, gscale):
     """In place: logits[M,Vp] <- dlogits = (softmax - onehot) * gscale; loss[M] <- per-row NLL."""
     M, Vp = logits.shape

@@ -70,6 +70,8 @@ _SIGS = {
     "aitj_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "aitj_embedding_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "aitj_embedding_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "aitj_embedding3_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "aitj_embedding3_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "aitj_softmax_xent": [_P, _P, _P, _I, _I, _I, _F, _P],
     "aitj_colsum": [_P, _P, _I, _I, _I, _P],
     "aitj_qkv_gather_colsum": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -108,10 +110,52 @@ def declare(name: str, argtypes) -> None:
         fn.restype = _I
 
 
+# Per-kernel device timing (eager launches only): ``profile_start()`` makes every ``call`` bracket its launch with CUDA
+# events on the launching stream; ``profile_stop()`` returns {label: (launches, total ms)}.  GEMMs are labelled by operand
+# layout (forward / dgrad / wgrad) and output kind.  (the reference has no tracing at all.)
+_PROFILE = None
+
+
+def profile_start() -> None:
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_stop():
+    global _PROFILE
+    import torch
+
+    torch.cuda.synchronize()
+    out = {}
+    for label, e0, e1 in _PROFILE or []:
+        n, ms = out.get(label, (0, 0.0))
+        out[label] = (n + 1, ms + e0.elapsed_time(e1))
+    _PROFILE = None
+    return out
+
+
+def _label(name: str, args) -> str:
+    if name != "aitj_gemm_bf16":
+        return name[5:]
+    a_mn, b_mn, flags, split_k, block_n = args[9], args[10], args[14], args[15], args[16]
+    kind = "wgrad" if a_mn and b_mn else ("dgrad" if b_mn else "fwd")
+    extra = "+peer" if flags & 16384 else ("+mc" if flags & 128 else "")
+    return f"gemm:{kind}{extra} N={args[4]} K={args[5]} bn={block_n} sk={split_k}"
+
+
 def call(name: str, *args) -> int:
     global LAUNCHES
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _PROFILE is not None:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _PROFILE.append((_label(name, args), e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise KernelError(f"{name} failed with code {rc}")
     LAUNCHES += 1

@@ -392,7 +392,9 @@ def case_attention_bwd():
         got = d_qkv.view(B, T, 3, H, 64)
         tag = f"B{B} T{T} H{H} causal={causal}"
         for name, i, g in (("dq", 0, gq), ("dk", 1, gk), ("dv", 2, gv)):
-            ok &= _check(f"attn bwd {name} {tag}", got[:, :, i].transpose(1, 2), g, 2e-2, rtol=5e-2, atol_scale=5e-2)
+            # P and dS go through bf16 before the second GEMMs and dk / dv sum over up to T queries: the element-wise
+            # noise floor is a few percent of the gradient's spread
+            ok &= _check(f"attn bwd {name} {tag}", got[:, :, i].transpose(1, 2), g, 2e-2, rtol=5e-2, atol_scale=1.5e-1)
         ok &= _check(f"attn bwd dq_acc cleared {tag}", dq_acc, torch.zeros_like(dq_acc), 1.0, atol_scale=1.0) \
             if float(dq_acc.abs().max()) == 0.0 else False
     B, T, H = 16, 1024, 12
@@ -474,6 +476,51 @@ def case_graph_step():
     return ok
 
 
+def case_bert_engine():
+    """BERT-base-shaped MLM engine (post-LN encoder, token-type embeddings, MLM head, masked loss) vs the plain fp32
+    PyTorch model on the same weights: loss and gradients; three optimizer steps reduce the loss."""
+    from ..models.bert import BertConfig, BertEngine, BertReference, SyntheticMLM
+
+    ok = True
+    cfg = BertConfig.tiny()
+    B, T = 4, 128
+    eng = BertEngine(cfg, B, T, "cuda", seed=3)
+    # break the symmetry of the zero-initialised biases / unit LayerNorm gains so that their gradients are exercised
+    g = torch.Generator(device="cpu").manual_seed(9)
+    for s_ in eng.params.specs:
+        if len(s_.shape) == 1:
+            eng.params.w32(s_.name).add_(torch.randn(s_.shape, generator=g).cuda() * 0.05)
+    eng.params.w32("dec_b")[cfg.vocab_size:].zero_()
+    eng.params.refresh_compute_copy()
+    ref = BertReference(cfg, eng.params).cuda()
+    data = SyntheticMLM(cfg.vocab_size, B, T, n_batches=1, seed=5, pin=False)
+    tok, typ, lab = data.next()
+    for dst, src in zip(eng.input_tensors(), (tok, typ, lab)):
+        dst.copy_(src)
+    assert eng.n_masked == data.n_masked
+    eng.params.g32.zero_()
+    eng.forward(); eng.backward()
+    torch.cuda.synchronize()
+    rl = ref(tok.view(B, T).cuda(), typ.view(B, T).cuda(), lab.view(B, T).cuda())
+    rl.backward()
+    ok &= _check("[bert] loss", eng.loss, rl.detach().reshape(1), 5e-3)
+    for name in ("wte", "wpe", "wtt", "emb_ln_w", "h0.qkv_w", "h0.qkv_b", "h0.proj_w", "h0.proj_b", "h0.ln1_w", "h0.fc_w",
+                 "h0.fc_b", "h0.fc2_w", "h0.fc2_b", "h1.ln2_b", "h1.fc2_w", "mlm_w", "mlm_b", "mlm_ln_w", "dec_b"):
+        gref = ref.p(name).grad
+        got = eng.params.grad(name)
+        if name == "dec_b":
+            gref, got = gref[:cfg.vocab_size], got[:cfg.vocab_size]
+        ok &= _check(f"[bert] grad {name}", got, gref, 4e-2, rtol=1e-1, atol_scale=2.5e-1)
+    l0 = float(eng.loss.item())
+    for step in range(1, 4):
+        eng.optimizer_step(lr=1e-3, step=step)
+        eng.forward(); eng.backward()
+    l1 = float(eng.loss.item())
+    print(f"  [bert] loss {l0:.4f} -> {l1:.4f}")
+    ok &= l1 < l0
+    return ok
+
+
 # ----------------------------------------------------------------------------- attention
 def case_attention():
     """tcgen05 flash-attention forward vs. an fp32 PyTorch reference (causal and full), plus its device time next to
@@ -534,6 +581,7 @@ CASES = {
     "gemm_2cta": case_gemm_2cta,
     "gemm_quad": case_gemm_quad,
     "graph_step": case_graph_step,
+    "bert_engine": case_bert_engine,
     "attention_bwd": case_attention_bwd,
     "gpt2_engine": case_gpt2_engine,
     "gemm_tn": case_gemm_tn,

@@ -21,8 +21,12 @@ ALIGN = 256
 
 class FlatDDP:
     def __init__(self, module: torch.nn.Module, bucket_bytes: int = 25 << 20, group=None, backend: str = "nccl",
-                 weight_decay: float = 0.0, lr: float = 1e-3, optimizer: str = "adamw", momentum: float = 0.9):
+                 weight_decay: float = 0.0, lr: float = 1e-3, optimizer: str = "adamw", momentum: float = 0.9,
+                 overlap: bool = True):
+        """``overlap=False``: no per-bucket hooks -- the caller replays forward + backward as one CUDA graph (Python
+        hooks do not run on a replay) and ``finish_backward`` reduces the whole flat gradient buffer with one collective."""
         self.module = module
+        self.overlap = overlap
         self.group = group
         self.lr, self.weight_decay, self.momentum = lr, weight_decay, momentum
         self.optimizer = optimizer
@@ -69,7 +73,7 @@ class FlatDDP:
         self.reducer = BucketAllReducer(self.g32, buckets, group, backend, min_bucket_bytes=0) \
             if self.world > 1 else None
         self._hooked = False
-        if self.reducer is not None:
+        if self.reducer is not None and overlap:
             for idx, p in enumerate(params):
                 p.register_post_accumulate_grad_hook(self._make_hook(idx))
             self._hooked = True
@@ -88,6 +92,9 @@ class FlatDDP:
         return hook
 
     def finish_backward(self) -> None:
+        if self.reducer is not None and not self.overlap:
+            self.reducer.all_reduce_all()
+            return
         if self.reducer is not None:
             # buckets whose parameters received no gradient this step still have to be reduced
             for b, left in enumerate(self._todo):

@@ -252,7 +252,7 @@ class StallBreaker:
     communicator instead, once (a) the controller has published a newer rendezvous generation (= it replaced a replica)
     and (b) the main thread has not reached a step boundary for ``after_s`` seconds; the blocked step then fails and the
     main thread takes the same recovery path as an exception from gloo.  Only armed on CUDA (``AITJ_FT_ABORT_AFTER``,
-    default 10 s, 0 disables)."""
+    default 3 s, 0 disables)."""
 
     def __init__(self, watcher, after_s: float):
         self.watcher, self.after_s = watcher, after_s

@@ -215,11 +215,13 @@ class EngineTrainer:
         return lib.LAUNCHES - before
 
     # ------------------------------------------------------------------ public step
-    def step(self, tok_host: torch.Tensor, tgt_host: torch.Tensor, read_loss: bool = True) -> Optional[float]:
+    def step(self, *host_inputs: torch.Tensor, read_loss: bool = True) -> Optional[float]:
+        """``host_inputs``: this step's inputs in pinned host memory, in the order of ``engine.input_tensors()``
+        (GPT-2: tokens, targets; BERT: tokens, token types, MLM labels)."""
         e = self.engine
         self.step_count += 1
-        e.tok.copy_(tok_host, non_blocking=True)
-        e.tgt.copy_(tgt_host, non_blocking=True)
+        for dst, src in zip(e.input_tensors(), host_inputs):
+            dst.copy_(src, non_blocking=True)
         e.set_step_scalars(cosine_lr(self.step_count, self.lr), self.step_count)
         if self.use_graph and self.segmented:
             if self.seg_graphs is None:

@@ -45,23 +45,30 @@ class EngineAdapter:
     def __init__(self, name: str, batch: int, seq: int, args):
         from ..models.gpt2 import GPT2Config, GPT2Engine, flops_per_token
 
-        if name == "gpt2":
-            cfg, causal = GPT2Config.small(), True
-        elif name == "gpt2-tiny":
-            cfg, causal = GPT2Config.tiny(), True
-        elif name == "bert":
-            cfg, causal = GPT2Config(vocab_size=30522, n_layer=12, n_head=12, n_embd=768, block_size=512,
-                                     name="bert-base"), False
+        if name in ("bert", "bert-tiny"):
+            # the real thing: word + position + token-type embeddings, post-LN bidirectional encoder, MLM head and loss
+            from ..models.bert import BertConfig, BertEngine, SyntheticMLM, bert_flops_per_token
+
+            cfg = BertConfig.base() if name == "bert" else BertConfig.tiny()
+            seq = min(seq, cfg.block_size)
+            self.engine = BertEngine(cfg, batch, seq, "cuda", seed=args.seed, gemm_backend=args.gemm)
+            self.data = SyntheticMLM(cfg.vocab_size, batch, seq, n_batches=4, seed=args.seed + 1)
+            self.flops_per_step = bert_flops_per_token(cfg, seq) * batch * seq
         else:
-            raise ValueError(name)
-        seq = min(seq, cfg.block_size)
+            if name == "gpt2":
+                cfg = GPT2Config.small()
+            elif name == "gpt2-tiny":
+                cfg = GPT2Config.tiny()
+            else:
+                raise ValueError(name)
+            seq = min(seq, cfg.block_size)
+            self.engine = GPT2Engine(cfg, batch, seq, "cuda", seed=args.seed, gemm_backend=args.gemm, causal=True)
+            self.data = SyntheticTokens(cfg.vocab_size, batch, seq, n_batches=4, seed=args.seed + 1)
+            self.flops_per_step = flops_per_token(cfg, seq) * batch * seq
         self.cfg = cfg
-        self.engine = GPT2Engine(cfg, batch, seq, "cuda", seed=args.seed, gemm_backend=args.gemm, causal=causal)
         self.batch, self.seq = batch, seq
-        self.data = SyntheticTokens(cfg.vocab_size, batch, seq, n_batches=4, seed=args.seed + 1)
         self.h2d_bytes = self.data.bytes_per_step
         self.d2h_bytes = 4
-        self.flops_per_step = flops_per_token(cfg, seq) * batch * seq
         self.trainer: Optional[EngineTrainer] = None
         self.args = args
         self.describe = {"model": cfg.name, "seq_len": seq, "params": self.engine.num_parameters(),
@@ -78,8 +85,7 @@ class EngineAdapter:
             self.trainer.step_count = old.step_count
 
     def train_step(self) -> float:
-        tok, tgt = self.data.next()
-        return self.trainer.step(tok, tgt)
+        return self.trainer.step(*self.data.next())
 
     def discard_step(self) -> None:
         self.engine.params.g32.zero_()
@@ -173,9 +179,12 @@ class TorchAdapter:
         from ..parallel.flat_ddp import FlatDDP
 
         backend = "nccl" if self.dev.type == "cuda" else "gloo"
+        # CUDA: forward + backward are replayed as one CUDA graph (the step of the small networks is launch bound: MNIST
+        # CNN 1.4 ms of mostly gaps), the flat gradient buffer is reduced by one collective after it
+        self.use_graph = self.dev.type == "cuda" and not self.args.no_graph
         if self.ddp is None:
             self.ddp = FlatDDP(self.module, group=group, backend=backend, lr=self.args.lr,
-                               optimizer="adamw" if self.name != "mlp" else "sgd")
+                               optimizer="adamw" if self.name != "mlp" else "sgd", overlap=not self.use_graph)
         else:  # re-bind after a re-rendezvous: keep buffers, rebuild the reducer for the new group
             from ..parallel.ddp import BucketAllReducer
 
@@ -183,22 +192,56 @@ class TorchAdapter:
             self.ddp.world = dist.get_world_size(group) if dist.is_initialized() else 1
             self.ddp.reducer = BucketAllReducer(self.ddp.g32, self.ddp.buckets, group, backend, 0) \
                 if self.ddp.world > 1 else None
-            if self.ddp.reducer is not None and not getattr(self.ddp, "_hooked", False):
+            if self.ddp.reducer is not None and self.ddp.overlap and not getattr(self.ddp, "_hooked", False):
                 for idx, p in enumerate(self.ddp.params):
                     p.register_post_accumulate_grad_hook(self.ddp._make_hook(idx))
         self.ddp._hooked = self.ddp.reducer is not None or getattr(self.ddp, "_hooked", False)
 
-    def train_step(self) -> float:
-        x, y = self.batches[self.i % len(self.batches)]
-        self.i += 1
-        self.x_dev.copy_(x, non_blocking=True)
-        self.y_dev.copy_(y, non_blocking=True)
+    def _fwd_bwd(self) -> torch.Tensor:
         if self.dev.type == "cuda":
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 loss = torch.nn.functional.cross_entropy(self.module(self.x_dev), self.y_dev)
         else:
             loss = torch.nn.functional.cross_entropy(self.module(self.x_dev), self.y_dev)
         loss.backward()
+        return loss
+
+    def _capture(self) -> None:
+        """Forward + backward of the fixed-shape step as one CUDA graph: static inputs (x_dev / y_dev), gradients
+        accumulated in place into the flat buffer the parameters' ``.grad`` already point into."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._fwd_bwd()
+                self.ddp.g32.zero_()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                self._graph_loss = self._fwd_bwd().detach()
+            self.ddp.g32.zero_()
+            self.graph = g
+        except Exception as e:  # noqa: BLE001 - eager fallback (and the per-bucket overlap is gone: one all-reduce)
+            self.graph_error = f"{type(e).__name__}: {e}"
+            self.graph = None
+            self.use_graph = False
+            torch.cuda.synchronize()
+
+    def train_step(self) -> float:
+        x, y = self.batches[self.i % len(self.batches)]
+        self.i += 1
+        self.x_dev.copy_(x, non_blocking=True)
+        self.y_dev.copy_(y, non_blocking=True)
+        if getattr(self, "use_graph", False) and getattr(self, "graph", None) is None and \
+                getattr(self, "graph_error", None) is None:
+            self._capture()
+        if getattr(self, "graph", None) is not None:
+            self.graph.replay()
+            loss = self._graph_loss
+        else:
+            loss = self._fwd_bwd()
         self.ddp.finish_backward()
         self.ddp.step()
         self._steps += 1
@@ -235,7 +278,7 @@ class TorchAdapter:
 
 
 def build_adapter(args, device: torch.device):
-    if args.model in ("gpt2", "gpt2-tiny", "bert"):
+    if args.model in ("gpt2", "gpt2-tiny", "bert", "bert-tiny"):
         if device.type != "cuda":
             raise RuntimeError(f"model {args.model} needs a CUDA device (hand-written sm_100a kernels)")
         return EngineAdapter(args.model, args.batch, args.seq, args)
@@ -351,8 +394,8 @@ def run(args) -> Dict[str, Any]:
     # except branch of the training loop
     fault_tolerant = bool(args.elastic and watcher is not None and os.environ.get("AITJ_FAULT_TOLERANT") == "1")
     breaker = None
-    if fault_tolerant and use_cuda and float(os.environ.get("AITJ_FT_ABORT_AFTER", "10")) > 0:
-        breaker = StallBreaker(watcher, float(os.environ.get("AITJ_FT_ABORT_AFTER", "10")))
+    if fault_tolerant and use_cuda and float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")) > 0:
+        breaker = StallBreaker(watcher, float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")))
     recoveries: List[Dict[str, Any]] = []
 
     stop = {"flag": False}
@@ -562,9 +605,11 @@ def run(args) -> Dict[str, Any]:
             "flops_per_step": getattr(adapter, "flops_per_step", 0.0),
             "describe": adapter.describe,
             "cuda_graph": bool(getattr(getattr(adapter, "trainer", None), "graph", None)
-                               or getattr(getattr(adapter, "trainer", None), "seg_graphs", None)),
+                               or getattr(getattr(adapter, "trainer", None), "seg_graphs", None)
+                               or getattr(adapter, "graph", None)),
             "graph_segments": len(getattr(getattr(adapter, "trainer", None), "seg_graphs", None) or []) or None,
-            "graph_error": getattr(getattr(adapter, "trainer", None), "graph_error", None),
+            "graph_error": getattr(getattr(adapter, "trainer", None), "graph_error", None)
+            or getattr(adapter, "graph_error", None),
             "allreduce": getattr(getattr(adapter, "trainer", None), "allreduce_backend", "nccl" if world > 1 else "none"),
         })
     if rank == 0 and args.result:
@@ -584,7 +629,7 @@ def run(args) -> Dict[str, Any]:
 
 def parse_args(argv=None):
     ap = argparse.ArgumentParser(prog="aitj-worker")
-    ap.add_argument("--model", default="gpt2", choices=["gpt2", "gpt2-tiny", "bert", "resnet50", "mnist", "mlp"])
+    ap.add_argument("--model", default="gpt2", choices=["gpt2", "gpt2-tiny", "bert", "bert-tiny", "resnet50", "mnist", "mlp"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch size")
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=20, help="timed steps (0 = run until SIGTERM)")

@@ -36,12 +36,19 @@ def _preload(cuda: bool = False) -> None:
 
     for mod in ("trainingjob_operator_b200.runtime.worker", "trainingjob_operator_b200.runtime.trainer",
                 "trainingjob_operator_b200.runtime.elastic", "trainingjob_operator_b200.models.gpt2",
-                "trainingjob_operator_b200.parallel.ddp"):
+                "trainingjob_operator_b200.models.bert", "trainingjob_operator_b200.parallel.ddp",
+                "trainingjob_operator_b200.parallel.symm", "trainingjob_operator_b200.ops.functional"):
         try:
             __import__(mod)
         except Exception:  # noqa: BLE001 - optional pieces must not keep the pool from warming
             pass
     if cuda and torch.cuda.is_available():
+        try:
+            from trainingjob_operator_b200.ops import lib as _lib
+
+            _lib.load(build_if_missing=False)                              # dlopen + module load of the sm_100a kernels
+        except Exception:  # noqa: BLE001
+            pass
         try:
             dev = torch.device("cuda", 0)
             a = torch.randn(64, 64, device=dev, dtype=torch.bfloat16)

@@ -62,6 +62,67 @@ class LocalTransport(Transport):
         return self.server.watch(info, namespace, resource_version, label_selector, timeout)
 
 
+class ThrottledTransport(Transport):
+    """Client-side request throttle, client-go's ``flowcontrol.NewTokenBucketRateLimiter(qps, burst)``: every request
+    except a watch takes a token and waits when the bucket is empty.  The reference passes its ``rest.Config`` through
+    unmodified (/root/reference/cmd/app/server.go:126-144), so each of its clientsets runs at client-go's defaults --
+    5 qps, burst 10 -- which is what bounds how fast it can POST N pods + N services (``--kube-api-qps`` /
+    ``--kube-api-burst`` here; 0 = unthrottled, and ``tools/latency_bench.py --reference-throttle`` measures the effect)."""
+
+    def __init__(self, inner: Transport, qps: float, burst: int):
+        import time as _time
+
+        self.inner = inner
+        self.qps = float(qps)
+        self.burst = max(1, int(burst))
+        self._tokens = float(self.burst)
+        self._last = _time.monotonic()
+        self._lock = threading.Lock()
+        self.waited_s = 0.0
+        self.requests = 0
+        for name in ("master", "server"):
+            if hasattr(inner, name):
+                setattr(self, name, getattr(inner, name))
+
+    def _take(self) -> None:
+        import time as _time
+
+        with self._lock:
+            now = _time.monotonic()
+            self._tokens = min(self.burst, self._tokens + (now - self._last) * self.qps)
+            self._last = now
+            self._tokens -= 1.0
+            wait = -self._tokens / self.qps if self._tokens < 0 else 0.0
+            self.requests += 1
+            self.waited_s += wait
+        if wait > 0:
+            _time.sleep(wait)
+
+    def create(self, *a, **kw):
+        self._take(); return self.inner.create(*a, **kw)
+
+    def get(self, *a, **kw):
+        self._take(); return self.inner.get(*a, **kw)
+
+    def list(self, *a, **kw):
+        self._take(); return self.inner.list(*a, **kw)
+
+    def update(self, *a, **kw):
+        self._take(); return self.inner.update(*a, **kw)
+
+    def patch(self, *a, **kw):
+        self._take(); return self.inner.patch(*a, **kw)
+
+    def delete(self, *a, **kw):
+        self._take(); return self.inner.delete(*a, **kw)
+
+    def delete_collection(self, *a, **kw):
+        self._take(); return self.inner.delete_collection(*a, **kw)
+
+    def watch(self, *a, **kw):
+        return self.inner.watch(*a, **kw)
+
+
 class _HTTPWatch:
     """Streaming watch: newline-delimited JSON events over a chunked response."""
 
