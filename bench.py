@@ -158,7 +158,10 @@ def run_e2e(a, n_gpus):
     # the node agent's warm pool (agent --warm-pool N): one parked interpreter per GPU slot with torch imported, a live
     # CUDA context and the kernel library loaded -- the steady state of a running daemon, reached before the job arrives
     pool = 0 if a.no_warm_pool else n_gpus
-    with LocalCluster(num_gpus=n_gpus, workdir=workdir, warm_pool=pool) as lc:
+    # gpu_visibility "all": a replica is bound to its GPU by LOCAL_RANK with its peers visible, because the workers'
+    # owner-sharded gradient path maps the peers' memory (CUDA symmetric memory needs distinct device indices per rank)
+    with LocalCluster(num_gpus=n_gpus, workdir=workdir, warm_pool=pool,
+                      gpu_visibility="all" if n_gpus > 1 else "pinned") as lc:
         if pool:
             t_pool = time.time()
             while lc.agent.warm_ready() < pool and time.time() - t_pool < 180:

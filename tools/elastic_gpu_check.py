@@ -50,7 +50,8 @@ def pids(lc):
 
 out = {"model": model, "gpus": n, "warm_pool": pool, "rescales": []}
 opt = TrainingJobOperatorOption(thread_num=2, scale_down_grace=60.0)
-with LocalCluster(num_gpus=n, option=opt, workdir=f"/tmp/aitj-elastic-{pool}", warm_pool=pool) as lc:
+with LocalCluster(num_gpus=n, option=opt, workdir=f"/tmp/aitj-elastic-{pool}", warm_pool=pool,
+                  gpu_visibility=os.environ.get("AITJ_GPU_VISIBILITY", "all")) as lc:
     if pool:
         wait(lambda: lc.agent.warm_ready() >= pool, 120)
     t_submit = time.time()

@@ -155,7 +155,13 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
     def __init__(self, clientset, num_gpus: Optional[int] = None, workdir: str = "/tmp/aitj-agent",
                  health_prober: Optional[Callable[[int], Tuple[bool, str]]] = None, health_period: float = 2.0,
                  cpu_slots: int = 64, image_map: Optional[Dict[str, List[str]]] = None,
-                 supervisor=None, node_prefix: str = "", warm_pool: int = 0):
+                 supervisor=None, node_prefix: str = "", warm_pool: int = 0, gpu_visibility: str = "pinned"):
+        """``gpu_visibility``: how a replica is tied to its GPU slot.  ``pinned`` (default): ``CUDA_VISIBLE_DEVICES`` holds
+        only the bound GPU(s) -- an opaque user container cannot touch anything else, which is what the reference's
+        per-pod resource limits give it.  ``all``: every GPU of the box stays visible (natural order) and the bound one is
+        named by ``LOCAL_RANK`` / ``AITJ_PINNED_GPU`` -- needed when the worker maps its peers' memory (CUDA symmetric
+        memory refuses ranks that all call their device "0": the owner-sharded gradient path, ``parallel.symm``)."""
+        self.gpu_visibility = gpu_visibility if gpu_visibility in ("pinned", "all") else "pinned"
         self.cs = clientset
         self.num_gpus = detect_gpu_count() if num_gpus is None else int(num_gpus)
         self.workdir = workdir
@@ -494,8 +500,10 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
 
     def _container_env(self, pod: dict, c: dict, gpus: List[int]) -> Dict[str, str]:
         env = {k: os.environ[k] for k in _PASS_ENV if k in os.environ}
-        env["CUDA_VISIBLE_DEVICES"] = ",".join(str(g) for g in gpus)
+        share = self.gpu_visibility == "all" and len(gpus) == 1 and self.num_gpus > 1
+        env["CUDA_VISIBLE_DEVICES"] = ",".join(str(g) for g in (range(self.num_gpus) if share else gpus))
         env["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
+        env["AITJ_PINNED_GPU"] = ",".join(str(g) for g in gpus)
         env.setdefault("NCCL_IB_DISABLE", "1")
         env.setdefault("NCCL_SOCKET_IFNAME", "lo")
         env["AITJ_POD_NAME"] = M.name_of(pod)
@@ -509,6 +517,8 @@ class NodeAgent(SchedulerMixin, WarmPoolMixin, LivenessMixin):
         for e in c.get("env") or []:
             if "name" in e:
                 env[str(e["name"])] = str(e.get("value", ""))
+        if share:
+            env["LOCAL_RANK"] = str(gpus[0])       # the bound GPU, among all the visible ones
         return env
 
     def _cpus_for(self, gpus: List[int]) -> List[int]:

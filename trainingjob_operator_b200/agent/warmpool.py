@@ -60,8 +60,10 @@ class WarmPoolMixin:
                     env = self._zygote_env()
                     cmd = [sys.executable, "-m", "trainingjob_operator_b200.runtime.zygote", fifo]
                     if gpu is not None:
-                        env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+                        share = self.gpu_visibility == "all" and self.num_gpus > 1
+                        env["CUDA_VISIBLE_DEVICES"] = ",".join(str(g) for g in range(self.num_gpus)) if share else str(gpu)
                         env["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
+                        env["AITJ_ZYGOTE_DEVICE"] = str(gpu) if share else "0"
                         cmd.append("--cuda")
                     self.sup.spawn(zid, cmd, env, "", os.path.join(self.log_dir, "zygotes.log"), "",
                                    self._cpus_for([gpu]) if gpu is not None else [])
@@ -117,7 +119,7 @@ class WarmPoolMixin:
             return False
         want_gpu: Optional[int] = None
         if self.num_gpus > 0:
-            vis = env.get("CUDA_VISIBLE_DEVICES", "")
+            vis = env.get("AITJ_PINNED_GPU", env.get("CUDA_VISIBLE_DEVICES", ""))
             if not vis.isdigit():
                 return False          # CPU-only or multi-GPU container: parked interpreters are pinned to one slot each
             want_gpu = int(vis)

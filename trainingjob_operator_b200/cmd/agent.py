@@ -22,6 +22,9 @@ def main(argv=None) -> int:
     ap.add_argument("--v", type=int, default=0)
     ap.add_argument("--warm-pool", type=int, default=-1,
                     help="parked pre-imported interpreters for fast replica start (-1 = one per GPU slot, 0 = off)")
+    ap.add_argument("--gpu-visibility", default="pinned", choices=["pinned", "all"],
+                    help="pinned: CUDA_VISIBLE_DEVICES holds only a replica's bound GPU; all: every GPU stays visible and "
+                         "LOCAL_RANK names the bound one (workers that map their peers' memory need this)")
     args = ap.parse_args(argv)
     klog.configure(args.v, True)
     master = resolve_master(TrainingJobOperatorOption(master_url=args.master, kubeconfig=args.kubeconfig))
@@ -31,7 +34,7 @@ def main(argv=None) -> int:
     from .local import _auto_pool
 
     agent = NodeAgent(new_for_config(master=master), num_gpus=args.gpus, workdir=args.workdir, image_map=image_map,
-                      warm_pool=_auto_pool(args.warm_pool, args.gpus))
+                      warm_pool=_auto_pool(args.warm_pool, args.gpus), gpu_visibility=args.gpu_visibility)
     stop = setup_signal_handler()
     agent.start(stop)
     print(f"aitj-agent up: {agent.num_gpus} GPU slot(s), master {master}", flush=True)

@@ -31,7 +31,7 @@ class LocalCluster:
     def __init__(self, num_gpus: Optional[int] = None, workdir: Optional[str] = None, wal: bool = False,
                  operators: int = 1, leader_elect: bool = False, http: bool = True, port: int = 0,
                  option: Optional[options_mod.TrainingJobOperatorOption] = None, health_prober=None,
-                 health_period: float = 1.0, verbosity: int = 0, warm_pool: int = 0):
+                 health_period: float = 1.0, verbosity: int = 0, warm_pool: int = 0, gpu_visibility: str = "pinned"):
         self.workdir = workdir or tempfile.mkdtemp(prefix="aitj-")
         os.makedirs(self.workdir, exist_ok=True)
         klog.configure(verbosity, True)
@@ -41,7 +41,7 @@ class LocalCluster:
         self.stop_event = threading.Event()
         self.clientset: Clientset = new_for_config(server=self.api)
         self._agent_kw = dict(num_gpus=num_gpus, workdir=self.workdir, health_prober=health_prober,
-                              health_period=health_period, warm_pool=warm_pool)
+                              health_period=health_period, warm_pool=warm_pool, gpu_visibility=gpu_visibility)
         self.agent = NodeAgent(new_for_config(server=self.api), **self._agent_kw)
         self._agent_stop = threading.Event()
         self.option = option or options_mod.TrainingJobOperatorOption()
@@ -195,6 +195,8 @@ def main(argv=None) -> int:
     up.add_argument("--v", type=int, default=0)
     up.add_argument("--warm-pool", type=int, default=-1,
                     help="parked pre-imported interpreters for fast replica start (-1 = one per GPU slot, 0 = off)")
+    up.add_argument("--gpu-visibility", default="pinned", choices=["pinned", "all"],
+                    help="see aitj-agent --gpu-visibility")
     options_group = up.add_argument_group("operator flags")
     options_group.add_argument("--thread-num", type=int, default=4)
     options_group.add_argument("--enable-creating-failed", action="store_true")
@@ -206,7 +208,8 @@ def main(argv=None) -> int:
     stop = setup_signal_handler()
     cluster = LocalCluster(num_gpus=args.gpus, workdir=args.workdir, wal=not args.no_wal, operators=args.operators,
                            leader_elect=args.leader_elect or args.operators > 1, port=args.port, option=opt,
-                           verbosity=args.v, warm_pool=_auto_pool(args.warm_pool, args.gpus))
+                           verbosity=args.v, warm_pool=_auto_pool(args.warm_pool, args.gpus),
+                           gpu_visibility=args.gpu_visibility)
     cluster.start()
     cfg_dir = os.path.expanduser("~/.aitj")
     os.makedirs(cfg_dir, exist_ok=True)

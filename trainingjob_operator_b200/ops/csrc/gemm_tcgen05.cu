@@ -140,83 +140,80 @@ __device__ __forceinline__ void stage_commit(const CUtensorMap* tm, uint8_t* b, 
 // arrival moves the block to its owner) is processed one tile later, when the bulk reduce-adds have long landed, so the
 // epilogue never waits for them.
 struct PeerPending {
-  unsigned int* ctr = nullptr;     // arrival counter of the sub-block; nullptr = nothing pending
-  float* first = nullptr;          // local address of its first element
-  long long delta = 0;             // bytes to the owner's copy
-  int rows = 0, cols = 0;          // valid extent
-  int row0 = 0, col0 = 0;          // its coordinates in the output tensor
-  int owner = 0;
-  // bulk move (TMA load of the finished block -> TMA reduce-add into the owner's copy): this warp's staging buffer and
-  // mbarrier, the local fp32 tensor map; bar == nullptr selects the move from registers (16-byte red.add's, which use
-  // NVLink far less efficiently than bulk packets)
-  uint8_t* sbuf = nullptr;
-  uint64_t* bar = nullptr;
-  uint32_t bar_phase = 0;
-  const CUtensorMap* tm_local = nullptr;
+  int row0 = -1, col0 = 0;         // coordinates of the pending sub-block in the output tensor; row0 < 0 = nothing pending
+  int cols = 0;                    // its width (32 rows x cols)
+  uint32_t bar_phase = 0;          // phase of this warp's move barrier
 };
 
-__device__ __forceinline__ void peer_finish(const GemmArgs& a, PeerPending& pd, int lane) {
-  if (pd.ctr == nullptr) return;
+// `bar` != nullptr (and a.peer_maps set): bulk move -- TMA load of the finished block into the warp's staging buffer, TMA
+// reduce-add into the owner's copy (bulk packets use NVLink far better than 16-byte red.add's); else move from registers.
+__device__ __forceinline__ void peer_finish(const GemmArgs& a, PeerPending& pd, const CUtensorMap* tm_local, uint8_t* sbuf,
+                                            uint64_t* bar, int lane) {
+  if (pd.row0 < 0) return;
+  const int row0 = pd.row0, col0 = pd.col0;
+  pd.row0 = -1;
+  float* first = reinterpret_cast<float*>(a.out) + static_cast<size_t>(row0) * a.ldc + col0;
+  const int owner = peer_owner(first - col0);
+  const long long delta = c_peers.delta[owner];
+  unsigned int* ctr = a.peer_counters + static_cast<size_t>(row0 >> 5) * ((a.N + 31) >> 5) + (col0 >> 5);
   unsigned int seen = 0;
   if (lane == 0) {
     __threadfence();
-    seen = atomicAdd(pd.ctr, 1u);
+    seen = atomicAdd(ctr, 1u);
   }
   seen = __shfl_sync(0xffffffffu, seen, 0);
-  if (seen == static_cast<unsigned int>(a.split_k - 1)) {
-    __threadfence();
-    // the finished block goes to its owner over NVLink; the local copy is cleared for the next step
-    if (pd.bar != nullptr && a.peer_maps != nullptr) {
-      fence_proxy_async_smem();
+  if (seen != static_cast<unsigned int>(a.split_k - 1)) return;
+  __threadfence();
+  // the finished block goes to its owner over NVLink; the local copy is cleared for the next step
+  const int rows = min(32, a.M - row0);
+  const int cols = min(pd.cols, a.N - col0);
+  if (bar != nullptr && a.peer_maps != nullptr) {
 #pragma unroll 1
-      for (int c = 0; c < pd.cols; c += 32) {
-        stage_acquire(lane);                                   // earlier bulk stores have read the staging buffer
-        if (lane == 0) {
-          mbar_arrive_expect_tx(pd.bar, 4096);
-          tma_load_2d(pd.sbuf, pd.tm_local, pd.bar, pd.col0 + c, pd.row0);
-        }
-        mbar_wait(pd.bar, pd.bar_phase);
-        pd.bar_phase ^= 1u;
-        if (lane == 0) {
-          tma_reduce_add_2d(a.peer_maps + pd.owner, pd.sbuf, pd.col0 + c, pd.row0);
-          tma_store_commit();
-        }
-        // clear the local copy (the load above has completed; nobody else touches this block any more)
-        const int ncol4 = min(32, pd.cols - c) >> 2;
-        for (int i = lane; i < pd.rows * ncol4; i += 32) {
-          const int r = i / ncol4, c4 = i - r * ncol4;
-          __stcg(reinterpret_cast<float4*>(pd.first + static_cast<size_t>(r) * a.ldc + c + c4 * 4),
-                 make_float4(0.f, 0.f, 0.f, 0.f));
-        }
+    for (int c = 0; c < cols; c += 32) {
+      stage_acquire(lane);                                   // earlier bulk stores have read the staging buffer
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, 4096);
+        tma_load_2d(sbuf, tm_local, bar, col0 + c, row0);
       }
-    } else {
-      const int vec_per_row = pd.cols >> 2;
-      const int total = pd.rows * vec_per_row;
-#pragma unroll 8
-      for (int i = lane; i < total; i += 32) {
-        const int r = i / vec_per_row, c4 = i - r * vec_per_row;
-        float* p = pd.first + static_cast<size_t>(r) * a.ldc + c4 * 4;
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
-        red_add_v4_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(p) + pd.delta), v.x, v.y, v.z, v.w);
-        __stcg(reinterpret_cast<float4*>(p), make_float4(0.f, 0.f, 0.f, 0.f));
+      mbar_wait(bar, pd.bar_phase);
+      pd.bar_phase ^= 1u;
+      if (lane == 0) {
+        tma_reduce_add_2d(a.peer_maps + owner, sbuf, col0 + c, row0);
+        tma_store_commit();
+      }
+      // clear the local copy (the load above has completed; nobody else touches this block any more)
+      const int ncol4 = min(32, cols - c) >> 2;
+      for (int i = lane; i < rows * ncol4; i += 32) {
+        const int r = i / ncol4, c4 = i - r * ncol4;
+        __stcg(reinterpret_cast<float4*>(first + static_cast<size_t>(r) * a.ldc + c + c4 * 4),
+               make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
-    if (lane == 0) *pd.ctr = 0u;
+  } else {
+    const int vec_per_row = cols >> 2;
+#pragma unroll 8
+    for (int i = lane; i < rows * vec_per_row; i += 32) {
+      const int r = i / vec_per_row, c4 = i - r * vec_per_row;
+      float* p = first + static_cast<size_t>(r) * a.ldc + c4 * 4;
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+      red_add_v4_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(p) + delta), v.x, v.y, v.z, v.w);
+      __stcg(reinterpret_cast<float4*>(p), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
   }
-  pd.ctr = nullptr;
+  if (lane == 0) *ctr = 0u;
 }
 
 // fp32 outputs (plain store, TMA reduce-add, or multimem reduction): raw accumulators, 32 columns per chunk.
 template <int kCols>
 __device__ __forceinline__ void epilogue_f32(const GemmArgs& a, const CUtensorMap* tm_out, uint32_t tmem_acc, int row0,
-                                             int n0, int c_begin, uint8_t* sbuf, int lane, PeerPending* pend = nullptr) {
+                                             int n0, int c_begin, uint8_t* sbuf, int lane, PeerPending* pend = nullptr,
+                                             uint64_t* move_bar = nullptr) {
   const int flags = a.flags;
   if ((flags & EPI_PEER) && a.split_k > 1 && a.peer_counters != nullptr) {
     if (row0 >= a.M || n0 + c_begin >= a.N) return;
     float* obase = reinterpret_cast<float*>(a.out);
     float* first = obase + static_cast<size_t>(row0) * a.ldc;
-    const int owner = peer_owner(first);
-    const long long delta = c_peers.delta[owner];
+    const long long delta = c_peers.delta[peer_owner(first)];
     // (1) split-K partial -> local copy, exactly like the single-GPU path
     int issued = 0;
 #pragma unroll 1
@@ -233,34 +230,25 @@ __device__ __forceinline__ void epilogue_f32(const GemmArgs& a, const CUtensorMa
       ++issued;
     }
     // the PREVIOUS tile's reduce-adds have landed once all but this tile's bulk groups are complete
-    if (pend != nullptr && pend->ctr != nullptr) {
+    if (pend != nullptr && pend->row0 >= 0) {
       if (lane == 0) {
         if (issued == kCols / 32) tma_store_wait<kCols / 32>();
         else tma_store_wait<0>();
       }
       __syncwarp();
-      peer_finish(a, *pend, lane);
+      peer_finish(a, *pend, tm_out, sbuf, move_bar, lane);
     }
     if (delta == 0) return;                 // this rank owns these rows: they are where they belong
-    PeerPending cur;
-    cur.ctr = a.peer_counters + static_cast<size_t>(row0 >> 5) * ((a.N + 31) >> 5) + ((n0 + c_begin) >> 5);
-    cur.first = first + n0 + c_begin;
-    cur.delta = delta;
-    cur.rows = min(32, a.M - row0);
-    cur.cols = min(kCols, a.N - (n0 + c_begin));
-    cur.row0 = row0;
-    cur.col0 = n0 + c_begin;
-    cur.owner = owner;
-    cur.sbuf = sbuf;
-    cur.tm_local = tm_out;
     if (pend != nullptr) {
-      cur.bar = pend->bar;                  // the warp's mbarrier and its phase live in the pending record
-      cur.bar_phase = pend->bar_phase;
-      *pend = cur;                          // processed with the next tile (or at the end of the kernel)
+      pend->row0 = row0;                    // processed with the next tile (or at the end of the kernel)
+      pend->col0 = n0 + c_begin;
+      pend->cols = kCols;
     } else {
+      PeerPending cur;
+      cur.row0 = row0; cur.col0 = n0 + c_begin; cur.cols = kCols;
       if (lane == 0) tma_store_wait<0>();
       __syncwarp();
-      peer_finish(a, cur, lane);
+      peer_finish(a, cur, tm_out, sbuf, nullptr, lane);
     }
     return;
   }
@@ -333,12 +321,12 @@ template <int kCols>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& a, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
                                               uint32_t tmem_acc, int row0, int n0, int c_begin,
                                               const __nv_bfloat16* sbias, uint8_t* sbuf, int lane,
-                                              PeerPending* pend = nullptr) {
+                                              PeerPending* pend = nullptr, uint64_t* move_bar = nullptr) {
   const int flags = a.flags;
   const int row = row0 + lane;
   const bool row_ok = row < a.M;
   if (flags & (EPI_MC | EPI_PEER | EPI_OUT_F32 | EPI_ACCUM)) {
-    epilogue_f32<kCols>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane, pend);
+    epilogue_f32<kCols>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane, pend, move_bar);
     return;
   }
   // bf16 output: 64 columns (128 B) per staged chunk
@@ -453,13 +441,13 @@ __device__ __forceinline__ void epilogue_cols64(const GemmArgs& a, const CUtenso
                                                 uint32_t tmem_acc, int row0, int n0, int c_begin,
                                                 const __nv_bfloat16* sbias, const StoreGroup& g, int lg, int lane,
                                                 uint64_t* side_bar = nullptr, uint32_t side_parity = 0,
-                                                PeerPending* pend = nullptr) {
+                                                PeerPending* pend = nullptr, uint64_t* move_bar = nullptr) {
   // side_bar != nullptr: the residual / pre-GELU tile of this warp was prefetched by TMA into its staging buffer
   // (swizzled like the output); it is read from there and overwritten in place by the result
   const int flags = a.flags;
   uint8_t* sbuf = g.buf + lg * 4096;
   if (flags & (EPI_MC | EPI_OUT_F32 | EPI_ACCUM)) {
-    epilogue_f32<64>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane, pend);
+    epilogue_f32<64>(a, tm_out, tmem_acc, row0, n0, c_begin, sbuf, lane, pend, move_bar);
     return;
   }
   const int col0 = n0 + c_begin;
@@ -723,7 +711,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     if (lane == 0) tma_store_wait<0>();
     __syncwarp();
-    peer_finish(args, pend, lane);
+    peer_finish(args, pend, &tmap_out, sbuf, nullptr, lane);
   }
 
   tc_fence_before();
@@ -737,7 +725,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // shared memory, and each CTA drains its own 128 accumulator rows from its TMEM.  Per-CTA operand traffic
 // drops from 48 KB to 32 KB per k-block (the 1-CTA kernel is L2->SM bandwidth bound at K=768..3072) and the
 // freed shared memory buys a 6-stage ring.
-template <bool kAMN, bool kBMN, int kEpiW>
+// kPeer: instantiated for the weight-gradient layout only -- carries the "pending finished block" state of the
+// owner-sharded split-K protocol across tiles (registers the other instantiations must not pay for)
+template <bool kAMN, bool kBMN, int kEpiW, bool kPeer = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiW, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
@@ -902,7 +892,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint64_t* my_side_bar = &side_bar[warp - 2];
     uint32_t side_phase = 0;
     PeerPending pend;
-    if (kEpiW == 16 && !side_tma) pend.bar = my_side_bar;     // free for the bulk move of finished gradient blocks
+    PeerPending* const pp = kPeer ? &pend : nullptr;
+    // the warp's side barrier is free for the bulk move of finished gradient blocks (no side prefetch with fp32 outputs)
+    uint64_t* const move_bar = (kPeer && kEpiW == 16 && !side_tma) ? my_side_bar : nullptr;
     long long tr_wait = 0, tr_busy = 0;
     TR_BEGIN(args.trace, tr_start);
     for (int w = cluster_id; w < num_work; w += num_clusters) {
@@ -932,11 +924,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           sg.row0_cta = wi.m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
           epilogue_cols64(args, &tmap_out, &tmap_aux, &tmap_out128, &tmap_aux128, t_acc, row0, wi.n_blk * kPairN,
                           half * 64, sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase,
-                          &pend);
+                          pp, move_bar);
           if (side_now) side_phase ^= 1u;
         } else {
           epilogue_tile<kPairN / 2>(args, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * (kPairN / 2),
-                                    sbias + acc * 256, sbuf, lane, &pend);
+                                    sbias + acc * 256, sbuf, lane, pp, move_bar);
         }
       }
       tc_fence_before();
@@ -946,8 +938,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait<0>();
-    __syncwarp();
-    peer_finish(args, pend, lane);
+    if constexpr (kPeer) {
+      __syncwarp();
+      peer_finish(args, pend, &tmap_out, sbuf, move_bar, lane);
+    }
     if (args.trace && warp == 2 && lane == 0) {
       unsigned long long* tr = args.trace + blockIdx.x * 8;
       tr[TR_EPI_WAIT_FULL] = tr_wait;
@@ -1154,7 +1148,6 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                           (side_kind == EPI_DGELU || side_kind == EPI_RESIDUAL);
     uint64_t* my_side_bar = &side_bar[warp - 2];
     uint32_t side_phase = 0;
-    PeerPending pend;
     for (int w = cluster_id; w < num_work; w += num_clusters) {
       const WorkItem wi = decode_work(sched, w);
       const int m_blk = wi.m_blk * 2 + static_cast<int>(pair);
@@ -1176,7 +1169,7 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int row0 = m_blk * kPairM + static_cast<int>(rank) * BLOCK_M + lg * 32;
         sg.row0_cta = m_blk * kPairM + static_cast<int>(rank) * BLOCK_M;
         epilogue_cols64(args, &tmap_out, &tmap_aux, &tmap_out, &tmap_aux, t_acc, row0, wi.n_blk * kPairN, half * 64,
-                        sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase, &pend);
+                        sbias + acc * 256, sg, lg, lane, side_now ? my_side_bar : nullptr, side_phase);
         if (side_now) side_phase ^= 1u;
       }
       tc_fence_before();
@@ -1185,8 +1178,6 @@ gemm_bf16_quad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait<0>();
-    __syncwarp();
-    peer_finish(args, pend, lane);
   }
 
   tc_fence_before();
@@ -1267,14 +1258,14 @@ static int pair_epilogue_warps() {
   return w;
 }
 
-template <bool kAMN, bool kBMN, int kEpiW>
+template <bool kAMN, bool kBMN, int kEpiW, bool kPeer = false>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx,
                             const CUtensorMap& to128, const CUtensorMap& tx128, const CUtensorMap& tside,
                             const GemmArgs& args, int max_ctas, cudaStream_t stream) {
   constexpr int kSmem = (kEpiW == 16 ? 5 : 6) * (BLOCK_M * BLOCK_K * 2 + 128 * BLOCK_K * 2) + kEpiW * 4096 + 1024 +
                         1024 + 256;
   static bool configured = false;
-  auto kern = gemm_bf16_2cta_kernel<kAMN, kBMN, kEpiW>;
+  auto kern = gemm_bf16_2cta_kernel<kAMN, kBMN, kEpiW, kPeer>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) return -20;
     configured = true;
@@ -1480,6 +1471,8 @@ int aitj_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
     if (!a_mn && b_mn) return launch_gemm_2cta<false, true, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream);   \
     if (a_mn && !b_mn) return launch_gemm_2cta<true, false, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream);   \
     return launch_gemm_2cta<true, true, W>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream);
+    if (peer_move && a_mn && b_mn && pair_epilogue_warps() == 16)
+      return launch_gemm_2cta<true, true, 16, true>(ta, tb, to, tx, to128, tx128, tside, args, max_ctas, stream);
     if (pair_epilogue_warps() == 16) { AITJ_PAIR(16) }
     AITJ_PAIR(8)
 #undef AITJ_PAIR

@@ -50,7 +50,8 @@ def _preload(cuda: bool = False) -> None:
         except Exception:  # noqa: BLE001
             pass
         try:
-            dev = torch.device("cuda", 0)
+            dev = torch.device("cuda", int(os.environ.get("AITJ_ZYGOTE_DEVICE", "0")))
+            torch.cuda.set_device(dev)
             a = torch.randn(64, 64, device=dev, dtype=torch.bfloat16)
             (a @ a).sum().item()                                           # context + cuBLAS handle
             x = torch.randn(1, 8, 16, 16, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
