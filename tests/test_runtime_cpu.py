@@ -335,3 +335,27 @@ def test_gathering_ranks_is_bounded_and_ends_early_on_a_newer_generation(tmp_pat
     # (c) everybody present
     outs = [p.communicate(timeout=90)[0] for p in launch([0, 1, 2], 3, 29743, 30, flag)]
     assert all("SUM 6" in o for o in outs), outs
+
+
+def test_owner_shard_bounds_are_balanced_and_aligned():
+    """Ownership bounds of the flat gradient space (parallel/symm.py): ascending, every bound a multiple of 256 elements
+    (the AdamW sweep's weight-decay blocks) and of 32 rows of the 2-D tensor it falls into (the wgrad epilogue sends
+    32-row groups to one owner), shares within a few percent of 1/N."""
+    from trainingjob_operator_b200.models.bert import BertConfig, bert_param_specs
+    from trainingjob_operator_b200.models.flat_params import FlatParams
+    from trainingjob_operator_b200.models.gpt2 import GPT2Config, gpt2_param_specs
+    from trainingjob_operator_b200.parallel.symm import shard_bounds
+
+    for specs in (gpt2_param_specs(GPT2Config.small()), gpt2_param_specs(GPT2Config.tiny()),
+                  bert_param_specs(BertConfig.base())):
+        P = FlatParams(specs, "cpu", with_optimizer_state=False)
+        for world in (2, 3, 4, 8):
+            b = shard_bounds(P.specs, P.total, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == P.total and b == sorted(b)
+            for x in b[1:-1]:
+                assert x % 256 == 0
+                s = next(s for s in P.specs if s.offset <= x <= s.offset + s.padded)
+                if len(s.shape) == 2 and s.offset < x < s.offset + s.numel:
+                    assert (x - s.offset) % (32 * s.shape[1]) == 0, (s.name, x)
+            shares = [(b[i + 1] - b[i]) * world / P.total for i in range(world)]
+            assert 0.9 < min(shares) and max(shares) < 1.1, shares

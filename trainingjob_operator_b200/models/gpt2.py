@@ -24,8 +24,14 @@ import torch.nn.functional as TF
 from .flat_params import FlatParams, ParamSpec
 
 
-# measured per-shape kernel choices (kind:NxK -> (block_n, split_k)); empty = CTA pair wherever a 256x256 tile fits
-_DEFAULT_GEMM_CFG: Dict[str, Tuple[int, int]] = {}
+# measured per-shape kernel choices (kind:NxK -> (block_n, split_k)) for the GPT-2 small step; everything else uses the CTA
+# pair wherever a 256x256 tile fits.  From tools/gemm_cfg_sweep.py (one change at a time in the captured step, same box,
+# profiles/r2_gemm_cfg_sweep.md): the 1-CTA 128x256 kernel wins where the epilogue is light and N is not a multiple of the
+# pair's wave (qkv / fc / lm_head forward, the proj and qkv input gradients), -0.03 .. -0.11 ms each.
+_DEFAULT_GEMM_CFG: Dict[str, Tuple[int, int]] = {
+    "fwd:2304x768": (256, 0), "fwd:3072x768": (256, 0), "fwd:50304x768": (256, 0),
+    "dgrad:768x768": (256, 0), "dgrad:768x2304": (256, 0),
+}
 
 _QKV_GATHER = os.environ.get("AITJ_QKV_GATHER", "1") != "0"
 _FUSE_COLSUM = os.environ.get("AITJ_FUSE_COLSUM", "1") != "0" and os.environ.get("AITJ_GEMM_EPI_WARPS", "16") != "8" \

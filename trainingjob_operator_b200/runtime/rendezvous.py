@@ -254,10 +254,15 @@ class StallBreaker:
     main thread takes the same recovery path as an exception from gloo.  Only armed on CUDA (``AITJ_FT_ABORT_AFTER``,
     default 3 s, 0 disables)."""
 
-    def __init__(self, watcher, after_s: float):
-        self.watcher, self.after_s = watcher, after_s
+    def __init__(self, watcher, after_s: float, action: str = "abort"):
+        """``action="abort"``: abort the communicator (faultTolerant jobs recover in place).  ``action="exit"``: this
+        replica cannot recover in place (owner-sharded state, no faultTolerant flag) -- it leaves with exit code 137 right
+        away, as the agent's hang detection would after ``AITJ_HANG_TIMEOUT``, so that a ``restartScope: Pod`` job whose
+        survivors sit in a dead collective is whole again in seconds instead of after the heartbeat time-out."""
+        self.watcher, self.after_s, self.action = watcher, after_s, action
         self.generation = 0
         self.last_progress = time.time()
+        self.in_step = False          # only a rank that sits inside a training step can be stuck behind a dead peer
         self.tripped = False
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, name="stall-breaker", daemon=True)
@@ -269,11 +274,24 @@ class StallBreaker:
 
     def _run(self) -> None:
         while not self._stop.wait(0.5):
-            if self.tripped or time.time() - self.last_progress < self.after_s or not dist.is_initialized():
+            if self.tripped or not self.in_step or time.time() - self.last_progress < self.after_s \
+                    or not dist.is_initialized():
                 continue
             latest = self.watcher.fetch_now()
             if latest is None or latest["generation"] <= self.generation:
                 continue
+            if self.action == "exit":
+                print(f"[worker] no step boundary for {time.time() - self.last_progress:.1f}s while generation "
+                      f"{latest['generation']} is pending: a peer is gone and this job does not recover in place -- "
+                      f"leaving (137) so the controller replaces this replica too", flush=True)
+                path = os.environ.get("AITJ_EXIT_FILE", "")
+                if path:
+                    try:
+                        with open(path, "w") as f:
+                            f.write("137")
+                    except OSError:
+                        pass
+                os._exit(137)
             print(f"[worker] no step boundary for {time.time() - self.last_progress:.1f}s while generation "
                   f"{latest['generation']} is pending: aborting the communicator", flush=True)
             self.tripped = True

@@ -379,6 +379,9 @@ def run(args) -> Dict[str, Any]:
     trace["rendezvous_done"] = time.time()
     heartbeat(force=True)
     adapter.bind(None)
+    print(f"[worker {rank}] world {world}: gradient sync = "
+          f"{getattr(getattr(adapter, 'trainer', None), 'allreduce_backend', 'flat buffer all-reduce (nccl / gloo)')}",
+          flush=True)
 
     restart_count = env_int("TRAININGJOB_REPLICA_RESTARTCOUNT", 0)
     start_step = 0
@@ -396,6 +399,10 @@ def run(args) -> Dict[str, Any]:
     breaker = None
     if fault_tolerant and use_cuda and float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")) > 0:
         breaker = StallBreaker(watcher, float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")))
+    elif watcher is not None and use_cuda and world > 1 and float(os.environ.get("AITJ_STALL_EXIT_AFTER", "3")) > 0:
+        # not faultTolerant: a rank stuck behind a dead peer cannot be repaired in place; once the controller has started
+        # to repair the job (newer generation) it leaves at once instead of waiting for the heartbeat time-out
+        breaker = StallBreaker(watcher, float(os.environ.get("AITJ_STALL_EXIT_AFTER", "3")), action="exit")
     recoveries: List[Dict[str, Any]] = []
 
     stop = {"flag": False}
@@ -470,7 +477,14 @@ def run(args) -> Dict[str, Any]:
                 t_epoch0 = time.time()
                 timed_from = step
                 launches0 = oplib.LAUNCHES
-            loss = adapter.train_step()
+            if breaker is not None:
+                breaker.progress(generation)
+                breaker.in_step = True
+            try:
+                loss = adapter.train_step()
+            finally:
+                if breaker is not None:
+                    breaker.in_step = False
             if breaker is not None and breaker.tripped:
                 raise RuntimeError("the communicator was aborted while this step was in flight")
         except RuntimeError as e:
