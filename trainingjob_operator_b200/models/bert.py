@@ -174,6 +174,10 @@ class BertEngine(GPT2Engine):
         self._dyn_host = torch.zeros(4, dtype=torch.float32).pin_memory() if self.dev.type == "cuda" else None
         self.pair = os.environ.get("AITJ_GEMM_PAIR", "1") != "0"
         self.gemm_cfg = {}
+        self.wgrad_stream = torch.cuda.Stream() if (self.dev.type == "cuda" and gemm_backend == "tcgen05" and
+                                                    os.environ.get("AITJ_WGRAD_STREAM", "0") != "0") else None
+        self._wgrad_done = None
+        self.segment_join = False
         self.grad_hook = None
         self._graph = None
         self.split_k = {}
@@ -229,8 +233,10 @@ class BertEngine(GPT2Engine):
         F.gelu_bwd(self.mlm_pre, d_g, d_u)
         F.colsum(d_u, P.grad("mlm_b"))
         self._wgrad(d_u, x_last, P.grad("mlm_w"))
-        self._dgrad(d_u, P.w16("mlm_w"), d_t)
-        self._d_cur = d_t                                    # gradient w.r.t. the last layer's output
+        self._dgrad(d_u, P.w16("mlm_w"), d_t)                # (the weight gradients above read dlogits, mlm_ln, d_u, x_last:
+        self._d_cur = d_t                                    #  none of them is written again before the next layer's join)
+        if self.segment_join:
+            self._join_wgrads()
 
     @torch.no_grad()
     def _bwd_layer(self, i: int) -> None:
@@ -238,12 +244,13 @@ class BertEngine(GPT2Engine):
         lb = self.layers[i]
         p = f"h{i}."
         x_in = self.layers[i - 1].out if i > 0 else self.x0
+        self._join_wgrads()                                  # last segment's weight gradients still read these buffers
         free = [t for t in self.d_x if t is not self._d_cur]
         d_r, d_y = free
         # x_{l+1} = LN2(y + MLP(y))
         F.layernorm_bwd(self._d_cur, lb.res2, P.w16(p + "ln2_w"), lb.ln2_mean, lb.ln2_rstd, d_r, P.grad(p + "ln2_w"),
                         P.grad(p + "ln2_b"), dxsum=P.grad(p + "fc2_b"))
-        self._wgrad(d_r, lb.fc_act, P.grad(p + "fc2_w"))
+        e_fc2 = self._wgrad(d_r, lb.fc_act, P.grad(p + "fc2_w"))
         self._dgrad(d_r, P.w16(p + "fc2_w"), self.d_fc, dgelu_aux=lb.fc_pre, colsum=P.grad(p + "fc_b"))
         self._wgrad(self.d_fc, lb.ln1, P.grad(p + "fc_w"))
         self._dgrad(self.d_fc, P.w16(p + "fc_w"), d_y, residual=d_r)            # + the skip connection's gradient
@@ -255,8 +262,12 @@ class BertEngine(GPT2Engine):
         self._dgrad(d_r1, P.w16(p + "proj_w"), self.d_att)
         self._attention_bwd(lb, self.d_att, self.d_qkv, P.grad(p + "qkv_b"))
         self._wgrad(self.d_qkv, x_in, P.grad(p + "qkv_w"))
+        if e_fc2 is not None:
+            torch.cuda.current_stream().wait_event(e_fc2)     # d_r is the buffer the fc2 weight gradient read
         self._dgrad(self.d_qkv, P.w16(p + "qkv_w"), d_r, residual=d_r1)
         self._d_cur = d_r
+        if self.segment_join:
+            self._join_wgrads()
 
     @torch.no_grad()
     def _bwd_tail(self) -> None:
@@ -266,6 +277,7 @@ class BertEngine(GPT2Engine):
                         P.grad("emb_ln_b"))
         F.embedding3_bwd(self.tok, self.typ, d_e, P.grad("wte"), P.grad("wpe"), P.grad("wtt"), self.T)
         P.push_small_grads()
+        self._join_wgrads()
 
     # ------------------------------------------------------------------ buckets (for DDP)
     def grad_buckets(self) -> List[Tuple[str, int, int]]:

@@ -179,6 +179,11 @@ class GPT2Engine:
             k, v = item.split("=")
             bn, _, sk = v.partition("/")
             self.gemm_cfg[k.strip()] = (int(bn), int(sk or 0))
+        # weight-gradient GEMMs on a side stream (AITJ_WGRAD_STREAM=0: in line); see _wgrad
+        self.wgrad_stream = torch.cuda.Stream() if (self.dev.type == "cuda" and gemm_backend == "tcgen05" and
+                                                    _os.environ.get("AITJ_WGRAD_STREAM", "0") != "0") else None
+        self._wgrad_done = None
+        self.segment_join = False     # True: every backward segment joins the side stream (segments are separate graphs)
         self.grad_hook = None  # called as hook(name_of_bucket) when a gradient bucket is complete
         self._graph = None
         self.split_k: Dict[Tuple[int, int], int] = {}
@@ -236,7 +241,35 @@ class GPT2Engine:
         return out
 
     def _wgrad(self, dy, x, dw):
-        """dw[N,K] (fp32) += dy[M,N]^T @ x[M,K]."""
+        """dw[N,K] (fp32) += dy[M,N]^T @ x[M,K].
+
+        Weight gradients are leaves of the backward graph: nothing in the backward chain reads them.  With
+        ``wgrad_stream`` they are launched on a side stream behind an event on the producer of ``dy``, so the tail of a
+        weight-gradient GEMM -- and, in the owner-sharded mode, the time its finished blocks need to drain over NVLink --
+        is filled by the input-gradient GEMMs / LayerNorm / attention kernels of the chain.  Returns the event that marks
+        its completion (``None`` when launched in line); ``_join_wgrads`` / explicit waits order later writers of ``dy``."""
+        side = self.wgrad_stream
+        if side is None:
+            self._wgrad_now(dy, x, dw)
+            return None
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            self._wgrad_now(dy, x, dw)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._wgrad_done = done
+        return done
+
+    def _join_wgrads(self) -> None:
+        """The current stream waits for every weight-gradient GEMM launched so far (the side stream is in order)."""
+        if self._wgrad_done is not None:
+            torch.cuda.current_stream().wait_event(self._wgrad_done)
+            self._wgrad_done = None
+
+    def _wgrad_now(self, dy, x, dw):
         F = self.F
         if self.backend == "tcgen05":
             key = (dw.shape[0], dw.shape[1])
@@ -374,6 +407,8 @@ class GPT2Engine:
         last = len(self.layers) - 1
         F.layernorm_bwd(self.d_ln, x_last, P.w16("lnf_w"), self.lnf_mean, self.lnf_rstd, self._d_cur, P.grad("lnf_w"),
                         P.grad("lnf_b"), dxsum=P.grad(f"h{last}.fc2_b") if last >= 0 else None)
+        if self.segment_join:
+            self._join_wgrads()
 
     @torch.no_grad()
     def _bwd_layer(self, i: int) -> None:
@@ -382,8 +417,11 @@ class GPT2Engine:
         lb = self.layers[i]
         p = f"h{i}."
         x_in = self.layers[i - 1].res2 if i > 0 else self.x0
+        # the previous segment's weight-gradient GEMMs still read d_fc / d_qkv / the residual-gradient buffers that this
+        # layer is about to overwrite
+        self._join_wgrads()
         # MLP (fc2_b's gradient = colsum(d_res) was already produced by the LayerNorm-backward that made d_res)
-        self._wgrad(d_res, lb.fc_act, P.grad(p + "fc2_w"))
+        e_fc2 = self._wgrad(d_res, lb.fc_act, P.grad(p + "fc2_w"))
         self._dgrad(d_res, P.w16(p + "fc2_w"), self.d_fc, dgelu_aux=lb.fc_pre, colsum=P.grad(p + "fc_b"))
         self._wgrad(self.d_fc, lb.ln2, P.grad(p + "fc_w"))
         self._dgrad(self.d_fc, P.w16(p + "fc_w"), self.d_ln)
@@ -396,16 +434,21 @@ class GPT2Engine:
         self._attention_bwd(lb, self.d_att, self.d_qkv, P.grad(p + "qkv_b"))
         self._wgrad(self.d_qkv, lb.ln1, P.grad(p + "qkv_w"))
         self._dgrad(self.d_qkv, P.w16(p + "qkv_w"), self.d_ln)
+        if e_fc2 is not None:
+            torch.cuda.current_stream().wait_event(e_fc2)     # `spare` is the buffer the fc2 weight gradient read
         F.layernorm_bwd(self.d_ln, x_in, P.w16(p + "ln1_w"), lb.ln1_mean, lb.ln1_rstd, spare,
                         P.grad(p + "ln1_w"), P.grad(p + "ln1_b"), dres=d_res,
                         dxsum=P.grad(f"h{i - 1}.fc2_b") if i > 0 else None)
         self._d_cur, self._d_spare = spare, d_res
+        if self.segment_join:
+            self._join_wgrads()
 
     @torch.no_grad()
     def _bwd_tail(self) -> None:
         F, P = self.F, self.params
         F.embedding_bwd(self.tok, self._d_cur, P.grad("wte"), P.grad("wpe"), self.T)
         P.push_small_grads()
+        self._join_wgrads()
 
     # ------------------------------------------------------------------ optimizer
     def set_step_scalars(self, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.95) -> None:

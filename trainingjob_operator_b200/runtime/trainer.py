@@ -110,6 +110,10 @@ class EngineTrainer:
         # the 2-GPU box), so collectives overlap the next segment's math and nothing else is launched eagerly.
         self.use_graph = use_graph and self.cuda
         self.segmented = self.reducer is not None
+        if hasattr(engine, "segment_join"):
+            # NCCL mode: a bucket's all-reduce starts when its segment's kernels are done, and segments are separate
+            # graphs -- each one joins the weight-gradient side stream at its end
+            engine.segment_join = self.segmented
         self.seg_graphs = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss_host = torch.zeros(1, dtype=torch.float32)
