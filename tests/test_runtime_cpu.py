@@ -5,6 +5,8 @@ import subprocess
 import sys
 import textwrap
 
+import pytest
+
 import torch
 
 from trainingjob_operator_b200.models.flat_params import FlatParams, ParamSpec
@@ -221,6 +223,50 @@ def test_staged_join_gates_scale_up_until_joiners_announce(monkeypatch):
         assert w.agree(dev) is None
         time.sleep(0.3)
         assert w.agree(dev)["generation"] == 4
+    finally:
+        w.stop()
+
+
+def test_generation_agreement_is_a_guarded_collective(monkeypatch):
+    """The per-step MAX all-reduce of the newest generation is where a survivor sits when its peer died right after
+    a step: it must count as "inside a step" for the StallBreaker, and an abort while it is in flight must surface
+    as the same RuntimeError as an aborted training step (4-rank NCCL recovery hung here)."""
+    from trainingjob_operator_b200.runtime import elastic as E
+
+    class FakeTransport:
+        def __init__(self, *a, **k):
+            pass
+
+        def get(self, info, ns, name):
+            return {"metadata": {}, "status": {"rendezvous": {"generation": 1, "worldSizes": {"trainer": 2},
+                                                              "masterPort": 1}}}
+
+    import trainingjob_operator_b200.store.transport as T
+
+    monkeypatch.setattr(T, "HTTPTransport", FakeTransport)
+
+    class Guard:
+        in_step = False
+        tripped = False
+
+    g = Guard()
+    seen = []
+
+    def fake_all_reduce(t, op=None):
+        seen.append(g.in_step)
+        if len(seen) == 2:
+            g.tripped = True            # the breaker aborted the communicator while we were blocked
+
+    monkeypatch.setattr(E.dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(E.dist, "get_world_size", lambda: 2)
+    monkeypatch.setattr(E.dist, "all_reduce", fake_all_reduce)
+    w = E.ElasticWatcher("http://x", "default", "job", "trainer", generation=1, poll=0.01, world=2)
+    try:
+        assert w.agree(torch.device("cpu"), guard=g) is None
+        assert seen == [True] and g.in_step is False
+        with pytest.raises(RuntimeError, match="aborted"):
+            w.agree(torch.device("cpu"), guard=g)
+        assert g.in_step is False
     finally:
         w.stop()
 

@@ -25,7 +25,8 @@ from trainingjob_operator_b200.cmd.local import LocalCluster  # noqa: E402
 from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption  # noqa: E402
 
 argv = [a for a in sys.argv[1:] if not a.startswith("--") and "=" not in a]
-cpu = "--cpu" in sys.argv
+cpu = "--cpu" in sys.argv or "--fake-gpus" in sys.argv
+fake_gpus = "--fake-gpus" in sys.argv     # CPU workers that still ask for (and get bound to) one GPU each: the scheduling path
 model = argv[0] if argv else ("mlp" if cpu else "bert")
 n = int(argv[1]) if len(argv) > 1 else 2
 pool = int(argv[2]) if len(argv) > 2 else 0
@@ -49,7 +50,7 @@ if hang:
 for kv in sys.argv[1:]:
     if "=" in kv and not kv.startswith("--"):
         c["env"].append({"name": kv.split("=", 1)[0], "value": kv.split("=", 1)[1]})
-if not cpu:
+if not cpu or fake_gpus:
     c["resources"] = {"limits": {"nvidia.com/gpu": 1}}
 job = {"apiVersion": "elasticdeeplearning.ai/v1", "kind": "AITrainingJob", "metadata": {"name": "ft"},
        "spec": {"frameworkType": "pytorch", "replicaSpecs": {"trainer": {
@@ -80,7 +81,8 @@ def first_step_at(lc):
 
 out = {"model": model, "replicas": n, "warm_pool": pool, "cpu": cpu, "victim_rank": victim, "restart_scope": scope,
        "hang_timeout_s": hang or None, "fault_tolerant": ft}
-with LocalCluster(num_gpus=0 if cpu else n, option=TrainingJobOperatorOption(thread_num=2),
+with LocalCluster(num_gpus=n if (fake_gpus or not cpu) else 0, option=TrainingJobOperatorOption(thread_num=2),
+                  health_prober=(lambda i: (True, "")) if fake_gpus else None,
                   workdir=tempfile.mkdtemp(prefix=f"aitj-fault-{pool}-"), warm_pool=pool) as lc:   # never a stale checkpoint
     if pool:
         wait(lambda: lc.agent.warm_ready() >= pool, 120)

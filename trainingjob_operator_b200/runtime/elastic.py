@@ -133,8 +133,10 @@ class ElasticWatcher:
         return None
 
     # ------------------------------------------------------------------ step-boundary agreement
-    def agree(self, device: torch.device) -> Optional[Dict[str, Any]]:
-        """Newest rendezvous record every current rank can adopt now, or None."""
+    def agree(self, device: torch.device, guard=None) -> Optional[Dict[str, Any]]:
+        """Newest rendezvous record every current rank can adopt now, or None.  ``guard`` (the worker's StallBreaker):
+        the MAX all-reduce below is a collective like any other -- a rank whose peer died after the previous step sits
+        in it, so it is marked as "inside a step" for the breaker (the bounded wait for joiners that follows is not)."""
         self._n += 1
         if self._n % self.check_every:
             return None
@@ -143,8 +145,16 @@ class ElasticWatcher:
         newest = mine
         if dist.is_initialized() and dist.get_world_size() > 1:
             t = torch.tensor([mine], dtype=torch.int64, device=device if device.type == "cuda" else "cpu")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            newest = int(t[0])
+            if guard is not None:
+                guard.in_step = True
+            try:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                newest = int(t[0])
+            finally:
+                if guard is not None:
+                    guard.in_step = False
+            if guard is not None and guard.tripped:
+                raise RuntimeError("the communicator was aborted while the generation agreement was in flight")
         if newest <= self.generation:
             return None
         return self._wait_for(newest)

@@ -432,7 +432,7 @@ def run(args) -> Dict[str, Any]:
         try:
             # ---- elastic: agree on the newest rendezvous generation at the step boundary ------------
             if watcher is not None and args.elastic:
-                target = watcher.agree(device)
+                target = watcher.agree(device, guard=breaker)
                 if target is not None and target["generation"] != generation:
                     t0 = time.time()
                     new_world = target["world"]
