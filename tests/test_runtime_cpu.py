@@ -271,6 +271,70 @@ def test_generation_agreement_is_a_guarded_collective(monkeypatch):
         w.stop()
 
 
+def test_stall_breaker_only_trips_inside_a_step_with_a_newer_generation_pending(monkeypatch):
+    """runtime/rendezvous.py StallBreaker, action="abort": (a) a newer generation is published, (b) the rank has been
+    inside one step for longer than the threshold -- both are needed; a rank waiting at a rendezvous is left alone."""
+    import time
+
+    from trainingjob_operator_b200.runtime import rendezvous as R
+
+    class Watcher:
+        gen = 1
+
+        def fetch_now(self):
+            return {"generation": self.gen, "world": 2, "port": 1}
+
+    torn = []
+    monkeypatch.setattr(R.dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(R, "teardown_group", lambda broken=False: torn.append(broken))
+    w = Watcher()
+    b = R.StallBreaker(w, after_s=0.2)
+    try:
+        b.progress(1)
+        b.in_step = True
+        time.sleep(1.0)
+        assert not b.tripped and not torn               # stuck for long, but nothing newer is pending
+        w.gen = 2
+        b.in_step = False
+        b.last_progress = time.time() - 10
+        time.sleep(1.0)
+        assert not b.tripped and not torn               # newer generation, but not inside a step (e.g. at a rendezvous)
+        b.in_step = True
+        deadline = time.time() + 3
+        while not b.tripped and time.time() < deadline:
+            time.sleep(0.05)
+        assert b.tripped and torn == [True]
+        time.sleep(0.7)
+        assert torn == [True]                           # once per trip
+    finally:
+        b.stop()
+
+
+def test_stall_exit_leaves_with_137_and_records_it(tmp_path):
+    """action="exit" (jobs that cannot recover in place): the stuck rank leaves like the agent's hang detection would --
+    exit code 137, written to $AITJ_EXIT_FILE for an adopting agent -- as soon as the controller is repairing the job."""
+    exit_file = tmp_path / "exit"
+    code = textwrap.dedent("""
+        import time
+        import torch.distributed as dist
+        from trainingjob_operator_b200.runtime import rendezvous as R
+        dist.is_initialized = lambda: True
+        class W:
+            def fetch_now(self):
+                return {"generation": 2, "world": 2, "port": 1}
+        b = R.StallBreaker(W(), after_s=0.1, action="exit")
+        b.progress(1)
+        b.in_step = True
+        time.sleep(5)
+        print("still here")
+    """)
+    env = dict(os.environ, AITJ_EXIT_FILE=str(exit_file), PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 137, (r.returncode, r.stdout, r.stderr)
+    assert "still here" not in r.stdout and "does not recover in place" in r.stdout
+    assert exit_file.read_text() == "137"
+
+
 def test_zygote_command_parsing():
     from trainingjob_operator_b200.runtime.zygote import split_python_command as sp
 
