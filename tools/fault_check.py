@@ -81,70 +81,108 @@ def first_step_at(lc):
 
 out = {"model": model, "replicas": n, "warm_pool": pool, "cpu": cpu, "victim_rank": victim, "restart_scope": scope,
        "hang_timeout_s": hang or None, "fault_tolerant": ft}
+STAGE = {"at": "cluster start"}
+
+
+def post_mortem(lc, err):
+    """A wait ran out: leave what is needed to see why -- the stage, the job's status / annotations and the tail of every
+    worker log -- in gpurun_out/ (a GPU box is gone after the call; round 2 lost a 4-GPU call to five silent time-outs)."""
+    rec = dict(out, failed_at=STAGE["at"], error=f"{type(err).__name__}: {err}")
+    try:
+        j = lc.jobs().get("ft")
+        rec["phase"] = j.status.phase
+        rec["conditions"] = [f"{c.type}: {c.message}" for c in j.status.conditions][-8:]
+        rec["restart_counts"] = j.status.restart_counts
+        rec["annotations"] = {k: v[:400] for k, v in (j.annotations or {}).items() if k.startswith("aitj.b200/")}
+        rec["rendezvous"] = getattr(j.status, "rendezvous", None) and j.status.rendezvous.__dict__
+    except Exception as e:  # noqa: BLE001
+        rec["job_read_error"] = repr(e)
+    try:
+        rec["processes"] = [sid for sid, _ in lc.agent.sup.list()]
+        logs = os.path.join(lc.workdir, "logs")
+        rec["logs"] = {fn: open(os.path.join(logs, fn), errors="replace").read()[-3000:]
+                       for fn in sorted(os.listdir(logs)) if fn.endswith(".log")}
+    except Exception as e:  # noqa: BLE001
+        rec["log_read_error"] = repr(e)
+    os.makedirs("gpurun_out", exist_ok=True)
+    tag = "ft" if ft else scope.lower()
+    path = f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_{tag}_FAILED_{int(time.time())}.json"
+    json.dump(rec, open(path, "w"), indent=1, default=str)
+    print(json.dumps({"failed_at": rec["failed_at"], "error": rec["error"], "post_mortem": path}), flush=True)
+
+
 with LocalCluster(num_gpus=n if (fake_gpus or not cpu) else 0, option=TrainingJobOperatorOption(thread_num=2),
                   health_prober=(lambda i: (True, "")) if fake_gpus else None,
-                  workdir=tempfile.mkdtemp(prefix=f"aitj-fault-{pool}-"), warm_pool=pool) as lc:   # never a stale checkpoint
-    if pool:
-        wait(lambda: lc.agent.warm_ready() >= pool, 120)
-    t_submit = time.time()
-    lc.apply(job)
-    wait(lambda: first_step_at(lc) > 0)
-    out["submit_to_first_step_s"] = round(time.time() - t_submit, 3)
-    time.sleep(3.0 if not cpu else 1.0)               # let it train and write a checkpoint
-    if pool:
-        wait(lambda: lc.agent.warm_ready() >= min(pool, n), 120)
-    pids = {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/ft-trainer-" in sid}
-    pid = pids[f"ft-trainer-{victim}"]
-    t_kill = time.time()
-    os.kill(pid, signal.SIGKILL)
-    if ft:
-        want_gen = 2
-        if second is not None:             # a second rank dies while the first loss is still being repaired
-            time.sleep(second_after)
-            os.kill(pids[f"ft-trainer-{second}"], signal.SIGKILL)
-            want_gen = 3
-            out["second_victim_rank"], out["second_after_s"] = second, second_after
-        rec = wait(lambda: (lambda r: r if r and r.get("generation", 0) >= want_gen and r.get("recovered_from") else None)(
-            json.loads(lc.jobs().get("ft").annotations.get("aitj.b200/rescale-trace", "null"))))
-        out["kill_to_first_step_s"] = round(rec["at"] - t_kill, 3)
-        out["recovery"] = {k: rec.get(k) for k in ("generation", "world", "seconds", "teardown_s", "init_pg_s",
-                                                    "sync_state_s", "first_step_s", "recovered_from")}
-        wait(lambda: (lambda j: j.status.phase == "Running" and
+                  workdir=tempfile.mkdtemp(prefix=f"aitj-fault-{pool}-"), warm_pool=pool) as lc:
+    try:
+      # never a stale checkpoint
+        if pool:
+            wait(lambda: lc.agent.warm_ready() >= pool, 120)
+        t_submit = time.time()
+        lc.apply(job)
+        STAGE["at"] = "submit -> first training step"
+        wait(lambda: first_step_at(lc) > 0, float(os.environ.get("AITJ_CHECK_FIRST_STEP_TIMEOUT", "240")))
+        out["submit_to_first_step_s"] = round(time.time() - t_submit, 3)
+        time.sleep(3.0 if not cpu else 1.0)               # let it train and write a checkpoint
+        if pool:
+            wait(lambda: lc.agent.warm_ready() >= min(pool, n), 120)
+        pids = {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/ft-trainer-" in sid}
+        pid = pids[f"ft-trainer-{victim}"]
+        t_kill = time.time()
+        os.kill(pid, signal.SIGKILL)
+        STAGE["at"] = f"SIGKILL of rank {victim} -> recovery record / Running again"
+        if ft:
+            want_gen = 2
+            if second is not None:             # a second rank dies while the first loss is still being repaired
+                time.sleep(second_after)
+                os.kill(pids[f"ft-trainer-{second}"], signal.SIGKILL)
+                want_gen = 3
+                out["second_victim_rank"], out["second_after_s"] = second, second_after
+            rec = wait(lambda: (lambda r: r if r and r.get("generation", 0) >= want_gen and r.get("recovered_from") else None)(
+                json.loads(lc.jobs().get("ft").annotations.get("aitj.b200/rescale-trace", "null"))))
+            out["kill_to_first_step_s"] = round(rec["at"] - t_kill, 3)
+            out["recovery"] = {k: rec.get(k) for k in ("generation", "world", "seconds", "teardown_s", "init_pg_s",
+                                                        "sync_state_s", "first_step_s", "recovered_from")}
+            wait(lambda: (lambda j: j.status.phase == "Running" and
+                          j.status.replica_statuses["trainer"].active == n)(lc.jobs().get("ft")))
+            out["kill_to_running_s"] = round(time.time() - t_kill, 3)
+            now = {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/ft-trainer-" in sid}
+            out["survivors_kept_their_process"] = all(now.get(k) == v for k, v in pids.items()
+                                                      if k not in (f"ft-trainer-{victim}", f"ft-trainer-{second}"))
+            j = lc.jobs().get("ft")
+            out["restart_counts"] = j.status.restart_counts
+            out["conditions"] = [c.type for c in j.status.conditions][-6:]
+            logv = open(os.path.join(lc.workdir, "logs", f"default_ft-trainer-{victim}_aitj-trainer.log")).read()
+            out["replacement_joined"] = [ln for ln in logv.splitlines() if "joined generation" in ln][-1:]
+            lc.jobs().delete("ft")
+            time.sleep(0.5)
+            os.makedirs("gpurun_out", exist_ok=True)
+            json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_ft.json", "w"), indent=1)
+            print(json.dumps(out))
+            sys.exit(0 if out["restart_counts"].get("trainer", 0) == (1 if second is None else 2) and
+                     out["survivors_kept_their_process"] and out["recovery"]["recovered_from"] else 1)
+        wait(lambda: (lambda j: j.status.phase == "Running" and j.status.restart_counts.get("trainer", 0) >= 1 and
                       j.status.replica_statuses["trainer"].active == n)(lc.jobs().get("ft")))
         out["kill_to_running_s"] = round(time.time() - t_kill, 3)
-        now = {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/ft-trainer-" in sid}
-        out["survivors_kept_their_process"] = all(now.get(k) == v for k, v in pids.items()
-                                                  if k not in (f"ft-trainer-{victim}", f"ft-trainer-{second}"))
+        wait(lambda: first_step_at(lc) > t_kill)
+        out["kill_to_first_step_s"] = round(first_step_at(lc) - t_kill, 3)
         j = lc.jobs().get("ft")
         out["restart_counts"] = j.status.restart_counts
         out["conditions"] = [c.type for c in j.status.conditions][-6:]
-        logv = open(os.path.join(lc.workdir, "logs", f"default_ft-trainer-{victim}_aitj-trainer.log")).read()
-        out["replacement_joined"] = [ln for ln in logv.splitlines() if "joined generation" in ln][-1:]
+        log0 = open(os.path.join(lc.workdir, "logs", "default_ft-trainer-0_aitj-trainer.log")).read()
+        out["resumed"] = [ln for ln in log0.splitlines() if "resumed from checkpoint" in ln][-1:]
+        if steps:
+            done = wait(lambda: (lambda j: j if j.status.phase in ("Succeed", "Failed", "Timeout", "NodeFail") else None)(
+                lc.jobs().get("ft")), 300)
+            out["final_phase"] = done.status.phase
+            out["final_restart_counts"] = done.status.restart_counts
+            out["metrics"] = json.loads(done.annotations.get("aitj.b200/metrics", "null"))
         lc.jobs().delete("ft")
         time.sleep(0.5)
-        os.makedirs("gpurun_out", exist_ok=True)
-        json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_ft.json", "w"), indent=1)
-        print(json.dumps(out))
-        sys.exit(0 if out["restart_counts"].get("trainer", 0) == (1 if second is None else 2) and
-                 out["survivors_kept_their_process"] and out["recovery"]["recovered_from"] else 1)
-    wait(lambda: (lambda j: j.status.phase == "Running" and j.status.restart_counts.get("trainer", 0) >= 1 and
-                  j.status.replica_statuses["trainer"].active == n)(lc.jobs().get("ft")))
-    out["kill_to_running_s"] = round(time.time() - t_kill, 3)
-    wait(lambda: first_step_at(lc) > t_kill)
-    out["kill_to_first_step_s"] = round(first_step_at(lc) - t_kill, 3)
-    j = lc.jobs().get("ft")
-    out["restart_counts"] = j.status.restart_counts
-    out["conditions"] = [c.type for c in j.status.conditions][-6:]
-    log0 = open(os.path.join(lc.workdir, "logs", "default_ft-trainer-0_aitj-trainer.log")).read()
-    out["resumed"] = [ln for ln in log0.splitlines() if "resumed from checkpoint" in ln][-1:]
-    if steps:
-        done = wait(lambda: (lambda j: j if j.status.phase in ("Succeed", "Failed", "Timeout", "NodeFail") else None)(
-            lc.jobs().get("ft")), 300)
-        out["final_phase"] = done.status.phase
-        out["final_restart_counts"] = done.status.restart_counts
-        out["metrics"] = json.loads(done.annotations.get("aitj.b200/metrics", "null"))
-    lc.jobs().delete("ft")
-    time.sleep(0.5)
+    except (TimeoutError, KeyError, OSError) as err:
+        post_mortem(lc, err)
+        raise
+
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open(f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_{scope.lower()}.json", "w"), indent=1)
 print(json.dumps(out))
