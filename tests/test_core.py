@@ -104,6 +104,35 @@ def test_store_versions_conflicts_watch_and_cascade(tmp_path):
     assert ei.value.reason == "NotFound"
 
 
+def test_store_cascade_follows_the_owner_index_through_updates_and_a_restart(tmp_path):
+    """Dependents are found through an owner-uid index (not a sweep over every object): it has to follow adoption
+    (owner added by an update), release (owner removed), deletion of a dependent, and a replay of the write-ahead log."""
+    wal = str(tmp_path / "s.wal")
+    s = core.Store(wal)
+    s.create("AITrainingJob", "ns", "j1", "uj1", b"{}", {}, [])
+    s.create("AITrainingJob", "ns", "j2", "uj2", b"{}", {}, [])
+    s.create("Pod", "ns", "orphan", "u0", b"{}", {}, [])
+    s.create("Pod", "ns", "p1", "u1", b"{}", {}, ["uj1"])
+    s.create("Pod", "ns", "p2", "u2", b"{}", {}, ["uj1"])
+    s.create("Pod", "ns", "gone", "u3", b"{}", {}, ["uj1"])
+    s.create("Event", "ns", "e1", "ue", b"{}", {}, [])
+    s.update("Pod", "ns", "orphan", "u0", b"{}", {}, ["uj1"], 0)      # adopted by j1
+    s.update("Pod", "ns", "p2", "u2", b"{}", {}, ["uj2"], 0)          # handed from j1 to j2
+    s.remove("Pod", "ns", "gone")                                      # a dependent that is deleted on its own
+    del s
+    s = core.Store(wal)                                                # the index is rebuilt from the log
+    removed = sorted(r["name"] for r in s.remove("AITrainingJob", "ns", "j1"))
+    assert removed == ["j1", "orphan", "p1"]
+    assert s.count("Pod") == 1 and s.count("Event") == 1
+    s.update("Pod", "ns", "p2", "u2", b"{}", {}, [], 0)               # released: no owner any more
+    assert [r["name"] for r in s.remove("AITrainingJob", "ns", "j2")] == ["j2"]
+    assert s.get("Pod", "ns", "p2")["owner_uids"] == []
+    # the same name re-created with another owner is not tied to the old one
+    s.create("AITrainingJob", "ns", "j1", "uj1b", b"{}", {}, [])
+    s.create("Pod", "ns", "p1", "u1b", b"{}", {}, ["uj1b"])
+    assert sorted(r["name"] for r in s.remove("AITrainingJob", "ns", "j1")) == ["j1", "p1"]
+
+
 def test_store_watch_replays_from_resource_version():
     s = core.Store()
     s.create("Pod", "ns", "a", "u1", b"{}", {}, [])

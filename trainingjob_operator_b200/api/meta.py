@@ -13,6 +13,7 @@ import datetime as _dt
 import uuid
 from typing import Any, Dict, Iterable, List, Optional, Tuple
 
+from ..core import _aitj_core as _core
 from . import constants as C
 
 TIME_FMT = "%Y-%m-%dT%H:%M:%SZ"
@@ -55,7 +56,9 @@ def new_uid() -> str:
 
 
 def deepcopy(obj):
-    return copy.deepcopy(obj)
+    """Private copy of an API object (a JSON-shaped tree): the native tree copy, ~16x faster than ``copy.deepcopy``,
+    which it falls back to for anything that is not a dict / list / scalar."""
+    return _core.jcopy(obj, copy.deepcopy)
 
 
 def meta(obj: Dict[str, Any]) -> Dict[str, Any]:

@@ -16,6 +16,7 @@ import dataclasses
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional
 
+from ..core import _aitj_core as _core
 from . import constants as C
 
 
@@ -23,17 +24,33 @@ def _j(name: str, omitempty: bool = True, **kw):
     return field(metadata={"json": name, "omitempty": omitempty}, **kw)
 
 
+def _jcopy(v):
+    """Private copy of a JSON-shaped value (the native tree copy; copy.deepcopy for anything else)."""
+    return _core.jcopy(v, copy.deepcopy)
+
+
+_FIELD_TABLES: Dict[type, tuple] = {}
+
+
+def _table(cls) -> tuple:
+    """(fields, known json names) of a dataclass, computed once: (attribute, json key, converter, omitempty, omitzero)."""
+    t = _FIELD_TABLES.get(cls)
+    if t is None:
+        rows = tuple((f.name, f.metadata.get("json", f.name), f.metadata.get("conv"), f.metadata.get("omitempty", True),
+                      f.metadata.get("omitzero", True)) for f in dataclasses.fields(cls))
+        t = _FIELD_TABLES[cls] = (rows, frozenset(r[1] for r in rows))
+    return t
+
+
 class _Serde:
     """dataclass <-> JSON dict with Go-style ``omitempty``."""
 
     def to_dict(self) -> Dict[str, Any]:
         out: Dict[str, Any] = {}
-        for f in dataclasses.fields(self):
-            name = f.metadata.get("json", f.name)
-            v = getattr(self, f.name)
-            if f.metadata.get("omitempty", True) and (v is None or v == "" or v == {} or v == [] or v is False
-                                                      or (isinstance(v, int) and not isinstance(v, bool) and v == 0
-                                                          and f.metadata.get("omitzero", True))):
+        for attr, name, _conv, omitempty, omitzero in _table(type(self))[0]:
+            v = getattr(self, attr)
+            if omitempty and (v is None or v == "" or v == {} or v == [] or v is False
+                              or (isinstance(v, int) and not isinstance(v, bool) and v == 0 and omitzero)):
                 continue
             out[name] = _dump(v)
         return out
@@ -41,19 +58,18 @@ class _Serde:
     @classmethod
     def from_dict(cls, d: Optional[Dict[str, Any]]):
         d = d or {}
+        rows, known = _table(cls)
         kwargs = {}
-        for f in dataclasses.fields(cls):
-            name = f.metadata.get("json", f.name)
-            if name not in d or d[name] is None:
+        for attr, name, conv, _oe, _oz in rows:
+            v = d.get(name)
+            if v is None:
                 continue
-            conv = f.metadata.get("conv")
-            v = d[name]
-            kwargs[f.name] = conv(v) if conv else copy.deepcopy(v)
+            kwargs[attr] = conv(v) if conv else _jcopy(v)
         obj = cls(**kwargs)
-        known = {f.metadata.get("json", f.name) for f in dataclasses.fields(cls)}
-        extra = {k: copy.deepcopy(v) for k, v in d.items() if k not in known}
-        if extra:
-            object.__setattr__(obj, "_extra", extra)
+        if len(d) > len(kwargs):
+            extra = {k: _jcopy(v) for k, v in d.items() if k not in known}
+            if extra:
+                object.__setattr__(obj, "_extra", extra)
         return obj
 
     def deepcopy(self):
@@ -66,7 +82,7 @@ def _dump(v):
         extra = getattr(v, "_extra", None)
         if extra:
             for k, x in extra.items():
-                d.setdefault(k, copy.deepcopy(x))
+                d.setdefault(k, _jcopy(x))
         return d
     if isinstance(v, dict):
         return {k: _dump(x) for k, x in v.items()}

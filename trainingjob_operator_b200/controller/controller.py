@@ -238,7 +238,7 @@ class TrainingJobController(TrainingJobHandlers):
             if not decision.ports_wanted:
                 break
             # the pass needs free loopback ports (a new MASTER_PORT, per-replica host ports): allocate, decide again
-            spare = tuple(E.allocate_port() for _ in range(decision.ports_wanted))
+            spare = tuple(E.allocate_ports(decision.ports_wanted))
             job = self.trainingjob_lister.aitrainingjobs(job.namespace).get(job.name)
             set_defaults_aitrainingjob(job)
         else:

@@ -20,12 +20,12 @@ controller computes from its informer caches, and a new ``MASTER_PORT`` is taken
 """
 from __future__ import annotations
 
-import socket
 import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 from ..api import constants as C
+from ..core import _aitj_core as _core
 from ..api import meta as M
 from ..api.types import AITrainingJob, Rendezvous
 from ..utils import metrics
@@ -39,24 +39,36 @@ LABEL_GPU_INDEX = "aitj.b200/gpu-index"
 
 _PORT_LOCK = threading.Lock()
 _RECENT_PORTS: List[int] = []
+_RECENT_SET: set = set()
+
+
+def allocate_ports(n: int) -> List[int]:
+    """``n`` distinct free loopback TCP ports.  The probe is one native call (``core.free_loopback_ports``: all probe
+    sockets are bound to port 0 before any is closed, so the kernel cannot hand a port out twice within a call); the
+    last few hundred results are remembered so that two jobs do not race to one port between the probe and the worker's
+    own bind.  One call per reconcile pass: a job's MASTER_PORT and all of its per-replica host ports at once."""
+    out: List[int] = []
+    with _PORT_LOCK:
+        for _ in range(4):
+            for port in _core.free_loopback_ports(n - len(out)):
+                if port not in _RECENT_SET:
+                    out.append(port)
+                    _RECENT_SET.add(port)
+                    _RECENT_PORTS.append(port)
+            if len(out) >= n:
+                break
+        while len(_RECENT_PORTS) > 512:
+            _RECENT_SET.discard(_RECENT_PORTS.pop(0))
+        if len(out) < n:          # every probe landed on a remembered port four times over: take what the kernel offers
+            out += _core.free_loopback_ports(n - len(out))
+    if len(out) < n:
+        raise OSError(f"could not find {n} free loopback ports")
+    return out
 
 
 def allocate_port() -> int:
-    """A free loopback TCP port (bind to 0; the last few are remembered so two jobs do not race to one)."""
-    with _PORT_LOCK:
-        port = 0
-        for _ in range(32):
-            s = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
-            try:
-                s.bind(("127.0.0.1", 0))
-                port = s.getsockname()[1]
-            finally:
-                s.close()
-            if port not in _RECENT_PORTS:
-                _RECENT_PORTS.append(port)
-                del _RECENT_PORTS[:-256]
-                return port
-        return port
+    """A free loopback TCP port (see ``allocate_ports``)."""
+    return allocate_ports(1)[0]
 
 
 @dataclass(frozen=True)

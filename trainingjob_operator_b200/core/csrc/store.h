@@ -19,11 +19,13 @@
 #include <memory>
 #include <mutex>
 #include <optional>
+#include <set>
 #include <sstream>
 #include <stdexcept>
 #include <string>
 #include <unistd.h>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 namespace aitj {
@@ -53,6 +55,7 @@ class Store {
     if (!wal_path.empty()) {
       wal_path_ = wal_path;
       replay();
+      rebuild_owner_index();
       // what was logged before this start cannot be replayed to a watcher: a watch from an older resourceVersion must
       // be told to re-list (Gone) instead of silently missing the events in between
       history_floor_ = rv_;
@@ -82,6 +85,7 @@ class Store {
     if (m.count(key)) throw StoreError("AlreadyExists", o.kind + " \"" + o.name + "\" already exists");
     o.rv = ++rv_;
     m[key] = o;
+    index_owners(o, key, true);
     log_put(o);
     publish("ADDED", o);
     return o;
@@ -100,6 +104,10 @@ class Store {
                                        "version and try again");
     if (o.uid.empty()) o.uid = it->second.uid;
     o.rv = ++rv_;
+    if (it->second.owner_uids != o.owner_uids) {
+      index_owners(it->second, key, false);
+      index_owners(o, key, true);
+    }
     it->second = o;
     log_put(o);
     publish("MODIFIED", o);
@@ -147,28 +155,34 @@ class Store {
     std::vector<StoredObject> removed;
     std::vector<std::string> frontier;
     StoredObject victim = it->second;
+    index_owners(victim, it->first, false);
     kit->second.erase(it);
     victim.rv = ++rv_;
     log_del(victim);
     publish("DELETED", victim);
     removed.push_back(victim);
     if (!victim.uid.empty()) frontier.push_back(victim.uid);
+    // dependents come from the owner index (uid -> objects that list it), not from a sweep over every stored object:
+    // under the throughput benchmark a sweep visited thousands of pods / services / events per delete, under the lock
     while (!frontier.empty()) {
       const std::string owner = frontier.back();
       frontier.pop_back();
-      for (auto& kk : objs_) {
-        for (auto oit = kk.second.begin(); oit != kk.second.end();) {
-          bool owned = false;
-          for (auto& u : oit->second.owner_uids) owned |= (u == owner);
-          if (!owned) { ++oit; continue; }
-          StoredObject dep = oit->second;
-          oit = kk.second.erase(oit);
-          dep.rv = ++rv_;
-          log_del(dep);
-          publish("DELETED", dep);
-          removed.push_back(dep);
-          if (!dep.uid.empty()) frontier.push_back(dep.uid);
-        }
+      auto oi = owned_by_.find(owner);
+      if (oi == owned_by_.end()) continue;
+      const std::set<std::pair<std::string, std::string>> deps = oi->second;   // erased from below
+      for (auto& kk : deps) {
+        auto dk = objs_.find(kk.first);
+        if (dk == objs_.end()) continue;
+        auto oit = dk->second.find(kk.second);
+        if (oit == dk->second.end()) continue;
+        StoredObject dep = oit->second;
+        index_owners(dep, oit->first, false);
+        dk->second.erase(oit);
+        dep.rv = ++rv_;
+        log_del(dep);
+        publish("DELETED", dep);
+        removed.push_back(dep);
+        if (!dep.uid.empty()) frontier.push_back(dep.uid);
       }
     }
     return removed;
@@ -260,6 +274,26 @@ class Store {
   }
 
  private:
+  // owner uid -> (kind, "ns/name") of the objects whose ownerReferences name it.  Caller holds mu_.
+  void index_owners(const StoredObject& o, const std::string& key, bool add) {
+    for (auto& u : o.owner_uids) {
+      if (add) {
+        owned_by_[u].insert({o.kind, key});
+      } else {
+        auto it = owned_by_.find(u);
+        if (it == owned_by_.end()) continue;
+        it->second.erase({o.kind, key});
+        if (it->second.empty()) owned_by_.erase(it);
+      }
+    }
+  }
+
+  void rebuild_owner_index() {
+    owned_by_.clear();
+    for (auto& kk : objs_)
+      for (auto& kv : kk.second) index_owners(kv.second, kv.first, true);
+  }
+
   struct Watcher {
     std::string kind, ns;
     std::mutex mu;
@@ -388,6 +422,7 @@ class Store {
   std::mutex mu_;
   uint64_t rv_ = 0;
   std::map<std::string, std::map<std::string, StoredObject>> objs_;
+  std::unordered_map<std::string, std::set<std::pair<std::string, std::string>>> owned_by_;
   std::deque<WatchEvent> history_;
   size_t history_cap_;
   uint64_t history_floor_ = 0;
