@@ -238,3 +238,83 @@ def test_housekeeping_expires_old_events_and_compacts_the_wal(tmp_path):
     assert again.get(pod, "default", "p")["metadata"]["annotations"]["i"] == "299"
     assert [e["metadata"]["name"] for e in again.list(ev)["items"]] == ["fresh"]
     assert int(again.get(pod, "default", "p")["metadata"]["resourceVersion"]) == int(p["metadata"]["resourceVersion"])
+
+
+def test_lean_header_parser_keeps_http_semantics():
+    """store/fasthttp.py replaces the e-mail-package header parsing of http.server / http.client: names are
+    case-insensitive, repeats are joined, folded lines continue a value, limits raise the stdlib's exceptions."""
+    import http.client
+    import io
+
+    from trainingjob_operator_b200.store.fasthttp import read_headers
+
+    raw = (b"Content-Type: application/json\r\ncontent-length:  12 \r\nX-Many: a\r\nx-many: b\r\n"
+           b"X-Fold: first\r\n\tsecond part\r\nnot a header line\r\nConnection: Keep-Alive\r\n\r\nBODY")
+    fp = io.BytesIO(raw)
+    h = read_headers(fp)
+    assert fp.read() == b"BODY"                                   # stops right after the blank line
+    assert h.get("Content-Length") == "12" and h["CONTENT-TYPE"] == "application/json" and "connection" in h
+    assert h.get("x-many") == "a, b" and h.get_all("X-Many") == ["a, b"]
+    assert h.get("x-fold") == "first second part"
+    assert h.get("missing") is None and h.get("missing", "d") == "d" and h.get_all("missing") is None
+    with pytest.raises(http.client.LineTooLong):
+        read_headers(io.BytesIO(b"X: " + b"a" * 70000 + b"\r\n\r\n"))
+    with pytest.raises(http.client.HTTPException):
+        read_headers(io.BytesIO(b"".join(b"H%d: v\r\n" % i for i in range(150)) + b"\r\n"))
+
+
+def test_http_server_request_line_keep_alive_and_errors_over_a_raw_socket():
+    """The handler's own parse_request: keep-alive on one connection (HTTP/1.1 default), `Connection: close` honoured,
+    HTTP/1.0 closes by default, a malformed request line gets 400, an over-long header line 431."""
+    import socket
+
+    api = APIServer()
+    srv = APIHTTPServer(api).start()
+
+    def read_response(f):
+        status = f.readline().decode()
+        headers = {}
+        while True:
+            line = f.readline()
+            if line in (b"\r\n", b""):
+                break
+            k, _, v = line.decode().partition(":")
+            headers[k.strip().lower()] = v.strip()
+        body = f.read(int(headers.get("content-length", 0)))
+        return status, headers, body
+
+    try:
+        s = socket.create_connection(("127.0.0.1", srv.port), timeout=5)
+        f = s.makefile("rb")
+        for _ in range(2):                                        # two requests on the same connection
+            s.sendall(b"GET /healthz HTTP/1.1\r\nHost: x\r\nACCEPT: */*\r\n\r\n")
+            status, _h, body = read_response(f)
+            assert status.startswith("HTTP/1.1 200") and body == b"ok"
+        s.sendall(b"GET /version HTTP/1.1\r\nHost: x\r\nconnection: CLOSE\r\n\r\n")
+        status, _h, _b = read_response(f)
+        assert status.startswith("HTTP/1.1 200")
+        assert f.read() == b""                                    # the server closed the connection
+        s.close()
+        s = socket.create_connection(("127.0.0.1", srv.port), timeout=5)
+        f = s.makefile("rb")
+        s.sendall(b"GET /healthz HTTP/1.0\r\n\r\n")
+        status, _h, body = read_response(f)
+        assert " 200" in status and body == b"ok" and f.read() == b""      # 1.0 without keep-alive: closed
+        s.close()
+        for bad, code in ((b"GARBAGE\r\n\r\n", b" 400 "), (b"GET /healthz HTTP/9.9\r\n\r\n", b" 400 "),
+                          (b"GET /healthz HTTP/1.1\r\nX: " + b"a" * 70000 + b"\r\n\r\n", b" 431 ")):
+            s = socket.create_connection(("127.0.0.1", srv.port), timeout=5)
+            s.sendall(bad)
+            assert code in s.makefile("rb").readline()
+            s.close()
+        # a body with a mixed-case Content-Length header is read in full
+        s = socket.create_connection(("127.0.0.1", srv.port), timeout=5)
+        f = s.makefile("rb")
+        body = json.dumps({"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "raw"}, "spec": {}}).encode()
+        s.sendall(b"POST /api/v1/namespaces/default/pods HTTP/1.1\r\nHost: x\r\ncOnTeNt-LeNgTh: %d\r\n"
+                  b"Content-Type: application/json; charset=utf-8\r\n\r\n" % len(body) + body)
+        status, _h, out = read_response(f)
+        assert " 201 " in status and json.loads(out)["metadata"]["name"] == "raw"
+        s.close()
+    finally:
+        srv.stop()

@@ -163,7 +163,9 @@ def main():
     jobs = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     replicas = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     threads = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-    out = {"default_queue": run(jobs, replicas, threads)}
+    path = "profiles/control_plane_throughput.json"
+    out = json.load(open(path)) if os.path.exists(path) else {}      # keeps the history sections and the daemon run
+    out["default_queue"] = run(jobs, replicas, threads)
     print(json.dumps(out["default_queue"]), flush=True)
     out["client_go_queue_10qps_burst100"] = run(jobs, replicas, threads, queue_qps=10.0, queue_burst=100)
     print(json.dumps(out["client_go_queue_10qps_burst100"]), flush=True)
@@ -171,7 +173,7 @@ def main():
                    "services (cleanPodPolicy All), final condition.  The reference additionally sits behind client-go's "
                    "5 qps / burst 10 REST throttle per clientset (SURVEY.md 2.2), which is not modelled here.")
     os.makedirs("profiles", exist_ok=True)
-    json.dump(out, open("profiles/control_plane_throughput.json", "w"), indent=1)
+    json.dump(out, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":

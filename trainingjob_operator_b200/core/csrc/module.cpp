@@ -157,7 +157,15 @@ PYBIND11_MODULE(_aitj_core, m) {
       .def("add_rate_limited", &WorkQueue::add_rate_limited)
       .def("forget", &WorkQueue::forget)
       .def("num_requeues", &WorkQueue::num_requeues)
-      .def("get", &WorkQueue::get, py::arg("timeout") = -1.0, py::call_guard<py::gil_scoped_release>())
+      .def("get",
+           [](WorkQueue& q, double timeout) -> std::optional<std::string> {
+             // an item that is already queued is taken with the interpreter lock held; the lock is given up only to wait
+             std::optional<std::string> key = q.get(0.0);
+             if (key || timeout == 0.0) return key;
+             py::gil_scoped_release rel;
+             return q.get(timeout);
+           },
+           py::arg("timeout") = -1.0)
       .def("done", &WorkQueue::done)
       .def("__len__", &WorkQueue::len)
       .def("len_waiting", &WorkQueue::len_waiting)
@@ -230,15 +238,30 @@ PYBIND11_MODULE(_aitj_core, m) {
            py::arg("kind"), py::arg("namespace") = "", py::arg("since_rv") = 0)
       .def("watch_next",
            [](Store& s, int64_t id, double timeout) -> py::object {
-             std::optional<WatchEvent> ev;
-             {
+             // queued event: taken with the interpreter lock held (giving it up for a call that returns at once costs
+             // the caller a switch interval under load); the lock is released only for a real wait
+             std::vector<WatchEvent> evs = s.watch_next_many(id, 0.0, 1, false);
+             if (evs.empty() && timeout > 0) {
                py::gil_scoped_release rel;
-               ev = s.watch_next(id, timeout);
+               evs = s.watch_next_many(id, timeout, 1, true);
              }
-             if (!ev) return py::none();
-             return py::make_tuple(ev->type, obj_to_dict(ev->obj));
+             if (evs.empty()) return py::none();
+             return py::make_tuple(evs[0].type, obj_to_dict(evs[0].obj));
            },
            py::arg("id"), py::arg("timeout") = 1.0)
+      .def("watch_next_many",
+           [](Store& s, int64_t id, double timeout, size_t max) {
+             std::vector<WatchEvent> evs = s.watch_next_many(id, 0.0, max, false);
+             if (evs.empty() && timeout > 0) {
+               py::gil_scoped_release rel;
+               evs = s.watch_next_many(id, timeout, max, true);
+             }
+             py::list out;
+             for (auto& ev : evs) out.append(py::make_tuple(ev.type, obj_to_dict(ev.obj)));
+             return out;
+           },
+           py::arg("id"), py::arg("timeout") = 1.0, py::arg("max") = 64,
+           "up to `max` queued events; waits up to `timeout` seconds only when none is queued")
       .def("watch_close", &Store::watch_close)
       .def("num_watchers", &Store::num_watchers)
       .def("count", &Store::count)

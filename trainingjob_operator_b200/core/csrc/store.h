@@ -230,6 +230,29 @@ class Store {
     return ev;
   }
 
+  // Up to `max` queued events: waits (at most timeout_s) only when nothing is queued.  `wait == false` never blocks --
+  // the binding calls it that way first, with the interpreter lock held, and gives the lock up only for a real wait.
+  std::vector<WatchEvent> watch_next_many(int64_t id, double timeout_s, size_t max, bool wait = true) {
+    std::vector<WatchEvent> out;
+    std::shared_ptr<Watcher> w;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = watchers_.find(id);
+      if (it == watchers_.end()) return out;
+      w = it->second;
+    }
+    std::unique_lock<std::mutex> lk(w->mu);
+    if (w->q.empty()) {
+      if (!wait) return out;
+      w->cv.wait_for(lk, std::chrono::duration<double>(timeout_s), [&] { return !w->q.empty() || w->closed; });
+    }
+    while (!w->q.empty() && out.size() < max) {
+      out.push_back(std::move(w->q.front()));
+      w->q.pop_front();
+    }
+    return out;
+  }
+
   void watch_close(int64_t id) {
     std::shared_ptr<Watcher> w;
     {

@@ -178,6 +178,18 @@ class WatchStream:
             return None
         return b'{"type":"' + etype.encode() + b'","object":' + self._server._raw_with_rv(rec) + b'}\n'
 
+    def poll_raw_many(self, timeout: float = 0.2, limit: int = 64) -> bytes:
+        """Every event that is queued right now (at most ``limit``; waits up to ``timeout`` for the first one) as JSON
+        lines in one buffer: a burst of writes costs a watcher one wake-up, one chunk and one flush, not one per event."""
+        if self._closed.is_set():
+            return b""
+        out = []
+        for etype, rec in self._server._store.watch_next_many(self._wid, timeout, limit):
+            if self._selector and not M.selector_matches(self._selector, rec.get("labels") or {}):
+                continue
+            out.append(b'{"type":"' + etype.encode() + b'","object":' + self._server._raw_with_rv(rec) + b'}\n')
+        return b"".join(out)
+
     @property
     def expired(self) -> bool:
         return self._closed.is_set() or (self._deadline is not None and time.monotonic() > self._deadline)

@@ -10,6 +10,7 @@ controller and agent).  The reference's generated REST client targets exactly th
 """
 from __future__ import annotations
 
+import http.client
 import json
 import re
 import socket
@@ -21,6 +22,7 @@ from typing import Any, Optional, Tuple
 from ..api import register as R
 from ..utils import metrics as metrics_mod
 from .apiserver import APIError, APIServer
+from .fasthttp import read_headers
 
 _PATH = re.compile(
     r"^/(?:api/(?P<corev>v1)|apis/(?P<group>[^/]+)/(?P<version>[^/]+))"
@@ -58,6 +60,43 @@ class _Handler(BaseHTTPRequestHandler):
 
     def log_message(self, fmt, *args):  # silence stderr access log
         pass
+
+    def parse_request(self) -> bool:
+        """``BaseHTTPRequestHandler.parse_request`` with the lean header parser (``store/fasthttp.py``): the stock one
+        runs the e-mail package over every request's header block, a third of this process' CPU time under load.
+        HTTP/1.0 and 1.1 request lines only (no HTTP/0.9 simple requests)."""
+        self.command = None
+        self.request_version = self.default_request_version
+        self.close_connection = True
+        requestline = str(self.raw_requestline, "iso-8859-1").rstrip("\r\n")
+        self.requestline = requestline
+        words = requestline.split()
+        if not words:
+            return False
+        if len(words) != 3 or words[2] not in ("HTTP/1.1", "HTTP/1.0"):
+            self.request_version = "HTTP/1.1"         # answer with a status line (an HTTP/0.9 reply has none)
+            self.send_error(400, f"Bad request syntax ({requestline!r})")
+            return False
+        self.command, self.path, self.request_version = words
+        if self.path.startswith("//"):
+            self.path = "/" + self.path.lstrip("/")
+        try:
+            self.headers = read_headers(self.rfile)
+        except http.client.LineTooLong as err:
+            self.send_error(431, "Line too long", str(err))
+            return False
+        except http.client.HTTPException as err:
+            self.send_error(431, "Too many headers", str(err))
+            return False
+        conn = self.headers.get("connection", "").lower()
+        if conn == "close":
+            self.close_connection = True
+        elif self.request_version == "HTTP/1.1" or conn == "keep-alive":
+            self.close_connection = False
+        if self.headers.get("expect", "").lower() == "100-continue" and self.request_version == "HTTP/1.1":
+            if not self.handle_expect_100():
+                return False
+        return True
 
     # ---------------------------------------------------------------- helpers
     @property
@@ -173,8 +212,8 @@ class _Handler(BaseHTTPRequestHandler):
         stopping = self.server.stopping  # type: ignore[attr-defined]
         try:
             while not stream.expired and not stopping.is_set():
-                raw = stream.poll_raw(0.25)
-                if raw is None:
+                raw = stream.poll_raw_many(0.25)
+                if not raw:
                     continue
                 self.wfile.write(f"{len(raw):x}\r\n".encode() + raw + b"\r\n")
                 self.wfile.flush()

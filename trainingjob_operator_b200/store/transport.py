@@ -17,6 +17,7 @@ from typing import Any, Dict, Optional
 
 from ..api import register as R
 from .apiserver import APIError, APIServer
+from .fasthttp import FastResponse
 
 
 class Transport:
@@ -166,7 +167,10 @@ class _HTTPWatch:
 
 class _NoDelayConnection(http.client.HTTPConnection):
     """http.client sends the request head and the body as two writes; without TCP_NODELAY the second one waits for the
-    server's delayed ACK (40 ms per request on loopback)."""
+    server's delayed ACK (40 ms per request on loopback).  Responses are parsed by ``fasthttp.FastResponse`` (no e-mail
+    package on the header block)."""
+
+    response_class = FastResponse
 
     def connect(self):
         super().connect()
