@@ -269,7 +269,9 @@ class APIServer:
                            f"{info.kind} \"{M.name_of(obj)}\" not found: refusing to create an orphan")
 
     # ------------------------------------------------------------------ verbs
-    def create(self, info: R.ResourceInfo, namespace: str, obj: Dict[str, Any]) -> Dict[str, Any]:
+    def create(self, info: R.ResourceInfo, namespace: str, obj: Dict[str, Any], as_bytes: bool = False):
+        """``as_bytes`` (the HTTP façade): the answer is the stored JSON with the resourceVersion spliced in -- the
+        bytes that were just produced for the store -- instead of a dict the caller would serialise a second time."""
         self.request_count += 1
         obj = M.deepcopy(obj)
         obj.setdefault("apiVersion", info.api_version)
@@ -298,6 +300,8 @@ class APIServer:
                                      M.owner_uids(obj))
         except core.StoreError as e:
             raise _wrap(e) from None
+        if as_bytes:
+            return self._raw_with_rv(rec)
         md["resourceVersion"] = str(rec["rv"])      # `obj` is our own copy and exactly what was stored: no re-parse
         return obj
 
@@ -333,7 +337,7 @@ class APIServer:
                 "metadata": {"resourceVersion": str(rv)}, "items": items}
 
     def update(self, info: R.ResourceInfo, namespace: str, name: str, obj: Dict[str, Any],
-               subresource: str = "", _cur: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+               subresource: str = "", _cur: Optional[Dict[str, Any]] = None, as_bytes: bool = False):
         """``_cur``: the live object the caller has just read and built ``obj`` from (``patch``); saves reading and
         parsing it a second time -- if it is stale the store's optimistic-concurrency check says so (Conflict)."""
         self.request_count += 1
@@ -383,11 +387,13 @@ class APIServer:
                                      M.owner_uids(new), expected)
         except core.StoreError as e:
             raise _wrap(e) from None
+        if as_bytes:
+            return self._raw_with_rv(rec)
         md["resourceVersion"] = str(rec["rv"])
         return new
 
     def patch(self, info: R.ResourceInfo, namespace: str, name: str, patch: Any,
-              patch_type: str = "application/merge-patch+json", subresource: str = "") -> Dict[str, Any]:
+              patch_type: str = "application/merge-patch+json", subresource: str = "", as_bytes: bool = False):
         """Read-modify-write with retry on conflict (merge, strategic-as-merge, or JSON patch)."""
         for _ in range(16):
             cur = self.get(info, namespace, name)
@@ -397,7 +403,7 @@ class APIServer:
                 new = merge_patch(cur, patch)
             new["metadata"]["resourceVersion"] = cur["metadata"]["resourceVersion"]
             try:
-                return self.update(info, namespace, name, new, subresource=subresource, _cur=cur)
+                return self.update(info, namespace, name, new, subresource=subresource, _cur=cur, as_bytes=as_bytes)
             except APIError as e:
                 if e.reason != "Conflict":
                     raise

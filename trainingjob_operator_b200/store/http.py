@@ -232,7 +232,7 @@ class _Handler(BaseHTTPRequestHandler):
             if r is None or r[2]:
                 raise APIError(404, "NotFound", f"the server could not find the requested resource ({u.path})")
             info, ns, _name, _sub = r
-            self._send_json(201, self.api.create(info, ns, self._body() or {}))
+            self._send_raw_json(201, self.api.create(info, ns, self._body() or {}, as_bytes=True))
         except APIError as e:
             self._error(e)
         except (ValueError, KeyError) as e:
@@ -245,7 +245,7 @@ class _Handler(BaseHTTPRequestHandler):
             if r is None or not r[2]:
                 raise APIError(404, "NotFound", f"the server could not find the requested resource ({u.path})")
             info, ns, name, sub = r
-            self._send_json(200, self.api.update(info, ns, name, self._body() or {}, sub))
+            self._send_raw_json(200, self.api.update(info, ns, name, self._body() or {}, sub, as_bytes=True))
         except APIError as e:
             self._error(e)
         except (ValueError, KeyError) as e:
@@ -261,7 +261,7 @@ class _Handler(BaseHTTPRequestHandler):
             ctype = (self.headers.get("Content-Type") or "application/merge-patch+json").split(";")[0].strip()
             if ctype == "application/strategic-merge-patch+json":
                 ctype = "application/merge-patch+json"
-            self._send_json(200, self.api.patch(info, ns, name, self._body(), ctype, sub))
+            self._send_raw_json(200, self.api.patch(info, ns, name, self._body(), ctype, sub, as_bytes=True))
         except APIError as e:
             self._error(e)
         except (ValueError, KeyError, IndexError) as e:
