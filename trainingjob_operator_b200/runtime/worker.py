@@ -344,6 +344,11 @@ def run(args) -> Dict[str, Any]:
         # NCCL's watchdog would take the process down on an asynchronous communicator error or a collective timeout
         # (TearDown / SkipCleanUp); a faultTolerant job handles the loss of a peer itself (StallBreaker + recovery below)
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        # A communicator that must be abortable with a peer already dead should not hold NVSwitch multicast (NVLS)
+        # objects: their teardown involves every member.  Precaution, not a measured fix -- in-place recovery is verified
+        # on 2 GPUs (where NCCL does not use NVLS); the 4-GPU attempts of round 2 ended without a diagnosis
+        # (profiles/r2_fault_recovery_gpu.md).  Costs the faultTolerant job's all-reduce the in-switch reduction.
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     trace = {"process_start": t_proc, "torch_imported": time.time()}
     heartbeat(force=True)
     watcher = ElasticWatcher.from_env(generation)
