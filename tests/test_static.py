@@ -30,8 +30,8 @@ def test_no_undefined_names_in_the_repo():
     assert not problems, "\n".join(problems)
 
 
-def _c_entry_points():
-    """name -> number of parameters of every ``int aitj_*(...)`` / ``void aitj_*(...)`` definition in the .cu sources."""
+def _c_entry_points(with_types=False):
+    """name -> number of parameters (or the parameter declarations) of every ``aitj_*`` definition in the .cu sources."""
     out = {}
     csrc = os.path.join(ROOT, "trainingjob_operator_b200", "ops", "csrc")
     for fn in sorted(os.listdir(csrc)):
@@ -41,9 +41,33 @@ def _c_entry_points():
         src = re.sub(r"//[^\n]*", "", src)
         for m in re.finditer(r"\b(?:int|void|long long|float)\s+(aitj_\w+)\s*\(([^)]*)\)\s*\{", src):
             params = m.group(2).strip()
-            n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
-            out[m.group(1)] = n
+            plist = [] if params in ("", "void") else [p.strip() for p in params.split(",") if p.strip()]
+            out[m.group(1)] = plist if with_types else len(plist)
     return out
+
+
+def test_ctypes_argument_types_match_the_c_declarations():
+    """A pointer passed as a 32-bit int or an element count passed as ``int`` where the kernel takes ``long long`` is a
+    bug that only shows on large tensors on the GPU box."""
+    import ctypes
+
+    from trainingjob_operator_b200.ops import lib
+
+    for name, params in _c_entry_points(with_types=True).items():
+        if name not in lib._SIGS:
+            continue
+        for i, (p, ct) in enumerate(zip(params, lib._SIGS[name])):
+            if "*" in p:
+                want = ctypes.c_void_p
+            elif re.match(r"(const\s+)?(long long|int64_t|size_t|uint64_t|unsigned long long)\b", p):
+                want = ctypes.c_longlong
+            elif re.match(r"(const\s+)?float\b", p):
+                want = ctypes.c_float
+            elif re.match(r"(const\s+)?(int|unsigned|unsigned int|uint32_t|bool)\b", p):
+                want = ctypes.c_int
+            else:
+                raise AssertionError(f"{name} argument {i}: unrecognised C type in '{p}'")
+            assert ct is want, f"{name} argument {i}: C declares '{p}', ctypes table says {ct.__name__}"
 
 
 def test_kernel_entry_points_agree_between_cuda_sources_ctypes_table_and_call_sites():
