@@ -1,0 +1,275 @@
+"""The engines, the trainer and the bucketed DDP path executed on CPU with the kernel entry points emulated in plain
+PyTorch (``tests/kernel_emulation.py``): what is checked is the control flow AROUND the hand-written kernels -- which the
+build container can otherwise never run -- against the fp32 reference models.  The kernels themselves are checked on the
+device (``tests/test_gpu_kernels.py``)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+import kernel_emulation as ke
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+
+def gpt2_pair(monkeypatch, env=None, seed=3):
+    from trainingjob_operator_b200.models.gpt2 import GPT2Config, GPT2Engine, GPT2Reference
+
+    ke.install(monkeypatch)
+    for k, v in (env or {}).items():
+        monkeypatch.setenv(k, v)
+    cfg = GPT2Config(vocab_size=1000, n_layer=2, n_head=4, n_embd=256, block_size=128, name="t")
+    B, T = 2, 128
+    eng = GPT2Engine(cfg, B, T, "cpu", seed=seed, gemm_backend="tcgen05")
+    g = torch.Generator().manual_seed(9)
+    for s_ in eng.params.specs:               # biases / LayerNorm gains away from their symmetric initial values
+        if len(s_.shape) == 1:
+            eng.params.w32(s_.name).add_(torch.randn(s_.shape, generator=g) * 0.05)
+    eng.params.refresh_compute_copy()
+    ref = GPT2Reference(cfg, eng.params)
+    tok = torch.randint(0, cfg.vocab_size, (B, T), generator=torch.Generator().manual_seed(5))
+    tgt = torch.roll(tok, -1, dims=1)
+    eng.tok.copy_(tok.view(-1))
+    eng.tgt.copy_(tgt.view(-1))
+    return cfg, eng, ref, tok, tgt
+
+
+GPT2_GRADS = ("wte", "wpe", "h0.qkv_w", "h0.qkv_b", "h0.proj_w", "h0.proj_b", "h0.fc_w", "h0.fc_b", "h0.fc2_w",
+              "h0.fc2_b", "h0.ln1_w", "h0.ln1_b", "h1.ln2_w", "h1.ln2_b", "h1.fc2_w", "h1.qkv_w", "lnf_w", "lnf_b")
+
+
+# (AITJ_ATTN=tcgen05 with the library backward calls a cuDNN-only aten op: that combination exists on the GPU only)
+@pytest.mark.parametrize("env", [{}, {"AITJ_ATTN": "tcgen05", "AITJ_ATTN_BWD": "tcgen05"},
+                                 {"AITJ_GEMM_CFG": "fwd:768x256=256,dgrad:256x768=128,wgrad:1024x256=512/4"},
+                                 {"AITJ_GEMM_PAIR": "0"}],
+                         ids=["default", "attn-fwd-bwd", "gemm-table", "no-pair"])
+def test_gpt2_engine_control_flow_matches_the_reference_model(monkeypatch, env):
+    """Forward + backward of the explicit engine: every gradient lands in the right slice of the flat buffer with the
+    right accumulate / overwrite behaviour (a wrong buffer rotation, a skipped bias gradient or a doubled accumulation
+    shows as an O(1) error; bf16 storage of activations costs ~1e-2)."""
+    cfg, eng, ref, tok, tgt = gpt2_pair(monkeypatch, env)
+    if env.get("AITJ_ATTN"):
+        assert eng.attn_impl == "tcgen05" and eng.attn_bwd_impl == env.get("AITJ_ATTN_BWD", "cudnn")
+    eng.params.g32.zero_()
+    eng.forward()
+    eng.backward()
+    loss = ref(tok, tgt)
+    loss.backward()
+    assert abs(float(eng.loss) - float(loss.detach())) < 2e-2 * float(loss.detach())
+    for name in GPT2_GRADS:
+        assert rel(eng.params.grad(name), ref.p(name).grad) < 6e-2, name
+    # a second backward ACCUMULATES (the optimizer sweep is what clears the buffer)
+    g1 = eng.params.grad("h0.fc_w").clone()
+    eng.forward()
+    eng.backward()
+    assert rel(eng.params.grad("h0.fc_w"), 2 * g1) < 1e-3
+    if "AITJ_GEMM_CFG" in env:
+        assert eng.gemm_cfg["wgrad:1024x256"] == (512, 4) and 128 in ke.CALLS["gemm_block_n"]
+    if env.get("AITJ_GEMM_PAIR") == "0":
+        assert 512 not in ke.CALLS["gemm_block_n"]
+
+
+def test_gpt2_engine_optimizer_reduces_the_loss_and_keeps_the_compute_copy_in_sync(monkeypatch):
+    cfg, eng, ref, tok, tgt = gpt2_pair(monkeypatch)
+    eng.params.g32.zero_()
+    eng.forward()
+    l0 = float(eng.loss)
+    for step in range(1, 6):
+        eng.backward()
+        eng.optimizer_step(lr=1e-3, step=step)
+        assert float(eng.params.g32.abs().max()) == 0.0          # cleared by the sweep
+        eng.forward()
+    assert float(eng.loss) < l0 - 0.05, (l0, float(eng.loss))
+    P = eng.params
+    assert torch.equal(P.p16, P.p32.to(torch.bfloat16))          # bf16 compute copy refreshed from the master weights
+    # gradient clipping: an absurd max_norm leaves the update direction, a tiny one shrinks the step
+    before = P.p32.clone()
+    eng.backward()
+    eng.optimizer_step(lr=1e-3, step=6, max_norm=1e-6)
+    small = float((P.p32 - before).abs().max())
+    assert 0 < small < 2e-3
+
+
+def test_bert_engine_control_flow_matches_the_reference_model(monkeypatch):
+    from trainingjob_operator_b200.models.bert import BertConfig, BertEngine, BertReference, SyntheticMLM
+
+    ke.install(monkeypatch)
+    cfg = BertConfig.tiny()
+    B, T = 2, 128
+    eng = BertEngine(cfg, B, T, "cpu", seed=3)
+    g = torch.Generator().manual_seed(9)
+    for s_ in eng.params.specs:
+        if len(s_.shape) == 1:
+            eng.params.w32(s_.name).add_(torch.randn(s_.shape, generator=g) * 0.05)
+    eng.params.w32("dec_b")[cfg.vocab_size:].zero_()
+    eng.params.refresh_compute_copy()
+    ref = BertReference(cfg, eng.params)
+    data = SyntheticMLM(cfg.vocab_size, B, T, n_batches=1, seed=5, pin=False)
+    tok, typ, lab = data.next()
+    for dst, src in zip(eng.input_tensors(), (tok, typ, lab)):
+        dst.copy_(src)
+    assert eng.n_masked == data.n_masked
+    eng.params.g32.zero_()
+    eng.forward()
+    eng.backward()
+    loss = ref(tok.view(B, T), typ.view(B, T), lab.view(B, T))
+    loss.backward()
+    assert abs(float(eng.loss) - float(loss.detach())) < 2e-2 * float(loss.detach())
+    for name in ("wte", "wpe", "wtt", "emb_ln_w", "emb_ln_b", "h0.qkv_w", "h0.qkv_b", "h0.proj_w", "h0.proj_b", "h0.ln1_w",
+                 "h0.ln1_b", "h0.fc_w", "h0.fc_b", "h0.fc2_w", "h0.fc2_b", "h0.ln2_w", "h1.ln2_b", "h1.fc2_w", "h1.qkv_w",
+                 "mlm_w", "mlm_b", "mlm_ln_w", "mlm_ln_b", "dec_b"):
+        gref, got = ref.p(name).grad, eng.params.grad(name)
+        if name == "dec_b":
+            gref, got = gref[:cfg.vocab_size], got[:cfg.vocab_size]
+        assert rel(got, gref) < 6e-2, name
+    l0 = float(eng.loss)
+    for step in range(1, 5):
+        eng.optimizer_step(lr=1e-3, step=step)
+        eng.forward()
+        eng.backward()
+    assert float(eng.loss) < l0
+
+
+def test_engine_trainer_steps_on_cpu_and_feeds_inputs_and_schedule(monkeypatch):
+    """EngineTrainer.step: host inputs -> device tensors, lr schedule into the device scalars, eager step (no CUDA graph
+    off-GPU), loss read back."""
+    from trainingjob_operator_b200.runtime.trainer import EngineTrainer, cosine_lr
+
+    cfg, eng, ref, tok, tgt = gpt2_pair(monkeypatch)
+    tr = EngineTrainer(eng, lr=1e-3, use_graph=True)
+    assert tr.use_graph is False and tr.reducer is None and tr.allreduce_backend == "none"
+    losses = [tr.step(tok.view(-1), tgt.view(-1)) for _ in range(5)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    assert abs(float(eng.dyn[0]) - cosine_lr(5, 1e-3)) < 1e-9
+    assert tr.step_count == 5
+
+
+DDP_SCRIPT = """
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import kernel_emulation as ke
+ke.install()
+from trainingjob_operator_b200.models.gpt2 import GPT2Config, GPT2Engine
+from trainingjob_operator_b200.runtime.trainer import EngineTrainer
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+cfg = GPT2Config(vocab_size=1000, n_layer=2, n_head=4, n_embd=256, block_size=128, name="t")
+eng = GPT2Engine(cfg, 2, 128, "cpu", seed=3, gemm_backend="tcgen05")
+tr = EngineTrainer(eng, lr=1e-3, use_graph=False, allreduce="nccl")
+assert tr.reducer is not None and tr.segmented and eng.segment_join is True
+g = torch.Generator().manual_seed(100 + rank)          # every rank its own data
+out = {{"rank": rank, "buckets": [b[0] for b in tr.reducer.buckets], "losses": []}}
+for step in range(4):
+    tok = torch.randint(0, cfg.vocab_size, (2 * 128,), generator=g)
+    out["losses"].append(tr.step(tok, torch.roll(tok, -1)))
+p = eng.params.p32.clone()
+ref = p.clone()
+dist.broadcast(ref, 0)
+out["max_param_diff_to_rank0"] = float((p - ref).abs().max())
+out["grad_left"] = float(eng.params.g32.abs().max())
+print("RESULT " + json.dumps(out), flush=True)
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.slow
+def test_bucketed_ddp_over_gloo_keeps_the_replicas_identical(tmp_path):
+    """The NCCL-mode trainer (bucket hooks fired by the backward segments, join before the optimizer, gradient divided by
+    the world size in the sweep) with two gloo ranks on different data: parameters stay bit-identical across ranks."""
+    script = tmp_path / "ddp.py"
+    script.write_text(textwrap.dedent(DDP_SCRIPT.format(root=ROOT)))
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    import json
+
+    res = []
+    for o, p in zip(outs, procs):
+        assert p.returncode == 0, o[-3000:]
+        res.append(json.loads(next(ln for ln in o.splitlines() if ln.startswith("RESULT "))[7:]))
+    assert all(r["max_param_diff_to_rank0"] == 0.0 for r in res), res
+    assert all(r["grad_left"] == 0.0 for r in res)
+    assert res[0]["losses"] != res[1]["losses"]                   # different data ...
+    assert all(r["losses"][-1] < r["losses"][0] for r in res)     # ... both learning
+
+
+WORKER_SCRIPT = """
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import kernel_emulation as ke
+ke.install()
+from trainingjob_operator_b200.runtime import worker as W
+W.build_adapter = lambda args, device: W.EngineAdapter(args.model, args.batch, args.seq, args, device="cpu")
+sys.exit(W.main(sys.argv[1:]))
+"""
+
+
+def run_workers(tmp_path, n, argv, env_extra=None, timeout=600):
+    """The real worker entry point (``runtime/worker.py main``) with the engine adapter on CPU: n gloo ranks."""
+    import json
+    import socket
+
+    script = tmp_path / "worker_cpu.py"
+    script.write_text(textwrap.dedent(WORKER_SCRIPT.format(root=ROOT)))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for r in range(n):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(n), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="2", AITJ_WORKDIR=str(tmp_path), TRAININGJOB_NAME="dry",
+                   **(env_extra or {}))
+        env.pop("AITJ_MASTER", None)
+        res = tmp_path / f"result{r}.json"
+        procs.append((res, subprocess.Popen([sys.executable, str(script), "--cpu", "--result", str(res)] + argv, env=env,
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    out = []
+    for res, p in procs:
+        log = p.communicate(timeout=timeout)[0]
+        assert p.returncode == 0, log[-4000:]
+        out.append((json.load(open(res)) if res.exists() else None, log))
+    return out
+
+
+@pytest.mark.slow
+def test_worker_loop_with_the_engine_adapter_single_rank_checkpoint_and_resume(tmp_path):
+    """``worker.run`` end to end on one rank: warm-up, timed region, checkpoints every 2 steps, result record; then the
+    same job restarted (TRAININGJOB_REPLICA_RESTARTCOUNT=1) resumes from the checkpoint past the warm-up and still
+    produces a throughput record."""
+    argv = ["--model", "gpt2-tiny", "--batch", "2", "--seq", "128", "--steps", "4", "--warmup", "3", "--ckpt-every", "2",
+            "--ckpt-dir", str(tmp_path / "ck")]
+    (r, log), = run_workers(tmp_path, 1, argv, {"AITJ_CKPT_ASYNC": "0"})
+    assert r and r["steps_done"] == 7 and r["world"] == 1 and r["samples_per_sec"] > 0, (r, log[-2000:])
+    assert r["loss_last"] < r["loss_first"]
+    (r2, log2), = run_workers(tmp_path, 1, argv, {"AITJ_CKPT_ASYNC": "0", "TRAININGJOB_REPLICA_RESTARTCOUNT": "1"})
+    assert "resumed from checkpoint at step 6" in log2, log2[-2000:]
+    assert r2 and r2["steps_done"] == 7 and r2["samples_per_sec"] > 0
+
+
+@pytest.mark.slow
+def test_worker_loop_with_the_engine_adapter_two_ranks(tmp_path):
+    """Two gloo ranks through rendezvous, the elected state hand-off (flat engine state), bucketed gradient sync and the
+    max-over-ranks timing: both ranks report the same loss trajectory end point and world size 2."""
+    argv = ["--model", "bert-tiny", "--batch", "2", "--seq", "128", "--steps", "3", "--warmup", "3"]
+    res = run_workers(tmp_path, 2, argv)
+    r0 = res[0][0]
+    assert r0 and r0["world"] == 2 and r0["global_batch"] == 4 and r0["steps_done"] == 6, (r0, res[0][1][-2000:])
+    assert "gradient sync" in res[0][1]

@@ -42,7 +42,9 @@ from .trainer import EngineTrainer, SyntheticTokens
 class EngineAdapter:
     """GPT-2 / BERT-shaped transformer on the hand-written engine (CUDA only)."""
 
-    def __init__(self, name: str, batch: int, seq: int, args):
+    def __init__(self, name: str, batch: int, seq: int, args, device: str = "cuda"):
+        """``device``: always "cuda" in a worker (``build_adapter``); the CPU dry-run tests pass "cpu" together with
+        emulated kernel entry points (tests/kernel_emulation.py) to execute the adapter's control flow."""
         from ..models.gpt2 import GPT2Config, GPT2Engine, flops_per_token
 
         if name in ("bert", "bert-tiny"):
@@ -51,8 +53,8 @@ class EngineAdapter:
 
             cfg = BertConfig.base() if name == "bert" else BertConfig.tiny()
             seq = min(seq, cfg.block_size)
-            self.engine = BertEngine(cfg, batch, seq, "cuda", seed=args.seed, gemm_backend=args.gemm)
-            self.data = SyntheticMLM(cfg.vocab_size, batch, seq, n_batches=4, seed=args.seed + 1)
+            self.engine = BertEngine(cfg, batch, seq, device, seed=args.seed, gemm_backend=args.gemm)
+            self.data = SyntheticMLM(cfg.vocab_size, batch, seq, n_batches=4, seed=args.seed + 1, pin=device != "cpu")
             self.flops_per_step = bert_flops_per_token(cfg, seq) * batch * seq
         else:
             if name == "gpt2":
@@ -62,7 +64,7 @@ class EngineAdapter:
             else:
                 raise ValueError(name)
             seq = min(seq, cfg.block_size)
-            self.engine = GPT2Engine(cfg, batch, seq, "cuda", seed=args.seed, gemm_backend=args.gemm, causal=True)
+            self.engine = GPT2Engine(cfg, batch, seq, device, seed=args.seed, gemm_backend=args.gemm, causal=True)
             self.data = SyntheticTokens(cfg.vocab_size, batch, seq, n_batches=4, seed=args.seed + 1)
             self.flops_per_step = flops_per_token(cfg, seq) * batch * seq
         self.cfg = cfg
