@@ -273,3 +273,77 @@ def test_worker_loop_with_the_engine_adapter_two_ranks(tmp_path):
     r0 = res[0][0]
     assert r0 and r0["world"] == 2 and r0["global_batch"] == 4 and r0["steps_done"] == 6, (r0, res[0][1][-2000:])
     assert "gradient sync" in res[0][1]
+
+
+@pytest.mark.slow
+def test_engine_worker_through_the_control_plane_elastic_rescale_and_in_place_recovery(tmp_path):
+    """The engine adapter (emulated kernels, CPU / gloo) as the workers of a ``faultTolerant`` elastic job submitted
+    through ``LocalCluster``: scale 1 -> 2 hands the flat engine state (fp32 master weights + moments) to the joiner and
+    re-binds the trainer; SIGKILL of rank 1 is repaired in place -- the survivor keeps its process, the replacement
+    receives the state again.  On GPUs this is the path of tools/elastic_gpu_check.py / fault_check.py --fault-tolerant."""
+    import json
+    import signal
+    import time
+
+    from trainingjob_operator_b200.api import constants as C
+    from trainingjob_operator_b200.cmd.local import LocalCluster
+    from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption
+
+    script = tmp_path / "worker_cpu.py"
+    script.write_text(textwrap.dedent(WORKER_SCRIPT.format(root=ROOT)))
+    worker = [sys.executable, str(script), "--cpu", "--model", "gpt2-tiny", "--batch", "2", "--seq", "128", "--steps", "0",
+              "--elastic", "--ckpt-every", "0", "--step-sleep", "0.05"]
+    job = {"apiVersion": C.API_VERSION, "kind": C.KIND, "metadata": {"name": "eng"},
+           "spec": {"frameworkType": "pytorch", "faultTolerant": True, "replicaSpecs": {"trainer": {
+               "replicas": 1, "minReplicas": 1, "maxReplicas": 2, "edlPolicy": "Manual", "restartPolicy": "OnFailure",
+               "restartLimit": 4,
+               "template": {"spec": {"terminationGracePeriodSeconds": 1, "containers": [{
+                   "name": "aitj-trainer", "command": worker, "workingDir": ROOT,
+                   "env": [{"name": "PYTHONPATH", "value": ROOT}, {"name": "OMP_NUM_THREADS", "value": "2"}]}]}}}}}}
+
+    def wait(fn, timeout=120.0):
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                v = fn()
+                if v:
+                    return v
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+        raise TimeoutError
+
+    def trace(lc, key):
+        return json.loads(lc.jobs().get("eng").annotations.get(f"aitj.b200/{key}", "null"))
+
+    def pids(lc):
+        return {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/eng-trainer-" in sid}
+
+    with LocalCluster(num_gpus=0, workdir=str(tmp_path / "wd"), option=TrainingJobOperatorOption(thread_num=2)) as lc:
+        try:
+            lc.apply(job)
+            wait(lambda: (trace(lc, "worker-trace") or {}).get("first_step_done"))
+            p0 = pids(lc)["eng-trainer-0"]
+            lc.jobs().patch("eng", {"spec": {"replicaSpecs": {"trainer": {"replicas": 2}}}})
+            rec = wait(lambda: (lambda r: r if r and r.get("world") == 2 else None)(trace(lc, "rescale-trace")))
+            assert rec["generation"] == 2 and pids(lc)["eng-trainer-0"] == p0
+            log1 = open(os.path.join(lc.workdir, "logs", "default_eng-trainer-1_aitj-trainer.log")).read()
+            assert "joined generation 2 (world 2) at step" in log1
+            # ---- SIGKILL rank 1: in-place recovery
+            os.kill(pids(lc)["eng-trainer-1"], signal.SIGKILL)
+            rec = wait(lambda: (lambda r: r if r and r.get("generation", 0) >= 3 and r.get("recovered_from") else None)(
+                trace(lc, "rescale-trace")))
+            assert rec["world"] == 2
+            j = wait(lambda: (lambda x: x if x.status.phase == "Running" and
+                              x.status.replica_statuses["trainer"].active == 2 else None)(lc.jobs().get("eng")))
+            assert j.status.restart_counts == {"trainer": 1}
+            assert pids(lc)["eng-trainer-0"] == p0                       # the survivor was never restarted
+            log0 = open(os.path.join(lc.workdir, "logs", "default_eng-trainer-0_aitj-trainer.log")).read()
+            assert "lost a peer" in log0 and "keeping state" in log0
+            # ---- scale back down: rank 1 leaves, rank 0 trains on alone
+            lc.jobs().patch("eng", {"spec": {"replicaSpecs": {"trainer": {"replicas": 1}}}})
+            rec = wait(lambda: (lambda r: r if r and r.get("world") == 1 else None)(trace(lc, "rescale-trace")))
+            assert pids(lc)["eng-trainer-0"] == p0
+        finally:
+            lc.jobs().delete("eng")
+            time.sleep(0.5)
