@@ -19,7 +19,7 @@ from trainingjob_operator_b200.api.types import AITrainingJob  # noqa: E402
 from trainingjob_operator_b200.controller import replay  # noqa: E402
 
 NOW = "2026-09-21T12:00:00Z"
-EPOCH = 1790000000.0
+EPOCH = 1789992000.0     # the same instant as NOW (a replay rebuilds `now` from this float)
 UID = "11111111-2222-3333-4444-555555555555"
 
 

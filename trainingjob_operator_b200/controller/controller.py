@@ -18,6 +18,7 @@ the replicas of a job that just finished).
 from __future__ import annotations
 
 import threading
+import datetime as _dt
 import time
 from typing import Dict, List, Optional, Tuple
 
@@ -260,9 +261,10 @@ class TrainingJobController(TrainingJobHandlers):
                 except APIError as e:
                     klog.error("cannot list nodes: %s", e.message)
         cluster = E.observe_cluster(job, nodes, self.pod_lister.peek()) if E.auto_roles(job) else None
+        t = time.time()       # ONE clock read: `now` and `now_epoch` are the same instant, so a recorded pass replays exactly
         return engine.Observation(job=job, pods=pods, services=services,
                                   ready_nodes=frozenset(M.name_of(n) for n in nodes if _node_is_ready(n)),
-                                  now=M.now(), now_epoch=time.time(),
+                                  now=_dt.datetime.fromtimestamp(t, _dt.timezone.utc), now_epoch=t,
                                   options=engine.EngineOptions.from_operator_option(self.option),
                                   cluster=cluster, spare_ports=spare_ports)
 

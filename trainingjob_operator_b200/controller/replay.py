@@ -32,7 +32,8 @@ def observation_to_json(obs: engine.Observation) -> Dict[str, Any]:
 
 def observation_from_json(d: Dict[str, Any]) -> engine.Observation:
     o = d["options"]
-    now = M.parse_time(d["now"]) or _dt.datetime.fromtimestamp(d["now_epoch"], _dt.timezone.utc)
+    # the float carries the sub-second part (drain / time-limit arithmetic uses it); "now" is the readable form
+    now = _dt.datetime.fromtimestamp(d["now_epoch"], _dt.timezone.utc) if d.get("now_epoch") else M.parse_time(d["now"])
     return engine.Observation(
         job=AITrainingJob.from_dict(d["job"]), pods=M.deepcopy(d["pods"]), services=M.deepcopy(d["services"]),
         ready_nodes=frozenset(d["ready_nodes"]), now=now, now_epoch=float(d["now_epoch"]),
