@@ -347,3 +347,141 @@ def test_engine_worker_through_the_control_plane_elastic_rescale_and_in_place_re
         finally:
             lc.jobs().delete("eng")
             time.sleep(0.5)
+
+
+HANG_WORKER_SCRIPT = """
+import os, sys, threading, time
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from trainingjob_operator_b200.runtime import worker as W, rendezvous as R
+
+# NCCL semantics on gloo: a collective whose peer died does not raise -- it never completes -- until the communicator is
+# aborted, after which it fails.  (gloo raises after the group's short time-out; that error is turned into the hang.)
+ABORT = threading.Event()
+
+def nccl_like(fn):
+    def w(*a, **k):
+        try:
+            return fn(*a, **k)
+        except RuntimeError as e:
+            t0 = time.time()
+            print(f"[emulation] collective failed ({{type(e).__name__}}): hanging like NCCL until the communicator is aborted", flush=True)
+            while not ABORT.is_set():
+                if time.time() - t0 > 90:
+                    print("[emulation] nobody aborted the communicator: this rank would hang for ever", flush=True)
+                    os._exit(99)
+                time.sleep(0.02)
+            raise RuntimeError("NCCL communicator was aborted") from None
+    return w
+
+_teardown = R.teardown_group
+def teardown(broken=False):
+    if broken:
+        ABORT.set()
+    _teardown(broken)
+R.teardown_group = W.teardown_group = teardown
+_init = R.init_process_group
+def init(*a, **k):
+    out = _init(*a, **k)
+    ABORT.clear()
+    return out
+R.init_process_group = init
+dist.all_reduce = nccl_like(dist.all_reduce)
+dist.broadcast = nccl_like(dist.broadcast)
+_build = W.build_adapter
+def build(args, device):
+    ad = _build(args, device)
+    ad.train_step = nccl_like(ad.train_step)
+    return ad
+W.build_adapter = build
+sys.exit(W.main(sys.argv[1:]))
+"""
+
+
+@pytest.mark.slow
+def test_stall_breaker_recovers_four_ranks_whose_collectives_hang_like_nccl(tmp_path):
+    """BASELINE config 4's shape (4 ranks, SIGKILL rank 3, ``faultTolerant``) with collectives that HANG when a peer dies,
+    as NCCL's do, instead of raising as gloo's do: every survivor sits inside its step (or inside the generation
+    agreement) until its StallBreaker -- armed with AITJ_STALL_BREAKER=force -- sees the newer generation and aborts the
+    communicator; then all three re-rendezvous with the replacement and go on, processes kept.  A second victim (rank 0,
+    the state source) is killed afterwards.  This is the logic that could not be diagnosed on 4 GPUs in round 2."""
+    import json
+    import signal
+    import time
+
+    from trainingjob_operator_b200.api import constants as C
+    from trainingjob_operator_b200.cmd.local import LocalCluster
+    from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption
+
+    script = tmp_path / "hang_worker.py"
+    script.write_text(textwrap.dedent(HANG_WORKER_SCRIPT.format(root=ROOT)))
+    worker = [sys.executable, str(script), "--cpu", "--model", "mlp", "--batch", "16", "--steps", "0", "--elastic",
+              "--ckpt-every", "10", "--step-sleep", "0.05"]
+    env = [{"name": "PYTHONPATH", "value": ROOT}, {"name": "OMP_NUM_THREADS", "value": "1"},
+           {"name": "AITJ_STALL_BREAKER", "value": "force"}, {"name": "AITJ_FT_ABORT_AFTER", "value": "1.5"},
+           {"name": "AITJ_COLLECTIVE_TIMEOUT", "value": "1"}]
+    job = {"apiVersion": C.API_VERSION, "kind": C.KIND, "metadata": {"name": "hang"},
+           "spec": {"frameworkType": "pytorch", "faultTolerant": True, "replicaSpecs": {"trainer": {
+               "replicas": 4, "minReplicas": 4, "maxReplicas": 4, "edlPolicy": "Manual", "restartPolicy": "OnFailure",
+               "restartLimit": 6,
+               "template": {"spec": {"terminationGracePeriodSeconds": 1, "containers": [{
+                   "name": "aitj-trainer", "command": worker, "workingDir": ROOT, "env": env}]}}}}}}
+
+    def wait(fn, timeout=150.0):
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                v = fn()
+                if v:
+                    return v
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+        raise TimeoutError
+
+    def ann(lc, key):
+        return json.loads(lc.jobs().get("hang").annotations.get(f"aitj.b200/{key}", "null"))
+
+    def pids(lc):
+        return {sid.split("/")[1]: p for sid, p in lc.agent.sup.list() if "/hang-trainer-" in sid}
+
+    def logs(lc, i):
+        return open(os.path.join(lc.workdir, "logs", f"default_hang-trainer-{i}_aitj-trainer.log")).read()
+
+    with LocalCluster(num_gpus=0, workdir=str(tmp_path / "wd"), option=TrainingJobOperatorOption(thread_num=2)) as lc:
+        try:
+            lc.apply(job)
+            wait(lambda: (ann(lc, "worker-trace") or {}).get("first_step_done"))
+            time.sleep(1.0)
+            before = pids(lc)
+            os.kill(before["hang-trainer-3"], signal.SIGKILL)
+            rec = wait(lambda: (lambda r: r if r and r.get("generation", 0) >= 2 and r.get("recovered_from") else None)(
+                ann(lc, "rescale-trace")))
+            assert rec["world"] == 4
+            wait(lambda: (lambda x: x.status.phase == "Running" and
+                          x.status.replica_statuses["trainer"].active == 4)(lc.jobs().get("hang")))
+            now = pids(lc)
+            assert all(now[k] == before[k] for k in ("hang-trainer-0", "hang-trainer-1", "hang-trainer-2")), (before, now)
+            tripped = [i for i in range(3) if "aborting the communicator" in logs(lc, i)]
+            assert tripped, "no survivor's breaker fired: the recovery did not go through the NCCL-like path"
+            assert all("hanging like NCCL" in logs(lc, i) for i in range(3))
+            assert lc.jobs().get("hang").status.restart_counts == {"trainer": 1}
+            # ---- second victim: rank 0 (the rank the others take their state from)
+            gen = ann(lc, "rescale-trace")["generation"]
+            before = pids(lc)
+            os.kill(before["hang-trainer-0"], signal.SIGKILL)
+            rec = wait(lambda: (lambda r: r if r and r.get("generation", 0) > gen and r.get("recovered_from") else None)(
+                ann(lc, "rescale-trace")))
+            wait(lambda: (lambda x: x.status.phase == "Running" and
+                          x.status.replica_statuses["trainer"].active == 4)(lc.jobs().get("hang")))
+            now = pids(lc)
+            assert all(now[k] == before[k] for k in ("hang-trainer-1", "hang-trainer-2", "hang-trainer-3"))
+            assert lc.jobs().get("hang").status.restart_counts == {"trainer": 2}
+        finally:
+            for i in range(4):
+                try:
+                    sys.stderr.write(f"---- rank {i}\\n" + logs(lc, i)[-1500:] + "\\n")
+                except Exception:  # noqa: BLE001
+                    pass
+            lc.jobs().delete("hang")
+            time.sleep(0.5)

@@ -331,6 +331,23 @@ def load_checkpoint(args, adapter) -> int:
     return int(meta["step"])
 
 
+def guarded(breaker, generation: int, fn):
+    """Run a collective-bearing ``fn`` as "inside a step" for the stall breaker: only a generation newer than
+    ``generation`` (= another peer was lost meanwhile) makes it abort the communicator; the abort surfaces as a
+    RuntimeError, which the training loop's recovery path handles."""
+    if breaker is None:
+        return fn()
+    breaker.progress(generation)
+    breaker.in_step = True
+    try:
+        out = fn()
+    finally:
+        breaker.in_step = False
+    if breaker.tripped:
+        raise RuntimeError("the communicator was aborted while the state hand-off was in flight")
+    return out
+
+
 # ------------------------------------------------------------------------------------ main loop
 def run(args) -> Dict[str, Any]:
     t_proc = time.time()
@@ -404,7 +421,10 @@ def run(args) -> Dict[str, Any]:
     # except branch of the training loop
     fault_tolerant = bool(args.elastic and watcher is not None and os.environ.get("AITJ_FAULT_TOLERANT") == "1")
     breaker = None
-    if fault_tolerant and use_cuda and float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")) > 0:
+    # (armed on CUDA, where a collective with a dead peer hangs instead of raising; AITJ_STALL_BREAKER=force arms it for
+    #  any backend -- the CPU tests use it with collectives that are made to hang the way NCCL's do)
+    hangs = use_cuda or os.environ.get("AITJ_STALL_BREAKER") == "force"
+    if fault_tolerant and hangs and float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")) > 0:
         breaker = StallBreaker(watcher, float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")))
     elif watcher is not None and use_cuda and world > 1 and float(os.environ.get("AITJ_STALL_EXIT_AFTER", "3")) > 0:
         # not faultTolerant: a rank stuck behind a dead peer cannot be repaired in place; once the controller has started
@@ -463,7 +483,7 @@ def run(args) -> Dict[str, Any]:
                         generation, world, port = got["generation"], got["world"], got["port"]
                     t2 = time.time()
                     adapter.bind(None)
-                    step = sync_state(adapter, step, device)
+                    step = guarded(breaker, generation, lambda: sync_state(adapter, step, device))
                     heartbeat(force=True)
                     watcher.adopted(generation, world)
                     pending_rescale = {"generation": generation, "world": world, "t0": t0,
@@ -544,7 +564,19 @@ def run(args) -> Dict[str, Any]:
                 breaker.tripped = False
                 breaker.progress(generation)
             adapter.bind(None)
-            step = sync_state(adapter, step, device)
+            # the hand-off is a chain of collectives on the new group: if ANOTHER peer dies under it, a still newer
+            # generation is published and the breaker must be able to get this rank out of it
+            try:
+                step = guarded(breaker, generation, lambda: sync_state(adapter, step, device))
+            except RuntimeError as e:
+                # (this block is outside the loop's try: handled here.)  The group is gone again; the step boundary's
+                # generation agreement finds the newest record and joins it through the ordinary rescale path.
+                print(f"[worker {rank}] another peer was lost during the state hand-off of generation {generation} "
+                      f"({type(e).__name__}); joining the next generation", flush=True)
+                teardown_group(broken=True)
+                if breaker is not None:
+                    breaker.tripped = False
+                continue
             heartbeat(force=True)
             watcher.adopted(generation, world)
             pending_rescale = {"generation": generation, "world": world, "t0": t0, "observed_at": t0,
