@@ -485,3 +485,68 @@ def test_stall_breaker_recovers_four_ranks_whose_collectives_hang_like_nccl(tmp_
                     pass
             lc.jobs().delete("hang")
             time.sleep(0.5)
+
+
+@pytest.mark.slow
+def test_stall_exit_makes_a_pod_scope_restart_whole_again_in_seconds(tmp_path):
+    """``restartScope: Pod`` without ``faultTolerant``: the controller re-creates only the killed replica; the survivor
+    sits in a collective that (NCCL-like) never returns.  Round 1 measured 32.7 s for this on GPUs because the survivor
+    was only removed by the agent's 20 s heartbeat time-out.  The worker's stall-exit breaker leaves with 137 as soon as
+    the controller's repair (a newer rendezvous generation) is visible, the controller replaces it too, and both
+    replicas resume from the checkpoint."""
+    import json
+    import signal
+    import time
+
+    from trainingjob_operator_b200.api import constants as C
+    from trainingjob_operator_b200.cmd.local import LocalCluster
+    from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption
+
+    script = tmp_path / "hang_worker.py"
+    script.write_text(textwrap.dedent(HANG_WORKER_SCRIPT.format(root=ROOT)))
+    worker = [sys.executable, str(script), "--cpu", "--model", "mlp", "--batch", "16", "--steps", "0", "--ckpt-every", "5",
+              "--step-sleep", "0.05"]
+    env = [{"name": "PYTHONPATH", "value": ROOT}, {"name": "OMP_NUM_THREADS", "value": "1"},
+           {"name": "AITJ_STALL_BREAKER", "value": "force"}, {"name": "AITJ_STALL_EXIT_AFTER", "value": "1.5"},
+           {"name": "AITJ_COLLECTIVE_TIMEOUT", "value": "1"}, {"name": "AITJ_HANG_TIMEOUT", "value": "60"}]
+    job = {"apiVersion": C.API_VERSION, "kind": C.KIND, "metadata": {"name": "podscope"},
+           "spec": {"frameworkType": "pytorch", "replicaSpecs": {"trainer": {
+               "replicas": 2, "restartPolicy": "OnFailure", "restartScope": "Pod", "restartLimit": 6,
+               "template": {"spec": {"terminationGracePeriodSeconds": 1, "containers": [{
+                   "name": "aitj-trainer", "command": worker, "workingDir": ROOT, "env": env}]}}}}}}
+
+    def wait(fn, timeout=120.0):
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                v = fn()
+                if v:
+                    return v
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+        raise TimeoutError
+
+    def first_step(lc):
+        return (json.loads(lc.jobs().get("podscope").annotations.get("aitj.b200/worker-trace", "null")) or {}).get(
+            "first_step_done", 0.0)
+
+    with LocalCluster(num_gpus=0, workdir=str(tmp_path / "wd"), option=TrainingJobOperatorOption(thread_num=2)) as lc:
+        try:
+            lc.apply(job)
+            wait(lambda: first_step(lc) > 0)
+            time.sleep(1.5)                                            # a checkpoint exists
+            pid = next(p for sid, p in lc.agent.sup.list() if "/podscope-trainer-1/" in sid)
+            t_kill = time.time()
+            os.kill(pid, signal.SIGKILL)
+            wait(lambda: first_step(lc) > t_kill)
+            took = first_step(lc) - t_kill
+            j = lc.jobs().get("podscope")
+            assert j.status.restart_counts == {"trainer": 2}, j.status.restart_counts     # the victim and the survivor
+            log0 = open(os.path.join(lc.workdir, "logs", "default_podscope-trainer-0_aitj-trainer.log")).read()
+            assert "does not recover in place" in log0 and "leaving (137)" in log0
+            assert "resumed from checkpoint" in log0
+            assert took < 15.0, took            # seconds, not the 60 s heartbeat time-out configured above
+        finally:
+            lc.jobs().delete("podscope")
+            time.sleep(0.5)

@@ -426,7 +426,7 @@ def run(args) -> Dict[str, Any]:
     hangs = use_cuda or os.environ.get("AITJ_STALL_BREAKER") == "force"
     if fault_tolerant and hangs and float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")) > 0:
         breaker = StallBreaker(watcher, float(os.environ.get("AITJ_FT_ABORT_AFTER", "3")))
-    elif watcher is not None and use_cuda and world > 1 and float(os.environ.get("AITJ_STALL_EXIT_AFTER", "3")) > 0:
+    elif watcher is not None and hangs and world > 1 and float(os.environ.get("AITJ_STALL_EXIT_AFTER", "3")) > 0:
         # not faultTolerant: a rank stuck behind a dead peer cannot be repaired in place; once the controller has started
         # to repair the job (newer generation) it leaves at once instead of waiting for the heartbeat time-out
         breaker = StallBreaker(watcher, float(os.environ.get("AITJ_STALL_EXIT_AFTER", "3")), action="exit")
