@@ -68,7 +68,10 @@ class FlatParams:
         CPU generator and copying them tensor by tensor took 2.5 s of a single core per worker (more than half of a
         warm-started worker's time to its first step); the device generator fills the flat buffer in milliseconds.  Every
         rank uses the same seed (Philox: same values on every GPU), and the elected state hand-off follows anyway."""
-        gen = torch.Generator(device=self.device)
+        import os
+
+        on_host = os.environ.get("AITJ_PARAM_INIT") == "cpu"     # the numerics self-check keeps its historical weights
+        gen = torch.Generator(device="cpu" if on_host else self.device)
         gen.manual_seed(seed)
         for s in self.specs:
             view = self.p32[s.offset:s.offset + s.numel].view(s.shape)
@@ -76,6 +79,8 @@ class FlatParams:
                 view.zero_()
             elif s.init == "ones":
                 view.fill_(1.0)
+            elif on_host:
+                view.copy_(torch.randn(s.shape, generator=gen, dtype=torch.float32) * s.std)
             else:
                 view.normal_(0.0, s.std, generator=gen)
         self.refresh_compute_copy()

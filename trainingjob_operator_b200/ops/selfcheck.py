@@ -7,10 +7,15 @@ Exit code 0 = pass.  ``tests/test_gpu_kernels.py`` drives it under ``@pytest.mar
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 import time
 
 import torch
+
+# The engine cases compare against tolerances that were settled on the weights a CPU generator draws for these seeds;
+# workers initialise on the device (models/flat_params.py), the self-check keeps the draw it was validated with.
+os.environ.setdefault("AITJ_PARAM_INIT", "cpu")
 
 from . import functional as F
 
