@@ -13,6 +13,7 @@ Never imported by the package: on a GPU box a missing kernel library raises (``o
 from __future__ import annotations
 
 import math
+import threading
 
 import torch
 import torch.nn.functional as TF
@@ -21,8 +22,100 @@ CALLS = {"n": 0, "gemm_block_n": []}
 _K0, _K1 = math.sqrt(2.0 / math.pi), 0.044715
 
 
+# ------------------------------------------------------------------------------------ owner-sharded mode (peer memory)
+# Several "ranks" live in ONE process (FakeShard objects of one FakeWorld).  A kernel that is given a PeerView -- the
+# LOCAL address of a gradient inside the symmetric buffer -- adds every piece into the copy of the rank that OWNS it;
+# the emulation finds the symmetric buffer by its storage and does the same with slices.
+_WORLDS = {}          # storage data_ptr of a rank's symmetric gradient buffer -> (FakeWorld, rank)
+
+
+class FakeShard:
+    """What ``parallel.symm.ShardedGradState`` offers the engine, without symmetric memory."""
+
+    available = True
+    reason = ""
+
+    def __init__(self, world: "FakeWorld", rank: int, params):
+        from trainingjob_operator_b200.parallel.symm import shard_bounds
+
+        self.fw, self.rank, self.world, self.params = world, rank, world.n, params
+        total = params.total
+        self.g = torch.zeros(total + 64, dtype=torch.float32)
+        self.w = torch.zeros(total, dtype=torch.bfloat16)
+        self.bounds = shard_bounds(params.specs, total, self.world)
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.w_mc = 0                                   # "multicast address" of w: element offset * 2
+        self.parts_mc = FakeWorld.PARTS_TOKEN + world.uid
+        _WORLDS[self.g.untyped_storage().data_ptr()] = (world, rank)
+        self.barriers = 0
+
+    @property
+    def parts(self):
+        return self.g[self.params.total:self.params.total + self.world]
+
+    def barrier(self):
+        """Every rank runs in its own thread: a real barrier, like the device-side one between the ranks' streams."""
+        self.barriers += 1
+        self.fw.sync.wait(timeout=120)
+
+
+class FakeWorld:
+    PARTS_TOKEN = 1 << 40
+    _next = 0
+
+    def __init__(self, n: int):
+        self.n = n
+        FakeWorld._next += 1
+        self.uid = FakeWorld._next
+        self.shards = []
+        self.sync = threading.Barrier(n)
+        _PARTS[FakeWorld.PARTS_TOKEN + self.uid] = self
+
+    def attach(self, params) -> FakeShard:
+        sh = FakeShard(self, len(self.shards), params)
+        self.shards.append(sh)
+        params.attach_shard(sh)
+        return sh
+
+
+_PARTS = {}
+_ADD_LOCK = threading.Lock()
+_CURRENT = {"world": None}      # the world whose bf16 copies an `adamw(p16_multicast=True)` sweep stores into
+
+
+def _peer_add(local: torch.Tensor, delta: torch.Tensor) -> None:
+    """``local`` (a view into one rank's symmetric gradient buffer) += delta, each element in its OWNER's copy."""
+    world, _rank = _WORLDS[local.untyped_storage().data_ptr()]
+    assert local.is_contiguous()
+    off, n = local.storage_offset(), local.numel()
+    flat = delta.reshape(-1).float()
+    with _ADD_LOCK:                                   # red.add is atomic; two threads' add_ on one slice are not
+        for o, sh in enumerate(world.shards):
+            a, b = max(off, sh.bounds[o]), min(off + n, sh.bounds[o + 1])
+            if b > a:
+                sh.g[a:b].add_(flat[a - off:b - off])
+
+
+class _PeerSink:
+    """Stands in for a PeerView destination inside the emulated kernels: ``add_`` goes to the owners."""
+
+    def __init__(self, pv):
+        self.t = pv.t
+        self.shape, self.dtype = pv.t.shape, pv.t.dtype
+
+    def add_(self, y):
+        _peer_add(self.t, y)
+        return self
+
+    def index_add_(self, dim, idx, src):
+        tmp = torch.zeros(self.t.shape, dtype=torch.float32)
+        tmp.index_add_(dim, idx, src)
+        _peer_add(self.t, tmp)
+        return self
+
+
 def _dst(t):
-    return t.t if hasattr(t, "is_peer") else t            # PeerView -> the local tensor
+    return _PeerSink(t) if hasattr(t, "is_peer") else t   # PeerView -> adds land in the owning rank's copy
 
 
 def _gelu_grad(x: torch.Tensor) -> torch.Tensor:
@@ -61,7 +154,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
         if accumulate:
             o.add_(y)
         else:
-            assert split_k == 1
+            assert split_k == 1 and not isinstance(o, _PeerSink), "owner-sharded outputs are reduce-only"
             o.copy_(y)
     else:
         assert o.dtype == torch.bfloat16 and not accumulate and split_k == 1
@@ -205,7 +298,6 @@ def sumsq(g, out):
 def adamw(p, g, m, v, p16, wd_mask, *, lr, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.1, step=1, sumsq_buf=None,
           max_norm=0.0, grad_div=1.0, zero_grad=True, dyn=None, sumsq_n=1, p16_multicast=False):
     CALLS["n"] += 1
-    assert not p16_multicast, "the owner-sharded path needs peer memory; not emulated"
     assert p.numel() % 4 == 0 and wd_mask.numel() * 256 >= p.numel()
     bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
     if dyn is not None:
@@ -222,7 +314,13 @@ def adamw(p, g, m, v, p16, wd_mask, *, lr, beta1=0.9, beta2=0.95, eps=1e-8, weig
     p.sub_(lr * ((m / bc1) / ((v / bc2).sqrt() + eps) + wd * p))
     if zero_grad:
         g.zero_()
-    p16.copy_(p)
+    if p16_multicast:
+        # `p16` is the multicast address of this range of the bf16 copy: one store lands in every rank's copy
+        lo = int(p16) // 2
+        for sh in _CURRENT["world"].shards:
+            sh.w[lo:lo + p.numel()].copy_(p)
+    else:
+        p16.copy_(p)
 
 
 def cast_f32_bf16(src, dst):
@@ -240,8 +338,21 @@ def gelu_bwd(x, dy, dx):
     dx.copy_(dy.float() * _gelu_grad(x.float()))
 
 
+def peer_push(dst_local, src):
+    CALLS["n"] += 1
+    _peer_add(dst_local, src)
+    src.zero_()
+
+
+def norm_share(parts_mc_ptr, mine, rank):
+    CALLS["n"] += 1
+    world = _PARTS[int(parts_mc_ptr)]
+    for sh in world.shards:
+        sh.parts[rank] = float(mine[0])
+
+
 def _needs_peer_memory(*_a, **_k):
-    raise AssertionError("peer-memory / multicast kernels are not emulated (owner-sharded and mc paths need GPUs)")
+    raise AssertionError("the multicast all-reduce (mc) path is not emulated")
 
 
 def install(monkeypatch=None) -> None:
@@ -254,7 +365,7 @@ def install(monkeypatch=None) -> None:
                  embedding3_bwd=embedding3_bwd, softmax_xent=softmax_xent, colsum=colsum, attention_fwd=attention_fwd,
                  attention_bwd=attention_bwd, qkv_gather_colsum=qkv_gather_colsum, sumsq=sumsq, adamw=adamw,
                  cast_f32_bf16=cast_f32_bf16, gelu_fwd=gelu_fwd, gelu_bwd=gelu_bwd, mc_push=_needs_peer_memory,
-                 peer_push=_needs_peer_memory, norm_share=_needs_peer_memory)
+                 peer_push=peer_push, norm_share=norm_share)
     # auto_split_k is host-side arithmetic: keep the real one (it asks num_sms(), which is emulated)
     for name, fn in table.items():
         if monkeypatch is not None:

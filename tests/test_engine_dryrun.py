@@ -550,3 +550,92 @@ def test_stall_exit_makes_a_pod_scope_restart_whole_again_in_seconds(tmp_path):
         finally:
             lc.jobs().delete("podscope")
             time.sleep(0.5)
+
+
+def test_owner_sharded_data_parallel_equals_one_replica_on_the_joint_batch(monkeypatch):
+    """The default multi-GPU algorithm (``AITJ_ALLREDUCE=rs``) with its peer-memory kernels emulated: two "ranks" (threads
+    with a real barrier where the device-side barriers are) each see half of a batch; gradient producers add every
+    piece into the copy of the rank that OWNS it, the owner clips on the exchanged partial norms and runs AdamW on its
+    shard only, and the bf16 parameters are stored into every rank's copy.  After three steps: (a) nothing is left in
+    any gradient buffer, (b) every rank holds the same bf16 parameters, (c) they equal -- to rounding -- those of ONE
+    engine that trained on the joint batch, as do the fp32 master weights of each rank's own shard."""
+    import threading
+
+    from trainingjob_operator_b200.models.gpt2 import GPT2Config, GPT2Engine
+
+    ke.install(monkeypatch)
+    cfg = GPT2Config(vocab_size=1000, n_layer=2, n_head=4, n_embd=256, block_size=128, name="t")
+    B, T, N, STEPS = 2, 128, 2, 3
+    g = torch.Generator().manual_seed(11)
+    toks = [torch.randint(0, cfg.vocab_size, (N * B, T), generator=g) for _ in range(STEPS)]
+
+    def perturb(eng):
+        gg = torch.Generator().manual_seed(9)
+        for s_ in eng.params.specs:
+            if len(s_.shape) == 1:
+                eng.params.w32(s_.name).add_(torch.randn(s_.shape, generator=gg) * 0.05)
+        eng.params.refresh_compute_copy()
+
+    # ---- reference: one replica, the joint batch
+    ref = GPT2Engine(cfg, N * B, T, "cpu", seed=3, gemm_backend="tcgen05")
+    perturb(ref)
+    for step in range(STEPS):
+        ref.tok.copy_(toks[step].view(-1))
+        ref.tgt.copy_(torch.roll(toks[step], -1, dims=1).reshape(-1))
+        ref.forward()
+        ref.backward()
+        ref.optimizer_step(lr=1e-3, step=step + 1, max_norm=0.5)
+
+    # ---- two owner-sharded ranks
+    fw = ke.FakeWorld(N)
+    ke._CURRENT["world"] = fw
+    engs = []
+    for r in range(N):
+        e = GPT2Engine(cfg, B, T, "cpu", seed=3, gemm_backend="tcgen05")
+        perturb(e)
+        fw.attach(e.params)
+        engs.append(e)
+    sh0 = fw.shards[0]
+    assert sh0.bounds[0] == 0 and sh0.bounds[-1] == engs[0].params.total and 0 < sh0.bounds[1] < sh0.bounds[2]
+    errors = []
+
+    def rank_main(r):
+        try:
+            e, sh = engs[r], fw.shards[r]
+            for step in range(STEPS):
+                mine = toks[step][r * B:(r + 1) * B]
+                e.tok.copy_(mine.reshape(-1))
+                e.tgt.copy_(torch.roll(mine, -1, dims=1).reshape(-1))
+                e.forward()
+                e.backward()
+                sh.barrier()                       # runtime/trainer.py:_device_step: every contribution has landed
+                e.optimizer_step(lr=1e-3, step=step + 1, max_norm=0.5, grad_div=float(N))
+                sh.barrier()                       # every rank's bf16 parameters arrived, every shard is zeroed
+        except Exception as ex:  # noqa: BLE001
+            errors.append((r, repr(ex)))
+            fw.sync.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(N)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    total = engs[0].params.total
+    for r, e in enumerate(engs):
+        sh = fw.shards[r]
+        assert sh.barriers == 3 * STEPS                                      # three device barriers per step
+        assert float(sh.g[:total].abs().max()) == 0.0                        # (a) owned range zeroed by the sweep,
+        assert float(e.params.g_small.abs().max()) == 0.0                    #     nothing left behind elsewhere
+        assert torch.equal(e.params.p16, engs[0].params.p16)                 # (b)
+        own = slice(sh.lo, sh.hi)
+        assert rel(e.params.p32[own], ref.params.p32[own]) < 2e-4, r         # (c) fp32 master weights of the shard
+    assert rel(engs[0].params.p16.float(), ref.params.p16.float()) < 2e-3    # (c) all-gathered bf16 copy
+    # the clip really engaged (max_norm 0.5 is below the gradient norm of this model), from the exchanged partial norms
+    assert float(fw.shards[0].parts[:N].sum()) > 0.25
+    # ... and with the right scale: the ranks' shards hold the SUM over ranks of per-rank mean gradients, the sweep divides
+    # by the world size, so sqrt(sum of partial square sums) / N is the joint batch's gradient norm (Adam's update is
+    # scale-invariant, so this is the assertion that sees a wrong grad_div or a double-counted contribution)
+    joint = float(ref.sumsq) ** 0.5
+    sharded = float(fw.shards[1].parts[:N].sum()) ** 0.5 / N
+    assert abs(sharded - joint) < 2e-3 * joint, (sharded, joint)
