@@ -639,3 +639,33 @@ def test_owner_sharded_data_parallel_equals_one_replica_on_the_joint_batch(monke
     joint = float(ref.sumsq) ** 0.5
     sharded = float(fw.shards[1].parts[:N].sum()) ** 0.5 / N
     assert abs(sharded - joint) < 2e-3 * joint, (sharded, joint)
+    # leaving the sharded mode (world shrank to one rank, re-bind after a re-rendezvous): private buffers again, the bf16
+    # parameters kept, gradients plain local tensors
+    P = engs[0].params
+    kept = P.p16.clone()
+    P.detach_shard()
+    assert P.shard is None and P.g_small is None and torch.equal(P.p16, kept) and P.p16 is not fw.shards[0].w
+    assert isinstance(P.grad("h0.fc_w"), torch.Tensor) and float(P.g32.abs().max()) == 0.0
+
+
+def test_bert_layout_can_be_owner_sharded(monkeypatch):
+    """The owner-sharded mode needs every 1-D parameter in one tail region of the flat layout and 32-row / 256-element
+    aligned ownership bounds: BERT's layout (three embedding tables, MLM head, decoder bias) qualifies, for 2..8 ranks."""
+    from trainingjob_operator_b200.models.bert import BertConfig, BertEngine
+    from trainingjob_operator_b200.parallel.symm import shard_bounds
+
+    ke.install(monkeypatch)
+    eng = BertEngine(BertConfig.tiny(), 2, 128, "cpu", seed=3)
+    P = eng.params
+    for world in (2, 3, 4, 8):
+        b = shard_bounds(P.specs, P.total, world)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == P.total and all(x % 256 == 0 for x in b)
+        assert all(b[i] <= b[i + 1] for i in range(world))
+        for x in b[1:-1]:                      # a bound inside a 2-D tensor sits on a multiple of 32 rows
+            s_ = next(s for s in P.specs if s.offset <= x < s.offset + s.padded)
+            if len(s_.shape) == 2 and x < s_.offset + s_.numel:
+                assert (x - s_.offset) % (32 * s_.shape[1]) == 0, (world, s_.name)
+    fw = ke.FakeWorld(2)
+    fw.attach(P)
+    lo, hi = P.small_range
+    assert all((len(s_.shape) == 1) == (lo <= s_.offset < hi) for s_ in P.specs)
