@@ -374,3 +374,87 @@ def install(monkeypatch=None) -> None:
             setattr(F, name, fn)
     CALLS["n"] = 0
     CALLS["gemm_block_n"] = []
+
+
+# ------------------------------------------------------------------------------------ streams (worst-case reordering)
+class LateStream:
+    """A side stream that runs everything AS LATE AS THE EVENTS ALLOW: kernels issued under ``torch.cuda.stream(side)`` are
+    queued with references to their (live) operand tensors and only executed when another stream waits for an event
+    recorded behind them.  A missing wait therefore shows up: the main stream has meanwhile overwritten an operand (or
+    reads a result that does not exist yet) and the numbers are wrong."""
+
+    def __init__(self):
+        self.queue = []
+        self.done = 0            # prefix of the queue that has been executed
+        self.reordered = 0       # kernels that ran after later main-stream work had been issued
+
+    def wait_event(self, ev):    # ordering INTO this stream: trivially met, nothing here runs early
+        pass
+
+    def run_until(self, pos: int) -> None:
+        while self.done < pos:
+            fn, issued_at = self.queue[self.done]
+            self.done += 1
+            if MAIN["issued"] > issued_at:
+                self.reordered += 1
+            fn()
+
+
+MAIN = {"issued": 0, "side": None}
+
+
+class _MainStream:
+    def wait_event(self, ev):
+        if ev.stream is not None:
+            ev.stream.run_until(ev.pos)
+
+
+class LateEvent:
+    def __init__(self, *a, **k):
+        self.stream, self.pos = None, 0
+
+    def record(self, stream=None):
+        stream = stream if stream is not None else (MAIN["side"] or _MAIN)
+        if isinstance(stream, LateStream):
+            self.stream, self.pos = stream, len(stream.queue)
+
+
+_MAIN = _MainStream()
+
+
+class _StreamCtx:
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        MAIN["side"] = self.stream if isinstance(self.stream, LateStream) else None
+
+    def __exit__(self, *exc):
+        MAIN["side"] = None
+        return False
+
+
+def install_late_streams(monkeypatch) -> None:
+    """``torch.cuda.{Stream, Event, stream, current_stream}`` replaced by the late-running model above; every emulated
+    kernel entry point becomes deferrable (it is queued when issued under a side stream)."""
+    from trainingjob_operator_b200.ops import functional as F
+
+    monkeypatch.setattr(torch.cuda, "Stream", LateStream)
+    monkeypatch.setattr(torch.cuda, "Event", LateEvent)
+    monkeypatch.setattr(torch.cuda, "stream", _StreamCtx)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: MAIN["side"] or _MAIN)
+    MAIN["issued"], MAIN["side"] = 0, None
+    for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "embedding_fwd", "embedding_bwd", "embedding3_fwd",
+                 "embedding3_bwd", "softmax_xent", "colsum", "attention_fwd", "attention_bwd", "qkv_gather_colsum", "sumsq",
+                 "adamw", "gelu_fwd", "gelu_bwd"):
+        real = getattr(F, name)
+
+        def kernel(*a, _real=real, **k):
+            side = MAIN["side"]
+            if side is not None:
+                side.queue.append((lambda: _real(*a, **k), MAIN["issued"]))
+                return None
+            MAIN["issued"] += 1
+            return _real(*a, **k)
+
+        monkeypatch.setattr(F, name, kernel)

@@ -669,3 +669,50 @@ def test_bert_layout_can_be_owner_sharded(monkeypatch):
     fw.attach(P)
     lo, hi = P.small_range
     assert all((len(s_.shape) == 1) == (lo <= s_.offset < hi) for s_ in P.specs)
+
+
+@pytest.mark.parametrize("model", ["gpt2", "bert"])
+@pytest.mark.parametrize("segment_join", [False, True], ids=["one-graph", "segments"])
+def test_side_stream_weight_gradients_have_no_ordering_hazard(monkeypatch, model, segment_join):
+    """``AITJ_WGRAD_STREAM=1`` launches the weight-gradient GEMMs on a side stream.  Here that stream runs everything as
+    LATE as its events allow (``kernel_emulation.LateStream``): if the main stream could overwrite an operand of a pending
+    weight-gradient GEMM, or read a gradient before it exists, the result differs from the reference model.  Checked for
+    both engines, in the one-graph mode and with a join at the end of every backward segment (bucketed DDP)."""
+    ke.install(monkeypatch)
+    if model == "gpt2":
+        cfg, eng, ref, tok, tgt = gpt2_pair(monkeypatch)
+        names, ref_loss = GPT2_GRADS, (lambda: ref(tok, tgt))
+    else:
+        from trainingjob_operator_b200.models.bert import BertConfig, BertEngine, BertReference, SyntheticMLM
+
+        cfg = BertConfig.tiny()
+        B, T = 2, 128
+        eng = BertEngine(cfg, B, T, "cpu", seed=3)
+        g = torch.Generator().manual_seed(9)
+        for s_ in eng.params.specs:
+            if len(s_.shape) == 1:
+                eng.params.w32(s_.name).add_(torch.randn(s_.shape, generator=g) * 0.05)
+        eng.params.w32("dec_b")[cfg.vocab_size:].zero_()
+        eng.params.refresh_compute_copy()
+        ref = BertReference(cfg, eng.params)
+        tok, typ, lab = SyntheticMLM(cfg.vocab_size, B, T, n_batches=1, seed=5, pin=False).next()
+        for dst, src in zip(eng.input_tensors(), (tok, typ, lab)):
+            dst.copy_(src)
+        names = ("wte", "wpe", "wtt", "h0.qkv_w", "h0.proj_w", "h0.fc_w", "h0.fc2_w", "h1.qkv_w", "h1.proj_w", "h1.fc_w",
+                 "h1.fc2_w", "mlm_w", "h0.fc_b", "h1.ln2_b")
+        ref_loss = lambda: ref(tok.view(B, T), typ.view(B, T), lab.view(B, T))          # noqa: E731
+    ke.install_late_streams(monkeypatch)          # (after the engines exist: wraps the emulated kernels installed above)
+    side = ke.LateStream()
+    eng.wgrad_stream = side
+    eng.segment_join = segment_join
+    eng.params.g32.zero_()
+    eng.forward()
+    eng.backward()
+    assert side.done == len(side.queue) > 0, "weight-gradient GEMMs left unexecuted: a join is missing"
+    if not segment_join:
+        assert side.reordered > 0           # the model really ran them behind later main-stream work
+    loss = ref_loss()
+    loss.backward()
+    for name in names:
+        gref, got = ref.p(name).grad, eng.params.grad(name)
+        assert rel(got, gref) < 6e-2, (name, rel(got, gref))

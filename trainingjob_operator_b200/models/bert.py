@@ -272,6 +272,9 @@ class BertEngine(GPT2Engine):
     @torch.no_grad()
     def _bwd_tail(self) -> None:
         F, P = self.F, self.params
+        # layer 0's weight-gradient GEMMs may still read the buffer d_e is about to occupy (found by the late-stream model
+        # of tests/kernel_emulation.py: h0.proj_w came out wrong with AITJ_WGRAD_STREAM=1)
+        self._join_wgrads()
         d_e = next(t for t in self.d_x if t is not self._d_cur)
         F.layernorm_bwd(self._d_cur, self.e0, P.w16("emb_ln_w"), self.e_mean, self.e_rstd, d_e, P.grad("emb_ln_w"),
                         P.grad("emb_ln_b"))
