@@ -52,44 +52,51 @@ out = {"model": model, "gpus": n, "warm_pool": pool, "rescales": []}
 opt = TrainingJobOperatorOption(thread_num=2, scale_down_grace=60.0)
 with LocalCluster(num_gpus=n, option=opt, workdir=f"/tmp/aitj-elastic-{pool}", warm_pool=pool,
                   gpu_visibility=os.environ.get("AITJ_GPU_VISIBILITY", "all")) as lc:
-    if pool:
-        wait(lambda: lc.agent.warm_ready() >= pool, 120)
-    t_submit = time.time()
-    lc.apply(job)
-    wait(lambda: "aitj.b200/worker-trace" in lc.jobs().get("elastic").annotations)
-    out["submit_to_first_step_s"] = round(time.time() - t_submit, 3)
-    base = pids(lc)
-    gen = 1
-    for target in [n, max(start, n // 2)]:
-        if target == lc.jobs().get("elastic").spec.replica_specs["trainer"].replicas:
-            continue
-        gen += 1
+    try:
         if pool:
-            wait(lambda: lc.agent.warm_ready() >= min(pool, max(0, target - start)), 120)
-        t0 = time.time()
-        lc.jobs().patch("elastic", {"spec": {"replicaSpecs": {"trainer": {"replicas": target}}}})
-        rec = wait(lambda: (lambda a: json.loads(a["aitj.b200/rescale-trace"])
-                            if json.loads(a.get("aitj.b200/rescale-trace", "{}")).get("generation") == gen else None)(
-            lc.jobs().get("elastic").annotations))
-        rec["target"] = target
-        rec["patch_to_first_step_s"] = round(time.time() - t0, 3)
-        wait(lambda: len([p for p in lc.pods(selector="TrainingJobName=elastic")
-                          if "aitj.b200/scale-down" not in (p["metadata"].get("annotations") or {})]) == target and
-             lc.jobs().get("elastic").status.phase == "Running", 120)
-        now = pids(lc)
-        rec["survivors_kept_pid"] = all(now.get(k) == v for k, v in base.items() if k in now)
-        out["rescales"].append(rec)
-        print("rescale", rec, flush=True)
-        time.sleep(2.0)
-    j = lc.jobs().get("elastic")
-    out["restart_counts"] = j.status.restart_counts
-    out["phase"] = j.status.phase
-    lc.jobs().delete("elastic")
-    time.sleep(1.0)
-    import shutil
-    dst = f"gpurun_out/elastic_logs_{model}_n{n}_pool{pool}"
-    shutil.rmtree(dst, ignore_errors=True)
-    shutil.copytree(os.path.join(lc.workdir, "logs"), dst, dirs_exist_ok=True)
+            wait(lambda: lc.agent.warm_ready() >= pool, 120)
+        t_submit = time.time()
+        lc.apply(job)
+        wait(lambda: "aitj.b200/worker-trace" in lc.jobs().get("elastic").annotations)
+        out["submit_to_first_step_s"] = round(time.time() - t_submit, 3)
+        base = pids(lc)
+        gen = 1
+        for target in [n, max(start, n // 2)]:
+            if target == lc.jobs().get("elastic").spec.replica_specs["trainer"].replicas:
+                continue
+            gen += 1
+            if pool:
+                wait(lambda: lc.agent.warm_ready() >= min(pool, max(0, target - start)), 120)
+            t0 = time.time()
+            lc.jobs().patch("elastic", {"spec": {"replicaSpecs": {"trainer": {"replicas": target}}}})
+            rec = wait(lambda: (lambda a: json.loads(a["aitj.b200/rescale-trace"])
+                                if json.loads(a.get("aitj.b200/rescale-trace", "{}")).get("generation") == gen else None)(
+                lc.jobs().get("elastic").annotations))
+            rec["target"] = target
+            rec["patch_to_first_step_s"] = round(time.time() - t0, 3)
+            wait(lambda: len([p for p in lc.pods(selector="TrainingJobName=elastic")
+                              if "aitj.b200/scale-down" not in (p["metadata"].get("annotations") or {})]) == target and
+                 lc.jobs().get("elastic").status.phase == "Running", 120)
+            now = pids(lc)
+            rec["survivors_kept_pid"] = all(now.get(k) == v for k, v in base.items() if k in now)
+            out["rescales"].append(rec)
+            print("rescale", rec, flush=True)
+            time.sleep(2.0)
+        j = lc.jobs().get("elastic")
+        out["restart_counts"] = j.status.restart_counts
+        out["phase"] = j.status.phase
+        lc.jobs().delete("elastic")
+        time.sleep(1.0)
+        import shutil
+        dst = f"gpurun_out/elastic_logs_{model}_n{n}_pool{pool}"
+        shutil.rmtree(dst, ignore_errors=True)
+        shutil.copytree(os.path.join(lc.workdir, "logs"), dst, dirs_exist_ok=True)
+    except (TimeoutError, KeyError, OSError) as err:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from _postmortem import dump
+
+        dump(lc, "elastic", out, "see the last line printed above", err, f"elastic_gpu_check_{model}_n{n}_pool{pool}")
+        raise
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open(f"gpurun_out/elastic_gpu_check_{model}_n{n}_pool{pool}.json", "w"), indent=1)
 print(json.dumps(out))

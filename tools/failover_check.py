@@ -52,22 +52,29 @@ opt.leader_election.lease_duration, opt.leader_election.renew_deadline, opt.lead
     lease, lease / 3.0, lease / 5.0
 out = {"model": model, "replicas": n, "steps": steps, "lease_s": lease, "crash": "--graceful" not in sys.argv}
 with LocalCluster(num_gpus=0 if cpu else n, operators=2, option=opt, workdir="/tmp/aitj-failover") as lc:
-    lock = lambda: json.loads(lc.clientset.core_v1().endpoints("kube-system").get("trainingjob-operator")  # noqa: E731
-                              ["metadata"]["annotations"]["control-plane.alpha.kubernetes.io/leader"])
-    lc.apply(job)
-    wait(lambda: "aitj.b200/worker-trace" in lc.jobs().get("ha").annotations)
-    pids = {sid: p for sid, p in lc.agent.sup.list()}
-    leader = lock()["holderIdentity"]
-    t0 = time.time()
-    lc.stop_operator(int(leader[-1]), crash="--graceful" not in sys.argv)
-    wait(lambda: lock()["holderIdentity"] not in ("", leader), timeout=lease * 3 + 30)
-    out["takeover_s"] = round(time.time() - t0, 3)
-    out["workers_untouched"] = {sid: p for sid, p in lc.agent.sup.list()} == pids
-    final = lc.wait_for_phase("ha", "Succeed", timeout=600)
-    out["phase"] = final.status.phase
-    out["restart_counts"] = final.status.restart_counts
-    out["metrics"] = json.loads(final.annotations.get("aitj.b200/metrics", "{}"))
-    out["new_leader"] = lock()["holderIdentity"]
+    try:
+        lock = lambda: json.loads(lc.clientset.core_v1().endpoints("kube-system").get("trainingjob-operator")  # noqa: E731
+                                  ["metadata"]["annotations"]["control-plane.alpha.kubernetes.io/leader"])
+        lc.apply(job)
+        wait(lambda: "aitj.b200/worker-trace" in lc.jobs().get("ha").annotations)
+        pids = {sid: p for sid, p in lc.agent.sup.list()}
+        leader = lock()["holderIdentity"]
+        t0 = time.time()
+        lc.stop_operator(int(leader[-1]), crash="--graceful" not in sys.argv)
+        wait(lambda: lock()["holderIdentity"] not in ("", leader), timeout=lease * 3 + 30)
+        out["takeover_s"] = round(time.time() - t0, 3)
+        out["workers_untouched"] = {sid: p for sid, p in lc.agent.sup.list()} == pids
+        final = lc.wait_for_phase("ha", "Succeed", timeout=600)
+        out["phase"] = final.status.phase
+        out["restart_counts"] = final.status.restart_counts
+        out["metrics"] = json.loads(final.annotations.get("aitj.b200/metrics", "{}"))
+        out["new_leader"] = lock()["holderIdentity"]
+    except (TimeoutError, KeyError, OSError) as err:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from _postmortem import dump
+
+        dump(lc, "ha", out, "see the last line printed above", err, f"failover_check_{model}_n{n}")
+        raise
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open(f"gpurun_out/failover_check_{model}_n{n}.json", "w"), indent=1)
 print(json.dumps(out))

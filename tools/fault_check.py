@@ -85,30 +85,9 @@ STAGE = {"at": "cluster start"}
 
 
 def post_mortem(lc, err):
-    """A wait ran out: leave what is needed to see why -- the stage, the job's status / annotations and the tail of every
-    worker log -- in gpurun_out/ (a GPU box is gone after the call; round 2 lost a 4-GPU call to five silent time-outs)."""
-    rec = dict(out, failed_at=STAGE["at"], error=f"{type(err).__name__}: {err}")
-    try:
-        j = lc.jobs().get("ft")
-        rec["phase"] = j.status.phase
-        rec["conditions"] = [f"{c.type}: {c.message}" for c in j.status.conditions][-8:]
-        rec["restart_counts"] = j.status.restart_counts
-        rec["annotations"] = {k: v[:400] for k, v in (j.annotations or {}).items() if k.startswith("aitj.b200/")}
-        rec["rendezvous"] = getattr(j.status, "rendezvous", None) and j.status.rendezvous.__dict__
-    except Exception as e:  # noqa: BLE001
-        rec["job_read_error"] = repr(e)
-    try:
-        rec["processes"] = [sid for sid, _ in lc.agent.sup.list()]
-        logs = os.path.join(lc.workdir, "logs")
-        rec["logs"] = {fn: open(os.path.join(logs, fn), errors="replace").read()[-3000:]
-                       for fn in sorted(os.listdir(logs)) if fn.endswith(".log")}
-    except Exception as e:  # noqa: BLE001
-        rec["log_read_error"] = repr(e)
-    os.makedirs("gpurun_out", exist_ok=True)
-    tag = "ft" if ft else scope.lower()
-    path = f"gpurun_out/fault_check_{model}_n{n}_pool{pool}_{tag}_FAILED_{int(time.time())}.json"
-    json.dump(rec, open(path, "w"), indent=1, default=str)
-    print(json.dumps({"failed_at": rec["failed_at"], "error": rec["error"], "post_mortem": path}), flush=True)
+    from _postmortem import dump
+
+    dump(lc, "ft", out, STAGE["at"], err, f"fault_check_{model}_n{n}_pool{pool}_{'ft' if ft else scope.lower()}")
 
 
 with LocalCluster(num_gpus=n if (fake_gpus or not cpu) else 0, option=TrainingJobOperatorOption(thread_num=2),
