@@ -263,6 +263,9 @@ class StallBreaker:
         self.generation = 0
         self.last_progress = time.time()
         self.in_step = False          # only a rank that sits inside a training step can be stuck behind a dead peer
+        # how long one step may take before it counts as stuck: ``after_s``, except for the first step after a (re-)bind,
+        # which legitimately takes seconds (kernel loading, CUDA-graph capture) -- the worker raises it for that step
+        self.patience = after_s
         self.tripped = False
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, name="stall-breaker", daemon=True)
@@ -274,7 +277,7 @@ class StallBreaker:
 
     def _run(self) -> None:
         while not self._stop.wait(0.5):
-            if self.tripped or not self.in_step or time.time() - self.last_progress < self.after_s \
+            if self.tripped or not self.in_step or time.time() - self.last_progress < self.patience \
                     or not dist.is_initialized():
                 continue
             latest = self.watcher.fetch_now()

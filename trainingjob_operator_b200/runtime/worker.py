@@ -445,6 +445,7 @@ def run(args) -> Dict[str, Any]:
     timed_from = -1          # first step inside the timed region (-1: not armed yet)
     step = joined_step
     first_step_done = False
+    warmed_generation = -1          # generation whose trainer has completed at least one step
     pending_rescale = None
     from ..ops import lib as oplib
 
@@ -506,12 +507,15 @@ def run(args) -> Dict[str, Any]:
                 launches0 = oplib.LAUNCHES
             if breaker is not None:
                 breaker.progress(generation)
+                # the first step on a freshly bound trainer captures CUDA graphs / loads kernels: seconds, not a stall
+                breaker.patience = breaker.after_s if warmed_generation == generation else max(breaker.after_s, 30.0)
                 breaker.in_step = True
             try:
                 loss = adapter.train_step()
             finally:
                 if breaker is not None:
                     breaker.in_step = False
+            warmed_generation = generation
             if breaker is not None and breaker.tripped:
                 raise RuntimeError("the communicator was aborted while this step was in flight")
         except RuntimeError as e:
