@@ -99,8 +99,11 @@ def test_e2e_job_on_gpu_through_the_control_plane(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.gpu2
 def test_fused_gemm_allreduce_matches_nccl_sum_on_two_gpus():
-    """GEMM->all-reduce fused through the NVSwitch multicast alias == local gradients + NCCL all-reduce."""
+    """tools/ddp_check.py on two GPUs: the owner-sharded gradient path (wgrad GEMM epilogue -> reduce-scatter to the owner
+    over NVLink peer memory, sharded AdamW, multicast all-gather) and the round-1 multicast all-reduce path against local
+    gradients + NCCL all-reduce."""
     import torch
 
     if torch.cuda.device_count() < 2:

@@ -40,6 +40,7 @@ def test_async_checkpoint_snapshots_in_stream_order_on_the_device(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.gpu2
 def test_fault_tolerant_recovery_keeps_the_survivor_on_its_gpu(tmp_path):
     """In-place recovery over NCCL (needs two GPUs): SIGKILL rank 1 of a faultTolerant BERT-shaped job; rank 0 keeps its
     process, CUDA context and state (the StallBreaker aborts the communicator it is stuck in), the replacement joins."""
