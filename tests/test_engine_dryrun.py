@@ -469,9 +469,13 @@ def test_stall_breaker_recovers_four_ranks_whose_collectives_hang_like_nccl(tmp_
             # ---- second victim: rank 0 (the rank the others take their state from)
             gen = ann(lc, "rescale-trace")["generation"]
             before = pids(lc)
+            t_kill = time.time()
             os.kill(before["hang-trainer-0"], signal.SIGKILL)
             rec = wait(lambda: (lambda r: r if r and r.get("generation", 0) > gen and r.get("recovered_from") else None)(
                 ann(lc, "rescale-trace")))
+            # the survivors' trainers were warm: the breaker's ordinary threshold applies (not the 30 s it grants the
+            # first step after a re-bind), also when the rank sits in the generation agreement rather than in the step
+            assert rec["at"] - t_kill < 15.0, rec["at"] - t_kill
             wait(lambda: (lambda x: x.status.phase == "Running" and
                           x.status.replica_statuses["trainer"].active == 4)(lc.jobs().get("hang")))
             now = pids(lc)

@@ -142,7 +142,8 @@ def test_every_pass_of_a_live_cluster_replays_to_the_decision_it_took(tmp_path, 
             time.sleep(0.01)
         raise TimeoutError
 
-    with LocalCluster(num_gpus=0, workdir=str(tmp_path / "wd"), option=TrainingJobOperatorOption(thread_num=2)) as lc:
+    opt = TrainingJobOperatorOption(thread_num=2, scale_down_grace=1.0)       # (default drain grace: 30 s)
+    with LocalCluster(num_gpus=0, workdir=str(tmp_path / "wd"), option=opt) as lc:
         lc.apply(job("ok", ["/bin/sh", "-c", "sleep 0.2"], 2))
         lc.apply(job("bad", ["/bin/sh", "-c", "sleep 0.1; exit 3"], 2))
         lc.apply(job("el", ["/bin/sleep", "600"], 2, minReplicas=1, maxReplicas=4, edlPolicy="Manual",

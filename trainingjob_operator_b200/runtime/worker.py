@@ -456,6 +456,8 @@ def run(args) -> Dict[str, Any]:
     while step < total and not stop["flag"]:
         if breaker is not None:
             breaker.progress(generation)
+            # the first step on a freshly bound trainer captures CUDA graphs / loads kernels: seconds, not a stall
+            breaker.patience = breaker.after_s if warmed_generation == generation else max(breaker.after_s, 30.0)
         failure = None
         try:
             # ---- elastic: agree on the newest rendezvous generation at the step boundary ------------
@@ -507,8 +509,6 @@ def run(args) -> Dict[str, Any]:
                 launches0 = oplib.LAUNCHES
             if breaker is not None:
                 breaker.progress(generation)
-                # the first step on a freshly bound trainer captures CUDA graphs / loads kernels: seconds, not a stall
-                breaker.patience = breaker.after_s if warmed_generation == generation else max(breaker.after_s, 30.0)
                 breaker.in_step = True
             try:
                 loss = adapter.train_step()
