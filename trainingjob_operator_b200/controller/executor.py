@@ -116,7 +116,11 @@ class Executor:
                 self.pod_control.create_pods_with_controller_ref(job.namespace, c.template, job, ref)
             except APIError as e:
                 self.expectations.creation_observed(gen_expectation_pods_key(job.key(), c.role))
-                if e.reason != "AlreadyExists":
+                # AlreadyExists: the informer is behind our own create.  An owner that no longer exists: the job was
+                # deleted while this pass ran on a cached copy (the API server refuses to create the orphan) -- nothing
+                # to retry, the deletion event ends the job's reconciliation.
+                gone = e.reason == "NotFound" and "refusing to create an orphan" in (e.message or "")
+                if e.reason != "AlreadyExists" and not gone:
                     errors.append(e)
                 return
             metrics.observe("aitj_pod_create_seconds", time.perf_counter() - t0)
