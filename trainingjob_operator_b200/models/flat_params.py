@@ -71,7 +71,7 @@ class FlatParams:
         import os
 
         on_host = os.environ.get("AITJ_PARAM_INIT") == "cpu"     # the numerics self-check keeps its historical weights
-        gen = torch.Generator(device="cpu" if on_host else self.device)
+        gen = torch.Generator(device="cpu" if on_host else self.p32.device)    # the buffer's concrete device (cuda:N)
         gen.manual_seed(seed)
         for s in self.specs:
             view = self.p32[s.offset:s.offset + s.numel].view(s.shape)
