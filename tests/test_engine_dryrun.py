@@ -720,3 +720,44 @@ def test_side_stream_weight_gradients_have_no_ordering_hazard(monkeypatch, model
     for name in names:
         gref, got = ref.p(name).grad, eng.params.grad(name)
         assert rel(got, gref) < 6e-2, (name, rel(got, gref))
+
+
+@pytest.mark.parametrize("model", ["gpt2", "bert"])
+@pytest.mark.parametrize("side_stream", [False, True], ids=["in-line", "side-stream"])
+def test_gradient_buckets_are_final_when_their_hook_fires(monkeypatch, model, side_stream):
+    """Bucketed DDP starts a bucket's all-reduce the moment the engine calls ``grad_hook(bucket)``: from then on nothing may
+    add to that slice of the flat gradient buffer (the tied embedding gets contributions from the head AND the tail; the
+    1-D parameters from every layer).  The hook here snapshots the slice; at the end of backward it must be unchanged --
+    also with the weight-gradient GEMMs on the late-running side stream, where the per-segment join is what guarantees it."""
+    ke.install(monkeypatch)
+    if model == "gpt2":
+        cfg, eng, ref, tok, tgt = gpt2_pair(monkeypatch)
+    else:
+        from trainingjob_operator_b200.models.bert import BertConfig, BertEngine, SyntheticMLM
+
+        cfg = BertConfig.tiny()
+        eng = BertEngine(cfg, 2, 128, "cpu", seed=3)
+        for dst, src in zip(eng.input_tensors(), SyntheticMLM(cfg.vocab_size, 2, 128, n_batches=1, seed=5, pin=False).next()):
+            dst.copy_(src)
+    if side_stream:
+        ke.install_late_streams(monkeypatch)
+        eng.wgrad_stream = ke.LateStream()
+    eng.segment_join = True                       # what EngineTrainer sets when a bucket reducer is attached
+    ranges = {name: (a, b) for name, a, b in eng.grad_buckets()}
+    assert sum(b - a for a, b in ranges.values()) == eng.params.total          # the buckets tile the whole buffer
+    seen = {}
+
+    def hook(name):
+        assert name in ranges and name not in seen, name
+        a, b = ranges[name]
+        seen[name] = eng.params.g32[a:b].clone()
+
+    eng.grad_hook = hook
+    eng.params.g32.zero_()
+    eng.forward()
+    eng.backward()
+    assert set(seen) == set(ranges)
+    for name, snap in seen.items():
+        a, b = ranges[name]
+        assert torch.equal(snap, eng.params.g32[a:b]), f"bucket {name} was still written after its hook"
+        assert float(snap.abs().max()) > 0
