@@ -135,6 +135,66 @@ static void stress_store() {
   CHECK(s.num_watchers() == 0);
 }
 
+// Owner index under concurrency: every thread creates jobs with dependents (some adopted later by an update, some
+// handed to another owner, some deleted on their own), deletes the jobs and checks the cascade took exactly the
+// dependents that belonged to it at that moment; a batched watcher drains every event in between.
+static void stress_store_cascade() {
+  Store s("", 1 << 16);
+  std::atomic<bool> stop{false};
+  std::atomic<long> events{0};
+  std::thread watcher([&] {
+    int64_t id = s.watch_open("Pod", "", 0);
+    while (!stop.load()) events += static_cast<long>(s.watch_next_many(id, 0.02, 32).size());
+    for (;;) {
+      auto batch = s.watch_next_many(id, 0.0, 64, false);
+      if (batch.empty()) break;
+      events += static_cast<long>(batch.size());
+    }
+    s.watch_close(id);
+  });
+  std::vector<std::thread> ts;
+  for (int t = 0; t < 4; ++t)
+    ts.emplace_back([&, t] {
+      for (int i = 0; i < 150; ++i) {
+        const std::string tag = std::to_string(t) + "-" + std::to_string(i);
+        StoredObject job;
+        job.kind = "AITrainingJob"; job.ns = "ns"; job.name = "j-" + tag; job.uid = "uj-" + tag; job.data = "{}";
+        s.create(job);
+        StoredObject other = job;
+        other.name = "o-" + tag; other.uid = "uo-" + tag;
+        s.create(other);
+        for (int k = 0; k < 4; ++k) {
+          StoredObject pod;
+          pod.kind = "Pod"; pod.ns = "ns"; pod.name = "p-" + tag + "-" + std::to_string(k);
+          pod.uid = "up-" + tag + "-" + std::to_string(k); pod.data = "{}";
+          if (k != 3) pod.owner_uids = {job.uid};            // k == 3 starts as an orphan
+          s.create(pod);
+        }
+        StoredObject adopt = s.get("Pod", "ns", "p-" + tag + "-3");
+        adopt.owner_uids = {job.uid};
+        s.update(adopt, 0);                                   // adopted by the job
+        StoredObject moved = s.get("Pod", "ns", "p-" + tag + "-0");
+        moved.owner_uids = {other.uid};
+        s.update(moved, 0);                                   // handed to the other owner
+        s.remove("Pod", "ns", "p-" + tag + "-1");            // a dependent that goes on its own
+        auto removed = s.remove("AITrainingJob", "ns", job.name);
+        CHECK(removed.size() == 3);                           // the job, p-2 and the adopted p-3
+        bool still = true;
+        try { (void)s.get("Pod", "ns", "p-" + tag + "-0"); } catch (const StoreError&) { still = false; }
+        CHECK(still);                                         // p-0 belongs to `other` now
+        removed = s.remove("AITrainingJob", "ns", other.name);
+        CHECK(removed.size() == 2);
+      }
+    });
+  for (auto& t : ts) t.join();
+  std::this_thread::sleep_for(std::chrono::milliseconds(50));
+  stop = true;
+  watcher.join();
+  CHECK(s.count("Pod") == 0 && s.count("AITrainingJob") == 0);
+  CHECK(events.load() == 4L * 150 * (4 + 2 + 4));             // per round: 4 ADDED, 2 MODIFIED, 4 DELETED pod events
+  CHECK(s.num_watchers() == 0);
+}
+
 static void stress_supervisor() {
   Supervisor sup;
   std::map<std::string, std::string> env{{"PATH", "/usr/bin:/bin"}};
@@ -224,6 +284,7 @@ int main() {
   stress_queue();
   stress_expectations();
   stress_store();
+  stress_store_cascade();
   stress_supervisor();
   std::puts("core stress ok");
   return 0;
