@@ -104,3 +104,17 @@ def test_kernel_entry_points_agree_between_cuda_sources_ctypes_table_and_call_si
                     f"{path}:{node.lineno}: {fname} called with {nargs} arguments, signature has {len(lib._SIGS[fname])}"
                 seen += 1
     assert seen >= 20, seen
+
+
+def test_every_environment_knob_is_documented():
+    """docs/ENVIRONMENT.md lists every ``AITJ_*`` variable the package reads or sets (compile-time macros excepted)."""
+    doc = open(os.path.join(ROOT, "docs", "ENVIRONMENT.md")).read()
+    macros = {"AITJ_DISPATCH", "AITJ_PAIR", "AITJ_MBAR_DEBUG", "AITJ_ATTN_DEBUG"}
+    used = set()
+    pkg = os.path.join(ROOT, "trainingjob_operator_b200")
+    for d, _dirs, names in os.walk(pkg):
+        for n in names:
+            if n.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                used |= set(re.findall(r"\bAITJ_[A-Z0-9_]+\b", open(os.path.join(d, n), errors="replace").read()))
+    missing = sorted(v for v in used - macros if v not in doc)
+    assert not missing, missing
