@@ -318,3 +318,34 @@ def test_http_server_request_line_keep_alive_and_errors_over_a_raw_socket():
         s.close()
     finally:
         srv.stop()
+
+
+def test_lean_header_parser_agrees_with_the_stdlib_parser_on_generated_blocks():
+    """Property test: for header blocks made of token names and printable values (the shapes HTTP clients send), the
+    lean parser returns what ``http.client.parse_headers`` returns for every name, in any letter case."""
+    import http.client
+    import io
+
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from trainingjob_operator_b200.store.fasthttp import read_headers
+
+    name = st.text(alphabet="abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789-", min_size=1, max_size=12)
+    value = st.text(alphabet=st.characters(min_codepoint=0x21, max_codepoint=0x7e), min_size=0, max_size=40)
+    pad = st.sampled_from(["", " ", "  ", "\t"])
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.tuples(name, pad, value, pad), min_size=0, max_size=12))
+    def check(items):
+        raw = "".join(f"{n}:{p1}{v}{p2}\r\n" for n, p1, v, p2 in items).encode("iso-8859-1") + b"\r\nrest"
+        ours = read_headers(io.BytesIO(raw))
+        ref = http.client.parse_headers(io.BytesIO(raw))
+        for n, _p1, _v, _p2 in items:
+            vals = ref.get_all(n)
+            assert vals is not None
+            for probe in (n, n.lower(), n.upper()):
+                assert ours.get(probe) == ", ".join(x.strip() for x in vals), (raw, n)
+        assert ours.get("x-not-there") is None and len(ours) == len({n.lower() for n, *_ in items})
+
+    check()

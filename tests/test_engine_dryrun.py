@@ -76,6 +76,32 @@ def test_gpt2_engine_control_flow_matches_the_reference_model(monkeypatch, env):
         assert 512 not in ke.CALLS["gemm_block_n"]
 
 
+def test_library_gemm_arm_of_the_engine_matches_the_reference_model(monkeypatch):
+    """``--gemm cublas`` (the A/B arm: library matmuls + standalone element-wise kernels instead of fused epilogues) walks
+    the other branch of every GEMM front-end; same gradients."""
+    from trainingjob_operator_b200.models.gpt2 import GPT2Config, GPT2Engine, GPT2Reference
+
+    ke.install(monkeypatch)
+    cfg = GPT2Config(vocab_size=1000, n_layer=2, n_head=4, n_embd=256, block_size=128, name="t")
+    B, T = 2, 128
+    eng = GPT2Engine(cfg, B, T, "cpu", seed=3, gemm_backend="cublas")
+    ref = GPT2Reference(cfg, eng.params)
+    tok = torch.randint(0, cfg.vocab_size, (B, T), generator=torch.Generator().manual_seed(5))
+    tgt = torch.roll(tok, -1, dims=1)
+    eng.tok.copy_(tok.view(-1))
+    eng.tgt.copy_(tgt.view(-1))
+    n0 = len(ke.CALLS["gemm_block_n"])
+    eng.params.g32.zero_()
+    eng.forward()
+    eng.backward()
+    assert len(ke.CALLS["gemm_block_n"]) == n0                    # no hand-written GEMM on this arm
+    loss = ref(tok, tgt)
+    loss.backward()
+    assert abs(float(eng.loss) - float(loss.detach())) < 2e-2 * float(loss.detach())
+    for name in ("wte", "wpe", "h0.qkv_w", "h0.qkv_b", "h0.proj_w", "h0.fc_w", "h0.fc_b", "h0.fc2_w", "h1.ln2_w", "lnf_b"):
+        assert rel(eng.params.grad(name), ref.p(name).grad) < 6e-2, name
+
+
 def test_gpt2_engine_optimizer_reduces_the_loss_and_keeps_the_compute_copy_in_sync(monkeypatch):
     cfg, eng, ref, tok, tgt = gpt2_pair(monkeypatch)
     eng.params.g32.zero_()
