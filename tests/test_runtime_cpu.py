@@ -469,3 +469,25 @@ def test_owner_shard_bounds_are_balanced_and_aligned():
                     assert (x - s.offset) % (32 * s.shape[1]) == 0, (s.name, x)
             shares = [(b[i + 1] - b[i]) * world / P.total for i in range(world)]
             assert 0.9 < min(shares) and max(shares) < 1.1, shares
+
+
+@pytest.mark.parametrize("name,batch,params", [("mnist", 32, 1_199_882), ("resnet50", 2, 25_557_032)])
+def test_nn_module_workers_step_on_cpu(name, batch, params):
+    """BASELINE configs 2 and 3 (MNIST CNN, ResNet-50 -- own definition, the canonical 25,557,032 parameters) through the
+    worker's nn.Module adapter: flat parameter / gradient buffers, fused optimizer sweep, state hand-off tensors."""
+    import types
+
+    from trainingjob_operator_b200.runtime import worker as W
+
+    args = types.SimpleNamespace(seed=0, lr=1e-3, no_graph=True, gemm="tcgen05")
+    ad = W.TorchAdapter(name, batch, args, torch.device("cpu"))
+    ad.bind(None)
+    assert sum(p.numel() for p in ad.module.parameters()) == params
+    losses = [float(ad.train_step()) for _ in range(2)]
+    assert all(l == l and abs(l) < 1e4 for l in losses)
+    state = ad.state_tensors()
+    assert state and all(t.dtype == torch.float32 for t in state)
+    snap = [t.clone() for t in state]
+    ad.train_step()
+    assert any(not torch.equal(a, b) for a, b in zip(snap, state))       # the state tensors ARE the live state
+    ad.after_state_load()
