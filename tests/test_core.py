@@ -293,3 +293,40 @@ def test_store_wal_cut_right_after_a_records_last_digit(tmp_path):
     del s2
     s3 = core.Store(wal)
     assert s3.count("Pod") == 2 and s3.current_rv() == 2
+
+
+def test_native_tree_copy_equals_deepcopy_on_random_json_trees():
+    """``core.jcopy`` (behind ``meta.deepcopy`` and the typed conversions): equal to ``copy.deepcopy`` on arbitrary JSON-shaped
+    trees, shares no container with its input, leaves non-JSON members to the fallback, and refuses cyclic input."""
+    import copy
+
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    leaves = st.one_of(st.none(), st.booleans(), st.integers(), st.floats(allow_nan=False), st.text(max_size=8),
+                       st.binary(max_size=4))
+    trees = st.recursive(leaves, lambda kids: st.one_of(st.lists(kids, max_size=4),
+                                                        st.dictionaries(st.text(max_size=5), kids, max_size=4)), max_leaves=25)
+
+    def containers(x, out):
+        if isinstance(x, (dict, list)):
+            out.append(id(x))
+            for v in (x.values() if isinstance(x, dict) else x):
+                containers(v, out)
+        return out
+
+    @settings(max_examples=300, deadline=None)
+    @given(trees)
+    def check(tree):
+        c = core.jcopy(tree, copy.deepcopy)
+        assert c == tree and type(c) is type(tree)
+        assert not (set(containers(tree, [])) & set(containers(c, [])))
+
+    check()
+    odd = {"t": (1, [2]), "s": {3}, "d": {"k": [1, {"z": None}]}}
+    c = core.jcopy(odd, copy.deepcopy)
+    assert c == odd and c["t"] is not odd["t"] and c["s"] is not odd["s"] and c["d"]["k"] is not odd["d"]["k"]
+    loop = []
+    loop.append(loop)
+    with pytest.raises(RecursionError):
+        core.jcopy(loop, copy.deepcopy)
