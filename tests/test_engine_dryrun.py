@@ -425,8 +425,10 @@ sys.exit(W.main(sys.argv[1:]))
 
 
 @pytest.mark.slow
-def test_stall_breaker_recovers_four_ranks_whose_collectives_hang_like_nccl(tmp_path):
-    """BASELINE config 4's shape (4 ranks, SIGKILL rank 3, ``faultTolerant``) with collectives that HANG when a peer dies,
+@pytest.mark.parametrize("model", ["mlp", "bert-tiny"])
+def test_stall_breaker_recovers_four_ranks_whose_collectives_hang_like_nccl(tmp_path, model):
+    """(``bert-tiny``: the engine adapter with emulated kernels -- the flat engine state is what is handed over.)
+    BASELINE config 4's shape (4 ranks, SIGKILL rank 3, ``faultTolerant``) with collectives that HANG when a peer dies,
     as NCCL's do, instead of raising as gloo's do: every survivor sits inside its step (or inside the generation
     agreement) until its StallBreaker -- armed with AITJ_STALL_BREAKER=force -- sees the newer generation and aborts the
     communicator; then all three re-rendezvous with the replacement and go on, processes kept.  A second victim (rank 0,
@@ -440,12 +442,20 @@ def test_stall_breaker_recovers_four_ranks_whose_collectives_hang_like_nccl(tmp_
     from trainingjob_operator_b200.cmd.options import TrainingJobOperatorOption
 
     script = tmp_path / "hang_worker.py"
-    script.write_text(textwrap.dedent(HANG_WORKER_SCRIPT.format(root=ROOT)))
-    worker = [sys.executable, str(script), "--cpu", "--model", "mlp", "--batch", "16", "--steps", "0", "--elastic",
-              "--ckpt-every", "10", "--step-sleep", "0.05"]
+    src = HANG_WORKER_SCRIPT.format(root=ROOT)
+    shape = ["--model", "mlp", "--batch", "16"]
+    if model != "mlp":
+        src = src.replace("_build = W.build_adapter", "sys.path.insert(0, os.path.join({root!r}, 'tests'))\n"
+                          "import kernel_emulation as ke\nke.install()\n"
+                          "_build = lambda args, device: W.EngineAdapter(args.model, args.batch, args.seq, args, device='cpu')"
+                          .format(root=ROOT))
+        shape = ["--model", model, "--batch", "2", "--seq", "128"]
+    script.write_text(textwrap.dedent(src))
+    worker = [sys.executable, str(script), "--cpu"] + shape + ["--steps", "0", "--elastic", "--ckpt-every", "10",
+                                                                "--step-sleep", "0.05"]
     env = [{"name": "PYTHONPATH", "value": ROOT}, {"name": "OMP_NUM_THREADS", "value": "1"},
            {"name": "AITJ_STALL_BREAKER", "value": "force"}, {"name": "AITJ_FT_ABORT_AFTER", "value": "1.5"},
-           {"name": "AITJ_COLLECTIVE_TIMEOUT", "value": "1"}]
+           {"name": "AITJ_COLLECTIVE_TIMEOUT", "value": "2"}]
     job = {"apiVersion": C.API_VERSION, "kind": C.KIND, "metadata": {"name": "hang"},
            "spec": {"frameworkType": "pytorch", "faultTolerant": True, "replicaSpecs": {"trainer": {
                "replicas": 4, "minReplicas": 4, "maxReplicas": 4, "edlPolicy": "Manual", "restartPolicy": "OnFailure",
